@@ -1,0 +1,467 @@
+"""NGSolve-compatible front end — the drop-in boundary of SURVEY 8(b).
+
+OpenCMP's ``models`` / ``solvers`` / ``helpers`` do ``import ngsolve as ngs`` and call a small subset of that API;
+this module provides that subset on top of the B200 backend, so those modules run unchanged once
+``opencmp_b200.install_as_ngsolve()`` has aliased it (``sys.modules['ngsolve']``).
+
+Symbols and their reference call sites:
+  Mesh / Boundaries ............ helpers/io.py:94-99, models/base_model.py:319
+  H1 / VectorH1 / L2 / HDiv / FESpace ... models/poisson.py:60-65, models/ins.py:95-128
+  GridFunction (.vec, .components, .Set) . models/base_model.py:321-341, solvers/transient_multistep.py:150-169
+  BilinearForm / LinearForm (.Assemble, .mat, .vec) ... solvers/base_solver.py:368-377
+  Preconditioner, mat.Inverse, solvers.CG/GMRes/MinRes/PreconditionedRichardson ... models/base_model.py:886-947
+  Integrate ..................... helpers/error.py:54-128
+
+All arithmetic on DOF vectors and matrices is delegated to a *backend*. The product backend is the CUDA C-ABI
+(backend.py); it raises if the extension or a GPU is missing — there is no CPU fallback. tests/ inject the oracle
+backend with ``set_backend`` to pin the lowering against the reference's golden error norms.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import symbolic as sym
+from .symbolic import (CoefficientFunction, Parameter, ProxyFunction, InnerProduct, OuterProduct, Norm, IfPos, Grad,
+                       grad, div, sqrt, sin, cos, tan, exp, log, atan, floor, ceil, tanh, erf, x, y, z, specialcf, dx,
+                       ds, Conj, DifferentialSymbol, SumOfIntegrals, CF, lower_form, field_arrays)
+from .mesh import Mesh as _Mesh, Region, load_mesh
+from . import space as _space
+from .space import FESpace as _FESpace
+
+pi = np.pi
+e = np.e
+
+_backend = None
+
+
+def set_backend(b) -> None:
+    global _backend
+    _backend = b
+
+
+def get_backend():
+    global _backend
+    if _backend is None:
+        from .backend import CudaBackend
+        _backend = CudaBackend()
+    return _backend
+
+
+# ---- mesh ------------------------------------------------------------------------------------------------------------
+class Mesh(_Mesh):
+    def __init__(self, src):
+        if isinstance(src, _Mesh):
+            self.__dict__.update(src.__dict__)
+        elif isinstance(src, (str, os.PathLike)):
+            self.__dict__.update(load_mesh(str(src)).__dict__)
+        else:
+            raise TypeError('Mesh() needs a file name or an opencmp_b200 mesh')
+
+    @property
+    def ngmesh(self):
+        return self
+
+    def __call__(self, *pt):
+        return MeshPoint(self, pt)
+
+
+class MeshPoint:
+    def __init__(self, mesh, pt):
+        self.mesh, self.pt = mesh, tuple(float(v) for v in pt)
+
+
+# ---- spaces ------------------------------------------------------------------------------------------------------------
+class FESpace(_FESpace):
+    def TrialFunction(self):
+        return _proxies(self, False)
+
+    def TestFunction(self):
+        return _proxies(self, True)
+
+    def TnT(self):
+        return self.TrialFunction(), self.TestFunction()
+
+
+def _proxies(fes, is_test):
+    if fes.components:
+        return tuple(ProxyFunction(fes, i, is_test) for i in range(len(fes.components)))
+    return ProxyFunction(fes, 0, is_test)
+
+
+def _mk(family):
+    def ctor(mesh, order=1, dirichlet='', dgjumps=False, RT=False, **kw):
+        if dirichlet is None:
+            dirichlet = ''
+        return FESpace(mesh, order=order, dirichlet=dirichlet, dgjumps=dgjumps, family=family, RT=RT)
+    ctor.__name__ = family
+    return ctor
+
+
+H1, VectorH1, L2, HDiv = _mk('H1'), _mk('VectorH1'), _mk('L2'), _mk('HDiv')
+
+
+# ---- vectors -----------------------------------------------------------------------------------------------------------
+class BaseVector:
+    """DOF vector; storage ``a`` is a backend array (torch.cuda float64 tensor, or ndarray under the test oracle)."""
+
+    def __init__(self, a):
+        self.a = a
+
+    def __len__(self):
+        return int(self.a.shape[0])
+
+    @property
+    def size(self):
+        return len(self)
+
+    @property
+    def data(self):
+        return self
+
+    @data.setter
+    def data(self, other):
+        if other is self:
+            return
+        src = other.a if isinstance(other, BaseVector) else other
+        get_backend().copy_into(self.a, src)
+
+    def CreateVector(self):
+        return BaseVector(get_backend().zeros(len(self)))
+
+    def Copy(self):
+        v = self.CreateVector()
+        v.data = self
+        return v
+
+    def Assign(self, other, scal=1.0):
+        self.data = scal * other
+
+    def __add__(self, o):
+        return BaseVector(self.a + o.a)
+
+    def __sub__(self, o):
+        return BaseVector(self.a - o.a)
+
+    def __neg__(self):
+        return BaseVector(-self.a)
+
+    def __mul__(self, s):
+        return BaseVector(self.a * float(s))
+
+    __rmul__ = __mul__
+
+    def __iadd__(self, o):
+        self.a += o.a
+        return self
+
+    def __isub__(self, o):
+        self.a -= o.a
+        return self
+
+    def __imul__(self, s):
+        self.a *= float(s)
+        return self
+
+    def InnerProduct(self, o):
+        return float(get_backend().dot(self.a, o.a))
+
+    def Norm(self):
+        return float(np.sqrt(get_backend().dot(self.a, self.a)))
+
+    def FV(self):
+        return self
+
+    def NumPy(self):
+        return get_backend().numpy_view(self.a)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return BaseVector(self.a[i])
+        return float(self.a[i])
+
+    def __setitem__(self, i, v):
+        if isinstance(v, BaseVector):
+            v = v.a
+        self.a[i] = v
+
+    def Range(self, lo, hi):
+        return BaseVector(self.a[lo:hi])
+
+
+class GridFunction(CoefficientFunction):
+    def __init__(self, fes, name: str = 'gfu', _root=None, _comp: Optional[int] = None, **kw):
+        self.space = fes
+        self.name = name
+        if _root is None:
+            self._root = self
+            self._blocks = list(range(len(fes.blocks)))
+            self.vec = BaseVector(get_backend().zeros(fes.ndof))
+            self._root_space = fes
+            self.components = [GridFunction(fes.components[i], name, _root=self, _comp=i)
+                               for i in range(len(fes.components))] if fes.components else []
+        else:
+            self._root = _root
+            rs = _root.space
+            self._root_space = rs
+            self._blocks = list(rs.comp_blocks[_comp])
+            rng = rs.component_range(_comp)
+            self.vec = BaseVector(_root.vec.a[rng.start:rng.stop])
+            self.components = []
+        val, g = field_arrays(self._root, self._root_space, self._blocks)
+        self.arr = val
+        self._g = g
+
+    def vec_numpy(self):
+        """Host copy of the ROOT dof vector (used by the test oracle only)."""
+        return get_backend().to_numpy(self._root.vec.a)
+
+    def _grad_cf(self):
+        return CoefficientFunction(_arr=self._g)
+
+    def Deriv(self):
+        return self._grad_cf()
+
+    @property
+    def dim(self):
+        return int(self.arr.size)
+
+    def Set(self, cf, definedon=None, VOL_or_BND=None, **kw):
+        from .project import set_gridfunction
+        set_gridfunction(self, CoefficientFunction._lift(cf), definedon)
+
+    def Update(self):
+        n = self.space.ndof
+        if len(self.vec) != n:
+            self.vec = BaseVector(get_backend().zeros(n))
+
+    def Save(self, filename, parallel=False):
+        np.save(_sol_path(filename), self.vec.NumPy())
+
+    def Load(self, filename, parallel=False):
+        self.vec.data = BaseVector(get_backend().from_numpy(np.load(_sol_path(filename))))
+
+    def __call__(self, *a, **k):
+        raise NotImplementedError('point evaluation of a GridFunction')
+
+
+def _sol_path(fn):
+    fn = str(fn)
+    return fn if fn.endswith('.npy') else fn + '.npy'
+
+
+# ---- forms -------------------------------------------------------------------------------------------------------------
+class _Form:
+    arity = 0
+
+    def __init__(self, fes, **flags):
+        self.space = fes
+        self.integrals = SumOfIntegrals([])
+        self._program = None
+        self.flags = flags
+
+    def __iadd__(self, other):
+        if isinstance(other, CoefficientFunction):
+            raise TypeError('add integrals (cf * dx), not bare coefficient functions, to a form')
+        self.integrals = self.integrals + other
+        self._program = None
+        return self
+
+    def program(self):
+        if self._program is None:
+            self._program = lower_form(self.space, self.integrals, self.arity)
+        return self._program
+
+
+class BilinearForm(_Form):
+    arity = 2
+
+    def __init__(self, fes, symmetric=False, check_unused=True, condense=False, **flags):
+        super().__init__(fes, **flags)
+        self.mat = None
+
+    def Assemble(self):
+        be = get_backend()
+        if self.mat is None:
+            self.mat = Matrix(self.space)
+        be.assemble_matrix(self.program(), self.mat)
+        return self
+
+
+class LinearForm(_Form):
+    arity = 1
+
+    def __init__(self, fes, **flags):
+        super().__init__(fes, **flags)
+        self.vec = BaseVector(get_backend().zeros(fes.ndof))
+
+    def Assemble(self):
+        get_backend().assemble_vector(self.program(), self.vec.a)
+        return self
+
+
+class Matrix:
+    """Assembled sparse matrix: CSR values on the backend over the space's fixed pattern."""
+
+    def __init__(self, fes):
+        self.space = fes
+        self.pattern = fes.pattern()
+        self.values = get_backend().zeros(self.pattern.nnz)
+        self.height = self.width = fes.ndof
+
+    @property
+    def nze(self):
+        return self.pattern.nnz
+
+    def __mul__(self, v):
+        if isinstance(v, BaseVector):
+            out = get_backend().zeros(self.height)
+            get_backend().spmv(self, v.a, out)
+            return BaseVector(out)
+        return NotImplemented
+
+    def Mult(self, x, y):
+        get_backend().spmv(self, x.a, y.a)
+
+    def CreateColVector(self):
+        return BaseVector(get_backend().zeros(self.height))
+
+    CreateRowVector = CreateColVector
+
+    def Inverse(self, freedofs=None, inverse: str = ''):
+        return _Inverse(self, freedofs, inverse)
+
+    def CSR(self):
+        be = get_backend()
+        return be.to_numpy(self.values), self.pattern.colidx, self.pattern.rowptr
+
+
+class _Inverse:
+    """``a.mat.Inverse(freedofs, inverse=...)`` — applied with ``inv * r`` (reference base_model.py:918-922)."""
+
+    def __init__(self, mat, freedofs, kind):
+        self.mat, self.freedofs, self.kind = mat, freedofs, kind
+
+    def __mul__(self, r):
+        out = get_backend().zeros(self.mat.height)
+        get_backend().solve_free(self.mat, r.a, out, self.freedofs)
+        return BaseVector(out)
+
+
+class Preconditioner:
+    def __init__(self, bf, type: str = 'local', **flags):
+        self.bf, self.type, self.flags = bf, type, flags
+        self.state = None
+
+    def Update(self):
+        if self.bf.mat is not None:
+            self.state = get_backend().precond_setup(self.bf.mat, self.type, self.bf.space.FreeDofs())
+
+
+class _Solvers:
+    @staticmethod
+    def CG(mat, rhs, pre=None, sol=None, tol=1e-12, maxsteps=100, printrates=False, initialize=True, **kw):
+        if sol is None:
+            sol = rhs.CreateVector()
+        get_backend().krylov('cg', mat, rhs.a, sol.a, pre, None, tol, maxsteps, initialize, printrates)
+        return sol
+
+    @staticmethod
+    def MinRes(mat, rhs, pre=None, sol=None, tol=1e-12, maxsteps=100, printrates=False, initialize=True, **kw):
+        if sol is None:
+            sol = rhs.CreateVector()
+        get_backend().krylov('minres', mat, rhs.a, sol.a, pre, None, tol, maxsteps, initialize, printrates)
+        return sol
+
+    @staticmethod
+    def GMRes(A, b, pre=None, freedofs=None, x=None, maxsteps=100, tol=None, printrates=False, **kw):
+        if x is None:
+            x = b.CreateVector()
+        get_backend().krylov('gmres', A, b.a, x.a, pre, freedofs, 1e-7 if tol is None else tol, maxsteps, False,
+                             printrates)
+        return x
+
+    @staticmethod
+    def PreconditionedRichardson(a, rhs, pre=None, freedofs=None, maxit=100, tol=1e-8, dampfactor=1.0,
+                                 printing=False, **kw):
+        mat = a.mat if hasattr(a, 'mat') else a
+        x = rhs.CreateVector()
+        get_backend().krylov('richardson', mat, rhs.a, x.a, pre, freedofs, tol, maxit, True, printing,
+                             damp=dampfactor)
+        return x
+
+
+solvers = _Solvers()
+
+
+# ---- reductions --------------------------------------------------------------------------------------------------------
+def Integrate(cf, mesh, VOL_or_BND=None, order: int = 5, definedon=None, **kw):
+    """``ngs.Integrate`` with its default order-5 rule (reference helpers/error.py:66-77)."""
+    cf = CoefficientFunction._lift(cf)
+    fes = _scalar_space(mesh)
+    if cf.arr.size == 1:
+        prog = lower_form(fes, cf * dx(definedon=definedon), 0, intorder=order)
+        return get_backend().integrate(prog)
+    return tuple(get_backend().integrate(lower_form(fes, cf[i] * dx(definedon=definedon), 0, intorder=order))
+                 for i in range(cf.arr.size))
+
+
+def _scalar_space(mesh):
+    sp_ = getattr(mesh, '_b200_scalar_space', None)
+    if sp_ is None or sp_.mesh.ne != mesh.ne:
+        sp_ = FESpace(mesh, order=0, family='L2')
+        mesh._b200_scalar_space = sp_
+    return sp_
+
+
+# ---- runtime stubs (reference run.py:57-61) ----------------------------------------------------------------------------
+class TaskManager:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def SetNumThreads(n):
+    return None
+
+
+class _Globals:
+    msg_level = 0
+
+
+ngsglobals = _Globals()
+
+
+class _Config:
+    USE_PARDISO = False
+    USE_MKL = False
+    USE_UMFPACK = True
+
+
+config = _Config()
+BND = 'BND'
+VOL = 'VOL'
+
+
+class BitArray:
+    def __init__(self, n):
+        self.a = np.zeros(int(n), dtype=bool) if not isinstance(n, np.ndarray) else n
+
+    def __len__(self):
+        return len(self.a)
+
+    def __getitem__(self, i):
+        return bool(self.a[i])
+
+    def __setitem__(self, i, v):
+        self.a[i] = v
+
+    def Set(self):
+        self.a[:] = True
+
+    def Clear(self):
+        self.a[:] = False

@@ -1,0 +1,192 @@
+"""``GridFunction.Set`` — local L2 projection followed by averaging of shared DOFs, expressed as a
+linear-form assembly so it runs through the same CUDA kernels as everything else.
+
+Hot-path use: ``Model.apply_dirichlet_bcs_to`` projects the (time dependent, region-wise) Dirichlet data onto the
+boundary DOFs every time step and every Picard iteration (reference opencmp/models/base_model.py:321-341,
+models/ins.py:337). One-off use: initial conditions (reference config_functions/initial_conditions.py).
+
+Trick: testing against the *dual* basis psi_i = sum_j (M^-1)_ij phi_j of the local mass matrix turns
+"assemble rhs, solve the local system" into a plain assembly  c_i = int f psi_i ; scatter-add over all items and a
+multiplication by 1/multiplicity gives the averaged projection. For affine cells the local mass matrix of a scalar
+block (and the normal-trace mass matrix of an HDiv block on a facet) is a reference matrix times a measure, so the
+dual tables are tabulated once on the host like any other basis table.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+
+from .basis import Basis
+from .ir import Coef
+from .quadrature import cell_rule, facet_rule_in_cell, facet_ref_geometry
+from .mesh import Region, local_topology
+from .space import Block, FESpace
+from .symbolic import CoefficientFunction, ProxyFunction, S, dx, ds, lower_form, SumOfIntegrals, specialcf
+
+
+class DualBasis(Basis):
+    """Value rows hold the dual functions of ``base`` on cells (mode 'cell') or of its facet traces ('facet')."""
+
+    def __init__(self, base: Basis, mode: str, deg: int):
+        self.cell_type, self.order, self.dim = base.cell_type, base.order, base.dim
+        self.kind = base.kind
+        self.entity_dofs = base.entity_dofs
+        self.ndof = base.ndof
+        self._cache = {}
+        self.base, self.mode, self.deg = base, mode, deg
+
+    def tabulate(self, pts):
+        raise NotImplementedError('dual tables exist only at their own rule')
+
+    def tabulate_cell(self, deg: int) -> np.ndarray:
+        assert self.mode == 'cell' and deg == self.deg
+        if 'c' not in self._cache:
+            tab = self.base.tabulate_cell(deg)
+            _, w = cell_rule(self.cell_type, deg)
+            if self.kind != 'scalar':
+                raise NotImplementedError('cell-wise dual basis for vector blocks')
+            phi = tab[:, 0, :]
+            M = phi.T @ (w[:, None] * phi)
+            out = np.zeros_like(tab)
+            out[:, 0, :] = phi @ np.linalg.inv(M)
+            self._cache['c'] = out
+        return self._cache['c']
+
+    def tabulate_facets(self, deg: int) -> np.ndarray:
+        assert self.mode == 'facet' and deg == self.deg
+        if 'f' not in self._cache:
+            tab = self.base.tabulate_facets(deg)                   # (nfc, nq, nrows, ndof)
+            _, w = facet_rule_in_cell(self.cell_type, deg)
+            tang, _ = facet_ref_geometry(self.cell_type)
+            out = np.zeros_like(tab)
+            trace = trace_local(self.base)
+            d = self.dim
+            for lf in range(tab.shape[0]):
+                idx = trace[lf]
+                if self.kind == 'scalar':
+                    phi = tab[lf][:, 0, idx]
+                    M = phi.T @ (w[:, None] * phi)
+                    out[lf][:, 0, idx] = phi @ np.linalg.inv(M)
+                else:
+                    t = tang[lf]
+                    nr = np.array([t[0, 1], -t[0, 0]]) if d == 2 else np.cross(t[0], t[1])
+                    vec = tab[lf][:, :d, :][:, :, idx]              # (nq, d, ntr)
+                    s = np.einsum('qci,c->qi', vec, nr)
+                    M = s.T @ (w[:, None] * s)
+                    out[lf][:, :d, idx] = np.einsum('qcj,ji->qci', vec, np.linalg.inv(M))
+            self._cache['f'] = out
+        return self._cache['f']
+
+
+def trace_local(basis: Basis):
+    """Per local facet: local dofs with a non-vanishing (normal) trace there."""
+    loc = local_topology(basis.cell_type)
+    out = []
+    for lf, fv in enumerate(loc['facets']):
+        fvs = set(fv)
+        idx, pos = [], 0
+        for (edim, le, cnt, tag) in basis.entity_dofs:
+            take = (tag == 'v' and le in fvs) or (tag == 'e' and set(loc['edges'][le]) <= fvs) or \
+                   (tag in ('f', 'lo', 'hi') and le == lf)
+            if take:
+                idx += list(range(pos, pos + cnt))
+            pos += cnt
+        out.append(idx)
+    return out
+
+
+class _ProjSpace(FESpace):
+    """Shallow copy of the blocks a GridFunction lives on, with dual tables swapped in."""
+
+    def __init__(self, root_space: FESpace, blocks, mode: str, deg: int):
+        self.mesh = root_space.mesh
+        self.name = 'projection'
+        self.components = []
+        self.dgjumps = False
+        self.order = root_space.order
+        self.blocks = []
+        for b in blocks:
+            src = root_space.blocks[b]
+            blk = Block.__new__(Block)
+            blk.__dict__.update(src.__dict__)
+            blk.basis = DualBasis(src.basis, mode, deg)
+            self.blocks.append(blk)
+        self.comp_blocks = [range(0, len(self.blocks))]
+        self.vector = [False]
+        self._finalize()
+
+
+_cache: Dict[tuple, tuple] = {}
+
+
+def set_gridfunction(gf, cf: CoefficientFunction, definedon: Optional[Region]) -> None:
+    from . import ngs
+    be = ngs.get_backend()
+    root_space = gf._root_space
+    mesh = root_space.mesh
+    blocks = gf._blocks
+    kinds = {root_space.blocks[b].kind for b in blocks}
+    bnd = definedon is not None and definedon.kind == 'bnd'
+    if not bnd and 'hdiv' in kinds:
+        _global_projection(gf, cf, definedon)
+        return
+    key = (id(gf._root), tuple(blocks), bnd, None if definedon is None else definedon.ids, id(cf))
+    hit = _cache.get(key)
+    if hit is None:
+        order = max(root_space.blocks[b].order for b in blocks)
+        deg = 2 * order
+        pspace = _ProjSpace(root_space, blocks, 'facet' if bnd else 'cell', deg)
+        v = ProxyFunction(pspace, 0, True)
+        meas = CoefficientFunction(Coef('meas', (), None))
+        if 'hdiv' in kinds:
+            n = specialcf.normal(mesh.dim)
+            integrand = (meas * (cf * n)) * (v * n)
+        else:
+            integrand = (cf / meas) * v if cf.arr.ndim == 0 or v.arr.ndim else (cf / meas) * v
+        measure = ds(definedon=definedon, skeleton=True) if bnd else dx(definedon=definedon)
+        prog = lower_form(pspace, integrand * measure, 1, intorder=deg)
+        # multiplicities
+        count = np.zeros(pspace.ndof)
+        cd = pspace.cell_dofs
+        if bnd:
+            sel = np.isin(mesh.bnd_region, list(definedon.ids))
+            f = mesh.bnd_facets[sel]
+            c, lf = mesh.facet_cells[f, 0], mesh.facet_local[f, 0]
+            off = 0
+            for blk in pspace.blocks:
+                tr = np.array(trace_local(blk.basis.base), dtype=np.int64)
+                dofs = cd[c[:, None], off + tr[lf]]
+                np.add.at(count, dofs.ravel(), 1.0)
+                off += blk.nloc
+        else:
+            cells = np.arange(mesh.ne) if definedon is None else \
+                np.nonzero(np.isin(mesh.cell_mat, list(definedon.ids)))[0]
+            np.add.at(count, cd[cells].ravel(), 1.0)
+        mask = count > 0
+        inv = np.where(mask, 1.0 / np.maximum(count, 1.0), 0.0)
+        hit = (prog, be.from_numpy(inv), be.from_numpy(mask.astype(np.float64)), be.zeros(pspace.ndof), cf)
+        _cache[key] = hit
+    prog, inv, mask, work, _keep = hit
+    be.assemble_vector(prog, work)
+    be.masked_assign(gf.vec.a, work, inv, mask)
+
+
+def _global_projection(gf, cf, definedon) -> None:
+    """Global L2 projection (mass-matrix CG) for vector blocks on cells: used for initial conditions only."""
+    from . import ngs
+    fes = gf.space
+    u, v = fes.TrialFunction(), fes.TestFunction()
+    if isinstance(u, tuple):
+        raise NotImplementedError('Set() on a compound GridFunction: set its components')
+    a = ngs.BilinearForm(fes)
+    a += (u * v) * dx
+    L = ngs.LinearForm(fes)
+    L += (cf * v) * dx(bonus_intorder=2)
+    a.Assemble()
+    L.Assemble()
+    pre = ngs.Preconditioner(a, 'local')
+    pre.Update()
+    sol = L.vec.CreateVector()
+    ngs.solvers.CG(mat=a.mat, rhs=L.vec, pre=pre, sol=sol, tol=1e-14, maxsteps=2000)
+    gf.vec.data = sol

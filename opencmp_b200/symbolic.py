@@ -1,0 +1,689 @@
+"""Symbolic layer: the NGSolve-style expression API that OpenCMP's models call, lowered to form programs (ir.py).
+
+Mirrors the symbols listed in SURVEY 8(b) "Symbolic" / "Measures": ``CoefficientFunction``, ``Parameter``, proxies
+(+ ``.Other()``, ``.Trace()``), ``Grad``, ``div``, ``InnerProduct``, ``OuterProduct``, ``Norm``, ``IfPos``,
+``sqrt/sin/cos/tan/exp``, ``x,y,z``, ``specialcf.normal / mesh_size``, ``dx``, ``ds`` (reference call sites e.g.
+``opencmp/models/poisson.py:71-158``, ``models/ins.py:178-321``, ``helpers/dg.py:22-83``, ``helpers/math.py:134-221``).
+
+Every tensor entry is a *bilinear polynomial* ``S``: a dict  (test_key, trial_key) -> Coef  where a key is ``None`` or
+``(row, side)`` — the physical operator row of the form's space and the facet side. Products distribute, so any
+integrand a model writes collapses to the entry list  sum_k  D_k(x) * testrow_k(v) * trialrow_k(u)  the CUDA kernels
+contract (B^T D B). Coefficient parts are hash-consed DAGs (ir.Coef) compiled to bytecode once per form.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from .ir import Coef, ZERO, ONE, Bytecode, Integral, FormProgram, resolve_piecewise, coef_leaves
+from .mesh import Region
+
+Key = Optional[Tuple[int, int]]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class S:
+    """Scalar bilinear polynomial in (test rows) x (trial rows) with Coef coefficients."""
+    __slots__ = ('t',)
+
+    def __init__(self, terms: Optional[Dict[Tuple[Key, Key], Coef]] = None):
+        self.t = terms if terms is not None else {}
+
+    @staticmethod
+    def coef(c: Coef) -> 'S':
+        return S({(None, None): c}) if not c.is_const(0.0) else S()
+
+    @staticmethod
+    def lift(v) -> 'S':
+        if isinstance(v, S):
+            return v
+        if isinstance(v, Coef):
+            return S.coef(v)
+        if isinstance(v, Parameter):
+            return S.coef(Coef('param', (), v))
+        return S.coef(Coef.const(v))
+
+    def is_coef(self) -> bool:
+        return all(k == (None, None) for k in self.t)
+
+    def as_coef(self) -> Coef:
+        if not self.is_coef():
+            raise TypeError('nonlinear function of a trial/test function is not supported')
+        return self.t.get((None, None), ZERO)
+
+    def __add__(self, o: 'S') -> 'S':
+        out = dict(self.t)
+        for k, c in o.t.items():
+            if k in out:
+                s = Coef.binary('add', out[k], c)
+                if s.is_const(0.0):
+                    del out[k]
+                else:
+                    out[k] = s
+            else:
+                out[k] = c
+        return S(out)
+
+    def __neg__(self) -> 'S':
+        return S({k: Coef.unary('neg', c) for k, c in self.t.items()})
+
+    def __sub__(self, o: 'S') -> 'S':
+        return self + (-o)
+
+    def __mul__(self, o: 'S') -> 'S':
+        out: Dict[Tuple[Key, Key], Coef] = {}
+        for (t1, u1), c1 in self.t.items():
+            for (t2, u2), c2 in o.t.items():
+                if (t1 is not None and t2 is not None) or (u1 is not None and u2 is not None):
+                    raise TypeError('product of two test (or two trial) functions in one integrand')
+                k = (t1 if t1 is not None else t2, u1 if u1 is not None else u2)
+                c = Coef.binary('mul', c1, c2)
+                if c.is_const(0.0):
+                    continue
+                out[k] = Coef.binary('add', out[k], c) if k in out else c
+        return S(out)
+
+    def scale(self, c: Coef) -> 'S':
+        if c.is_const(0.0):
+            return S()
+        return S({k: Coef.binary('mul', v, c) for k, v in self.t.items()})
+
+    def other(self) -> 'S':
+        flip = lambda k: None if k is None else (k[0], 1 - k[1])
+        return S({(flip(t), flip(u)): _other_coef(c) for (t, u), c in self.t.items()})
+
+
+def _other_coef(c: Coef, memo: Optional[dict] = None) -> Coef:
+    memo = {} if memo is None else memo
+    if id(c) in memo:
+        return memo[id(c)]
+    if c.op == 'field':
+        gf, blk, row, side = c.val
+        out = Coef('field', (), (gf, blk, row, 1 - side))
+    elif not c.args:
+        out = c
+    else:
+        new = tuple(_other_coef(a, memo) for a in c.args)
+        if all(n is o for n, o in zip(new, c.args)):
+            out = c
+        elif c.op == 'ifpos':
+            out = Coef.ifpos(*new)
+        elif len(new) == 1:
+            out = Coef.unary(c.op, new[0])
+        else:
+            out = Coef.binary(c.op, new[0], new[1])
+    memo[id(c)] = out
+    return out
+
+
+_S0 = S()
+
+
+def _obj(shape) -> np.ndarray:
+    a = np.empty(shape, dtype=object)
+    a.fill(_S0)
+    return a
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class CoefficientFunction:
+    """Tensor (rank <= 2) of ``S`` entries with NGSolve operator semantics."""
+    __array_priority__ = 1000
+
+    def __init__(self, value=None, dims: Optional[Sequence[int]] = None, _arr: Optional[np.ndarray] = None):
+        if _arr is not None:
+            self.arr = _arr
+            return
+        if isinstance(value, CoefficientFunction):
+            arr = value.arr
+        elif isinstance(value, (tuple,)):
+            parts = [CoefficientFunction(v) for v in value]
+            flat: List[S] = []
+            for p in parts:
+                flat += list(p.arr.reshape(-1))
+            arr = np.empty(len(flat), dtype=object)
+            for i, s in enumerate(flat):
+                arr[i] = s
+        elif isinstance(value, list):
+            # region-wise coefficient: one entry per boundary / material index (boundary_conditions.py:182-203)
+            parts = [CoefficientFunction(v if v is not None else 0.0) for v in value]
+            shape = parts[0].arr.shape if parts else ()
+            for p in parts:
+                if p.arr.shape != shape and p.arr.shape != ():
+                    shape = p.arr.shape
+            arr = _obj(shape)
+            for idx in np.ndindex(*shape) if shape else [()]:
+                lst = tuple((p.arr[idx] if p.arr.shape == shape else p.arr[()]).as_coef() for p in parts)
+                arr[idx] = S.coef(Coef('piecewise', (), ('any', lst)))
+        else:
+            arr = np.empty((), dtype=object)
+            arr[()] = S.lift(value)
+        if dims is not None:
+            arr = arr.reshape(tuple(dims))
+        self.arr = arr
+
+    # ---- shape ------------------------------------------------------------------------------------------------
+    @property
+    def dims(self) -> tuple:
+        return tuple(self.arr.shape)
+
+    @property
+    def dim(self) -> int:
+        return int(self.arr.size)
+
+    @property
+    def shape(self) -> tuple:
+        return tuple(self.arr.shape)
+
+    def __len__(self):
+        if self.arr.ndim == 0:
+            raise TypeError('scalar coefficient function has no len()')
+        return self.arr.shape[0]
+
+    def __getitem__(self, idx) -> 'CoefficientFunction':
+        sub = self.arr[idx]
+        if not isinstance(sub, np.ndarray):
+            a = np.empty((), dtype=object)
+            a[()] = sub
+            sub = a
+        return CoefficientFunction(_arr=sub)
+
+    def __iter__(self):
+        if self.arr.ndim == 0:
+            raise TypeError('scalar coefficient function is not iterable')
+        return (self[i] for i in range(self.arr.shape[0]))
+
+    @property
+    def trans(self) -> 'CoefficientFunction':
+        return CoefficientFunction(_arr=self.arr.T.copy())
+
+    # ---- arithmetic -------------------------------------------------------------------------------------------
+    @staticmethod
+    def _lift(o) -> 'CoefficientFunction':
+        return o if isinstance(o, CoefficientFunction) else CoefficientFunction(o)
+
+    def _ew(self, o, fn) -> 'CoefficientFunction':
+        o = CoefficientFunction._lift(o)
+        a, b = self.arr, o.arr
+        if a.shape != b.shape:
+            if a.ndim == 0 or a.size == 1 and b.ndim:
+                a = np.broadcast_to(a.reshape(()), b.shape)
+            elif b.ndim == 0 or b.size == 1:
+                b = np.broadcast_to(b.reshape(()), a.shape)
+            else:
+                raise ValueError('shape mismatch {} vs {}'.format(a.shape, b.shape))
+        out = _obj(a.shape)
+        for idx in (np.ndindex(*a.shape) if a.shape else [()]):
+            out[idx] = fn(a[idx], b[idx])
+        return CoefficientFunction(_arr=out)
+
+    def __add__(self, o):
+        return self._ew(o, lambda x, y: x + y)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self._ew(o, lambda x, y: x - y)
+
+    def __rsub__(self, o):
+        return CoefficientFunction._lift(o)._ew(self, lambda x, y: x - y)
+
+    def __neg__(self):
+        out = _obj(self.arr.shape)
+        for idx in (np.ndindex(*self.arr.shape) if self.arr.shape else [()]):
+            out[idx] = -self.arr[idx]
+        return CoefficientFunction(_arr=out)
+
+    def __mul__(self, o):
+        if isinstance(o, DifferentialSymbol):
+            return SumOfIntegrals([(self, o)])
+        o = CoefficientFunction._lift(o)
+        a, b = self.arr, o.arr
+        if a.ndim == 0 or b.ndim == 0:
+            return self._ew(o, lambda x, y: x * y)
+        if a.ndim == 1 and b.ndim == 1:
+            return InnerProduct(self, o)
+        if a.ndim == 2 and b.ndim == 1:
+            out = _obj((a.shape[0],))
+            for i in range(a.shape[0]):
+                acc = _S0
+                for j in range(a.shape[1]):
+                    acc = acc + a[i, j] * b[j]
+                out[i] = acc
+            return CoefficientFunction(_arr=out)
+        if a.ndim == 1 and b.ndim == 2:
+            out = _obj((b.shape[1],))
+            for j in range(b.shape[1]):
+                acc = _S0
+                for i in range(b.shape[0]):
+                    acc = acc + a[i] * b[i, j]
+                out[j] = acc
+            return CoefficientFunction(_arr=out)
+        out = _obj((a.shape[0], b.shape[1]))
+        for i in range(a.shape[0]):
+            for j in range(b.shape[1]):
+                acc = _S0
+                for k in range(a.shape[1]):
+                    acc = acc + a[i, k] * b[k, j]
+                out[i, j] = acc
+        return CoefficientFunction(_arr=out)
+
+    def __rmul__(self, o):
+        return CoefficientFunction._lift(o) * self
+
+    def __truediv__(self, o):
+        o = CoefficientFunction._lift(o)
+        if o.arr.size != 1:
+            raise TypeError('division by a non-scalar coefficient function')
+        d = o.arr.reshape(())[()].as_coef()
+        inv = Coef.binary('div', ONE, d)
+        out = _obj(self.arr.shape)
+        for idx in (np.ndindex(*self.arr.shape) if self.arr.shape else [()]):
+            s = self.arr[idx]
+            out[idx] = S({k: Coef.binary('div', c, d) for k, c in s.t.items()}) if inv is not None else s
+        return CoefficientFunction(_arr=out)
+
+    def __rtruediv__(self, o):
+        return CoefficientFunction._lift(o) / self
+
+    def __pow__(self, o):
+        o = CoefficientFunction._lift(o)
+        return self._ew(o, lambda x, y: S.coef(Coef.binary('pow', x.as_coef(), y.as_coef())))
+
+    def __rpow__(self, o):
+        return CoefficientFunction._lift(o) ** self
+
+    # ---- facet sides ------------------------------------------------------------------------------------------
+    def Other(self, bnd=None) -> 'CoefficientFunction':
+        out = _obj(self.arr.shape)
+        for idx in (np.ndindex(*self.arr.shape) if self.arr.shape else [()]):
+            out[idx] = self.arr[idx].other()
+        return self._like(out)
+
+    def Trace(self) -> 'CoefficientFunction':
+        return self
+
+    def _like(self, arr) -> 'CoefficientFunction':
+        return CoefficientFunction(_arr=arr)
+
+    def __str__(self) -> str:
+        kinds = set()
+        for s in self.arr.reshape(-1):
+            for (t, u) in s.t:
+                if u is not None:
+                    kinds.add('trial-function')
+                if t is not None:
+                    kinds.add('test-function')
+        return 'coef {} dims={}'.format(' '.join(sorted(kinds)) or 'function', self.dims)
+
+    def map_coef(self, fn) -> 'CoefficientFunction':
+        out = _obj(self.arr.shape)
+        for idx in (np.ndindex(*self.arr.shape) if self.arr.shape else [()]):
+            out[idx] = S.coef(fn(self.arr[idx].as_coef()))
+        return CoefficientFunction(_arr=out)
+
+
+CF = CoefficientFunction
+
+
+class Parameter(CoefficientFunction):
+    """Mutable scalar leaf (reference: t_param / dt_param lists, solvers/base_solver.py:240-254)."""
+
+    def __init__(self, value: float = 0.0):
+        self._value = float(value)
+        arr = np.empty((), dtype=object)
+        arr[()] = S.coef(Coef('param', (), self))
+        self.arr = arr
+
+    def Get(self) -> float:
+        return self._value
+
+    def Set(self, v: float) -> None:
+        self._value = float(v)
+
+    def __hash__(self):
+        return id(self)
+
+    def __eq__(self, other):
+        return self is other
+
+
+# ---- functions ---------------------------------------------------------------------------------------------------
+def _unary(name):
+    def fn(a):
+        if not isinstance(a, CoefficientFunction):
+            return CoefficientFunction(a).map_coef(lambda c: Coef.unary(name, c))
+        return a.map_coef(lambda c: Coef.unary(name, c))
+    fn.__name__ = name
+    return fn
+
+
+sqrt, sin, cos, tan, exp, log, atan, floor, ceil = (_unary(n) for n in
+                                                    ('sqrt', 'sin', 'cos', 'tan', 'exp', 'log', 'atan', 'floor', 'ceil'))
+tanh, erf = _unary('tanh'), _unary('erf')
+
+
+def IfPos(c, a, b) -> CoefficientFunction:
+    c, a, b = (CoefficientFunction._lift(v) for v in (c, a, b))
+    cc = c.arr.reshape(())[()].as_coef()
+    shape = a.arr.shape if a.arr.ndim >= b.arr.ndim else b.arr.shape
+    out = _obj(shape)
+    for idx in (np.ndindex(*shape) if shape else [()]):
+        av = (a.arr[idx] if a.arr.shape == shape else a.arr[()]).as_coef()
+        bv = (b.arr[idx] if b.arr.shape == shape else b.arr[()]).as_coef()
+        out[idx] = S.coef(Coef.ifpos(cc, av, bv))
+    return CoefficientFunction(_arr=out)
+
+
+def InnerProduct(a, b) -> CoefficientFunction:
+    a, b = CoefficientFunction._lift(a), CoefficientFunction._lift(b)
+    if a.arr.size != b.arr.size:
+        raise ValueError('InnerProduct of different sizes {} {}'.format(a.dims, b.dims))
+    acc = _S0
+    for x, y in zip(a.arr.reshape(-1), b.arr.reshape(-1)):
+        acc = acc + x * y
+    out = np.empty((), dtype=object)
+    out[()] = acc
+    return CoefficientFunction(_arr=out)
+
+
+def OuterProduct(a, b) -> CoefficientFunction:
+    a, b = CoefficientFunction._lift(a), CoefficientFunction._lift(b)
+    av, bv = a.arr.reshape(-1), b.arr.reshape(-1)
+    out = _obj((av.size, bv.size))
+    for i in range(av.size):
+        for j in range(bv.size):
+            out[i, j] = av[i] * bv[j]
+    return CoefficientFunction(_arr=out)
+
+
+def Norm(a) -> CoefficientFunction:
+    a = CoefficientFunction._lift(a)
+    if a.arr.size == 1:
+        return a.map_coef(lambda c: Coef.unary('abs', c)) if a.arr.ndim == 0 else \
+            CoefficientFunction(_arr=a.arr.reshape(())).map_coef(lambda c: Coef.unary('abs', c))
+    acc = ZERO
+    for s in a.arr.reshape(-1):
+        c = s.as_coef()
+        acc = Coef.binary('add', acc, Coef.binary('mul', c, c))
+    return CoefficientFunction(Coef.unary('sqrt', acc))
+
+
+def Conj(a):
+    return a
+
+
+def _coord(axis: int) -> CoefficientFunction:
+    return CoefficientFunction(Coef('coord', (), axis))
+
+
+x, y, z = _coord(0), _coord(1), _coord(2)
+
+
+class _SpecialCF:
+    @staticmethod
+    def normal(dim: int) -> CoefficientFunction:
+        return CoefficientFunction(tuple(CoefficientFunction(Coef('normal', (), a)) for a in range(dim)))
+
+    @property
+    def mesh_size(self) -> CoefficientFunction:
+        return CoefficientFunction(Coef('h', (), None))
+
+
+specialcf = _SpecialCF()
+
+
+# ---- proxies -----------------------------------------------------------------------------------------------------
+class ProxyFunction(CoefficientFunction):
+    """Trial / test function of component ``comp`` of a space (reference: base_model.py:287-288)."""
+
+    def __init__(self, fes, comp: int, is_test: bool, side: int = 0, arr=None, grad_arr=None):
+        self.fes, self.comp, self.is_test, self.side = fes, comp, is_test, side
+        if arr is None:
+            arr, grad_arr = _proxy_arrays(fes, comp, is_test, side)
+        self.arr = arr
+        self._grad = grad_arr
+
+    def Other(self, bnd=None) -> 'ProxyFunction':
+        arr, g = _proxy_arrays(self.fes, self.comp, self.is_test, 1 - self.side)
+        return ProxyFunction(self.fes, self.comp, self.is_test, 1 - self.side, arr, g)
+
+    def Trace(self) -> 'ProxyFunction':
+        return self
+
+    def Deriv(self) -> CoefficientFunction:
+        return CoefficientFunction(_arr=self._grad)
+
+    def Operator(self, name: str) -> CoefficientFunction:
+        if name.lower() in ('grad', 'hesse') and name.lower() == 'grad':
+            return self.Deriv()
+        if name.lower() == 'div':
+            return div(self)
+        raise NotImplementedError('proxy operator {}'.format(name))
+
+    @property
+    def space(self):
+        return self.fes
+
+
+def _proxy_arrays(fes, comp: int, is_test: bool, side: int):
+    """value array and gradient array of a component; rows follow space.row_offsets."""
+    dim = fes.mesh.dim
+    blks = list(fes.comp_blocks[comp])
+    ro = fes.row_offsets
+
+    def leaf(row):
+        key = (row, side)
+        return S({(key, None): ONE}) if is_test else S({(None, key): ONE})
+
+    first = fes.blocks[blks[0]]
+    if first.kind == 'hdiv':
+        r0 = ro[blks[0]]
+        val = _obj((dim,))
+        grad = _obj((dim, dim))
+        for c in range(dim):
+            val[c] = leaf(r0 + c)
+            for a in range(dim):
+                grad[c, a] = leaf(r0 + dim + c * dim + a)
+        return val, grad
+    if len(blks) == 1:
+        r0 = ro[blks[0]]
+        val = np.empty((), dtype=object)
+        val[()] = leaf(r0)
+        grad = _obj((dim,))
+        for a in range(dim):
+            grad[a] = leaf(r0 + 1 + a)
+        return val, grad
+    val = _obj((len(blks),))
+    grad = _obj((len(blks), dim))
+    for c, b in enumerate(blks):
+        val[c] = leaf(ro[b])
+        for a in range(dim):
+            grad[c, a] = leaf(ro[b] + 1 + a)
+    return val, grad
+
+
+def Grad(f) -> CoefficientFunction:
+    if isinstance(f, ProxyFunction):
+        return f.Deriv()
+    if hasattr(f, '_grad_cf'):
+        return f._grad_cf()
+    raise TypeError('Grad() needs a trial/test function or a GridFunction')
+
+
+grad = Grad
+
+
+def div(f) -> CoefficientFunction:
+    g = Grad(f)
+    if g.arr.ndim != 2:
+        raise TypeError('div() of a scalar function')
+    acc = _S0
+    for i in range(g.arr.shape[0]):
+        acc = acc + g.arr[i, i]
+    out = np.empty((), dtype=object)
+    out[()] = acc
+    return CoefficientFunction(_arr=out)
+
+
+def field_arrays(gf_root, fes_root, blocks: Sequence[int], side: int = 0):
+    """value / gradient arrays of a GridFunction living on ``blocks`` of ``fes_root`` (Coef 'field' leaves)."""
+    dim = fes_root.mesh.dim
+    blks = list(blocks)
+
+    def leaf(blk, row):
+        return S.coef(Coef('field', (), (gf_root, blk, row, side)))
+
+    first = fes_root.blocks[blks[0]]
+    if first.kind == 'hdiv':
+        val = _obj((dim,))
+        grad = _obj((dim, dim))
+        for c in range(dim):
+            val[c] = leaf(blks[0], c)
+            for a in range(dim):
+                grad[c, a] = leaf(blks[0], dim + c * dim + a)
+        return val, grad
+    if len(blks) == 1:
+        val = np.empty((), dtype=object)
+        val[()] = leaf(blks[0], 0)
+        grad = _obj((dim,))
+        for a in range(dim):
+            grad[a] = leaf(blks[0], 1 + a)
+        return val, grad
+    val = _obj((len(blks),))
+    grad = _obj((len(blks), dim))
+    for c, b in enumerate(blks):
+        val[c] = leaf(b, 0)
+        for a in range(dim):
+            grad[c, a] = leaf(b, 1 + a)
+    return val, grad
+
+
+# ---- measures and integrals --------------------------------------------------------------------------------------
+class DifferentialSymbol:
+    def __init__(self, kind: str, skeleton: bool = False, definedon: Optional[Region] = None,
+                 bonus_intorder: int = 0, element_boundary: bool = False):
+        self.kind = kind                 # 'vol' or 'bnd'
+        self.skeleton = skeleton
+        self.definedon = definedon
+        self.bonus = bonus_intorder
+        self.element_boundary = element_boundary
+
+    def __call__(self, definedon=None, skeleton: Optional[bool] = None, bonus_intorder: Optional[int] = None,
+                 element_boundary: Optional[bool] = None, **kw) -> 'DifferentialSymbol':
+        if isinstance(definedon, str):
+            raise TypeError('definedon must be a mesh Region (use mesh.Boundaries(name))')
+        return DifferentialSymbol(self.kind, self.skeleton if skeleton is None else skeleton,
+                                  self.definedon if definedon is None else definedon,
+                                  self.bonus if bonus_intorder is None else bonus_intorder,
+                                  self.element_boundary if element_boundary is None else element_boundary)
+
+    def __rmul__(self, o):
+        return CoefficientFunction._lift(o) * self
+
+
+dx = DifferentialSymbol('vol')
+ds = DifferentialSymbol('bnd')
+
+
+class SumOfIntegrals:
+    def __init__(self, items: List[Tuple[CoefficientFunction, DifferentialSymbol]]):
+        self.items = items
+
+    def __add__(self, o):
+        if isinstance(o, SumOfIntegrals):
+            return SumOfIntegrals(self.items + o.items)
+        if o is None:
+            return self
+        return NotImplemented
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self + (-1.0) * o
+
+    def __neg__(self):
+        return (-1.0) * self
+
+    def __mul__(self, s):
+        return SumOfIntegrals([(CoefficientFunction._lift(s) * cf, m) for cf, m in self.items])
+
+    __rmul__ = __mul__
+
+
+# ---- lowering ------------------------------------------------------------------------------------------------------
+def lower_form(fes, integrals: SumOfIntegrals, arity: int, intorder: Optional[int] = None) -> FormProgram:
+    """Group the entries of all integrals by (kind, region) and compile one bytecode per group."""
+    mesh = fes.mesh
+    nrows = fes.nrows
+    groups: Dict[tuple, Dict[Tuple[Key, Key], Coef]] = {}
+    for cf, m in integrals.items:
+        if cf.arr.size != 1:
+            raise ValueError('integrand must be scalar, got dims {}'.format(cf.dims))
+        s: S = cf.arr.reshape(())[()]
+        if m.kind == 'vol' and not m.skeleton:
+            kind, rkind = 'cell', 'mat'
+            nreg = len(mesh.mat_names)
+        elif m.kind == 'vol':
+            kind, rkind, nreg = 'ifacet', None, 1
+        else:
+            kind, rkind, nreg = 'bfacet', 'bnd', len(mesh.bnd_names)
+        if m.element_boundary:
+            raise NotImplementedError('dx(element_boundary=True) is not supported')
+        region_ids = list(m.definedon.ids) if (m.definedon is not None and rkind is not None) else None
+        pw = coef_leaves(list(s.t.values()), 'piecewise')
+        if pw and rkind is not None:
+            ids = region_ids if region_ids is not None else list(range(nreg))
+            for rid in ids:
+                g = groups.setdefault((kind, (rid,), m.bonus), {})
+                memo: dict = {}
+                for k, c in s.t.items():
+                    c2 = resolve_piecewise(c, 'any', rid, memo)
+                    if c2.is_const(0.0):
+                        continue
+                    g[k] = Coef.binary('add', g[k], c2) if k in g else c2
+        else:
+            g = groups.setdefault((kind, tuple(region_ids) if region_ids is not None else None, m.bonus), {})
+            for k, c in s.t.items():
+                g[k] = Coef.binary('add', g[k], c) if k in g else c
+    out: List[Integral] = []
+    base_deg = (2 * fes.order) if intorder is None else intorder
+    for (kind, rids, bonus), terms in groups.items():
+        terms = {k: c for k, c in terms.items() if not c.is_const(0.0)}
+        if not terms:
+            continue
+        ent = []
+        outs = []
+        for (t, u), c in terms.items():
+            if arity == 2 and (t is None or u is None):
+                raise ValueError('bilinear form integrand lacks a trial or test function')
+            if arity == 1 and (t is None or u is not None):
+                raise ValueError('linear form integrand must contain exactly one test function')
+            if arity == 0 and (t is not None or u is not None):
+                raise ValueError('functional integrand must not contain trial/test functions')
+            tr = -1 if t is None else t[0] + t[1] * nrows
+            ur = -1 if u is None else u[0] + u[1] * nrows
+            if kind != 'ifacet' and ((t is not None and t[1]) or (u is not None and u[1])):
+                continue     # .Other() of a proxy away from interior facets is zero
+            ent.append((tr, ur, len(outs)))
+            outs.append(c)
+        if not ent:
+            continue
+        order = np.lexsort((np.array([e[1] for e in ent]), np.array([e[0] for e in ent])))
+        ent = [(ent[i][0], ent[i][1], k) for k, i in enumerate(order)]
+        outs = [outs[i] for i in order]
+        prog = Bytecode(outs)
+        if kind == 'cell':
+            items = None
+            if rids is not None:
+                items = np.nonzero(np.isin(mesh.cell_mat, list(rids)))[0]
+        elif kind == 'ifacet':
+            items = mesh.interior_facets
+        else:
+            sel = np.ones(len(mesh.bnd_facets), bool) if rids is None else np.isin(mesh.bnd_region, list(rids))
+            items = mesh.bnd_facets[sel]
+            if items.size == 0:
+                continue
+        out.append(Integral(kind, base_deg + bonus, np.array(ent, dtype=np.int32), prog, items))
+    return FormProgram(fes, arity, out)

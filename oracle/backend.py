@@ -1,0 +1,178 @@
+"""Oracle backend — TEST INFRASTRUCTURE ONLY.
+
+Implements the backend protocol of opencmp_b200/ngs.py with NumPy/SciPy on the host so that tests can (a) run the
+NGSolve-style front end (and, when /root/reference is mounted, unmodified OpenCMP models) against the reference's
+golden error norms, and (b) produce the expected values the CUDA path is compared with. Never imported by the
+product package.
+
+Krylov restatements follow the textbook algorithms NGSolve's pure-Python ``ngsolve.solvers`` implements
+(call sites reference opencmp/models/base_model.py:924-944): preconditioned CG with the
+sqrt(<r, P r>) stopping rule, right-projected GMRES on the free DOFs with Givens rotations, MINRES, damped Richardson.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from . import fem
+
+
+class OracleBackend:
+    name = 'oracle'
+
+    # ---- storage -------------------------------------------------------------------------------------------------
+    def zeros(self, n):
+        return np.zeros(int(n))
+
+    def from_numpy(self, a):
+        return np.array(a, dtype=np.float64)
+
+    def to_numpy(self, a):
+        return np.asarray(a)
+
+    def numpy_view(self, a):
+        return a
+
+    def copy_into(self, dst, src):
+        dst[:] = src
+
+    def dot(self, a, b):
+        return float(np.dot(a, b))
+
+    def masked_assign(self, dst, src, inv, mask):
+        m = mask > 0
+        dst[m] = src[m] * inv[m]
+
+    # ---- assembly ------------------------------------------------------------------------------------------------
+    def assemble_matrix(self, program, mat):
+        mat.values[:] = fem.assemble_matrix(program)
+
+    def assemble_vector(self, program, out):
+        out[:] = fem.assemble_vector(program)
+
+    def integrate(self, program):
+        return fem.integrate(program)
+
+    # ---- linear algebra ------------------------------------------------------------------------------------------
+    def _csr(self, mat):
+        return fem.csr_matrix(mat.space, mat.values)
+
+    def spmv(self, mat, x, out):
+        out[:] = self._csr(mat) @ x
+
+    def solve_free(self, mat, r, out, freedofs):
+        free = np.ones(mat.height, bool) if freedofs is None else np.asarray(freedofs, bool)
+        out[:] = fem.solve_direct(self._csr(mat), r, np.zeros_like(r), free)
+
+    def precond_setup(self, mat, kind, free):
+        A = self._csr(mat)
+        free = np.asarray(free, bool)
+        idx = np.nonzero(free)[0]
+        if kind in ('local', 'jacobi'):
+            d = A.diagonal()
+            inv = np.where(free & (d != 0), 1.0 / np.where(d != 0, d, 1.0), 0.0)
+            return lambda v: inv * v
+        if kind == 'direct':
+            lu = spla.splu(A[idx][:, idx].tocsc())
+
+            def app(v):
+                o = np.zeros_like(v)
+                o[idx] = lu.solve(v[idx])
+                return o
+            return app
+        raise NotImplementedError('oracle preconditioner {}'.format(kind))
+
+    def krylov(self, kind, mat, b, x, pre, freedofs, tol, maxit, initialize, printrates, damp=1.0):
+        A = self._csr(mat)
+        n = A.shape[0]
+        if pre is not None and pre.state is None:
+            pre.Update()
+        P = pre.state if pre is not None else (lambda v: v)
+        free = None if freedofs is None else np.asarray(freedofs, bool)
+        proj = (lambda v: v) if free is None else (lambda v: np.where(free, v, 0.0))
+        if kind == 'cg':
+            x[:] = cg(A, b, x, P, tol, maxit, initialize)
+        elif kind == 'gmres':
+            x[:] = gmres(A, b, x, P, proj, tol, maxit)
+        elif kind == 'minres':
+            if initialize:
+                x[:] = 0.0
+            M = spla.LinearOperator((n, n), matvec=P)
+            r0 = b - A @ x
+            dx, _ = spla.minres(A, r0, M=M, rtol=tol, maxiter=maxit)
+            x += dx
+        elif kind == 'richardson':
+            x[:] = 0.0
+            r = proj(b - A @ x)
+            r0 = np.linalg.norm(r)
+            for _ in range(maxit):
+                x += damp * proj(P(r))
+                r = proj(b - A @ x)
+                if np.linalg.norm(r) < tol * r0:
+                    break
+        else:
+            raise ValueError(kind)
+
+
+def cg(A, b, x, P, tol, maxit, initialize):
+    u = np.zeros_like(b) if initialize else x.copy()
+    d = b - A @ u
+    w = P(d)
+    wdn = float(w @ d)
+    err0 = np.sqrt(abs(wdn))
+    if wdn == 0:
+        return u
+    s = w.copy()
+    for _ in range(maxit):
+        w = A @ s
+        wd = wdn
+        alpha = wd / float(s @ w)
+        u += alpha * s
+        d -= alpha * w
+        w = P(d)
+        wdn = float(w @ d)
+        s = w + (wdn / wd) * s
+        if np.sqrt(abs(wd)) < tol * err0:
+            break
+    return u
+
+
+def gmres(A, b, x, P, proj, tol, maxit):
+    """Left-preconditioned GMRES without restart on the projected system."""
+    u = x.copy()
+    r = P(proj(b - A @ u))
+    beta = np.linalg.norm(r)
+    if beta == 0:
+        return u
+    m = maxit
+    Q = [r / beta]
+    H = np.zeros((m + 1, m))
+    cs, sn = np.zeros(m), np.zeros(m)
+    g = np.zeros(m + 1)
+    g[0] = beta
+    k_used = 0
+    for k in range(m):
+        w = P(proj(A @ Q[k]))
+        for i in range(k + 1):
+            H[i, k] = Q[i] @ w
+            w = w - H[i, k] * Q[i]
+        H[k + 1, k] = np.linalg.norm(w)
+        for i in range(k):
+            t = cs[i] * H[i, k] + sn[i] * H[i + 1, k]
+            H[i + 1, k] = -sn[i] * H[i, k] + cs[i] * H[i + 1, k]
+            H[i, k] = t
+        den = np.hypot(H[k, k], H[k + 1, k])
+        cs[k], sn[k] = (1.0, 0.0) if den == 0 else (H[k, k] / den, H[k + 1, k] / den)
+        H[k, k] = cs[k] * H[k, k] + sn[k] * H[k + 1, k]
+        H[k + 1, k] = 0.0
+        g[k + 1] = -sn[k] * g[k]
+        g[k] = cs[k] * g[k]
+        k_used = k + 1
+        if abs(g[k + 1]) < tol * beta or den == 0:
+            break
+        Q.append(w / np.linalg.norm(w))
+    yk = np.linalg.solve(np.triu(H[:k_used, :k_used]), g[:k_used])
+    for i in range(k_used):
+        u += yk[i] * Q[i]
+    return u
