@@ -1,0 +1,129 @@
+/* opencmp_b200 — C ABI of the B200 backend for OpenCMP's assembly + linear-solve hot path.
+ *
+ * The reference has no FFI of its own: its hot path calls NGSolve's Python API. Each entry point
+ * below names the NGSolve call (and the OpenCMP call site, path:line under the reference tree) it stands in for.
+ * All pointers are raw device pointers unless marked "host"; sizes are element counts; every function returns
+ * 0 on success and a negative code otherwise (ocmp_last_error() gives the text). Nothing throws across the ABI.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ */
+#ifndef OPENCMP_B200_H
+#define OPENCMP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCMP_MAX_FVEC 8      /* distinct DOF vectors a single integral may read (wind, u^n, phi, masks ...) */
+#define OCMP_MAX_REGS 48     /* registers of the coefficient bytecode machine (ir.py MAX_REGS) */
+
+/* ---- plans: flat descriptors of one lowered integral (built by opencmp_b200/backend.py from ir.Integral) ------ */
+
+/* Coefficient program of an integral: evaluated at every (item, quadrature point). */
+typedef struct {
+    int dim;                 /* 2 | 3 */
+    int kind;                /* 0 cell, 1 interior facet, 2 boundary facet */
+    int nq;                  /* quadrature points per item */
+    int nout;                /* output slots D_k */
+    int ninstr, nreg;
+    int nfgroups, nfslots;
+    const int* items;        /* item -> cell / facet id, NULL = identity */
+    const double* geo;       /* per cell: x0[dim], J[dim*dim] (J[i*dim+a] = dx_i/dxi_a), Jinv[dim*dim], det */
+    const int* facet_cells;  /* (nfacets, 2) */
+    const int* facet_local;  /* (nfacets, 2) */
+    const double* qpts;      /* cell: (nq, dim); facet: (nfc, nq, dim) reference coordinates */
+    const double* qw;        /* (nq) */
+    const double* fref;      /* facets: per local facet outward reference normal (dim) then tangents ((dim-1)*dim) */
+    const int* code;         /* (ninstr, 4): op | dst << 8, a, b, c — opcode table in ir.py */
+    const double* consts;
+    const double* params;    /* run-time scalars (t, dt, ...), refreshed per call */
+    const int* fgroup;       /* (nfgroups, 8): vec, dofarr, side, kind, nloc, nrows, tab_off, dof_off ; see below */
+    const int* fgroup2;      /* (nfgroups, 2): dof_stride, dof_add */
+    const int* fslot;        /* (nfslots, 2): group, physical row */
+    const double* ftab;      /* reference tables of the field blocks */
+    const double* fvec[OCMP_MAX_FVEC];
+    const int* fdof[OCMP_MAX_FVEC];
+} ocmp_coef_plan;
+
+/* Contraction plan: B^T D B per item, scatter through the element -> nnz map. */
+typedef struct {
+    int dim, kind, nq, nside;
+    int nblk;                /* blocks per side */
+    int nloc;                /* local dofs per side */
+    int sbsz;                /* doubles of one side's physical table at one quadrature point */
+    int zsz;                 /* doubles of the Z rows of one item */
+    int nact;                /* active (structurally non-zero) local entries per item */
+    int nslots;              /* D slots (== coef plan nout) */
+    int eb;                  /* items per CTA */
+    const int* items;
+    const double* geo;
+    const int* facet_cells;
+    const int* facet_local;
+    const int* blk;          /* (nblk, 6): kind, nloc, nrows, tab_off, loc_off, sb_off */
+    const double* tab;       /* reference tables of the form's blocks at this rule */
+    const int* zdesc;        /* (zsz, 4): entry k0, k1, sB base (side*sbsz + sb_off + j), row stride */
+    const int* ent;          /* (nent, 2): slot, trial row inside its block */
+    const int* adesc;        /* (nact, 4): sB base (side*sbsz + sb_off + i), row stride, seg start, seg count */
+    const int* amap;         /* (nact): test side << 30 | trial side << 29 | (i * nloc + j) */
+    const int* seg;          /* (nseg, 2): test row inside its block, z offset (incl. j) */
+    const int* cell2nnz;     /* (ncells, nloc*nloc) */
+    const int* facet2nnz;    /* (n interior facets, 2, nloc*nloc) indexed by item */
+    const int* cell_dofs;    /* (ncells, nloc) — vector assembly */
+} ocmp_contract_plan;
+
+/* ---- assembly: stands in for BilinearForm.Assemble / LinearForm.Assemble (reference
+ *      opencmp/solvers/base_solver.py:368-377) and ngs.Integrate (opencmp/helpers/error.py:66-77) ------------- */
+int ocmp_eval_coefficients(const ocmp_coef_plan* plan, int item0, int nitems, double* dbuf, void* stream);
+int ocmp_contract_matrix(const ocmp_contract_plan* plan, int item0, int nitems, const double* dbuf,
+                         double* values, void* stream);
+int ocmp_contract_vector(const ocmp_contract_plan* plan, int item0, int nitems, const double* dbuf,
+                         double* vec, void* stream);
+int ocmp_sum(const double* x, long long n, double* out_accumulate, void* stream);
+
+/* ---- sparse / dense vector kernels: stand in for `a.mat * x`, BaseVector arithmetic and InnerProduct
+ *      (reference opencmp/models/base_model.py:918-922) ------------------------------------------------------- */
+int ocmp_spmv(int nrows, const int* rowptr, const int* colidx, const double* vals, const double* x, double* y,
+              void* stream);
+int ocmp_dot(long long n, const double* x, const double* y, double* out, void* stream);
+int ocmp_axpby(long long n, double a, const double* x, double b, double* y, void* stream);   /* y = a x + b y */
+int ocmp_masked_assign(long long n, double* dst, const double* src, const double* inv, const double* mask,
+                       void* stream);
+
+/* ---- preconditioners: stand in for ngs.Preconditioner(a, type) + .Update() (reference
+ *      opencmp/models/base_model.py:365-383, opencmp/solvers/base_solver.py:711-719) -------------------------- */
+/* point Jacobi on the free dofs: dinv[i] = free[i] && diag != 0 ? 1/diag : 0 */
+int ocmp_jacobi_setup(int nrows, const int* diagpos, const double* vals, const double* freemask, double* dinv,
+                      void* stream);
+/* additive Schwarz over dof patches: gather dense blocks through `patch2nnz`, invert them (batched Gauss-Jordan) */
+int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const int* patch2nnz, const double* vals,
+                   const double* freemask, double* inv_blocks, void* stream);
+int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const double* inv_blocks, const double* r, double* z,
+                   long long n, void* stream);
+
+/* ---- Krylov: stand in for ngs.solvers.CG / GMRes / PreconditionedRichardson and for mat.Inverse applied to a
+ *      residual (reference opencmp/models/base_model.py:886-947) ---------------------------------------------- */
+typedef struct {
+    int nrows;
+    const int* rowptr;
+    const int* colidx;
+    const double* vals;
+    const double* freemask;  /* 1.0 free / 0.0 constrained, NULL = all free */
+    int pre_kind;            /* 0 none, 1 Jacobi (dinv), 2 additive Schwarz patches */
+    const double* dinv;
+    int npatch, bs;
+    const int* patch_dofs;
+    const double* inv_blocks;
+} ocmp_system;
+
+/* kind: 0 CG, 1 GMRES(restart), 2 Richardson. x holds the initial guess (and Dirichlet values) on entry.
+ * Stops when the preconditioned residual norm drops below tol * initial. iters / resid are host outputs. */
+int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, double* x, double tol, int maxit, int restart,
+                double damp, double* work, long long work_len, int* iters, double* resid, void* stream);
+long long ocmp_krylov_work_len(int nrows, int kind, int restart);
+
+const char* ocmp_last_error(void);
+int ocmp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

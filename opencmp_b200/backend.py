@@ -1,0 +1,481 @@
+"""CUDA backend: ctypes binding of the C ABI (include/opencmp_b200.h) with PyTorch tensors as device buffers.
+
+This is the product path behind opencmp_b200/ngs.py. It raises if the shared library or a CUDA device is missing —
+there is deliberately no CPU fallback (the NumPy oracle lives under oracle/ and is test infrastructure only).
+
+Per mesh / space the exported arrays are uploaded once (geometry, connectivity, DOF lists, CSR pattern, scatter
+maps, reference tables); per ``Assemble()`` only the run-time parameter array and the field-vector pointers change.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from .ir import FormProgram, Integral
+from .quadrature import cell_rule, facet_rule_in_cell, facet_ref_geometry
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libopencmp_b200.so')
+MAX_FVEC = 8
+
+
+class CoefPlan(C.Structure):
+    _fields_ = [('dim', C.c_int), ('kind', C.c_int), ('nq', C.c_int), ('nout', C.c_int), ('ninstr', C.c_int),
+                ('nreg', C.c_int), ('nfgroups', C.c_int), ('nfslots', C.c_int),
+                ('items', C.c_void_p), ('geo', C.c_void_p), ('facet_cells', C.c_void_p), ('facet_local', C.c_void_p),
+                ('qpts', C.c_void_p), ('qw', C.c_void_p), ('fref', C.c_void_p), ('code', C.c_void_p),
+                ('consts', C.c_void_p), ('params', C.c_void_p), ('fgroup', C.c_void_p), ('fgroup2', C.c_void_p),
+                ('fslot', C.c_void_p), ('ftab', C.c_void_p),
+                ('fvec', C.c_void_p * MAX_FVEC), ('fdof', C.c_void_p * MAX_FVEC)]
+
+
+class ContractPlan(C.Structure):
+    _fields_ = [('dim', C.c_int), ('kind', C.c_int), ('nq', C.c_int), ('nside', C.c_int), ('nblk', C.c_int),
+                ('nloc', C.c_int), ('sbsz', C.c_int), ('zsz', C.c_int), ('nact', C.c_int), ('nslots', C.c_int),
+                ('eb', C.c_int),
+                ('items', C.c_void_p), ('geo', C.c_void_p), ('facet_cells', C.c_void_p), ('facet_local', C.c_void_p),
+                ('blk', C.c_void_p), ('tab', C.c_void_p), ('zdesc', C.c_void_p), ('ent', C.c_void_p),
+                ('adesc', C.c_void_p), ('amap', C.c_void_p), ('seg', C.c_void_p), ('cell2nnz', C.c_void_p),
+                ('facet2nnz', C.c_void_p), ('cell_dofs', C.c_void_p)]
+
+
+class System(C.Structure):
+    _fields_ = [('nrows', C.c_int), ('rowptr', C.c_void_p), ('colidx', C.c_void_p), ('vals', C.c_void_p),
+                ('freemask', C.c_void_p), ('pre_kind', C.c_int), ('dinv', C.c_void_p), ('npatch', C.c_int),
+                ('bs', C.c_int), ('patch_dofs', C.c_void_p), ('inv_blocks', C.c_void_p)]
+
+
+def load_library() -> C.CDLL:
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError('opencmp_b200: {} is missing — build it with `python -c "import __graft_entry__ as g; '
+                           'g.build()"`; there is no CPU fallback'.format(_LIB_PATH))
+    lib = C.CDLL(_LIB_PATH)
+    lib.ocmp_last_error.restype = C.c_char_p
+    lib.ocmp_krylov_work_len.restype = C.c_longlong
+    lib.ocmp_krylov_work_len.argtypes = [C.c_int, C.c_int, C.c_int]
+    P = C.c_void_p
+    lib.ocmp_eval_coefficients.argtypes = [C.POINTER(CoefPlan), C.c_int, C.c_int, P, P]
+    lib.ocmp_contract_matrix.argtypes = [C.POINTER(ContractPlan), C.c_int, C.c_int, P, P, P]
+    lib.ocmp_contract_vector.argtypes = [C.POINTER(ContractPlan), C.c_int, C.c_int, P, P, P]
+    lib.ocmp_sum.argtypes = [P, C.c_longlong, P, P]
+    lib.ocmp_spmv.argtypes = [C.c_int, P, P, P, P, P, P]
+    lib.ocmp_dot.argtypes = [C.c_longlong, P, P, P, P]
+    lib.ocmp_axpby.argtypes = [C.c_longlong, C.c_double, P, C.c_double, P, P]
+    lib.ocmp_masked_assign.argtypes = [C.c_longlong, P, P, P, P, P]
+    lib.ocmp_jacobi_setup.argtypes = [C.c_int, P, P, P, P, P]
+    lib.ocmp_asm_setup.argtypes = [C.c_int, C.c_int, P, P, P, P, P, P]
+    lib.ocmp_asm_apply.argtypes = [C.c_int, C.c_int, P, P, P, P, C.c_longlong, P]
+    lib.ocmp_krylov.argtypes = [C.POINTER(System), C.c_int, P, P, C.c_double, C.c_int, C.c_int, C.c_double, P,
+                                C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_double), P]
+    return lib
+
+
+EXPORTED = ['ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
+            'ocmp_dot', 'ocmp_axpby', 'ocmp_masked_assign', 'ocmp_jacobi_setup', 'ocmp_asm_setup', 'ocmp_asm_apply',
+            'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version']
+
+
+def _ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class _Precond:
+    def __init__(self, kind, **kw):
+        self.kind = kind
+        self.__dict__.update(kw)
+
+
+class CudaBackend:
+    name = 'cuda'
+
+    def __init__(self, device: Optional[int] = None):
+        import torch
+        self.torch = torch
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError('opencmp_b200: no CUDA device visible — the backend has no CPU fallback')
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        self._mesh_cache: Dict[int, dict] = {}
+        self._space_cache: Dict[int, dict] = {}
+        self._plan_cache: Dict[int, list] = {}
+        self._dbuf = None
+        self._scal = torch.zeros(64, dtype=torch.float64, device=self.device)
+        self.launches = 0
+        self.last_iters = 0
+        self.last_resid = 0.0
+        self.chunk_bytes = 48 << 20
+
+    # ---- helpers -----------------------------------------------------------------------------------------------
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError('opencmp_b200 C ABI error {}: {}'.format(rc, self.lib.ocmp_last_error().decode()))
+
+    def _up(self, a, dtype=None):
+        t = self.torch.from_numpy(np.ascontiguousarray(a if dtype is None else np.asarray(a, dtype=dtype)))
+        return t.to(self.device)
+
+    def zeros(self, n):
+        return self.torch.zeros(int(n), dtype=self.torch.float64, device=self.device)
+
+    def from_numpy(self, a):
+        return self._up(np.asarray(a, dtype=np.float64))
+
+    def to_numpy(self, a):
+        return a.detach().cpu().numpy()
+
+    def numpy_view(self, a):
+        return a.detach().cpu().numpy()
+
+    def copy_into(self, dst, src):
+        dst.copy_(src)
+
+    def dot(self, a, b):
+        self._ck(self.lib.ocmp_dot(a.numel(), a.data_ptr(), b.data_ptr(), self._scal.data_ptr(), self._stream()))
+        self.launches += 1
+        return float(self._scal[0].item())
+
+    def masked_assign(self, dst, src, inv, mask):
+        self._ck(self.lib.ocmp_masked_assign(dst.numel(), dst.data_ptr(), src.data_ptr(), inv.data_ptr(),
+                                             mask.data_ptr(), self._stream()))
+        self.launches += 1
+
+    # ---- exported arrays ---------------------------------------------------------------------------------------
+    def mesh_data(self, mesh) -> dict:
+        key = id(mesh)
+        d = self._mesh_cache.get(key)
+        if d is None or d['ne'] != mesh.ne:
+            J = mesh.jacobians()
+            geo = np.concatenate([mesh.origins(), J.reshape(mesh.ne, -1), np.linalg.inv(J).reshape(mesh.ne, -1),
+                                  np.linalg.det(J)[:, None]], axis=1)
+            tang, nrm = facet_ref_geometry(mesh.cell_type)
+            fref = np.concatenate([nrm, tang.reshape(tang.shape[0], -1)], axis=1)
+            d = dict(ne=mesh.ne, geo=self._up(geo), facet_cells=self._up(mesh.facet_cells),
+                     facet_local=self._up(mesh.facet_local), fref=self._up(fref), keep=mesh)
+            self._mesh_cache[key] = d
+        return d
+
+    def space_data(self, fes) -> dict:
+        key = id(fes)
+        d = self._space_cache.get(key)
+        if d is None or d['ndof'] != fes.ndof:
+            d = dict(ndof=fes.ndof, cell_dofs=self._up(fes.cell_dofs), keep=fes)
+            self._space_cache[key] = d
+        return d
+
+    def pattern_data(self, fes) -> dict:
+        d = self.space_data(fes)
+        if 'rowptr' not in d:
+            pat = fes.pattern()
+            d.update(rowptr=self._up(pat.rowptr.astype(np.int32)), colidx=self._up(pat.colidx),
+                     cell2nnz=self._up(pat.cell2nnz), facet2nnz=self._up(pat.facet2nnz), diag=self._up(pat.diag),
+                     nnz=pat.nnz)
+        return d
+
+    # ---- plan construction -------------------------------------------------------------------------------------
+    def _tables(self, basis, kind: str, deg: int) -> np.ndarray:
+        return (basis.tabulate_cell(deg) if kind == 'cell' else basis.tabulate_facets(deg)).reshape(-1)
+
+    def _build_plans(self, program: FormProgram, integ: Integral) -> dict:
+        fes = program.fes
+        mesh = fes.mesh
+        dim = mesh.dim
+        md = self.mesh_data(mesh)
+        kind_id = {'cell': 0, 'ifacet': 1, 'bfacet': 2}[integ.kind]
+        prog = integ.prog
+        if integ.kind == 'cell':
+            qp, qw = cell_rule(mesh.cell_type, integ.deg)
+        else:
+            qp, qw = facet_rule_in_cell(mesh.cell_type, integ.deg)
+        nq = len(qw)
+        keep: List = []
+
+        def up(a, dtype):
+            t = self._up(np.asarray(a, dtype=dtype))
+            keep.append(t)
+            return t
+
+        nitems = mesh.ne if integ.items is None else len(integ.items)
+        items = None if integ.items is None else up(integ.items, np.int32)
+        cp = CoefPlan()
+        cp.dim, cp.kind, cp.nq, cp.nout = dim, kind_id, nq, prog.nout
+        cp.ninstr, cp.nreg = prog.code.shape[0], prog.nreg
+        cp.items = _ptr(items)
+        cp.geo, cp.facet_cells, cp.facet_local = md['geo'].data_ptr(), md['facet_cells'].data_ptr(), \
+            md['facet_local'].data_ptr()
+        cp.qpts, cp.qw, cp.fref = up(qp, np.float64).data_ptr(), up(qw, np.float64).data_ptr(), md['fref'].data_ptr()
+        cp.code = up(prog.code, np.int32).data_ptr()
+        cp.consts = up(prog.consts_arr, np.float64).data_ptr()
+        params = up(np.zeros(max(1, len(prog.params))), np.float64)
+        cp.params = params.data_ptr()
+        # field groups
+        roots: List = []
+        spaces: List = []
+        groups: Dict[tuple, int] = {}
+        fgroup, fgroup2, fslot, ftab = [], [], [], []
+        toff = 0
+        for (gf, blk, row, side) in prog.fields:
+            rs = gf.space
+            if gf not in roots:
+                roots.append(gf)
+            if rs not in spaces:
+                spaces.append(rs)
+            gkey = (id(gf), blk, side)
+            if gkey not in groups:
+                groups[gkey] = len(fgroup)
+                b = rs.blocks[blk]
+                tab = self._tables(b.basis, 'cell' if integ.kind == 'cell' else 'facet', integ.deg)
+                fgroup.append([roots.index(gf), spaces.index(rs), side, 0 if b.kind == 'scalar' else 1, b.nloc,
+                               b.basis.nrows, toff, rs.loc_offsets[blk]])
+                fgroup2.append([rs.nloc, 0])
+                ftab.append(tab)
+                toff += tab.size
+            fslot.append([groups[gkey], row])
+        if len(roots) > MAX_FVEC:
+            raise ValueError('an integral reads more than {} distinct DOF vectors'.format(MAX_FVEC))
+        cp.nfgroups, cp.nfslots = len(fgroup), len(fslot)
+        cp.fgroup = up(np.array(fgroup if fgroup else [[0] * 8]), np.int32).data_ptr()
+        cp.fgroup2 = up(np.array(fgroup2 if fgroup2 else [[0, 0]]), np.int32).data_ptr()
+        cp.fslot = up(np.array(fslot if fslot else [[0, 0]]), np.int32).data_ptr()
+        cp.ftab = up(np.concatenate(ftab) if ftab else np.zeros(1), np.float64).data_ptr()
+        for i, rs in enumerate(spaces):
+            cp.fdof[i] = self.space_data(rs)['cell_dofs'].data_ptr()
+        plan = dict(coef=cp, params=params, roots=roots, nitems=nitems, nq=nq, keep=keep, contract=None)
+        if program.arity == 0:
+            return plan
+        # ---- contraction plan ------------------------------------------------------------------------------
+        nside = 2 if integ.kind == 'ifacet' else 1
+        blocks = fes.blocks
+        nblk = len(blocks)
+        tkind = 'cell' if integ.kind == 'cell' else 'facet'
+        blk_tab, tabs = [], []
+        toff = sboff = 0
+        sb_off = []
+        for b, lo in zip(blocks, fes.loc_offsets):
+            tab = self._tables(b.basis, tkind, integ.deg)
+            blk_tab.append([0 if b.kind == 'scalar' else 1, b.nloc, b.basis.nrows, toff, lo, sboff])
+            sb_off.append(sboff)
+            tabs.append(tab)
+            toff += tab.size
+            sboff += b.basis.nrows * b.nloc
+        sbsz = sboff
+        nrows_tot = fes.nrows
+        ro = fes.row_offsets
+
+        def decode(row):
+            side, rr = divmod(int(row), nrows_tot)
+            b = max(i for i in range(nblk) if ro[i] <= rr)
+            return side, b, rr - ro[b]
+
+        xp = ContractPlan()
+        xp.dim, xp.kind, xp.nq, xp.nside, xp.nblk, xp.nloc = dim, kind_id, nq, nside, nblk, fes.nloc
+        xp.sbsz, xp.nslots = sbsz, prog.nout
+        xp.items = _ptr(items)
+        xp.geo, xp.facet_cells, xp.facet_local = cp.geo, cp.facet_cells, cp.facet_local
+        xp.blk = up(np.array(blk_tab), np.int32).data_ptr()
+        xp.tab = up(np.concatenate(tabs), np.float64).data_ptr()
+        sd = self.space_data(fes)
+        xp.cell_dofs = sd['cell_dofs'].data_ptr()
+        if program.arity == 1:
+            ent = []
+            for tr, _, slot in integ.entries:
+                s, b, r = decode(tr)
+                ent.append([slot, ((s * nblk + b) << 8) | r])
+            xp.ent = up(np.array(ent), np.int32).data_ptr()
+            xp.zsz = len(ent)
+            xp.eb = 1
+            plan['contract'] = xp
+            return plan
+        pd = self.pattern_data(fes)
+        xp.cell2nnz, xp.facet2nnz = pd['cell2nnz'].data_ptr(), pd['facet2nnz'].data_ptr()
+        segs: Dict[tuple, list] = {}
+        for tr, ur, slot in integ.entries:
+            st, bt, rt = decode(tr)
+            su, bu, ru = decode(ur)
+            segs.setdefault((st, bt, rt, su, bu), []).append((slot, ru))
+        zdesc, ent, seg_z = [], [], {}
+        zoff = 0
+        for key in sorted(segs):
+            st, bt, rt, su, bu = key
+            k0 = len(ent)
+            ent += [[slot, ru] for slot, ru in segs[key]]
+            k1 = len(ent)
+            nl = blocks[bu].nloc
+            seg_z[key] = zoff
+            for j in range(nl):
+                zdesc.append([k0, k1, su * sbsz + sb_off[bu] + j, nl])
+            zoff += nl
+        pairs: Dict[tuple, list] = {}
+        for key in sorted(segs):
+            st, bt, rt, su, bu = key
+            pairs.setdefault((st, bt, su, bu), []).append((rt, seg_z[key]))
+        seg_arr, adesc, amap = [], [], []
+        for (st, bt, su, bu), lst in sorted(pairs.items()):
+            s0 = len(seg_arr)
+            seg_arr += [[rt, z] for rt, z in lst]
+            ns = len(lst)
+            nlt, nlu = blocks[bt].nloc, blocks[bu].nloc
+            lot, lou = fes.loc_offsets[bt], fes.loc_offsets[bu]
+            for i in range(nlt):
+                for j in range(nlu):
+                    adesc.append([st * sbsz + sb_off[bt] + i, nlt, s0 | (ns << 24), j])
+                    amap.append((st << 30) | (su << 29) | ((lot + i) * fes.nloc + lou + j))
+        xp.zsz, xp.nact = zoff, len(adesc)
+        xp.zdesc = up(np.array(zdesc), np.int32).data_ptr()
+        xp.ent = up(np.array(ent), np.int32).data_ptr()
+        xp.seg = up(np.array(seg_arr), np.int32).data_ptr()
+        xp.adesc = up(np.array(adesc), np.int32).data_ptr()
+        xp.amap = up(np.array(amap, dtype=np.int64).astype(np.uint32).view(np.int32), np.int32).data_ptr()
+        gs = dim + 2 * dim * dim + 1
+        eb_pick = 1
+        for eb in (16, 8, 4, 2, 1):
+            tpe = 256 // eb
+            need = -(-xp.nact // tpe)
+            smem = 8 * (eb * nside * sbsz + eb * zoff + eb * prog.nout + eb * nside * gs) + 16 * eb
+            if need <= 16 and smem <= 96 * 1024:
+                eb_pick = eb
+                break
+        xp.eb = eb_pick
+        plan['contract'] = xp
+        return plan
+
+    def _plans(self, program: FormProgram) -> list:
+        key = id(program)
+        hit = self._plan_cache.get(key)
+        if hit is None or hit[0] is not program:
+            hit = (program, [self._build_plans(program, integ) for integ in program.integrals])
+            self._plan_cache[key] = hit
+        return hit[1]
+
+    def _run(self, program: FormProgram, out, mode: str):
+        torch = self.torch
+        st = self._stream()
+        for integ, plan in zip(program.integrals, self._plans(program)):
+            cp = plan['coef']
+            vals = program.param_values(integ)
+            plan['params'].copy_(torch.from_numpy(vals))
+            for i, gf in enumerate(plan['roots']):
+                cp.fvec[i] = gf.vec.a.data_ptr()
+            nq, nout, nitems = plan['nq'], cp.nout, plan['nitems']
+            chunk = max(256, min(nitems, self.chunk_bytes // (8 * nq * nout)))
+            need = chunk * nq * nout
+            if self._dbuf is None or self._dbuf.numel() < need:
+                self._dbuf = torch.empty(need, dtype=torch.float64, device=self.device)
+            for i0 in range(0, nitems, chunk):
+                n = min(chunk, nitems - i0)
+                self._ck(self.lib.ocmp_eval_coefficients(C.byref(cp), i0, n, self._dbuf.data_ptr(), st))
+                self.launches += 1
+                if mode == 'matrix':
+                    self._ck(self.lib.ocmp_contract_matrix(C.byref(plan['contract']), i0, n, self._dbuf.data_ptr(),
+                                                           out.data_ptr(), st))
+                elif mode == 'vector':
+                    self._ck(self.lib.ocmp_contract_vector(C.byref(plan['contract']), i0, n, self._dbuf.data_ptr(),
+                                                           out.data_ptr(), st))
+                else:
+                    self._ck(self.lib.ocmp_sum(self._dbuf.data_ptr(), n * nq * nout, out.data_ptr(), st))
+                self.launches += 1
+
+    # ---- assembly ----------------------------------------------------------------------------------------------
+    def assemble_matrix(self, program, mat):
+        mat.values.zero_()
+        self._run(program, mat.values, 'matrix')
+
+    def assemble_vector(self, program, out):
+        out.zero_()
+        self._run(program, out, 'vector')
+
+    def integrate(self, program):
+        self._scal[1].zero_()
+        self._run(program, self._scal[1:2], 'sum')
+        return float(self._scal[1].item())
+
+    # ---- linear algebra ----------------------------------------------------------------------------------------
+    def spmv(self, mat, x, out):
+        pd = self.pattern_data(mat.space)
+        self._ck(self.lib.ocmp_spmv(mat.height, pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(),
+                                    mat.values.data_ptr(), x.data_ptr(), out.data_ptr(), self._stream()))
+        self.launches += 1
+
+    def _mask(self, fes_or_n, free):
+        if free is None:
+            return None
+        arr = np.asarray(free.a if hasattr(free, 'a') else free, dtype=bool)
+        return self._up(arr.astype(np.float64))
+
+    def precond_setup(self, mat, kind, free):
+        pd = self.pattern_data(mat.space)
+        fm = self._mask(mat.space, free)
+        st = self._stream()
+        if kind in ('local', 'jacobi'):
+            dinv = self.zeros(mat.height)
+            self._ck(self.lib.ocmp_jacobi_setup(mat.height, pd['diag'].data_ptr(), mat.values.data_ptr(), _ptr(fm),
+                                                dinv.data_ptr(), st))
+            self.launches += 1
+            return _Precond(1, dinv=dinv, fm=fm)
+        if kind in ('asm', 'direct', 'multigrid', 'h1amg', 'bddc', 'block'):
+            # cell-patch additive Schwarz: every cell's dofs form one (overlapping) patch
+            fes = mat.space
+            sd = self.space_data(fes)
+            ne, bs = fes.cell_dofs.shape
+            inv = self.torch.empty(ne * bs * bs, dtype=self.torch.float64, device=self.device)
+            self._ck(self.lib.ocmp_asm_setup(ne, bs, sd['cell_dofs'].data_ptr(), pd['cell2nnz'].data_ptr(),
+                                             mat.values.data_ptr(), _ptr(fm), inv.data_ptr(), st))
+            self.launches += 1
+            return _Precond(2, inv=inv, npatch=ne, bs=bs, pdofs=sd['cell_dofs'], fm=fm)
+        raise NotImplementedError('preconditioner type {}'.format(kind))
+
+    def _system(self, mat, fm, pre) -> System:
+        pd = self.pattern_data(mat.space)
+        s = System()
+        s.nrows = mat.height
+        s.rowptr, s.colidx, s.vals = pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(), mat.values.data_ptr()
+        s.freemask = _ptr(fm)
+        s.pre_kind = 0
+        if pre is not None:
+            s.pre_kind = pre.kind
+            if pre.kind == 1:
+                s.dinv = pre.dinv.data_ptr()
+            else:
+                s.npatch, s.bs = pre.npatch, pre.bs
+                s.patch_dofs, s.inv_blocks = pre.pdofs.data_ptr(), pre.inv.data_ptr()
+        return s
+
+    def krylov(self, kind, mat, b, x, pre, freedofs, tol, maxit, initialize, printrates, damp=1.0, restart=None):
+        state = None
+        if pre is not None:
+            if pre.state is None:
+                pre.Update()
+            state = pre.state
+        fm = self._mask(mat.space, freedofs)
+        if fm is None and state is not None:
+            fm = state.fm
+        if initialize:
+            x.zero_()
+        kid = {'cg': 0, 'gmres': 1, 'minres': 1, 'richardson': 2}[kind]
+        restart = min(maxit, 200) if restart is None else restart
+        sys_ = self._system(mat, fm, state)
+        wl = self.lib.ocmp_krylov_work_len(mat.height, kid, restart)
+        work = self.torch.empty(wl, dtype=self.torch.float64, device=self.device)
+        it, res = C.c_int(0), C.c_double(0.0)
+        self._ck(self.lib.ocmp_krylov(C.byref(sys_), kid, b.data_ptr(), x.data_ptr(), float(tol), int(maxit),
+                                      int(restart), float(damp), work.data_ptr(), wl, C.byref(it), C.byref(res),
+                                      self._stream()))
+        self.last_iters, self.last_resid = it.value, res.value
+        if printrates:
+            print('{}: {} iterations, residual {:.3e}'.format(kind, it.value, res.value))
+
+    def solve_free(self, mat, r, out, freedofs):
+        """Stand-in for ``mat.Inverse(freedofs) * r``: GMRES + cell-patch additive Schwarz driven to 1e-13."""
+        free = np.ones(mat.height, bool) if freedofs is None else freedofs
+        state = self.precond_setup(mat, 'asm', free)
+
+        class _P:
+            pass
+        p = _P()
+        p.state = state
+        out.zero_()
+        self.krylov('gmres', mat, r, out, p, free, 1e-13, 4000, False, False, restart=100)

@@ -1,0 +1,491 @@
+// Assembly kernels of the opencmp_b200 backend (sm_100a).
+//
+//   k_coef      evaluates the coefficient bytecode of one integral at every (item, quadrature point):
+//               geometry (x, n, h, measure), field values from DOF vectors, then the register machine -> D slots.
+//   k_contract  forms the local matrices  A = sum_q B^T (D B)  with physical basis tables staged in shared memory,
+//               accumulators in registers, and scatter-adds them through the element -> nnz map (no colouring).
+//   k_lin       the same for linear forms (local vectors, scatter through the cell dof lists).
+//
+// Stand in for NGSolve's SymbolicBilinearFormIntegrator / SymbolicLinearFormIntegrator element loops that
+// `a.Assemble()` / `L.Assemble()` run (reference opencmp/solvers/base_solver.py:368-377).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/opencmp_b200.h"
+#include "ocmp_common.cuh"
+
+enum { OP_CONST = 0, OP_PARAM, OP_COORD, OP_NORMAL, OP_MESHSIZE, OP_FIELD, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG,
+       OP_ABS, OP_SQRT, OP_SIN, OP_COS, OP_TAN, OP_EXP, OP_LOG, OP_POW, OP_IFPOS, OP_MIN, OP_MAX, OP_TANH, OP_ERF,
+       OP_FLOOR, OP_CEIL, OP_ROUND, OP_TRUNC, OP_SGN, OP_ATAN, OP_OUT, OP_MOV, OP_MEASURE };
+
+#define MAX_FSLOTS 40
+#define MAX_ROWS 12
+
+template <int DIM> struct GeoT { static constexpr int GS = DIM + 2 * DIM * DIM + 1; };
+
+// physical rows of one block from its reference-row sums R (scalar: value + gradient; hdiv: Piola value + gradient)
+template <int DIM>
+__device__ __forceinline__ void phys_rows(int kind, const double* __restrict__ R, const double* __restrict__ J,
+                                          const double* __restrict__ Jinv, double det, double* __restrict__ PH) {
+    if (kind == 0) {
+        PH[0] = R[0];
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < DIM; ++b) s += Jinv[b * DIM + a] * R[1 + b];
+            PH[1 + a] = s;
+        }
+    } else {
+        const double idet = 1.0 / det;
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < DIM; ++b) s += J[c * DIM + b] * R[b];
+            PH[c] = s * idet;
+        }
+        // grad_{c,a} = sum_{b,m} J[c][b] R[DIM + b*DIM + m] Jinv[m][a] / det
+        double T[DIM * DIM];
+#pragma unroll
+        for (int b = 0; b < DIM; ++b)
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) {
+                double s = 0.0;
+#pragma unroll
+                for (int m = 0; m < DIM; ++m) s += R[DIM + b * DIM + m] * Jinv[m * DIM + a];
+                T[b * DIM + a] = s;
+            }
+#pragma unroll
+        for (int c = 0; c < DIM; ++c)
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) {
+                double s = 0.0;
+#pragma unroll
+                for (int b = 0; b < DIM; ++b) s += J[c * DIM + b] * T[b * DIM + a];
+                PH[DIM + c * DIM + a] = s * idet;
+            }
+    }
+}
+
+template <int DIM>
+__device__ __forceinline__ double facet_measure(const double* __restrict__ J, const double* __restrict__ tref) {
+    double T[(DIM - 1) * DIM];
+#pragma unroll
+    for (int k = 0; k < DIM - 1; ++k)
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) s += J[i * DIM + a] * tref[k * DIM + a];
+            T[k * DIM + i] = s;
+        }
+    if (DIM == 2) return sqrt(T[0] * T[0] + T[1] * T[1]);
+    const double cx = T[1] * T[DIM + 2] - T[2] * T[DIM + 1];
+    const double cy = T[2] * T[DIM + 0] - T[0] * T[DIM + 2];
+    const double cz = T[0] * T[DIM + 1] - T[1] * T[DIM + 0];
+    return sqrt(cx * cx + cy * cy + cz * cz);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(128) k_coef(const __grid_constant__ ocmp_coef_plan P, int item0, int nitems,
+                                              double* __restrict__ dbuf) {
+    constexpr int GS = GeoT<DIM>::GS;
+    const long long total = (long long)nitems * P.nq;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int it = (int)(gid / P.nq), q = (int)(gid % P.nq);
+    const int id = P.items ? __ldg(P.items + item0 + it) : item0 + it;
+    int cell[2], lf[2];
+    if (P.kind == 0) {
+        cell[0] = id; lf[0] = 0; cell[1] = id; lf[1] = 0;
+    } else {
+        cell[0] = __ldg(P.facet_cells + 2 * id); lf[0] = __ldg(P.facet_local + 2 * id);
+        cell[1] = __ldg(P.facet_cells + 2 * id + 1); lf[1] = __ldg(P.facet_local + 2 * id + 1);
+        if (cell[1] < 0) { cell[1] = cell[0]; lf[1] = lf[0]; }
+    }
+    const double* g0 = P.geo + (long long)cell[0] * GS;
+    const double* J0 = g0 + DIM;
+    const double* Ji0 = g0 + DIM + DIM * DIM;
+    const double det0 = g0[GS - 1];
+    const double* xi = P.qpts + ((P.kind == 0 ? 0 : lf[0] * P.nq) + q) * DIM;
+    double X[3] = {0.0, 0.0, 0.0}, N[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+        double s = g0[i];
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) s += J0[i * DIM + a] * xi[a];
+        X[i] = s;
+    }
+    double measure, h;
+    if (P.kind == 0) {
+        measure = fabs(det0);
+        h = (DIM == 2) ? sqrt(measure) : cbrt(measure);
+    } else {
+        const double* fr = P.fref + lf[0] * DIM * DIM;
+        measure = facet_measure<DIM>(J0, fr + DIM);
+        double nn = 0.0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) s += Ji0[a * DIM + i] * fr[a];
+            N[i] = s; nn += s * s;
+        }
+        nn = 1.0 / sqrt(nn);
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) N[i] *= nn;
+        h = fabs(det0) / measure;
+    }
+    // ---- field values -------------------------------------------------------------------------------------
+    double fval[MAX_FSLOTS];
+    for (int g = 0; g < P.nfgroups; ++g) {
+        const int* fg = P.fgroup + 8 * g;
+        const int vec = fg[0], darr = fg[1], side = fg[2], kind = fg[3], nloc = fg[4], nrows = fg[5], toff = fg[6],
+                  doff = fg[7];
+        const int dstride = P.fgroup2[2 * g], dadd = P.fgroup2[2 * g + 1];
+        const int c = cell[side];
+        const double* tab = P.ftab + toff + (long long)((P.kind == 0 ? 0 : lf[side] * P.nq) + q) * nrows * nloc;
+        const int* dofs = P.fdof[darr] + (long long)c * dstride + doff;
+        const double* v = P.fvec[vec];
+        double R[MAX_ROWS];
+#pragma unroll
+        for (int r = 0; r < MAX_ROWS; ++r) R[r] = 0.0;
+        for (int i = 0; i < nloc; ++i) {
+            const double ci = __ldg(v + (__ldg(dofs + i) + dadd));
+#pragma unroll
+            for (int r = 0; r < MAX_ROWS; ++r)
+                if (r < nrows) R[r] += ci * __ldg(tab + r * nloc + i);
+        }
+        const double* gs = P.geo + (long long)c * GS;
+        double PH[MAX_ROWS];
+        phys_rows<DIM>(kind, R, gs + DIM, gs + DIM + DIM * DIM, gs[GS - 1], PH);
+        for (int s = 0; s < P.nfslots; ++s)
+            if (P.fslot[2 * s] == g) {
+                const int row = P.fslot[2 * s + 1];
+                double val = 0.0;
+#pragma unroll
+                for (int r = 0; r < MAX_ROWS; ++r)
+                    if (r == row) val = PH[r];
+                fval[s] = val;
+            }
+    }
+    // ---- register machine ---------------------------------------------------------------------------------
+    double r[OCMP_MAX_REGS];
+    const long long ostride = total;
+    const double wq = P.qw[q] * measure;
+    for (int pc = 0; pc < P.ninstr; ++pc) {
+        const int4 ins = __ldg(reinterpret_cast<const int4*>(P.code) + pc);
+        const int op = ins.x & 0xff, d = ins.x >> 8;
+        double v;
+        switch (op) {
+            case OP_CONST: v = P.consts[ins.y]; break;
+            case OP_PARAM: v = P.params[ins.y]; break;
+            case OP_COORD: v = X[ins.y]; break;
+            case OP_NORMAL: v = N[ins.y]; break;
+            case OP_MESHSIZE: v = h; break;
+            case OP_MEASURE: v = measure; break;
+            case OP_FIELD: v = fval[ins.y]; break;
+            case OP_ADD: v = r[ins.y] + r[ins.z]; break;
+            case OP_SUB: v = r[ins.y] - r[ins.z]; break;
+            case OP_MUL: v = r[ins.y] * r[ins.z]; break;
+            case OP_DIV: v = r[ins.y] / r[ins.z]; break;
+            case OP_NEG: v = -r[ins.y]; break;
+            case OP_ABS: v = fabs(r[ins.y]); break;
+            case OP_SQRT: v = sqrt(r[ins.y]); break;
+            case OP_SIN: v = sin(r[ins.y]); break;
+            case OP_COS: v = cos(r[ins.y]); break;
+            case OP_TAN: v = tan(r[ins.y]); break;
+            case OP_EXP: v = exp(r[ins.y]); break;
+            case OP_LOG: v = log(r[ins.y]); break;
+            case OP_POW: v = pow(r[ins.y], r[ins.z]); break;
+            case OP_IFPOS: v = r[ins.y] > 0.0 ? r[ins.z] : r[ins.w]; break;
+            case OP_MIN: v = fmin(r[ins.y], r[ins.z]); break;
+            case OP_MAX: v = fmax(r[ins.y], r[ins.z]); break;
+            case OP_TANH: v = tanh(r[ins.y]); break;
+            case OP_ERF: v = erf(r[ins.y]); break;
+            case OP_FLOOR: v = floor(r[ins.y]); break;
+            case OP_CEIL: v = ceil(r[ins.y]); break;
+            case OP_ROUND: v = rint(r[ins.y]); break;
+            case OP_TRUNC: v = trunc(r[ins.y]); break;
+            case OP_SGN: v = (r[ins.y] > 0.0) - (r[ins.y] < 0.0); break;
+            case OP_ATAN: v = atan(r[ins.y]); break;
+            case OP_MOV: v = r[ins.y]; break;
+            case OP_OUT: dbuf[(long long)ins.y * ostride + gid] = r[ins.z] * wq; continue;
+            default: v = 0.0; break;
+        }
+        r[d] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Shared helper: physical table of local dof `il` of block (kind,nloc,nrows) at quadrature point q into out[r*nloc]
+template <int DIM>
+__device__ __forceinline__ void dof_phys_rows(int kind, int nloc, int nrows, const double* __restrict__ tabq, int il,
+                                              const double* __restrict__ g, double* __restrict__ PH) {
+    constexpr int GS = GeoT<DIM>::GS;
+    double R[MAX_ROWS];
+#pragma unroll
+    for (int r = 0; r < MAX_ROWS; ++r) R[r] = (r < nrows) ? __ldg(tabq + r * nloc + il) : 0.0;
+    phys_rows<DIM>(kind, R, g + DIM, g + DIM + DIM * DIM, g[GS - 1], PH);
+}
+
+template <int DIM, int NACC>
+__global__ void __launch_bounds__(256) k_contract(const __grid_constant__ ocmp_contract_plan P, int item0, int nitems,
+                                                  const double* __restrict__ dbuf, double* __restrict__ values) {
+    constexpr int GS = GeoT<DIM>::GS;
+    extern __shared__ double smem[];
+    const int EB = P.eb, TPE = 256 / EB;
+    const int nside = P.nside;
+    double* sB = smem;                                   // [EB][nside][sbsz]
+    double* sZ = sB + EB * nside * P.sbsz;               // [EB][zsz]
+    double* sD = sZ + EB * P.zsz;                        // [EB][nslots]
+    double* sG = sD + EB * P.nslots;                     // [EB][nside][GS]
+    int* sI = reinterpret_cast<int*>(sG + EB * nside * GS);   // [EB][4]: cell0, cell1, lf0, lf1
+    const int tid = threadIdx.x;
+    const int e_own = tid / TPE, lane = tid % TPE;
+    const long long dstride = (long long)nitems * P.nq;
+    const int ngroups = (nitems + EB - 1) / EB;
+    const int n2 = P.nloc * P.nloc;
+
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        __syncthreads();
+        if (tid < EB) {
+            const int it = grp * EB + tid;
+            int c0 = -1, c1 = -1, l0 = 0, l1 = 0;
+            if (it < nitems) {
+                const int id = P.items ? __ldg(P.items + item0 + it) : item0 + it;
+                if (P.kind == 0) { c0 = id; }
+                else {
+                    c0 = __ldg(P.facet_cells + 2 * id); l0 = __ldg(P.facet_local + 2 * id);
+                    c1 = __ldg(P.facet_cells + 2 * id + 1); l1 = __ldg(P.facet_local + 2 * id + 1);
+                }
+            }
+            sI[4 * tid] = c0; sI[4 * tid + 1] = c1; sI[4 * tid + 2] = l0; sI[4 * tid + 3] = l1;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < EB * nside * GS; idx += 256) {
+            const int e = idx / (nside * GS), rem = idx % (nside * GS), s = rem / GS, k = rem % GS;
+            const int c = sI[4 * e + s];
+            sG[idx] = (c >= 0) ? __ldg(P.geo + (long long)c * GS + k) : (k == GS - 1 ? 1.0 : 0.0);
+        }
+        double acc[NACC];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+
+        for (int q = 0; q < P.nq; ++q) {
+            __syncthreads();
+            for (int idx = tid; idx < EB * P.nslots; idx += 256) {
+                const int e = idx / P.nslots, k = idx % P.nslots, it = grp * EB + e;
+                sD[idx] = (it < nitems) ? __ldg(dbuf + (long long)k * dstride + (long long)it * P.nq + q) : 0.0;
+            }
+            for (int idx = tid; idx < EB * nside * P.nloc; idx += 256) {
+                const int e = idx / (nside * P.nloc), rem = idx % (nside * P.nloc), s = rem / P.nloc, i = rem % P.nloc;
+                int b = 0;
+                while (b + 1 < P.nblk && i >= __ldg(P.blk + 6 * (b + 1) + 4)) ++b;
+                const int* bd = P.blk + 6 * b;
+                const int kind = __ldg(bd), nl = __ldg(bd + 1), nr = __ldg(bd + 2), toff = __ldg(bd + 3),
+                          loff = __ldg(bd + 4), sboff = __ldg(bd + 5);
+                const int il = i - loff;
+                const int c = sI[4 * e + s];
+                double* out = sB + (e * nside + s) * P.sbsz + sboff + il;
+                if (c < 0) {
+                    for (int r = 0; r < nr; ++r) out[r * nl] = 0.0;
+                } else {
+                    const int lfq = (P.kind == 0 ? 0 : sI[4 * e + 2 + s] * P.nq) + q;
+                    double PH[MAX_ROWS];
+                    dof_phys_rows<DIM>(kind, nl, nr, P.tab + toff + (long long)lfq * nr * nl, il,
+                                       sG + (e * nside + s) * GS, PH);
+#pragma unroll
+                    for (int r = 0; r < MAX_ROWS; ++r)
+                        if (r < nr) out[r * nl] = PH[r];
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < EB * P.zsz; idx += 256) {
+                const int e = idx / P.zsz, z = idx % P.zsz;
+                const int4 zd = __ldg(reinterpret_cast<const int4*>(P.zdesc) + z);
+                const double* bb = sB + e * nside * P.sbsz + zd.z;
+                const double* dd = sD + e * P.nslots;
+                double s = 0.0;
+                for (int k = zd.x; k < zd.y; ++k) {
+                    const int2 en = __ldg(reinterpret_cast<const int2*>(P.ent) + k);
+                    s += dd[en.x] * bb[en.y * zd.w];
+                }
+                sZ[idx] = s;
+            }
+            __syncthreads();
+            {
+                const double* bE = sB + e_own * nside * P.sbsz;
+                const double* zE = sZ + e_own * P.zsz;
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) {
+                    const int ai = lane + a * TPE;
+                    if (ai < P.nact) {
+                        const int4 ad = __ldg(reinterpret_cast<const int4*>(P.adesc) + ai);
+                        const int s0 = ad.z & 0xffffff, ns = ad.z >> 24;
+                        double v = acc[a];
+                        for (int s = s0; s < s0 + ns; ++s) {
+                            const int2 sg = __ldg(reinterpret_cast<const int2*>(P.seg) + s);
+                            v = fma(bE[ad.x + sg.x * ad.y], zE[sg.y + ad.w], v);
+                        }
+                        acc[a] = v;
+                    }
+                }
+            }
+        }
+        // ---- scatter-add through the element -> nnz map ------------------------------------------------------
+        const int it = grp * EB + e_own;
+        if (it < nitems) {
+            const int c0 = sI[4 * e_own], c1 = sI[4 * e_own + 1];
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) {
+                const int ai = lane + a * TPE;
+                if (ai < P.nact) {
+                    const int m = __ldg(P.amap + ai);
+                    const int st = (m >> 30) & 1, su = (m >> 29) & 1, ij = m & 0x1fffffff;
+                    int pos;
+                    if (st == su) pos = __ldg(P.cell2nnz + (long long)(st ? c1 : c0) * n2 + ij);
+                    else pos = __ldg(P.facet2nnz + ((long long)(item0 + it) * 2 + st) * n2 + ij);
+                    atomicAdd(values + pos, acc[a]);
+                }
+            }
+        }
+    }
+}
+
+// linear forms: one thread per (item, side, local dof)
+template <int DIM>
+__global__ void __launch_bounds__(128) k_lin(const __grid_constant__ ocmp_contract_plan P, int item0, int nitems,
+                                             const double* __restrict__ dbuf, double* __restrict__ vec) {
+    constexpr int GS = GeoT<DIM>::GS;
+    const long long total = (long long)nitems * P.nside * P.nloc;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int it = (int)(gid / (P.nside * P.nloc)), rem = (int)(gid % (P.nside * P.nloc));
+    const int s = rem / P.nloc, i = rem % P.nloc;
+    const int id = P.items ? __ldg(P.items + item0 + it) : item0 + it;
+    int c, lf = 0;
+    if (P.kind == 0) c = id;
+    else { c = __ldg(P.facet_cells + 2 * id + s); lf = __ldg(P.facet_local + 2 * id + s); }
+    if (c < 0) return;
+    int b = 0;
+    while (b + 1 < P.nblk && i >= P.blk[6 * (b + 1) + 4]) ++b;
+    const int* bd = P.blk + 6 * b;
+    const int kind = bd[0], nl = bd[1], nr = bd[2], toff = bd[3], loff = bd[4];
+    const int il = i - loff, sbk = s * P.nblk + b;
+    // does any entry test against this side-block?
+    const int nent = P.zsz;
+    bool any = false;
+    for (int k = 0; k < nent; ++k) any |= ((P.ent[2 * k + 1] >> 8) == sbk);
+    if (!any) return;
+    const double* g = P.geo + (long long)c * GS;
+    const long long dstride = (long long)nitems * P.nq;
+    double acc = 0.0;
+    for (int q = 0; q < P.nq; ++q) {
+        const int lfq = (P.kind == 0 ? 0 : lf * P.nq) + q;
+        double PH[MAX_ROWS];
+        dof_phys_rows<DIM>(kind, nl, nr, P.tab + toff + (long long)lfq * nr * nl, il, g, PH);
+        for (int k = 0; k < nent; ++k) {
+            const int code = P.ent[2 * k + 1];
+            if ((code >> 8) != sbk) continue;
+            const int row = code & 0xff;
+            double val = 0.0;
+#pragma unroll
+            for (int r = 0; r < MAX_ROWS; ++r)
+                if (r == row) val = PH[r];
+            acc = fma(__ldg(dbuf + (long long)P.ent[2 * k] * dstride + (long long)it * P.nq + q), val, acc);
+        }
+    }
+    atomicAdd(vec + __ldg(P.cell_dofs + (long long)c * P.nloc + i), acc);
+}
+
+__global__ void __launch_bounds__(256) k_sum(const double* __restrict__ x, long long n, double* __restrict__ out) {
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s += x[i];
+    s = block_reduce_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// ---- C ABI ------------------------------------------------------------------------------------------------------
+extern "C" int ocmp_eval_coefficients(const ocmp_coef_plan* plan, int item0, int nitems, double* dbuf, void* stream) {
+    if (nitems <= 0) return 0;
+    if (plan->nfslots > MAX_FSLOTS) return ocmp_fail(-2, "too many field slots in one integral");
+    if (plan->nreg > OCMP_MAX_REGS) return ocmp_fail(-2, "coefficient program needs too many registers");
+    const long long total = (long long)nitems * plan->nq;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->dim == 2) k_coef<2><<<blocks, threads, 0, st>>>(*plan, item0, nitems, dbuf);
+    else if (plan->dim == 3) k_coef<3><<<blocks, threads, 0, st>>>(*plan, item0, nitems, dbuf);
+    else return ocmp_fail(-1, "dim must be 2 or 3");
+    return ocmp_check("ocmp_eval_coefficients");
+}
+
+static size_t contract_smem(const ocmp_contract_plan* p) {
+    const int gs = p->dim + 2 * p->dim * p->dim + 1;
+    return sizeof(double) * ((size_t)p->eb * p->nside * p->sbsz + (size_t)p->eb * p->zsz + (size_t)p->eb * p->nslots +
+                             (size_t)p->eb * p->nside * gs) + sizeof(int) * 4 * p->eb;
+}
+
+template <int DIM, int NACC>
+static int launch_contract(const ocmp_contract_plan* plan, int item0, int nitems, const double* dbuf, double* values,
+                           cudaStream_t st) {
+    const size_t smem = contract_smem(plan);
+    if (smem > 220 * 1024) return ocmp_fail(-3, "contraction plan needs more than 220 KB of shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(k_contract<DIM, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    const int ngroups = (nitems + plan->eb - 1) / plan->eb;
+    int sms = ocmp_sm_count();
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contract<DIM, NACC>, 256, smem);
+    if (per_sm < 1) per_sm = 1;
+    const int grid = ngroups < sms * per_sm ? ngroups : sms * per_sm;
+    k_contract<DIM, NACC><<<grid, 256, smem, st>>>(*plan, item0, nitems, dbuf, values);
+    return ocmp_check("ocmp_contract_matrix");
+}
+
+extern "C" int ocmp_contract_matrix(const ocmp_contract_plan* plan, int item0, int nitems, const double* dbuf,
+                                    double* values, void* stream) {
+    if (nitems <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int eb = plan->eb;
+    if (eb < 1 || eb > 16 || (eb & (eb - 1))) return ocmp_fail(-1, "eb must be a power of two <= 16");
+    const int tpe = 256 / eb;
+    const int need = (plan->nact + tpe - 1) / tpe;
+    if (plan->dim == 2) {
+        if (need <= 16) return launch_contract<2, 16>(plan, item0, nitems, dbuf, values, st);
+        if (need <= 32) return launch_contract<2, 32>(plan, item0, nitems, dbuf, values, st);
+    } else if (plan->dim == 3) {
+        if (need <= 16) return launch_contract<3, 16>(plan, item0, nitems, dbuf, values, st);
+        if (need <= 32) return launch_contract<3, 32>(plan, item0, nitems, dbuf, values, st);
+    } else return ocmp_fail(-1, "dim must be 2 or 3");
+    return ocmp_fail(-3, "local matrix too large for the register-accumulator kernel");
+}
+
+extern "C" int ocmp_contract_vector(const ocmp_contract_plan* plan, int item0, int nitems, const double* dbuf,
+                                    double* vec, void* stream) {
+    if (nitems <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)nitems * plan->nside * plan->nloc;
+    const unsigned blocks = (unsigned)((total + 127) / 128);
+    if (plan->dim == 2) k_lin<2><<<blocks, 128, 0, st>>>(*plan, item0, nitems, dbuf, vec);
+    else if (plan->dim == 3) k_lin<3><<<blocks, 128, 0, st>>>(*plan, item0, nitems, dbuf, vec);
+    else return ocmp_fail(-1, "dim must be 2 or 3");
+    return ocmp_check("ocmp_contract_vector");
+}
+
+extern "C" int ocmp_sum(const double* x, long long n, double* out, void* stream) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    const int cap = ocmp_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    k_sum<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+    return ocmp_check("ocmp_sum");
+}

@@ -1,0 +1,487 @@
+// Sparse / dense vector kernels, preconditioners and Krylov drivers of the opencmp_b200 backend (sm_100a).
+//
+// Stand in for NGSolve's SparseMatrix<double>::Mult, BaseVector arithmetic, Preconditioner(a,'local'|...) and the
+// pure-Python ngsolve.solvers CG / GMRes / PreconditionedRichardson that Model.linear_solve dispatches to
+// (reference opencmp/models/base_model.py:886-947).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "../../include/opencmp_b200.h"
+#include "ocmp_common.cuh"
+
+// ---- error plumbing ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+int ocmp_fail(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+int ocmp_check(const char* where) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+        return -100;
+    }
+    return 0;
+}
+int ocmp_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+extern "C" const char* ocmp_last_error(void) { return g_err; }
+extern "C" int ocmp_version(void) { return 100; }
+
+// ---- SpMV: CSR, LPR lanes cooperate on one row -----------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256) k_spmv(int nrows, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                              const double* __restrict__ val, const double* __restrict__ x,
+                                              double* __restrict__ y) {
+    const int lane = threadIdx.x % LPR;
+    const long long row0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    const long long stride = (long long)gridDim.x * blockDim.x / LPR;
+    for (long long row = row0; row < nrows; row += stride) {
+        const int a = __ldg(rowptr + row), b = __ldg(rowptr + row + 1);
+        double s = 0.0;
+        for (int k = a + lane; k < b; k += LPR) s = fma(__ldg(val + k), __ldg(x + __ldg(col + k)), s);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LPR);
+        if (lane == 0) y[row] = s;
+    }
+}
+
+extern "C" int ocmp_spmv(int nrows, const int* rowptr, const int* colidx, const double* vals, const double* x,
+                         double* y, void* stream) {
+    if (nrows <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = 256;
+    const long long want = ((long long)nrows * 16 + threads - 1) / threads;
+    const long long cap = (long long)ocmp_sm_count() * 64;
+    const unsigned blocks = (unsigned)(want < cap ? want : cap);
+    k_spmv<16><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, vals, x, y);
+    return ocmp_check("ocmp_spmv");
+}
+
+// ---- level-1 ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dot(long long n, const double* __restrict__ x, const double* __restrict__ y,
+                                             double* __restrict__ out) {
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s = fma(x[i], y[i], s);
+    s = block_reduce_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+__global__ void __launch_bounds__(256) k_axpby(long long n, double a, const double* __restrict__ x, double b,
+                                               double* __restrict__ y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = (b == 0.0) ? a * x[i] : fma(a, x[i], b * y[i]);
+}
+
+__global__ void __launch_bounds__(256) k_masked_assign(long long n, double* __restrict__ dst,
+                                                       const double* __restrict__ src, const double* __restrict__ inv,
+                                                       const double* __restrict__ mask) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        if (mask[i] > 0.0) dst[i] = src[i] * inv[i];
+}
+
+// z = m .* (a .* r)   (a, m optional)
+__global__ void __launch_bounds__(256) k_had(long long n, const double* __restrict__ a, const double* __restrict__ m,
+                                             const double* __restrict__ r, double* __restrict__ z) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double v = r[i];
+        if (a) v *= a[i];
+        if (m) v *= m[i];
+        z[i] = v;
+    }
+}
+
+// r = m .* (b - r)
+__global__ void __launch_bounds__(256) k_resid(long long n, const double* __restrict__ b, const double* __restrict__ m,
+                                               double* __restrict__ r) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double v = b[i] - r[i];
+        if (m) v *= m[i];
+        r[i] = v;
+    }
+}
+
+// out[j] += <V_j, w>, j < k <= 8 ; V_j = V + j*ld
+template <int K>
+__global__ void __launch_bounds__(256) k_mdot(long long n, const double* __restrict__ V, long long ld, int k,
+                                              const double* __restrict__ w, double* __restrict__ out) {
+    double s[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) s[j] = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const double wi = w[i];
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (j < k) s[j] = fma(V[j * ld + i], wi, s[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < k) {
+            const double t = block_reduce_sum(s[j]);
+            if (threadIdx.x == 0) atomicAdd(out + j, t);
+        }
+    }
+}
+
+// w += sum_j c[j] V_j  (c on device)
+__global__ void __launch_bounds__(256) k_maxpy(long long n, const double* __restrict__ V, long long ld, int k,
+                                               const double* __restrict__ c, double* __restrict__ w) {
+    extern __shared__ double sc[];
+    for (int j = threadIdx.x; j < k; j += blockDim.x) sc[j] = c[j];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double s = w[i];
+        for (int j = 0; j < k; ++j) s = fma(sc[j], V[j * ld + i], s);
+        w[i] = s;
+    }
+}
+
+static inline unsigned grid_for(long long n) {
+    long long b = (n + 255) / 256;
+    const long long cap = (long long)ocmp_sm_count() * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+extern "C" int ocmp_dot(long long n, const double* x, const double* y, double* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(out, 0, sizeof(double), st);
+    if (n > 0) k_dot<<<grid_for(n), 256, 0, st>>>(n, x, y, out);
+    return ocmp_check("ocmp_dot");
+}
+extern "C" int ocmp_axpby(long long n, double a, const double* x, double b, double* y, void* stream) {
+    if (n > 0) k_axpby<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, a, x, b, y);
+    return ocmp_check("ocmp_axpby");
+}
+extern "C" int ocmp_masked_assign(long long n, double* dst, const double* src, const double* inv, const double* mask,
+                                  void* stream) {
+    if (n > 0) k_masked_assign<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, dst, src, inv, mask);
+    return ocmp_check("ocmp_masked_assign");
+}
+
+// ---- preconditioners -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_jacobi_setup(int n, const int* __restrict__ diagpos,
+                                                      const double* __restrict__ vals, const double* __restrict__ fm,
+                                                      double* __restrict__ dinv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = vals[diagpos[i]];
+    const bool free_ = fm ? fm[i] > 0.0 : true;
+    dinv[i] = (free_ && d != 0.0) ? 1.0 / d : 0.0;
+}
+
+extern "C" int ocmp_jacobi_setup(int nrows, const int* diagpos, const double* vals, const double* freemask,
+                                 double* dinv, void* stream) {
+    if (nrows > 0)
+        k_jacobi_setup<<<(nrows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nrows, diagpos, vals, freemask, dinv);
+    return ocmp_check("ocmp_jacobi_setup");
+}
+
+// One CTA per patch: gather the dense block, impose identity rows/cols on constrained dofs, invert [A | I] by
+// Gauss-Jordan with partial pivoting in shared memory, store the inverse transposed (inv[j*bs + i] = (A^-1)_{ij}).
+__global__ void __launch_bounds__(256) k_asm_setup(int npatch, int bs, const int* __restrict__ pdofs,
+                                                   const int* __restrict__ p2nnz, const double* __restrict__ vals,
+                                                   const double* __restrict__ fm, double* __restrict__ inv) {
+    extern __shared__ double M[];          // bs x 2bs, then fcol[bs]
+    double* fcol = M + bs * 2 * bs;
+    __shared__ int spiv;
+    const int w2 = 2 * bs;
+    for (int p = blockIdx.x; p < npatch; p += gridDim.x) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < bs * bs; idx += blockDim.x) {
+            const int i = idx / bs, j = idx % bs;
+            const int di = pdofs[(long long)p * bs + i], dj = pdofs[(long long)p * bs + j];
+            const int pos = p2nnz[(long long)p * bs * bs + idx];
+            double v = (pos >= 0 && di >= 0 && dj >= 0) ? vals[pos] : 0.0;
+            const bool fi = di >= 0 && (!fm || fm[di] > 0.0), fj = dj >= 0 && (!fm || fm[dj] > 0.0);
+            if (!fi || !fj) v = (i == j) ? 1.0 : 0.0;
+            M[i * w2 + j] = v;
+            M[i * w2 + bs + j] = (i == j) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        for (int k = 0; k < bs; ++k) {
+            if (threadIdx.x < 32) {
+                double best = -1.0;
+                int bi = k;
+                for (int i = k + threadIdx.x; i < bs; i += 32) {
+                    const double a = fabs(M[i * w2 + k]);
+                    if (a > best) { best = a; bi = i; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_down_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                    if (ob > best) { best = ob; bi = oi; }
+                }
+                if (threadIdx.x == 0) spiv = bi;
+            }
+            __syncthreads();
+            const int pr = spiv;
+            if (pr != k)
+                for (int j = threadIdx.x; j < w2; j += blockDim.x) {
+                    const double t = M[k * w2 + j];
+                    M[k * w2 + j] = M[pr * w2 + j];
+                    M[pr * w2 + j] = t;
+                }
+            __syncthreads();
+            double piv = M[k * w2 + k];
+            if (fabs(piv) < 1e-300) piv = 1e-300;
+            const double ip = 1.0 / piv;
+            __syncthreads();
+            for (int j = threadIdx.x; j < w2; j += blockDim.x) M[k * w2 + j] *= ip;
+            for (int i = threadIdx.x; i < bs; i += blockDim.x) fcol[i] = (i == k) ? 0.0 : M[i * w2 + k];
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < bs * w2; idx += blockDim.x) {
+                const int i = idx / w2, j = idx % w2;
+                M[idx] = fma(-fcol[i], M[k * w2 + j], M[idx]);
+            }
+            __syncthreads();
+        }
+        for (int idx = threadIdx.x; idx < bs * bs; idx += blockDim.x) {
+            const int j = idx / bs, i = idx % bs;
+            inv[(long long)p * bs * bs + idx] = M[i * w2 + bs + j];
+        }
+    }
+}
+
+extern "C" int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const int* patch2nnz, const double* vals,
+                              const double* freemask, double* inv_blocks, void* stream) {
+    if (npatch <= 0) return 0;
+    const size_t smem = sizeof(double) * ((size_t)bs * 2 * bs + bs);
+    if (smem > 220 * 1024) return ocmp_fail(-3, "patch too large for shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(k_asm_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    const int cap = ocmp_sm_count() * 4;
+    k_asm_setup<<<npatch < cap ? npatch : cap, 256, smem, (cudaStream_t)stream>>>(npatch, bs, patch_dofs, patch2nnz,
+                                                                                  vals, freemask, inv_blocks);
+    return ocmp_check("ocmp_asm_setup");
+}
+
+// one warp per patch: z[dofs] += A_p^-1 r[dofs]
+__global__ void __launch_bounds__(256) k_asm_apply(int npatch, int bs, const int* __restrict__ pdofs,
+                                                   const double* __restrict__ inv, const double* __restrict__ r,
+                                                   double* __restrict__ z) {
+    extern __shared__ double sr[];         // [warps][bs]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    double* rr = sr + warp * bs;
+    for (long long p = (long long)blockIdx.x * wpb + warp; p < npatch; p += (long long)gridDim.x * wpb) {
+        const int* d = pdofs + p * bs;
+        __syncwarp();
+        for (int j = lane; j < bs; j += 32) {
+            const int dj = __ldg(d + j);
+            rr[j] = dj >= 0 ? __ldg(r + dj) : 0.0;
+        }
+        __syncwarp();
+        const double* A = inv + p * bs * bs;
+        for (int i = lane; i < bs; i += 32) {
+            double s = 0.0;
+            for (int j = 0; j < bs; ++j) s = fma(__ldg(A + j * bs + i), rr[j], s);
+            const int di = __ldg(d + i);
+            if (di >= 0) atomicAdd(z + di, s);
+        }
+    }
+}
+
+extern "C" int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const double* inv_blocks, const double* r,
+                              double* z, long long n, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(z, 0, sizeof(double) * n, st);
+    if (npatch <= 0) return 0;
+    const int wpb = 8;
+    const size_t smem = sizeof(double) * wpb * bs;
+    long long blocks = (npatch + wpb - 1) / wpb;
+    const long long cap = (long long)ocmp_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    k_asm_apply<<<(unsigned)blocks, wpb * 32, smem, st>>>(npatch, bs, patch_dofs, inv_blocks, r, z);
+    return ocmp_check("ocmp_asm_apply");
+}
+
+// ---- Krylov drivers ---------------------------------------------------------------------------------------------
+namespace {
+struct Ctx {
+    const ocmp_system* s;
+    cudaStream_t st;
+    long long n;
+    double* dscal;      // device scratch scalars (>= 64)
+    double hscal[64];
+
+    void A(const double* x, double* y) const {
+        ocmp_spmv(s->nrows, s->rowptr, s->colidx, s->vals, x, y, st);
+    }
+    // z = P (already masked r); result masked
+    void P(const double* r, double* z) const {
+        if (s->pre_kind == 1) k_had<<<grid_for(n), 256, 0, st>>>(n, s->dinv, nullptr, r, z);
+        else if (s->pre_kind == 2) {
+            ocmp_asm_apply(s->npatch, s->bs, s->patch_dofs, s->inv_blocks, r, z, n, st);
+            if (s->freemask) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, s->freemask, z, z);
+        } else k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, s->freemask, r, z);
+    }
+    void mask(double* v) const {
+        if (s->freemask) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, s->freemask, v, v);
+    }
+    double dot(const double* x, const double* y) {
+        ocmp_dot(n, x, y, dscal, st);
+        cudaMemcpyAsync(hscal, dscal, sizeof(double), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        return hscal[0];
+    }
+    void axpby(double a, const double* x, double b, double* y) const { ocmp_axpby(n, a, x, b, y, st); }
+    void mdot(const double* V, int k, const double* w, double* hout) {
+        cudaMemsetAsync(dscal, 0, sizeof(double) * k, st);
+        for (int j0 = 0; j0 < k; j0 += 8) {
+            const int kk = (k - j0) < 8 ? (k - j0) : 8;
+            k_mdot<8><<<grid_for(n), 256, 0, st>>>(n, V + (long long)j0 * n, n, kk, w, dscal + j0);
+        }
+        cudaMemcpyAsync(hout, dscal, sizeof(double) * k, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+    }
+    void maxpy(const double* V, int k, const double* hc, double* w) {
+        cudaMemcpyAsync(dscal, hc, sizeof(double) * k, cudaMemcpyHostToDevice, st);
+        k_maxpy<<<grid_for(n), 256, sizeof(double) * k, st>>>(n, V, n, k, dscal, w);
+    }
+};
+}  // namespace
+
+extern "C" long long ocmp_krylov_work_len(int nrows, int kind, int restart) {
+    const long long n = nrows;
+    if (kind == 0) return 4 * n + 64;
+    if (kind == 1) return (long long)(restart + 1) * n + 2 * n + 2 * (restart + 2) + 64;
+    return 2 * n + 64;
+}
+
+extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, double* x, double tol, int maxit,
+                           int restart, double damp, double* work, long long work_len, int* iters, double* resid,
+                           void* stream) {
+    const long long n = sys->nrows;
+    if (work_len < ocmp_krylov_work_len(sys->nrows, kind, restart)) return ocmp_fail(-4, "krylov work array too small");
+    Ctx c;
+    c.s = sys; c.st = (cudaStream_t)stream; c.n = n;
+    int it = 0;
+    double res = 0.0;
+    if (kind == 0) {                       // preconditioned CG on the free dofs
+        double *r = work, *z = work + n, *p = work + 2 * n, *Ap = work + 3 * n;
+        c.dscal = work + 4 * n;
+        c.A(x, r);
+        k_resid<<<grid_for(n), 256, 0, c.st>>>(n, b, sys->freemask, r);
+        c.P(r, z);
+        c.axpby(1.0, z, 0.0, p);
+        double rz = c.dot(r, z);
+        const double err0 = sqrt(fabs(rz));
+        res = err0;
+        if (rz != 0.0) {
+            for (it = 0; it < maxit;) {
+                c.A(p, Ap);
+                c.mask(Ap);
+                const double pAp = c.dot(p, Ap);
+                const double alpha = rz / pAp;
+                c.axpby(alpha, p, 1.0, x);
+                c.axpby(-alpha, Ap, 1.0, r);
+                c.P(r, z);
+                const double rzn = c.dot(r, z);
+                c.axpby(1.0, z, rzn / rz, p);
+                ++it;
+                res = sqrt(fabs(rzn));
+                rz = rzn;
+                if (res < tol * err0 || rzn == 0.0) break;
+            }
+        }
+    } else if (kind == 1) {                // left-preconditioned restarted GMRES, CGS2 orthogonalisation
+        const int m = restart;
+        double* V = work;
+        double* w = work + (long long)(m + 1) * n;
+        double* t = w + n;
+        c.dscal = t + n;
+        std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), h(m + 2), h2(m + 2), yv(m);
+        double beta0 = -1.0;
+        bool done = false;
+        while (!done && it < maxit) {
+            c.A(x, t);
+            k_resid<<<grid_for(n), 256, 0, c.st>>>(n, b, sys->freemask, t);
+            c.P(t, V);
+            double beta = sqrt(c.dot(V, V));
+            if (beta0 < 0.0) beta0 = beta;
+            res = beta;
+            if (beta == 0.0 || beta < tol * beta0) break;
+            c.axpby(0.0, V, 1.0 / beta, V);      // V0 *= 1/beta
+            std::fill(g.begin(), g.end(), 0.0);
+            g[0] = beta;
+            int k = 0;
+            for (; k < m && it < maxit; ++k) {
+                c.A(V + (long long)k * n, t);
+                c.mask(t);
+                c.P(t, w);
+                c.mdot(V, k + 1, w, h.data());
+                for (int j = 0; j <= k; ++j) h2[j] = -h[j];
+                c.maxpy(V, k + 1, h2.data(), w);
+                c.mdot(V, k + 1, w, h2.data());          // second Gram-Schmidt pass
+                for (int j = 0; j <= k; ++j) { h[j] += h2[j]; h2[j] = -h2[j]; }
+                c.maxpy(V, k + 1, h2.data(), w);
+                const double hn = sqrt(c.dot(w, w));
+                for (int j = 0; j <= k; ++j) H[(size_t)j * m + k] = h[j];
+                H[(size_t)(k + 1) * m + k] = hn;
+                for (int i = 0; i < k; ++i) {
+                    const double a = H[(size_t)i * m + k], bb = H[(size_t)(i + 1) * m + k];
+                    H[(size_t)i * m + k] = cs[i] * a + sn[i] * bb;
+                    H[(size_t)(i + 1) * m + k] = -sn[i] * a + cs[i] * bb;
+                }
+                const double a = H[(size_t)k * m + k], bb = H[(size_t)(k + 1) * m + k];
+                const double den = hypot(a, bb);
+                cs[k] = den == 0.0 ? 1.0 : a / den;
+                sn[k] = den == 0.0 ? 0.0 : bb / den;
+                H[(size_t)k * m + k] = cs[k] * a + sn[k] * bb;
+                H[(size_t)(k + 1) * m + k] = 0.0;
+                g[k + 1] = -sn[k] * g[k];
+                g[k] = cs[k] * g[k];
+                ++it;
+                res = fabs(g[k + 1]);
+                if (hn > 0.0) {
+                    double* vn = V + (long long)(k + 1) * n;
+                    c.axpby(1.0 / hn, w, 0.0, vn);
+                }
+                if (res < tol * beta0 || hn == 0.0) { done = true; ++k; break; }
+            }
+            for (int i = k - 1; i >= 0; --i) {
+                double s = g[i];
+                for (int j = i + 1; j < k; ++j) s -= H[(size_t)i * m + j] * yv[j];
+                yv[i] = s / H[(size_t)i * m + i];
+            }
+            c.maxpy(V, k, yv.data(), x);
+        }
+    } else if (kind == 2) {                // damped preconditioned Richardson
+        double *r = work, *z = work + n;
+        c.dscal = work + 2 * n;
+        double r0 = -1.0;
+        for (it = 0; it < maxit; ++it) {
+            c.A(x, r);
+            k_resid<<<grid_for(n), 256, 0, c.st>>>(n, b, sys->freemask, r);
+            res = sqrt(c.dot(r, r));
+            if (r0 < 0.0) r0 = res;
+            if (res < tol * r0 || res == 0.0) break;
+            c.P(r, z);
+            c.axpby(damp, z, 1.0, x);
+        }
+    } else return ocmp_fail(-1, "unknown krylov kind");
+    cudaStreamSynchronize(c.st);
+    if (iters) *iters = it;
+    if (resid) *resid = res;
+    return ocmp_check("ocmp_krylov");
+}

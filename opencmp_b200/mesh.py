@@ -509,3 +509,32 @@ def structured_3d(N: Sequence[int], scale: Sequence[float] = (1.0, 1.0, 1.0),
     info = dict(N=(nx, ny, nz), scale=tuple(scale), offset=tuple(offset), cell=cell)
     return Mesh(3, ctype, pts, cells, bnd, bidx, ['back', 'left', 'front', 'right', 'bottom', 'top'],
                 structured=info)
+
+
+def delaunay_rectangle(n: int, seed: int = 0, size: Sequence[float] = (1.0, 1.0),
+                       names: Sequence[str] = ('bottom', 'right', 'top', 'left')) -> Mesh:
+    """Unstructured triangle mesh of [0,Lx]x[0,Ly]: Delaunay triangulation of jittered interior points plus evenly
+    spaced boundary points. Used by the tests and benches in place of the reference's Netgen-generated .vol files
+    (which do not travel to the GPU box)."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    lx, ly = float(size[0]), float(size[1])
+    nx = max(2, int(round(n * lx / max(lx, ly))))
+    ny = max(2, int(round(n * ly / max(lx, ly))))
+    gx, gy = np.meshgrid(np.arange(1, nx) / nx, np.arange(1, ny) / ny)
+    inner = np.stack([gx.ravel(), gy.ravel()], 1)
+    inner += rng.uniform(-0.3, 0.3, inner.shape) / np.array([nx, ny])
+    tx, ty = np.arange(nx + 1) / nx, np.arange(1, ny) / ny
+    bnd = np.concatenate([np.stack([tx, 0 * tx], 1), np.stack([tx, 0 * tx + 1], 1),
+                          np.stack([0 * ty, ty], 1), np.stack([0 * ty + 1, ty], 1)])
+    pts = np.concatenate([bnd, inner]) * np.array([lx, ly])
+    tri = Delaunay(pts).simplices
+    P = pts[tri]
+    area = 0.5 * np.abs(np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]))
+    tri = tri[area > 1e-12 * lx * ly]
+    tmp = Mesh(2, 'tri', pts, tri, np.zeros((0, 2), np.int64), np.zeros(0, np.int32), list(names))
+    bf = tmp.facets[tmp.bnd_facets].astype(np.int64)
+    mid = 0.5 * (pts[bf[:, 0]] + pts[bf[:, 1]])
+    eps = 1e-9
+    idx = np.where(mid[:, 1] < eps, 0, np.where(mid[:, 0] > lx - eps, 1, np.where(mid[:, 1] > ly - eps, 2, 3)))
+    return Mesh(2, 'tri', pts, tri, bf, idx.astype(np.int32), list(names))

@@ -1,0 +1,139 @@
+"""Shared weak-form builders for the parity tests.
+
+Each builder writes the forms the way the reference's model classes do (file:line cited per builder) against the
+NGSolve-style front end, so the same code runs on the CUDA backend and on the oracle.
+"""
+import numpy as np
+
+from opencmp_b200.mesh import delaunay_rectangle, structured_2d
+
+
+def _ngs():
+    import opencmp_b200.ngs as ngs
+    return ngs
+
+
+def dg_funcs(ngs, mesh, nu):
+    """reference helpers/ngsolve_.py:48-70"""
+    n = ngs.specialcf.normal(mesh.dim)
+    h = ngs.specialcf.mesh_size
+    return n, h, nu / h
+
+
+def jump(q):
+    return q - q.Other()
+
+
+def grad_avg(ngs, q):
+    return 0.5 * (ngs.Grad(q) + ngs.Grad(q.Other()))
+
+
+def avg(q):
+    return 0.5 * (q + q.Other())
+
+
+def poisson(mesh, order, DG, family='H1', transient_dt=None):
+    """Poisson forms: reference opencmp/models/poisson.py:71-158 (+ mass term of base_model.py:418-497)."""
+    ngs = _ngs()
+    m = ngs.Mesh(mesh)
+    dnames = 'top|bottom'
+    fes = ngs.FESpace([getattr(ngs, family)(m, order=order, dirichlet=dnames, dgjumps=DG)], dgjumps=DG)
+    u, v = fes.TrialFunction()[0], fes.TestFunction()[0]
+    dt = ngs.Parameter(1.0 if transient_dt is None else transient_dt)
+    t = ngs.Parameter(0.25)
+    dc = ngs.CoefficientFunction(0.5)
+    exact = ngs.sin(ngs.pi * ngs.x) * ngs.cos(ngs.pi * ngs.y) * ngs.exp(-t)
+    f = 2 * ngs.pi ** 2 * dc * exact
+    gradex = ngs.CoefficientFunction((ngs.pi * ngs.cos(ngs.pi * ngs.x) * ngs.cos(ngs.pi * ngs.y) * ngs.exp(-t),
+                                      -ngs.pi * ngs.sin(ngs.pi * ngs.x) * ngs.sin(ngs.pi * ngs.y) * ngs.exp(-t)))
+    n, h, alpha = dg_funcs(ngs, m, 10.0 * order ** 2)
+    a = ngs.BilinearForm(fes)
+    a += dt * dc * ngs.InnerProduct(ngs.Grad(u), ngs.Grad(v)) * ngs.dx
+    L = ngs.LinearForm(fes)
+    L += dt * f * v * ngs.dx
+    ds_d = ngs.ds(skeleton=DG, definedon=m.Boundaries(dnames))
+    ds_n = ngs.ds(skeleton=DG, definedon=m.Boundaries('left|right'))
+    if DG:
+        a += dt * dc * (-u * n * ngs.Grad(v) - ngs.Grad(u) * n * v + alpha * u * v) * ds_d
+        ju, jv = jump(u), jump(v)
+        a += dt * dc * (-ju * n * grad_avg(ngs, v) - grad_avg(ngs, u) * n * jv + alpha * ju * jv) * ngs.dx(skeleton=True)
+        L += dt * dc * (alpha * exact * v - exact * n * ngs.Grad(v)) * ds_d
+    L += dt * dc * (gradex * n) * v * ds_n          # Neumann data
+    if transient_dt is not None:
+        a += u * v * ngs.dx
+    gfu = ngs.GridFunction(fes)
+    return dict(ngs=ngs, mesh=m, fes=fes, a=a, L=L, gfu=gfu, exact=exact, dnames=dnames, params=(dt, t))
+
+
+def stokes(mesh, order, DG, wind=None, dt_val=1.0, mass=False, walls='wall', nu=1e-3):
+    """Stokes / Oseen forms: reference opencmp/models/stokes.py:43-129 and models/ins.py:178-321."""
+    ngs = _ngs()
+    m = ngs.Mesh(mesh)
+    if DG:
+        V = ngs.HDiv(m, order=order, dirichlet=walls, dgjumps=True)
+        Q = ngs.L2(m, order=order - 1, dgjumps=True)
+    else:
+        V = ngs.VectorH1(m, order=order, dirichlet=walls)
+        Q = ngs.H1(m, order=order - 1)
+    fes = ngs.FESpace([V, Q], dgjumps=DG)
+    (u, p), (v, q) = fes.TrialFunction(), fes.TestFunction()
+    dt = ngs.Parameter(dt_val)
+    kv = ngs.CoefficientFunction(nu)
+    n, h, alpha = dg_funcs(ngs, m, 10.0 * order ** 2)
+    uex = ngs.CoefficientFunction((5.0 / (2 * nu) * (0.2 * ngs.y - ngs.y * ngs.y), 0.0))
+    pex = 5.0 * (1.0 - ngs.x) + 5.0
+    a = ngs.BilinearForm(fes)
+    a += dt * kv * ngs.InnerProduct(ngs.Grad(u), ngs.Grad(v)) * ngs.dx
+    a += dt * (-ngs.div(u) * q - ngs.div(v) * p - 1e-10 * p * q) * ngs.dx
+    L = ngs.LinearForm(fes)
+    L += dt * v * ngs.CoefficientFunction((0.0, 0.0)) * ngs.dx
+    W = None
+    if wind is not None:
+        W = ngs.GridFunction(V)
+        W.vec.data = ngs.BaseVector(ngs.get_backend().from_numpy(wind(V.ndof)))
+        a += -dt * ngs.InnerProduct(ngs.OuterProduct(u, W), ngs.Grad(v)) * ngs.dx
+    ds_w = ngs.ds(skeleton=DG, definedon=m.Boundaries(walls))
+    if DG:
+        a += dt * (kv * alpha * u * v - kv * ngs.InnerProduct(ngs.Grad(u), ngs.OuterProduct(v, n))
+                   - kv * ngs.InnerProduct(ngs.Grad(v), ngs.OuterProduct(u, n))) * ds_w
+        ju, jv = jump(u), jump(v)
+        a += dt * (kv * alpha * ngs.InnerProduct(ju, jv)
+                   - kv * ngs.InnerProduct(grad_avg(ngs, u), ngs.OuterProduct(jv, n))
+                   - kv * ngs.InnerProduct(grad_avg(ngs, v), ngs.OuterProduct(ju, n))) * ngs.dx(skeleton=True)
+        L += dt * (kv * alpha * uex * v - kv * ngs.InnerProduct(ngs.Grad(v), ngs.OuterProduct(uex, n))) * ds_w
+        if W is not None:
+            a += dt * v * (0.5 * W * n * u + 0.5 * ngs.Norm(W * n) * u) * ds_w
+            a += dt * jv * (W * n * avg(u) + 0.5 * ngs.Norm(W * n) * ju) * ngs.dx(skeleton=True)
+            L += dt * v * (-0.5 * W * n * uex + 0.5 * ngs.Norm(W * n) * uex) * ds_w
+    for marker, pval in (('inlet', 10.0), ('outlet', 5.0)):
+        dsm = ngs.ds(skeleton=DG, definedon=m.Boundaries(marker))
+        L += dt * v * (-pval * n) * dsm
+        if W is not None:
+            a += dt * v * (ngs.IfPos(W * n, W * n, 0.0) * u) * dsm
+    if mass:
+        a += u * v * ngs.dx
+    gfu = ngs.GridFunction(fes)
+    return dict(ngs=ngs, mesh=m, fes=fes, a=a, L=L, gfu=gfu, uex=uex, pex=pex, walls=walls, W=W, V=V, params=(dt,))
+
+
+def channel_mesh(n=12, seed=3):
+    return delaunay_rectangle(n, seed, size=(1.0, 0.2), names=('wall', 'outlet', 'wall', 'inlet'))
+
+
+def square_mesh(n=6, seed=1):
+    return delaunay_rectangle(n, seed)
+
+
+def random_wind(ndof, seed=5, scale=0.3):
+    return scale * np.random.default_rng(seed).uniform(-1.0, 1.0, ndof)
+
+
+def direct_solve(case, be_numpy=True):
+    """``Model.linear_solve`` direct branch, reference base_model.py:918-922."""
+    ngs = case['ngs']
+    a, L, gfu, fes = case['a'], case['L'], case['gfu'], case['fes']
+    inv = a.mat.Inverse(fes.FreeDofs())
+    r = L.vec.CreateVector()
+    r.data = L.vec - a.mat * gfu.vec
+    gfu.vec.data += inv * r
+    return gfu.vec.NumPy().copy()

@@ -1,0 +1,152 @@
+"""GPU parity: CUDA path (through the C ABI) vs the NumPy oracle on identical exported inputs.
+
+Tolerances (north star, BASELINE.json): sparsity pattern / DOF maps are shared inputs (bit-exact by construction);
+assembled matrix and vector entries within 1e-12 relative to the largest entry; solution fields and integrals
+within 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+MAT_TOL = 1e-12
+SOL_TOL = 1e-9
+
+
+def _with(backend_name, fn):
+    import opencmp_b200.ngs as ngs
+    if backend_name == 'oracle':
+        from oracle.backend import OracleBackend
+        be = OracleBackend()
+    else:
+        from opencmp_b200.backend import CudaBackend
+        be = CudaBackend()
+    old = ngs._backend
+    ngs.set_backend(be)
+    try:
+        return fn()
+    finally:
+        ngs.set_backend(old)
+
+
+def _assembled(build):
+    def run():
+        c = build()
+        ngs = c['ngs']
+        g = c['gfu']
+        if 'exact' in c:
+            g.components[0].Set(c['exact'], definedon=c['mesh'].Boundaries(c['dnames']))
+        else:
+            g.components[0].Set(c['uex'], definedon=c['mesh'].Boundaries(c['walls']))
+        c['a'].Assemble()
+        c['L'].Assemble()
+        vals = np.array(c['a'].mat.CSR()[0], dtype=np.float64)
+        rhs = c['L'].vec.NumPy().copy()
+        bc = g.vec.NumPy().copy()
+        x = np.random.default_rng(0).uniform(-1, 1, len(rhs))
+        xv = ngs.BaseVector(ngs.get_backend().from_numpy(x))
+        y = (c['a'].mat * xv).NumPy().copy()
+        return dict(vals=vals, rhs=rhs, bc=bc, y=y, case=c)
+    return run
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+CASES = {
+    'poisson_h1_p2': lambda: cases.poisson(cases.square_mesh(), 2, False),
+    'poisson_h1_p3': lambda: cases.poisson(cases.square_mesh(), 3, False),
+    'poisson_h1_p1_transient': lambda: cases.poisson(cases.square_mesh(), 1, False, transient_dt=0.01),
+    'poisson_l2_dg_p2': lambda: cases.poisson(cases.square_mesh(), 2, True, family='L2'),
+    'poisson_h1_dg_p3': lambda: cases.poisson(cases.square_mesh(), 3, True),
+    'stokes_th_p3': lambda: cases.stokes(cases.channel_mesh(), 3, False),
+    'stokes_th_p2_oseen': lambda: cases.stokes(cases.channel_mesh(), 2, False,
+                                                wind=lambda n: cases.random_wind(n)),
+    'stokes_hdiv_dg_p3': lambda: cases.stokes(cases.channel_mesh(), 3, True),
+    'ins_hdiv_dg_p3_oseen': lambda: cases.stokes(cases.channel_mesh(), 3, True, wind=lambda n: cases.random_wind(n),
+                                                  dt_val=0.01, mass=True),
+    'ins_hdiv_dg_p1_oseen': lambda: cases.stokes(cases.channel_mesh(), 1, True, wind=lambda n: cases.random_wind(n),
+                                                  dt_val=0.01, mass=True),
+    'poisson_quad_q2': lambda: cases.poisson(cases.structured_2d([5, 4], cell='quad'), 2, False),
+}
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_assembly_matches_oracle(name):
+    ref = _with('oracle', _assembled(CASES[name]))
+    got = _with('cuda', _assembled(CASES[name]))
+    assert got['vals'].shape == ref['vals'].shape
+    assert _rel(got['bc'], ref['bc']) < 1e-11 or np.abs(ref['bc']).max() == 0
+    assert _rel(got['vals'], ref['vals']) < MAT_TOL
+    assert _rel(got['rhs'], ref['rhs']) < MAT_TOL
+    assert _rel(got['y'], ref['y']) < 1e-12
+
+
+def test_integrate_matches_oracle():
+    def run():
+        c = cases.poisson(cases.square_mesh(), 2, False)
+        ngs = c['ngs']
+        g = c['gfu']
+        g.vec.data = ngs.BaseVector(ngs.get_backend().from_numpy(
+            np.random.default_rng(1).uniform(-1, 1, c['fes'].ndof)))
+        u = g.components[0]
+        return [ngs.Integrate((u - c['exact']) * (u - c['exact']), c['mesh']),
+                ngs.Integrate(ngs.InnerProduct(ngs.Grad(u), ngs.Grad(u)), c['mesh']),
+                ngs.Integrate(ngs.CoefficientFunction(1.0), c['mesh'])]
+    ref = _with('oracle', run)
+    got = _with('cuda', run)
+    assert np.allclose(got, ref, rtol=SOL_TOL, atol=0)
+    assert abs(ref[2] - 1.0) < 1e-12
+
+
+def test_poisson_cg_solution():
+    """CG + Jacobi ('local') on the GPU vs sparse LU in the oracle: reference base_model.py:924-927 vs :918-922."""
+    def run_gpu():
+        c = cases.poisson(cases.square_mesh(10), 2, False)
+        ngs = c['ngs']
+        c['gfu'].components[0].Set(c['exact'], definedon=c['mesh'].Boundaries(c['dnames']))
+        c['a'].Assemble()
+        c['L'].Assemble()
+        pre = ngs.Preconditioner(c['a'], 'local')
+        pre.Update()
+        ngs.solvers.CG(mat=c['a'].mat, rhs=c['L'].vec, pre=pre, sol=c['gfu'].vec, tol=1e-14, maxsteps=2000,
+                       initialize=False)
+        err = np.sqrt(ngs.Integrate((c['gfu'].components[0] - c['exact']) ** 2, c['mesh']))
+        return c['gfu'].vec.NumPy().copy(), err
+
+    def run_ref():
+        c = cases.poisson(cases.square_mesh(10), 2, False)
+        ngs = c['ngs']
+        c['gfu'].components[0].Set(c['exact'], definedon=c['mesh'].Boundaries(c['dnames']))
+        c['a'].Assemble()
+        c['L'].Assemble()
+        sol = cases.direct_solve(c)
+        err = np.sqrt(ngs.Integrate((c['gfu'].components[0] - c['exact']) ** 2, c['mesh']))
+        return sol, err
+    ref, eref = _with('oracle', run_ref)
+    got, egot = _with('cuda', run_gpu)
+    assert _rel(got, ref) < SOL_TOL
+    assert abs(egot - eref) < SOL_TOL * eref + 1e-14
+
+
+@pytest.mark.parametrize('DG', [False, True])
+def test_stokes_solution(DG):
+    """GMRES + cell-patch additive Schwarz on the GPU vs sparse LU in the oracle (Stokes Poiseuille,
+    reference pytests/full_system/stokes)."""
+    def run():
+        c = cases.stokes(cases.channel_mesh(10), 2, DG)
+        ngs = c['ngs']
+        c['gfu'].components[0].Set(c['uex'], definedon=c['mesh'].Boundaries(c['walls']))
+        c['a'].Assemble()
+        c['L'].Assemble()
+        sol = cases.direct_solve(c)
+        u = c['gfu'].components[0]
+        err = np.sqrt(ngs.Integrate(ngs.InnerProduct(u - c['uex'], u - c['uex']), c['mesh']))
+        return sol, err
+    ref, eref = _with('oracle', run)
+    got, egot = _with('cuda', run)
+    assert _rel(got, ref) < SOL_TOL
+    assert eref < 1e-8 and egot < 1e-8
