@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py — one JSON line for the OpenCMP hot path on B200.
+
+Workload (BASELINE.json metric "INS s/timestep, assembly Mnnz/s, SpMV GB/s"; configs[2] scaled to SURVEY 8(d)'s
+throughput size): one time step of the 2-D incompressible Navier-Stokes Taylor-Green problem on a structured
+N x N x 2 triangle mesh of [0,pi]^2, HDiv-DG order 3 / L2 order 2, Oseen linearisation, implicit Euler — Dirichlet
+projection, full re-assembly of matrix and right-hand side, additive-Schwarz setup, GMRES solve and the two L2-norm
+integrals per Picard iteration, exactly the sequence of opencmp/solvers/base_solver.py:521-587 and
+opencmp/models/ins.py:323-355 (see opencmp_b200/workloads.py).
+
+`value` = seconds per time step with all inputs resident in HBM; `e2e` = the same step with the previous solution
+and wind uploaded from pinned host memory and the new solution read back inside the timed region.
+`--impl reference` times the CPU restatement (oracle/, NumPy/SciPy + sparse LU, the reference's own default
+`linear_solver = direct`) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--N', type=int, default=128, help='cells per direction of the structured mesh')
+    ap.add_argument('--order', type=int, default=3)
+    ap.add_argument('--cpu-N', type=int, default=20, help='mesh size of the bounded CPU sample')
+    ap.add_argument('--no-cpu', action='store_true')
+    return ap.parse_args()
+
+
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        hi = [s for s in sm if s >= 0.5 * max(sm)] if sm else []
+        return {'sm_mhz': statistics.median(hi) if hi else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_step_seconds(N, order, steps=1):
+    """Oracle (CPU restatement, NumPy/SciPy; NOT NGSolve) timed on one Picard-iterated time step."""
+    import opencmp_b200.ngs as ngs
+    from oracle.backend import OracleBackend
+    from opencmp_b200.workloads import INSTaylorGreen
+    old = ngs._backend
+    ngs.set_backend(OracleBackend())
+    try:
+        w = INSTaylorGreen(N, order=order, linear_solver='direct', preconditioner=None)
+        w.step()                          # warm-up (lowering, tabulation caches)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            w.step()
+        dt = (time.perf_counter() - t0) / steps
+        return dt, w.mesh.ne, w.ndof, w.nnz
+    finally:
+        ngs.set_backend(old)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cells_full = 2 * args.N * args.N
+    times = []
+    ne = ndof = nnz = 0
+    for _ in range(max(1, args.warmup // 3)):
+        cpu_step_seconds(args.cpu_N, args.order)
+    for _ in range(args.steps):
+        dt, ne, ndof, nnz = cpu_step_seconds(args.cpu_N, args.order)
+        times.append(dt)
+    per = sum(times) / len(times)
+    scaled = per * cells_full / ne
+    sample = ('one time step (2 Picard iterations: assemble + SciPy SuperLU) at N={} ({} cells, {} DOFs), '
+              'scaled linearly by cell count x{:.1f} to N={}'.format(args.cpu_N, ne, ndof, cells_full / ne, args.N))
+    line = {'impl': 'reference', 'metric': 'INS s/timestep', 'value': scaled, 'unit': 's', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': scaled * 1e3, 'higher_is_better': False,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(args, 'cpu'),
+            'cpu_baseline': {'value': scaled, 'unit': 's', 'cores': 1, 'kind': 'port', 'sample': sample,
+                             'sample_value_s': per},
+            'e2e': {'value': scaled, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, where):
+    return {'workload': 'INS Taylor-Green 2D, structured {0}x{0}x2 triangles on [0,pi]^2, HDiv-DG order {1} / L2 order {2}, '
+                        'Oseen + implicit Euler, dt=1e-3, nu=1 (examples/INS scaled up)'.format(args.N, args.order,
+                                                                                               args.order - 1),
+            'N': args.N, 'order': args.order, 'linear_solver': 'GMRES(200)+cell-patch additive Schwarz, tol 1e-10'
+            if where == 'gpu' else 'direct (SuperLU)', 'nonlinear_max_iterations': 3,
+            'l2': 'inputs larger than L2 (CSR matrix ~0.8 GB at N=128); no explicit flush',
+            'parallelism': 'replicas' if args.gpus > 1 else 'single'}
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import opencmp_b200.ngs as ngs
+    from opencmp_b200.backend import CudaBackend, read_profile
+    from opencmp_b200.workloads import INSTaylorGreen
+    be = CudaBackend(local)
+    ngs.set_backend(be)
+    lib = be.lib
+    t_setup = time.perf_counter()
+    w = INSTaylorGreen(args.N, order=args.order)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    ndof, nnz, ne = w.ndof, w.nnz, w.mesh.ne
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        w.step()
+    # ---- timed region: K steps, device-resident ------------------------------------------------------------
+    lib.ocmp_profile_reset()
+    lib.ocmp_profile_enable(1)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.ocmp_launch_count()
+    e0.record()
+    picard = lin_its = 0
+    for _ in range(args.steps):
+        w.linear_iterations = []
+        w.step()
+        picard += w.picard_iterations
+        lin_its += sum(w.linear_iterations)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler is not None else None
+    launches = int(lib.ocmp_launch_count() - l0)
+    prof = read_profile(lib)
+    lib.ocmp_profile_enable(0)
+    # ---- e2e: host buffers in, solution out, copies inside the timed region -------------------------------------
+    h_prev = torch.empty(ndof, dtype=torch.float64).pin_memory()
+    h_wind = torch.empty(w.V.ndof, dtype=torch.float64).pin_memory()
+    h_out = torch.empty(ndof, dtype=torch.float64).pin_memory()
+    h_prev.copy_(w.gfu.vec.a)
+    h_wind.copy_(w.W.vec.a)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        w.gfu_0.vec.a.copy_(h_prev, non_blocking=True)
+        w.gfu.vec.a.copy_(h_prev, non_blocking=True)
+        w.W.vec.a.copy_(h_wind, non_blocking=True)
+        w.step()
+        h_out.copy_(w.gfu.vec.a, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h_prev.copy_(h_out)
+        h_wind.copy_(h_out[:w.V.ndof])
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    eu, ep = w.errors()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    sec = ms / 1e3 / args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
+    sp = prof['spmv']
+    spmv_bytes = nnz * 12 + ndof * 12 + ndof * 8
+    spmv_ms = sp['ms'] / max(1, sp['count'])
+    spmv_gbs = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if sp['count'] else 0.0
+    asm_ms = prof['coef']['ms'] + prof['contract_matrix']['ms'] + prof['contract_vector']['ms']
+    n_asm = max(1, picard)
+    asm_mnnz = nnz / (asm_ms / n_asm * 1e-3) / 1e6 if asm_ms > 0 else 0.0
+    share = {k: round(v['ms'] / ms, 4) for k, v in prof.items()}
+    line = {
+        'metric': 'INS s/timestep', 'value': sec, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': False, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, 'gpu'),
+        'problem': {'cells': ne, 'dofs': ndof, 'nnz': nnz, 'picard_per_step': picard / args.steps,
+                    'gmres_its_per_step': lin_its / args.steps, 'l2_err_u': eu, 'l2_err_p': ep,
+                    'setup_s': t_setup},
+        'assembly_mnnz_per_s': asm_mnnz, 'spmv_gbs': spmv_gbs,
+        'roofline': {'kernel': 'k_spmv (CSR FP64 values + int32 columns)', 'bound': 'hbm', 'achieved': spmv_gbs,
+                     'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs / peak, 'frac_of_8000_nominal': spmv_gbs / 8000.0,
+                     'peak_source': peak_src, 'bytes_per_launch': spmv_bytes, 'launches': sp['count'],
+                     'avg_launch_ms': spmv_ms, 'traffic': None},
+        'kernel_time_share': share,
+        'e2e': {'value': ms_e2e / 1e3 / args.steps, 'unit': 's', 'h2d_bytes_per_step': int(8 * (2 * ndof + w.V.ndof)),
+                'd2h_bytes_per_step': int(8 * ndof)},
+        'gpu_launches': launches, 'clocks': clocks,
+    }
+    if not args.no_cpu and world == 1:
+        try:
+            per, cne, cnd, _ = cpu_step_seconds(args.cpu_N, args.order)
+            line['cpu_baseline'] = {
+                'value': per * ne / cne, 'unit': 's', 'cores': 1, 'kind': 'port',
+                'sample': 'CPU restatement (NumPy/SciPy, not NGSolve): one time step at N={} ({} cells, {} DOFs) took '
+                          '{:.2f} s; scaled linearly by cell count x{:.1f}'.format(args.cpu_N, cne, cnd, per, ne / cne)}
+        except Exception as exc:                                    # pragma: no cover
+            line['cpu_baseline'] = {'value': None, 'unit': 's', 'cores': 1, 'kind': 'port', 'sample': repr(exc)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

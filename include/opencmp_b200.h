@@ -93,32 +93,61 @@ int ocmp_masked_assign(long long n, double* dst, const double* src, const double
 /* point Jacobi on the free dofs: dinv[i] = free[i] && diag != 0 ? 1/diag : 0 */
 int ocmp_jacobi_setup(int nrows, const int* diagpos, const double* vals, const double* freemask, double* dinv,
                       void* stream);
-/* additive Schwarz over dof patches: gather dense blocks through `patch2nnz`, invert them (batched Gauss-Jordan) */
-int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const int* patch2nnz, const double* vals,
-                   const double* freemask, double* inv_blocks, void* stream);
+/* additive Schwarz over dof patches (patch_dofs: npatch x bs, padded with -1): gather the dense blocks from the CSR
+ * matrix and invert them in shared memory (batched Gauss-Jordan with partial pivoting) */
+int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
+                   const double* vals, const double* freemask, double* inv_blocks, void* stream);
 int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const double* inv_blocks, const double* r, double* z,
                    long long n, void* stream);
 
 /* ---- Krylov: stand in for ngs.solvers.CG / GMRes / PreconditionedRichardson and for mat.Inverse applied to a
  *      residual (reference opencmp/models/base_model.py:886-947) ---------------------------------------------- */
-typedef struct {
+struct ocmp_mg_level;
+typedef struct ocmp_system {
     int nrows;
     const int* rowptr;
     const int* colidx;
     const double* vals;
     const double* freemask;  /* 1.0 free / 0.0 constrained, NULL = all free */
-    int pre_kind;            /* 0 none, 1 Jacobi (dinv), 2 additive Schwarz patches */
+    int pre_kind;            /* 0 none, 1 Jacobi (dinv), 2 additive Schwarz patches, 3 geometric multigrid V-cycle,
+                                4 explicit inverse stored as CSR (coarsest multigrid level) */
     const double* dinv;
     int npatch, bs;
     const int* patch_dofs;
     const double* inv_blocks;
+    const double* patch_weight; /* optional per-dof weight applied after the additive patch solves (restricted / averaged AS) */
+    int nlevels;             /* pre_kind 3: levels[0] coarsest ... levels[nlevels-1] = this system */
+    const struct ocmp_mg_level* levels;
+    const int* inv_rowptr;   /* pre_kind 4 */
+    const int* inv_colidx;
+    const double* inv_vals;
 } ocmp_system;
+
+/* One multigrid level: operator + smoother (sys), transfer from the next coarser level, work space.
+ * Stands in for ngs.Preconditioner(a, 'multigrid') (reference opencmp/models/base_model.py:365-383). */
+typedef struct ocmp_mg_level {
+    ocmp_system sys;
+    int ncoarse;
+    const int* p_rowptr; const int* p_colidx; const double* p_vals;   /* prolongation (nrows x ncoarse), CSR */
+    const int* r_rowptr; const int* r_colidx; const double* r_vals;   /* restriction = its transpose, CSR */
+    double* work;            /* 4 * nrows doubles: x, b, r, t */
+    int nu;                  /* pre- and post-smoothing sweeps */
+    double omega;            /* smoother damping */
+} ocmp_mg_level;
 
 /* kind: 0 CG, 1 GMRES(restart), 2 Richardson. x holds the initial guess (and Dirichlet values) on entry.
  * Stops when the preconditioned residual norm drops below tol * initial. iters / resid are host outputs. */
 int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, double* x, double tol, int maxit, int restart,
                 double damp, double* work, long long work_len, int* iters, double* resid, void* stream);
 long long ocmp_krylov_work_len(int nrows, int kind, int restart);
+
+/* ---- instrumentation: per-category device time from CUDA events recorded around every launch on its own stream.
+ * categories: 0 spmv, 1 asm_apply, 2 coefficient eval, 3 matrix contraction, 4 vector contraction, 5 multi-dot,
+ * 6 multi-axpy, 7 other vector kernels, 8 preconditioner setup */
+void ocmp_profile_enable(int on);
+void ocmp_profile_reset(void);
+int ocmp_profile_read(int category, long long* count, double* ms);
+long long ocmp_launch_count(void);
 
 const char* ocmp_last_error(void);
 int ocmp_version(void);

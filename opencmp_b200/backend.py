@@ -44,7 +44,15 @@ class ContractPlan(C.Structure):
 class System(C.Structure):
     _fields_ = [('nrows', C.c_int), ('rowptr', C.c_void_p), ('colidx', C.c_void_p), ('vals', C.c_void_p),
                 ('freemask', C.c_void_p), ('pre_kind', C.c_int), ('dinv', C.c_void_p), ('npatch', C.c_int),
-                ('bs', C.c_int), ('patch_dofs', C.c_void_p), ('inv_blocks', C.c_void_p)]
+                ('bs', C.c_int), ('patch_dofs', C.c_void_p), ('inv_blocks', C.c_void_p), ('patch_weight', C.c_void_p),
+                ('nlevels', C.c_int), ('levels', C.c_void_p), ('inv_rowptr', C.c_void_p), ('inv_colidx', C.c_void_p),
+                ('inv_vals', C.c_void_p)]
+
+
+class MGLevel(C.Structure):
+    _fields_ = [('sys', System), ('ncoarse', C.c_int), ('p_rowptr', C.c_void_p), ('p_colidx', C.c_void_p),
+                ('p_vals', C.c_void_p), ('r_rowptr', C.c_void_p), ('r_colidx', C.c_void_p), ('r_vals', C.c_void_p),
+                ('work', C.c_void_p), ('nu', C.c_int), ('omega', C.c_double)]
 
 
 def load_library() -> C.CDLL:
@@ -65,14 +73,32 @@ def load_library() -> C.CDLL:
     lib.ocmp_axpby.argtypes = [C.c_longlong, C.c_double, P, C.c_double, P, P]
     lib.ocmp_masked_assign.argtypes = [C.c_longlong, P, P, P, P, P]
     lib.ocmp_jacobi_setup.argtypes = [C.c_int, P, P, P, P, P]
-    lib.ocmp_asm_setup.argtypes = [C.c_int, C.c_int, P, P, P, P, P, P]
+    lib.ocmp_asm_setup.argtypes = [C.c_int, C.c_int, P, P, P, P, P, P, P]
     lib.ocmp_asm_apply.argtypes = [C.c_int, C.c_int, P, P, P, P, C.c_longlong, P]
     lib.ocmp_krylov.argtypes = [C.POINTER(System), C.c_int, P, P, C.c_double, C.c_int, C.c_int, C.c_double, P,
                                 C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_double), P]
+    lib.ocmp_profile_enable.argtypes = [C.c_int]
+    lib.ocmp_profile_enable.restype = None
+    lib.ocmp_profile_reset.restype = None
+    lib.ocmp_profile_read.argtypes = [C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
+    lib.ocmp_launch_count.restype = C.c_longlong
     return lib
 
 
-EXPORTED = ['ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
+PROFILE_CATEGORIES = ['spmv', 'asm_apply', 'coef', 'contract_matrix', 'contract_vector', 'multi_dot', 'multi_axpy',
+                      'vector', 'precond_setup']
+
+
+def read_profile(lib) -> dict:
+    out = {}
+    for i, name in enumerate(PROFILE_CATEGORIES):
+        cnt, ms = C.c_longlong(0), C.c_double(0.0)
+        lib.ocmp_profile_read(i, C.byref(cnt), C.byref(ms))
+        out[name] = dict(count=int(cnt.value), ms=float(ms.value))
+    return out
+
+
+EXPORTED = ['ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
             'ocmp_dot', 'ocmp_axpby', 'ocmp_masked_assign', 'ocmp_jacobi_setup', 'ocmp_asm_setup', 'ocmp_asm_apply',
             'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version']
 
@@ -406,27 +432,72 @@ class CudaBackend:
         arr = np.asarray(free.a if hasattr(free, 'a') else free, dtype=bool)
         return self._up(arr.astype(np.float64))
 
-    def precond_setup(self, mat, kind, free):
+    def precond_setup(self, mat, kind, free, form=None, state=None, mask=None):
         pd = self.pattern_data(mat.space)
-        fm = self._mask(mat.space, free)
+        fm = mask if mask is not None else self._mask(mat.space, free)
         st = self._stream()
+        if kind == 'multigrid':
+            from .multigrid import MultigridState
+            if state is None or getattr(state, 'kind', 0) != 3:
+                state = MultigridState(self, form, nu=int(os.environ.get('OCMP_MG_NU', '2')),
+                                       omega=float(os.environ.get('OCMP_MG_OMEGA', '0.7')))
+            return state.update(mat)
         if kind in ('local', 'jacobi'):
             dinv = self.zeros(mat.height)
             self._ck(self.lib.ocmp_jacobi_setup(mat.height, pd['diag'].data_ptr(), mat.values.data_ptr(), _ptr(fm),
                                                 dinv.data_ptr(), st))
             self.launches += 1
             return _Precond(1, dinv=dinv, fm=fm)
-        if kind in ('asm', 'direct', 'multigrid', 'h1amg', 'bddc', 'block'):
-            # cell-patch additive Schwarz: every cell's dofs form one (overlapping) patch
+        if kind in ('asm', 'asm_cell', 'direct', 'h1amg', 'bddc', 'block'):
+            # overlapping additive Schwarz: vertex-star patches (all dofs of the cells around a vertex) by default,
+            # cell patches for kind 'asm_cell'; averaged by the patch multiplicity of every dof
             fes = mat.space
-            sd = self.space_data(fes)
-            ne, bs = fes.cell_dofs.shape
-            inv = self.torch.empty(ne * bs * bs, dtype=self.torch.float64, device=self.device)
-            self._ck(self.lib.ocmp_asm_setup(ne, bs, sd['cell_dofs'].data_ptr(), pd['cell2nnz'].data_ptr(),
-                                             mat.values.data_ptr(), _ptr(fm), inv.data_ptr(), st))
+            pt = self._patches(fes, 'cell' if kind == 'asm_cell' else os.environ.get('OCMP_PATCH', 'vertex'))
+            npatch, bs = pt['npatch'], pt['bs']
+            if pt.get('inv') is None:
+                pt['inv'] = self.torch.empty(npatch * bs * bs, dtype=self.torch.float64, device=self.device)
+            self._ck(self.lib.ocmp_asm_setup(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(),
+                                             pd['colidx'].data_ptr(), mat.values.data_ptr(), _ptr(fm),
+                                             pt['inv'].data_ptr(), st))
             self.launches += 1
-            return _Precond(2, inv=inv, npatch=ne, bs=bs, pdofs=sd['cell_dofs'], fm=fm)
+            return _Precond(2, inv=pt['inv'], npatch=npatch, bs=bs, pdofs=pt['dofs'], fm=fm, wgt=pt['wgt'])
         raise NotImplementedError('preconditioner type {}'.format(kind))
+
+    def _patches(self, fes, kind: str) -> dict:
+        sd = self.space_data(fes)
+        key = 'patch_' + kind
+        if key in sd:
+            return sd[key]
+        cd = fes.cell_dofs
+        if kind == 'cell':
+            dofs = cd
+        else:
+            m = fes.mesh
+            ne, nvc = m.cells.shape
+            order = np.argsort(m.cells.ravel(), kind='stable')
+            vsorted = m.cells.ravel()[order]
+            cell_of = order // nvc
+            start = np.searchsorted(vsorted, np.arange(m.nv + 1))
+            cnt = np.diff(start)
+            maxc = int(cnt.max())
+            # padded (nv, maxc) table of star cells, -1 padded
+            star = -np.ones((m.nv, maxc), dtype=np.int64)
+            pos = np.arange(len(vsorted)) - start[vsorted]
+            star[vsorted, pos] = cell_of
+            big = np.where(star[:, :, None] >= 0, cd[np.maximum(star, 0)], np.iinfo(np.int32).max)
+            big = np.sort(big.reshape(m.nv, -1), axis=1)
+            dup = np.concatenate([np.zeros((m.nv, 1), bool), big[:, 1:] == big[:, :-1]], axis=1)
+            big[dup] = np.iinfo(np.int32).max
+            big = np.sort(big, axis=1)
+            bs = int((big < np.iinfo(np.int32).max).sum(axis=1).max())
+            dofs = big[:, :bs].copy()
+            dofs[dofs == np.iinfo(np.int32).max] = -1
+        dofs = np.ascontiguousarray(dofs, dtype=np.int32)
+        mult = np.bincount(dofs[dofs >= 0].ravel(), minlength=fes.ndof).astype(np.float64)
+        out = dict(npatch=dofs.shape[0], bs=dofs.shape[1], dofs=self._up(dofs),
+                   wgt=self._up(1.0 / np.maximum(mult, 1.0)), inv=None)
+        sd[key] = out
+        return out
 
     def _system(self, mat, fm, pre) -> System:
         pd = self.pattern_data(mat.space)
@@ -439,9 +510,16 @@ class CudaBackend:
             s.pre_kind = pre.kind
             if pre.kind == 1:
                 s.dinv = pre.dinv.data_ptr()
+            elif pre.kind == 3:
+                top = pre.levels[pre.nlevels - 1].sys
+                for name in ('npatch', 'bs', 'patch_dofs', 'inv_blocks', 'patch_weight'):
+                    setattr(s, name, getattr(top, name))
+                s.nlevels = pre.nlevels
+                s.levels = C.addressof(pre.levels)
             else:
                 s.npatch, s.bs = pre.npatch, pre.bs
                 s.patch_dofs, s.inv_blocks = pre.pdofs.data_ptr(), pre.inv.data_ptr()
+                s.patch_weight = _ptr(pre.wgt)
         return s
 
     def krylov(self, kind, mat, b, x, pre, freedofs, tol, maxit, initialize, printrates, damp=1.0, restart=None):

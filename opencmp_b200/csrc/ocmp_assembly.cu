@@ -419,6 +419,7 @@ extern "C" int ocmp_eval_coefficients(const ocmp_coef_plan* plan, int item0, int
     const int threads = 128;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps(PROF_COEF, st);
     if (plan->dim == 2) k_coef<2><<<blocks, threads, 0, st>>>(*plan, item0, nitems, dbuf);
     else if (plan->dim == 3) k_coef<3><<<blocks, threads, 0, st>>>(*plan, item0, nitems, dbuf);
     else return ocmp_fail(-1, "dim must be 2 or 3");
@@ -447,6 +448,7 @@ static int launch_contract(const ocmp_contract_plan* plan, int item0, int nitems
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contract<DIM, NACC>, 256, smem);
     if (per_sm < 1) per_sm = 1;
     const int grid = ngroups < sms * per_sm ? ngroups : sms * per_sm;
+    ProfScope ps(PROF_CONTRACT, st);
     k_contract<DIM, NACC><<<grid, 256, smem, st>>>(*plan, item0, nitems, dbuf, values);
     return ocmp_check("ocmp_contract_matrix");
 }
@@ -475,6 +477,7 @@ extern "C" int ocmp_contract_vector(const ocmp_contract_plan* plan, int item0, i
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)nitems * plan->nside * plan->nloc;
     const unsigned blocks = (unsigned)((total + 127) / 128);
+    ProfScope ps(PROF_LIN, st);
     if (plan->dim == 2) k_lin<2><<<blocks, 128, 0, st>>>(*plan, item0, nitems, dbuf, vec);
     else if (plan->dim == 3) k_lin<3><<<blocks, 128, 0, st>>>(*plan, item0, nitems, dbuf, vec);
     else return ocmp_fail(-1, "dim must be 2 or 3");
@@ -486,6 +489,7 @@ extern "C" int ocmp_sum(const double* x, long long n, double* out, void* stream)
     long long blocks = (n + 255) / 256;
     const int cap = ocmp_sm_count() * 8;
     if (blocks > cap) blocks = cap;
+    ProfScope ps(PROF_VEC, (cudaStream_t)stream);
     k_sum<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out);
     return ocmp_check("ocmp_sum");
 }

@@ -5,6 +5,16 @@
 int ocmp_fail(int code, const char* msg);
 int ocmp_check(const char* where);
 int ocmp_sm_count();
+// optional per-category device timing (CUDA events on the launching stream) and launch counting
+enum { PROF_SPMV = 0, PROF_ASM_APPLY, PROF_COEF, PROF_CONTRACT, PROF_LIN, PROF_MDOT, PROF_MAXPY, PROF_VEC,
+       PROF_SETUP, PROF_NCAT };
+void ocmp_prof_begin(int cat, cudaStream_t st);
+void ocmp_prof_end(int cat, cudaStream_t st);
+struct ProfScope {
+    int cat; cudaStream_t st;
+    ProfScope(int c, cudaStream_t s) : cat(c), st(s) { ocmp_prof_begin(c, s); }
+    ~ProfScope() { ocmp_prof_end(cat, st); }
+};
 
 __device__ __forceinline__ double warp_reduce_sum(double v) {
 #pragma unroll

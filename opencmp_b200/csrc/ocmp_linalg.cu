@@ -35,6 +35,63 @@ int ocmp_sm_count() {
     }
     return sms;
 }
+// ---- profiling / launch counting ---------------------------------------------------------------------------------
+namespace {
+struct ProfCat {
+    std::vector<cudaEvent_t> ev;     // begin/end pairs not yet folded into ms
+    double ms = 0.0;
+    long long count = 0;
+};
+ProfCat g_cat[PROF_NCAT];
+std::vector<cudaEvent_t> g_pool;
+bool g_prof = false;
+long long g_launches = 0;
+cudaEvent_t prof_event() {
+    if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_fold(ProfCat& c) {
+    for (size_t i = 0; i + 1 < c.ev.size(); i += 2) {
+        float ms = 0.f;
+        cudaEventSynchronize(c.ev[i + 1]);
+        cudaEventElapsedTime(&ms, c.ev[i], c.ev[i + 1]);
+        c.ms += ms;
+        g_pool.push_back(c.ev[i]);
+        g_pool.push_back(c.ev[i + 1]);
+    }
+    c.ev.clear();
+}
+}  // namespace
+void ocmp_prof_begin(int cat, cudaStream_t st) {
+    ++g_launches;
+    if (!g_prof) return;
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, st);
+    g_cat[cat].ev.push_back(e);
+}
+void ocmp_prof_end(int cat, cudaStream_t st) {
+    if (!g_prof) return;
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, st);
+    g_cat[cat].ev.push_back(e);
+    g_cat[cat].count++;
+    if (g_cat[cat].ev.size() > 4096) prof_fold(g_cat[cat]);
+}
+extern "C" void ocmp_profile_enable(int on) { g_prof = on != 0; }
+extern "C" void ocmp_profile_reset(void) {
+    for (auto& c : g_cat) { prof_fold(c); c.ms = 0.0; c.count = 0; }
+    g_launches = 0;
+}
+extern "C" int ocmp_profile_read(int cat, long long* count, double* ms) {
+    if (cat < 0 || cat >= PROF_NCAT) return -1;
+    prof_fold(g_cat[cat]);
+    if (count) *count = g_cat[cat].count;
+    if (ms) *ms = g_cat[cat].ms;
+    return 0;
+}
+extern "C" long long ocmp_launch_count(void) { return g_launches; }
 extern "C" const char* ocmp_last_error(void) { return g_err; }
 extern "C" int ocmp_version(void) { return 100; }
 
@@ -64,6 +121,7 @@ extern "C" int ocmp_spmv(int nrows, const int* rowptr, const int* colidx, const 
     const long long want = ((long long)nrows * 16 + threads - 1) / threads;
     const long long cap = (long long)ocmp_sm_count() * 64;
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
+    ProfScope ps(PROF_SPMV, st);
     k_spmv<16><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, vals, x, y);
     return ocmp_check("ocmp_spmv");
 }
@@ -162,15 +220,18 @@ static inline unsigned grid_for(long long n) {
 extern "C" int ocmp_dot(long long n, const double* x, const double* y, double* out, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(out, 0, sizeof(double), st);
+    ProfScope ps(PROF_VEC, st);
     if (n > 0) k_dot<<<grid_for(n), 256, 0, st>>>(n, x, y, out);
     return ocmp_check("ocmp_dot");
 }
 extern "C" int ocmp_axpby(long long n, double a, const double* x, double b, double* y, void* stream) {
+    ProfScope ps(PROF_VEC, (cudaStream_t)stream);
     if (n > 0) k_axpby<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, a, x, b, y);
     return ocmp_check("ocmp_axpby");
 }
 extern "C" int ocmp_masked_assign(long long n, double* dst, const double* src, const double* inv, const double* mask,
                                   void* stream) {
+    ProfScope ps(PROF_VEC, (cudaStream_t)stream);
     if (n > 0) k_masked_assign<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, dst, src, inv, mask);
     return ocmp_check("ocmp_masked_assign");
 }
@@ -188,31 +249,41 @@ __global__ void __launch_bounds__(256) k_jacobi_setup(int n, const int* __restri
 
 extern "C" int ocmp_jacobi_setup(int nrows, const int* diagpos, const double* vals, const double* freemask,
                                  double* dinv, void* stream) {
+    ProfScope ps(PROF_SETUP, (cudaStream_t)stream);
     if (nrows > 0)
         k_jacobi_setup<<<(nrows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nrows, diagpos, vals, freemask, dinv);
     return ocmp_check("ocmp_jacobi_setup");
 }
 
-// One CTA per patch: gather the dense block, impose identity rows/cols on constrained dofs, invert [A | I] by
-// Gauss-Jordan with partial pivoting in shared memory, store the inverse transposed (inv[j*bs + i] = (A^-1)_{ij}).
+// One CTA per patch: gather the dense block straight from the CSR matrix (binary search of each column in its row),
+// impose identity rows/cols on constrained or padded dofs, invert it IN PLACE by Gauss-Jordan with partial pivoting
+// in shared memory and store the inverse transposed (inv[j*bs + i] = (A^-1)_{ij}) for coalesced application.
 __global__ void __launch_bounds__(256) k_asm_setup(int npatch, int bs, const int* __restrict__ pdofs,
-                                                   const int* __restrict__ p2nnz, const double* __restrict__ vals,
-                                                   const double* __restrict__ fm, double* __restrict__ inv) {
-    extern __shared__ double M[];          // bs x 2bs, then fcol[bs]
-    double* fcol = M + bs * 2 * bs;
+                                                   const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                   const double* __restrict__ vals, const double* __restrict__ fm,
+                                                   double* __restrict__ inv) {
+    extern __shared__ double M[];          // bs x bs, then fcol[bs], then piv[bs] (int)
+    double* fcol = M + bs * bs;
+    int* piv = reinterpret_cast<int*>(fcol + bs);
     __shared__ int spiv;
-    const int w2 = 2 * bs;
     for (int p = blockIdx.x; p < npatch; p += gridDim.x) {
         __syncthreads();
         for (int idx = threadIdx.x; idx < bs * bs; idx += blockDim.x) {
             const int i = idx / bs, j = idx % bs;
             const int di = pdofs[(long long)p * bs + i], dj = pdofs[(long long)p * bs + j];
-            const int pos = p2nnz[(long long)p * bs * bs + idx];
-            double v = (pos >= 0 && di >= 0 && dj >= 0) ? vals[pos] : 0.0;
             const bool fi = di >= 0 && (!fm || fm[di] > 0.0), fj = dj >= 0 && (!fm || fm[dj] > 0.0);
+            double v = 0.0;
             if (!fi || !fj) v = (i == j) ? 1.0 : 0.0;
-            M[i * w2 + j] = v;
-            M[i * w2 + bs + j] = (i == j) ? 1.0 : 0.0;
+            else {
+                int lo = __ldg(rowptr + di), hi = __ldg(rowptr + di + 1) - 1;
+                while (lo <= hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int c = __ldg(colidx + mid);
+                    if (c == dj) { v = vals[mid]; break; }
+                    if (c < dj) lo = mid + 1; else hi = mid - 1;
+                }
+            }
+            M[idx] = v;
         }
         __syncthreads();
         for (int k = 0; k < bs; ++k) {
@@ -220,7 +291,7 @@ __global__ void __launch_bounds__(256) k_asm_setup(int npatch, int bs, const int
                 double best = -1.0;
                 int bi = k;
                 for (int i = k + threadIdx.x; i < bs; i += 32) {
-                    const double a = fabs(M[i * w2 + k]);
+                    const double a = fabs(M[i * bs + k]);
                     if (a > best) { best = a; bi = i; }
                 }
 #pragma unroll
@@ -229,41 +300,53 @@ __global__ void __launch_bounds__(256) k_asm_setup(int npatch, int bs, const int
                     const int oi = __shfl_down_sync(0xffffffffu, bi, o);
                     if (ob > best) { best = ob; bi = oi; }
                 }
-                if (threadIdx.x == 0) spiv = bi;
+                if (threadIdx.x == 0) { spiv = bi; piv[k] = bi; }
             }
             __syncthreads();
             const int pr = spiv;
             if (pr != k)
-                for (int j = threadIdx.x; j < w2; j += blockDim.x) {
-                    const double t = M[k * w2 + j];
-                    M[k * w2 + j] = M[pr * w2 + j];
-                    M[pr * w2 + j] = t;
+                for (int j = threadIdx.x; j < bs; j += blockDim.x) {
+                    const double t = M[k * bs + j];
+                    M[k * bs + j] = M[pr * bs + j];
+                    M[pr * bs + j] = t;
                 }
             __syncthreads();
-            double piv = M[k * w2 + k];
-            if (fabs(piv) < 1e-300) piv = 1e-300;
-            const double ip = 1.0 / piv;
+            double pv = M[k * bs + k];
+            if (fabs(pv) < 1e-300) pv = 1e-300;
+            const double ip = 1.0 / pv;
+            for (int i = threadIdx.x; i < bs; i += blockDim.x) fcol[i] = (i == k) ? 0.0 : M[i * bs + k];
             __syncthreads();
-            for (int j = threadIdx.x; j < w2; j += blockDim.x) M[k * w2 + j] *= ip;
-            for (int i = threadIdx.x; i < bs; i += blockDim.x) fcol[i] = (i == k) ? 0.0 : M[i * w2 + k];
+            for (int j = threadIdx.x; j < bs; j += blockDim.x) M[k * bs + j] = (j == k) ? ip : M[k * bs + j] * ip;
+            for (int i = threadIdx.x; i < bs; i += blockDim.x)
+                if (i != k) M[i * bs + k] = 0.0;
             __syncthreads();
-            for (int idx = threadIdx.x; idx < bs * w2; idx += blockDim.x) {
-                const int i = idx / w2, j = idx % w2;
-                M[idx] = fma(-fcol[i], M[k * w2 + j], M[idx]);
+            for (int idx = threadIdx.x; idx < bs * bs; idx += blockDim.x) {
+                const int i = idx / bs, j = idx % bs;
+                if (i != k) M[idx] = fma(-fcol[i], M[k * bs + j], M[idx]);
             }
+            __syncthreads();
+        }
+        for (int k = bs - 1; k >= 0; --k) {       // undo the row interchanges as column interchanges
+            const int pr = piv[k];
+            if (pr != k)
+                for (int i = threadIdx.x; i < bs; i += blockDim.x) {
+                    const double t = M[i * bs + k];
+                    M[i * bs + k] = M[i * bs + pr];
+                    M[i * bs + pr] = t;
+                }
             __syncthreads();
         }
         for (int idx = threadIdx.x; idx < bs * bs; idx += blockDim.x) {
             const int j = idx / bs, i = idx % bs;
-            inv[(long long)p * bs * bs + idx] = M[i * w2 + bs + j];
+            inv[(long long)p * bs * bs + idx] = M[i * bs + j];
         }
     }
 }
 
-extern "C" int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const int* patch2nnz, const double* vals,
-                              const double* freemask, double* inv_blocks, void* stream) {
+extern "C" int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
+                              const double* vals, const double* freemask, double* inv_blocks, void* stream) {
     if (npatch <= 0) return 0;
-    const size_t smem = sizeof(double) * ((size_t)bs * 2 * bs + bs);
+    const size_t smem = sizeof(double) * ((size_t)bs * bs + bs) + sizeof(int) * bs;
     if (smem > 220 * 1024) return ocmp_fail(-3, "patch too large for shared memory");
     static size_t configured = 0;
     if (smem > configured) {
@@ -271,10 +354,12 @@ extern "C" int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const i
         configured = smem;
     }
     const int cap = ocmp_sm_count() * 4;
-    k_asm_setup<<<npatch < cap ? npatch : cap, 256, smem, (cudaStream_t)stream>>>(npatch, bs, patch_dofs, patch2nnz,
+    ProfScope ps(PROF_SETUP, (cudaStream_t)stream);
+    k_asm_setup<<<npatch < cap ? npatch : cap, 256, smem, (cudaStream_t)stream>>>(npatch, bs, patch_dofs, rowptr, colidx,
                                                                                   vals, freemask, inv_blocks);
     return ocmp_check("ocmp_asm_setup");
 }
+
 
 // one warp per patch: z[dofs] += A_p^-1 r[dofs]
 __global__ void __launch_bounds__(256) k_asm_apply(int npatch, int bs, const int* __restrict__ pdofs,
@@ -311,6 +396,7 @@ extern "C" int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const d
     long long blocks = (npatch + wpb - 1) / wpb;
     const long long cap = (long long)ocmp_sm_count() * 8;
     if (blocks > cap) blocks = cap;
+    ProfScope ps(PROF_ASM_APPLY, st);
     k_asm_apply<<<(unsigned)blocks, wpb * 32, smem, st>>>(npatch, bs, patch_dofs, inv_blocks, r, z);
     return ocmp_check("ocmp_asm_apply");
 }
@@ -327,15 +413,71 @@ struct Ctx {
     void A(const double* x, double* y) const {
         ocmp_spmv(s->nrows, s->rowptr, s->colidx, s->vals, x, y, st);
     }
+    // one application of the smoother / local preconditioner of system `sy`: z = S r (r masked, result masked)
+    static void smooth(const ocmp_system* sy, cudaStream_t st, const double* r, double* z) {
+        const long long n = sy->nrows;
+        if (sy->pre_kind == 1) {
+            ProfScope ps(PROF_VEC, st);
+            k_had<<<grid_for(n), 256, 0, st>>>(n, sy->dinv, nullptr, r, z);
+        } else if (sy->pre_kind == 2 || sy->pre_kind == 3) {
+            ocmp_asm_apply(sy->npatch, sy->bs, sy->patch_dofs, sy->inv_blocks, r, z, n, st);
+            if (sy->freemask || sy->patch_weight) {
+                ProfScope ps(PROF_VEC, st);
+                k_had<<<grid_for(n), 256, 0, st>>>(n, sy->patch_weight, sy->freemask, z, z);
+            }
+        } else if (sy->pre_kind == 4) {
+            ocmp_spmv(sy->nrows, sy->inv_rowptr, sy->inv_colidx, sy->inv_vals, r, z, st);
+            if (sy->freemask) {
+                ProfScope ps(PROF_VEC, st);
+                k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, z, z);
+            }
+        } else {
+            ProfScope ps(PROF_VEC, st);
+            k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, r, z);
+        }
+    }
+    // V-cycle on level l: x = MG(b); b is masked on entry, x is masked on exit
+    static void vcycle(const ocmp_mg_level* L, int l, cudaStream_t st, const double* b, double* x) {
+        const ocmp_mg_level& lv = L[l];
+        const ocmp_system* sy = &lv.sys;
+        const long long n = sy->nrows;
+        if (l == 0) { smooth(sy, st, b, x); return; }
+        double* r = lv.work + 2 * n;
+        double* t = lv.work + 3 * n;
+        smooth(sy, st, b, x);
+        ocmp_axpby(n, 0.0, x, lv.omega, x, st);
+        for (int s = 1; s < lv.nu; ++s) {
+            ocmp_spmv(sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
+            k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
+            smooth(sy, st, r, t);
+            ocmp_axpby(n, lv.omega, t, 1.0, x, st);
+        }
+        ocmp_spmv(sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
+        k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
+        const ocmp_mg_level& lc = L[l - 1];
+        const long long nc = lc.sys.nrows;
+        double* xc = lc.work;
+        double* bc = lc.work + nc;
+        ocmp_spmv((int)nc, lv.r_rowptr, lv.r_colidx, lv.r_vals, r, bc, st);
+        if (lc.sys.freemask) k_had<<<grid_for(nc), 256, 0, st>>>(nc, nullptr, lc.sys.freemask, bc, bc);
+        vcycle(L, l - 1, st, bc, xc);
+        ocmp_spmv(sy->nrows, lv.p_rowptr, lv.p_colidx, lv.p_vals, xc, t, st);
+        if (sy->freemask) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, t, t);
+        ocmp_axpby(n, 1.0, t, 1.0, x, st);
+        for (int s = 0; s < lv.nu; ++s) {
+            ocmp_spmv(sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
+            k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
+            smooth(sy, st, r, t);
+            ocmp_axpby(n, lv.omega, t, 1.0, x, st);
+        }
+    }
     // z = P (already masked r); result masked
     void P(const double* r, double* z) const {
-        if (s->pre_kind == 1) k_had<<<grid_for(n), 256, 0, st>>>(n, s->dinv, nullptr, r, z);
-        else if (s->pre_kind == 2) {
-            ocmp_asm_apply(s->npatch, s->bs, s->patch_dofs, s->inv_blocks, r, z, n, st);
-            if (s->freemask) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, s->freemask, z, z);
-        } else k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, s->freemask, r, z);
+        if (s->pre_kind == 3 && s->nlevels > 1) vcycle(s->levels, s->nlevels - 1, st, r, z);
+        else smooth(s, st, r, z);
     }
     void mask(double* v) const {
+        ProfScope ps(PROF_VEC, st);
         if (s->freemask) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, s->freemask, v, v);
     }
     double dot(const double* x, const double* y) {
@@ -346,16 +488,19 @@ struct Ctx {
     }
     void axpby(double a, const double* x, double b, double* y) const { ocmp_axpby(n, a, x, b, y, st); }
     void mdot(const double* V, int k, const double* w, double* hout) {
+        ocmp_prof_begin(PROF_MDOT, st);
         cudaMemsetAsync(dscal, 0, sizeof(double) * k, st);
         for (int j0 = 0; j0 < k; j0 += 8) {
             const int kk = (k - j0) < 8 ? (k - j0) : 8;
             k_mdot<8><<<grid_for(n), 256, 0, st>>>(n, V + (long long)j0 * n, n, kk, w, dscal + j0);
         }
+        ocmp_prof_end(PROF_MDOT, st);
         cudaMemcpyAsync(hout, dscal, sizeof(double) * k, cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
     }
     void maxpy(const double* V, int k, const double* hc, double* w) {
         cudaMemcpyAsync(dscal, hc, sizeof(double) * k, cudaMemcpyHostToDevice, st);
+        ProfScope ps(PROF_MAXPY, st);
         k_maxpy<<<grid_for(n), 256, sizeof(double) * k, st>>>(n, V, n, k, dscal, w);
     }
 };

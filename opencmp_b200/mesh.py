@@ -226,8 +226,12 @@ class Mesh:
         bidx = np.concatenate([self.bnd_region, self.bnd_region])
         fine = Mesh(2, 'tri', newP, cells, bnd, bidx, self.bnd_names,
                     np.repeat(self.cell_mat, 4), self.mat_names)
+        # keep the coarse level for geometric multigrid: children of coarse cell e are fine cells 4e .. 4e+3
+        coarse = Mesh.__new__(Mesh)
+        coarse.__dict__.update({k: v for k, v in self.__dict__.items() if k != '_b200_scalar_space'})
         self.__dict__.update(fine.__dict__)
         self.__dict__.pop('_b200_scalar_space', None)
+        self.coarse = coarse
         return self
 
     def Curve(self, order: int) -> None:

@@ -1,0 +1,163 @@
+"""Geometric multigrid preconditioner on the uniform-refinement hierarchy kept by ``Mesh.Refine()``.
+
+Stands in for ``ngs.Preconditioner(a, 'multigrid')`` (reference opencmp/models/base_model.py:365-383 lists the types
+OpenCMP forwards to NGSolve: local, direct, multigrid, h1amg, bddc). The spaces of a uniformly refined affine mesh are
+nested, so the prolongation of every block (H1 / L2: plain pull-back, HDiv: contravariant Piola pull-back) is an exact
+embedding; it is tabulated once per *child class* (the affine map fine reference cell -> coarse reference cell takes
+only a handful of values under red refinement) and scattered into one CSR matrix on the host.
+
+Levels below the finest re-discretise the field-independent part of the bilinear form (convection by the Oseen wind
+and other DOF-vector weighted terms only act on the finest level, through the smoother and the Krylov method around
+the cycle). The cycle itself runs inside the C ABI (ocmp_krylov with pre_kind = 3): vertex-patch additive Schwarz
+smoothing, CSR restriction / prolongation, explicit inverse on the coarsest level.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import numpy as np
+import scipy.sparse as sp
+
+from .quadrature import cell_rule
+from .space import FESpace
+
+
+def mesh_levels(mesh) -> list:
+    """[coarsest, ..., finest] as kept by Mesh.Refine()."""
+    out = [mesh]
+    while getattr(out[-1], 'coarse', None) is not None:
+        out.append(out[-1].coarse)
+    return out[::-1]
+
+
+def clone_space(fes: FESpace, mesh) -> FESpace:
+    """Same space family / order / Dirichlet names on another mesh."""
+    cls = type(fes)
+    if fes.components:
+        return cls([clone_space(c, mesh) for c in fes.components], dgjumps=fes.dgjumps)
+    b = fes.blocks[0]
+    return cls(mesh, order=fes.order, dirichlet=b.dirichlet or '', dgjumps=fes.dgjumps, family=fes.name)
+
+
+def prolongation(fes_c: FESpace, fes_f: FESpace) -> sp.csr_matrix:
+    """(ndof_f x ndof_c) embedding of the coarse space into the fine space; fine cell k has parent k // 4."""
+    mc, mf = fes_c.mesh, fes_f.mesh
+    if mf.ne != 4 * mc.ne:
+        raise ValueError('prolongation needs a uniformly refined mesh')
+    dim = mf.dim
+    Jc, Jf = mc.jacobians(), mf.jacobians()
+    parent = np.arange(mf.ne) // 4
+    Jci = np.linalg.inv(Jc)[parent]
+    A = np.einsum('eab,ebc->eac', Jci, Jf)                              # xi_c = A xi_f + b
+    b = np.einsum('eab,eb->ea', Jci, mf.origins() - mc.origins()[parent])
+    key = np.round(np.concatenate([A.reshape(mf.ne, -1), b], axis=1), 9)
+    classes, cls_of = np.unique(key, axis=0, return_inverse=True)
+    cls_of = cls_of.reshape(-1)
+    rows, cols, vals = [], [], []
+    cdf, cdc = fes_f.cell_dofs.astype(np.int64), fes_c.cell_dofs.astype(np.int64)
+    for blk_f, blk_c, lo_f, lo_c in zip(fes_f.blocks, fes_c.blocks, fes_f.loc_offsets, fes_c.loc_offsets):
+        bf, bc = blk_f.basis, blk_c.basis
+        deg = 2 * bf.order + 1
+        pts, w = cell_rule(mf.cell_type, deg)
+        tf = bf.tabulate(pts)                                           # (nq, nrows, nloc_f)
+        nv = 1 if bf.kind == 'scalar' else dim
+        phi_f = tf[:, :nv, :]
+        M = np.einsum('q,qci,qcj->ij', w, phi_f, phi_f)
+        Minv = np.linalg.inv(M)
+        for k, row in enumerate(classes):
+            Ak = row[:dim * dim].reshape(dim, dim)
+            bk = row[dim * dim:]
+            tc = bc.tabulate(pts @ Ak.T + bk)[:, :nv, :]                # coarse functions at the mapped points
+            if bf.kind != 'scalar':
+                tc = np.linalg.det(Ak) * np.einsum('ab,qbj->qaj', np.linalg.inv(Ak), tc)
+            Ploc = Minv @ np.einsum('q,qci,qcj->ij', w, phi_f, tc)      # (nloc_f, nloc_c)
+            cells = np.nonzero(cls_of == k)[0]
+            r = cdf[cells][:, lo_f:lo_f + blk_f.nloc]
+            c = cdc[parent[cells]][:, lo_c:lo_c + blk_c.nloc]
+            nz = np.abs(Ploc) > 1e-13
+            ii, jj = np.nonzero(nz)
+            rows.append(r[:, ii].ravel())
+            cols.append(c[:, jj].ravel())
+            vals.append(np.broadcast_to(Ploc[ii, jj], (len(cells), len(ii))).ravel())
+    rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+    key = rows * np.int64(fes_c.ndof) + cols
+    _, first = np.unique(key, return_index=True)
+    P = sp.csr_matrix((vals[first], (rows[first], cols[first])), shape=(fes_f.ndof, fes_c.ndof))
+    P.sort_indices()
+    return P
+
+
+# ---- device side: level hierarchy handed to the C ABI (pre_kind = 3) ---------------------------------------------
+class MultigridState:
+    """Built by ``CudaBackend.precond_setup(..., 'multigrid')``; refreshed on every ``Preconditioner.Update()``."""
+    kind = 3
+
+    def __init__(self, be, bf, nu: int = 2, omega: float = 1.0):
+        import ctypes as C
+        from .backend import MGLevel
+        from .symbolic import lower_form
+        from . import ngs
+        self.be, self.bf = be, bf
+        fes = bf.space
+        meshes = mesh_levels(fes.mesh)
+        self.nlevels = len(meshes)
+        if self.nlevels < 2:
+            raise ValueError("Preconditioner type 'multigrid' needs a mesh refined with Mesh.Refine()")
+        self.spaces = [clone_space(fes, m) for m in meshes[:-1]] + [fes]
+        self.programs = [lower_form(s, bf.integrals, 2, drop_fields=True) for s in self.spaces[:-1]]
+        self.mats = [ngs.Matrix(s) for s in self.spaces[:-1]]
+        self.transfers = []
+        for lo, hi in zip(self.spaces[:-1], self.spaces[1:]):
+            P = prolongation(lo, hi)
+            R = P.T.tocsr()
+            R.sort_indices()
+            self.transfers.append(tuple(be._up(a) for a in (P.indptr.astype(np.int32), P.indices.astype(np.int32),
+                                                            P.data, R.indptr.astype(np.int32),
+                                                            R.indices.astype(np.int32), R.data)))
+        self.work = [be.zeros(4 * s.ndof) for s in self.spaces]
+        self.masks = [be._up(s.FreeDofs().astype(np.float64)) for s in self.spaces]
+        n0 = self.spaces[0].ndof
+        pat0 = self.spaces[0].pattern()
+        t = be.torch
+        self.rows0 = be._up(np.repeat(np.arange(n0), np.diff(pat0.rowptr)).astype(np.int64))
+        self.cols0 = be._up(pat0.colidx.astype(np.int64))
+        self.inv_rowptr = be._up((np.arange(n0 + 1, dtype=np.int64) * n0).astype(np.int32))
+        self.inv_colidx = be._up(np.tile(np.arange(n0, dtype=np.int32), n0))
+        self.inv_vals = None
+        self.levels = (MGLevel * self.nlevels)()
+        self.nu, self.omega = nu, omega
+        self.fm = self.masks[-1]
+        self.smoothers = [None] * self.nlevels
+
+    def update(self, fine_mat):
+        be = self.be
+        t = be.torch
+        for l in range(self.nlevels - 1):
+            be.assemble_matrix(self.programs[l], self.mats[l])
+        # coarsest level: explicit inverse of the free-free block (identity on constrained dofs)
+        n0 = self.spaces[0].ndof
+        dense = t.zeros((n0, n0), dtype=t.float64, device=be.device)
+        dense[self.rows0, self.cols0] = self.mats[0].values
+        m = self.masks[0]
+        dense = dense * m[:, None] * m[None, :] + t.diag(1.0 - m)
+        self.inv_vals = t.linalg.inv(dense).contiguous().view(-1)
+        for l in range(self.nlevels):
+            mat = fine_mat if l == self.nlevels - 1 else self.mats[l]
+            lv = self.levels[l]
+            if l == 0:
+                sys_ = be._system(mat, self.masks[0], None)
+                sys_.pre_kind = 4
+                sys_.inv_rowptr, sys_.inv_colidx = self.inv_rowptr.data_ptr(), self.inv_colidx.data_ptr()
+                sys_.inv_vals = self.inv_vals.data_ptr()
+            else:
+                sm = be.precond_setup(mat, 'asm', self.spaces[l].FreeDofs(), mask=self.masks[l])
+                self.smoothers[l] = sm
+                sys_ = be._system(mat, self.masks[l], sm)
+                P = self.transfers[l - 1]
+                lv.ncoarse = self.spaces[l - 1].ndof
+                lv.p_rowptr, lv.p_colidx, lv.p_vals = (a.data_ptr() for a in P[:3])
+                lv.r_rowptr, lv.r_colidx, lv.r_vals = (a.data_ptr() for a in P[3:])
+            lv.sys = sys_
+            lv.work = self.work[l].data_ptr()
+            lv.nu, lv.omega = self.nu, self.omega
+        return self

@@ -357,7 +357,8 @@ class Preconditioner:
 
     def Update(self):
         if self.bf.mat is not None:
-            self.state = get_backend().precond_setup(self.bf.mat, self.type, self.bf.space.FreeDofs())
+            self.state = get_backend().precond_setup(self.bf.mat, self.type, self.bf.space.FreeDofs(), form=self.bf,
+                                                     state=self.state)
 
 
 class _Solvers:
@@ -380,7 +381,7 @@ class _Solvers:
         if x is None:
             x = b.CreateVector()
         get_backend().krylov('gmres', A, b.a, x.a, pre, freedofs, 1e-7 if tol is None else tol, maxsteps, False,
-                             printrates)
+                             printrates, restart=kw.get('restart'))
         return x
 
     @staticmethod

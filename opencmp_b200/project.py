@@ -186,7 +186,8 @@ def _global_projection(gf, cf, definedon) -> None:
     a.Assemble()
     L.Assemble()
     pre = ngs.Preconditioner(a, 'local')
-    pre.Update()
+    # the projection acts on every dof, constrained or not
+    pre.state = ngs.get_backend().precond_setup(a.mat, 'local', np.ones(fes.ndof, dtype=bool))
     sol = L.vec.CreateVector()
     ngs.solvers.CG(mat=a.mat, rhs=L.vec, pre=pre, sol=sol, tol=1e-14, maxsteps=2000)
     gf.vec.data = sol

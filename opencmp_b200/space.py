@@ -240,27 +240,45 @@ class Pattern:
             d0, d1 = cd[fc[:, 0]], cd[fc[:, 1]]
             keys.append((d0[:, :, None] * n + d1[:, None, :]).reshape(-1))
             keys.append((d1[:, :, None] * n + d0[:, None, :]).reshape(-1))
-        ukey = np.unique(np.concatenate(keys))
+        ar = np.arange(int(n), dtype=np.int64)
+        ukey, maps = _unique_and_locate(keys, keys + [ar * n + ar])
         self.nnz = int(ukey.shape[0])
         self.n = int(n)
+        if self.nnz >= 2 ** 31:
+            raise ValueError('pattern with more than 2^31 entries: partition the mesh across GPUs')
         rows = ukey // n
         self.colidx = np.ascontiguousarray(ukey - rows * n, dtype=np.int32)
         rowptr = np.zeros(self.n + 1, dtype=np.int64)
         rowptr[1:] = np.bincount(rows, minlength=self.n)
-        self.rowptr = np.ascontiguousarray(np.cumsum(rowptr), dtype=np.int32 if self.nnz < 2 ** 31 else np.int64)
-        if self.nnz >= 2 ** 31:
-            raise ValueError('pattern with more than 2^31 entries: partition the mesh across GPUs')
-        self.cell2nnz = np.ascontiguousarray(np.searchsorted(ukey, keys[0]).reshape(ne, nloc * nloc), dtype=np.int32)
+        self.rowptr = np.ascontiguousarray(np.cumsum(rowptr), dtype=np.int32)
+        self.cell2nnz = np.ascontiguousarray(maps[0].reshape(ne, nloc * nloc), dtype=np.int32)
         if len(keys) > 1:
             nif = len(m.interior_facets)
-            self.facet2nnz = np.ascontiguousarray(np.stack(
-                [np.searchsorted(ukey, keys[1]).reshape(nif, nloc * nloc),
-                 np.searchsorted(ukey, keys[2]).reshape(nif, nloc * nloc)], axis=1), dtype=np.int32)
+            self.facet2nnz = np.ascontiguousarray(np.stack([maps[1].reshape(nif, nloc * nloc),
+                                                            maps[2].reshape(nif, nloc * nloc)], axis=1), dtype=np.int32)
         else:
             self.facet2nnz = np.zeros((0, 2, nloc * nloc), dtype=np.int32)
         # position of the diagonal entries (Jacobi, Dirichlet handling)
-        ar = np.arange(self.n, dtype=np.int64)
-        self.diag = np.ascontiguousarray(np.searchsorted(ukey, ar * n + ar), dtype=np.int32)
+        self.diag = np.ascontiguousarray(maps[-1], dtype=np.int32)
+
+
+def _unique_and_locate(key_lists, queries):
+    """Sorted unique int64 keys of ``key_lists`` and the position of every query key in them. One-off set-up work:
+    done with torch on the GPU when one is visible (sort / searchsorted of 10^8 keys), with NumPy otherwise."""
+    big = sum(k.size for k in key_lists) > (1 << 22)
+    if big:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                dev = torch.device('cuda', torch.cuda.current_device())
+                ukey = torch.unique(torch.cat([torch.from_numpy(k).to(dev) for k in key_lists]))
+                maps = [torch.searchsorted(ukey, torch.from_numpy(np.ascontiguousarray(q)).to(dev)).to(torch.int32)
+                        .cpu().numpy() for q in queries]
+                return ukey.cpu().numpy(), maps
+        except ImportError:
+            pass
+    ukey = np.unique(np.concatenate(key_lists))
+    return ukey, [np.searchsorted(ukey, q) for q in queries]
 
 
 # NGSolve-style constructors -----------------------------------------------------------------------------------

@@ -613,7 +613,8 @@ class SumOfIntegrals:
 
 
 # ---- lowering ------------------------------------------------------------------------------------------------------
-def lower_form(fes, integrals: SumOfIntegrals, arity: int, intorder: Optional[int] = None) -> FormProgram:
+def lower_form(fes, integrals: SumOfIntegrals, arity: int, intorder: Optional[int] = None,
+               drop_fields: bool = False) -> FormProgram:
     """Group the entries of all integrals by (kind, region) and compile one bytecode per group."""
     mesh = fes.mesh
     nrows = fes.nrows
@@ -622,6 +623,8 @@ def lower_form(fes, integrals: SumOfIntegrals, arity: int, intorder: Optional[in
         if cf.arr.size != 1:
             raise ValueError('integrand must be scalar, got dims {}'.format(cf.dims))
         s: S = cf.arr.reshape(())[()]
+        if drop_fields:       # coarse multigrid levels keep only the DOF-vector independent part of the form
+            s = S({k: c for k, c in s.t.items() if not coef_leaves([c], 'field')})
         if m.kind == 'vol' and not m.skeleton:
             kind, rkind = 'cell', 'mat'
             nreg = len(mesh.mat_names)

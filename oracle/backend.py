@@ -65,7 +65,7 @@ class OracleBackend:
         free = np.ones(mat.height, bool) if freedofs is None else np.asarray(freedofs, bool)
         out[:] = fem.solve_direct(self._csr(mat), r, np.zeros_like(r), free)
 
-    def precond_setup(self, mat, kind, free):
+    def precond_setup(self, mat, kind, free, form=None, state=None, mask=None):
         A = self._csr(mat)
         free = np.asarray(free, bool)
         idx = np.nonzero(free)[0]
@@ -83,7 +83,7 @@ class OracleBackend:
             return app
         raise NotImplementedError('oracle preconditioner {}'.format(kind))
 
-    def krylov(self, kind, mat, b, x, pre, freedofs, tol, maxit, initialize, printrates, damp=1.0):
+    def krylov(self, kind, mat, b, x, pre, freedofs, tol, maxit, initialize, printrates, damp=1.0, restart=None):
         A = self._csr(mat)
         n = A.shape[0]
         if pre is not None and pre.state is None:
