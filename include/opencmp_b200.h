@@ -143,7 +143,7 @@ long long ocmp_krylov_work_len(int nrows, int kind, int restart);
 
 /* ---- instrumentation: per-category device time from CUDA events recorded around every launch on its own stream.
  * categories: 0 spmv, 1 asm_apply, 2 coefficient eval, 3 matrix contraction, 4 vector contraction, 5 multi-dot,
- * 6 multi-axpy, 7 other vector kernels, 8 preconditioner setup */
+ * 6 multi-axpy, 7 other vector kernels, 8 preconditioner setup, 9 SpMVs inside the multigrid cycle */
 void ocmp_profile_enable(int on);
 void ocmp_profile_reset(void);
 int ocmp_profile_read(int category, long long* count, double* ms);

@@ -86,7 +86,7 @@ def load_library() -> C.CDLL:
 
 
 PROFILE_CATEGORIES = ['spmv', 'asm_apply', 'coef', 'contract_matrix', 'contract_vector', 'multi_dot', 'multi_axpy',
-                      'vector', 'precond_setup']
+                      'vector', 'precond_setup', 'spmv_multigrid']
 
 
 def read_profile(lib) -> dict:

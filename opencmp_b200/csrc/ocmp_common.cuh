@@ -5,9 +5,13 @@
 int ocmp_fail(int code, const char* msg);
 int ocmp_check(const char* where);
 int ocmp_sm_count();
+int ocmp_patch_invert_registers(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
+                                const double* fm, double* inv, int* flag_dev, cudaStream_t st);
+int ocmp_patch_apply_cta(int npatch, int bs, const int* pd, const double* inv, const double* r, double* z,
+                         cudaStream_t st);
 // optional per-category device timing (CUDA events on the launching stream) and launch counting
 enum { PROF_SPMV = 0, PROF_ASM_APPLY, PROF_COEF, PROF_CONTRACT, PROF_LIN, PROF_MDOT, PROF_MAXPY, PROF_VEC,
-       PROF_SETUP, PROF_NCAT };
+       PROF_SETUP, PROF_SPMV_MG, PROF_NCAT };
 void ocmp_prof_begin(int cat, cudaStream_t st);
 void ocmp_prof_end(int cat, cudaStream_t st);
 struct ProfScope {

@@ -113,15 +113,20 @@ __global__ void __launch_bounds__(256) k_spmv(int nrows, const int* __restrict__
     }
 }
 
+static int spmv_cat(int cat, int nrows, const int* rowptr, const int* colidx, const double* vals, const double* x,
+                    double* y, cudaStream_t st);
 extern "C" int ocmp_spmv(int nrows, const int* rowptr, const int* colidx, const double* vals, const double* x,
                          double* y, void* stream) {
+    return spmv_cat(PROF_SPMV, nrows, rowptr, colidx, vals, x, y, (cudaStream_t)stream);
+}
+static int spmv_cat(int cat, int nrows, const int* rowptr, const int* colidx, const double* vals, const double* x,
+                    double* y, cudaStream_t st) {
     if (nrows <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
     const int threads = 256;
     const long long want = ((long long)nrows * 16 + threads - 1) / threads;
     const long long cap = (long long)ocmp_sm_count() * 64;
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
-    ProfScope ps(PROF_SPMV, st);
+    ProfScope ps(cat, st);
     k_spmv<16><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, vals, x, y);
     return ocmp_check("ocmp_spmv");
 }
@@ -355,6 +360,19 @@ extern "C" int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const i
     }
     const int cap = ocmp_sm_count() * 4;
     ProfScope ps(PROF_SETUP, (cudaStream_t)stream);
+    {   // fast path: register-tiled Gauss-Jordan without pivoting; falls back below if a pivot vanishes
+        static int* flag_dev = nullptr;
+        if (!flag_dev) cudaMalloc(&flag_dev, sizeof(int));
+        cudaStream_t st = (cudaStream_t)stream;
+        cudaMemsetAsync(flag_dev, 0, sizeof(int), st);
+        if (ocmp_patch_invert_registers(npatch, bs, patch_dofs, rowptr, colidx, vals, freemask, inv_blocks, flag_dev,
+                                        st)) {
+            int flag = 0;
+            cudaMemcpyAsync(&flag, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            if (!flag) return ocmp_check("ocmp_asm_setup");
+        }
+    }
     k_asm_setup<<<npatch < cap ? npatch : cap, 256, smem, (cudaStream_t)stream>>>(npatch, bs, patch_dofs, rowptr, colidx,
                                                                                   vals, freemask, inv_blocks);
     return ocmp_check("ocmp_asm_setup");
@@ -391,6 +409,10 @@ extern "C" int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const d
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(z, 0, sizeof(double) * n, st);
     if (npatch <= 0) return 0;
+    if (bs >= 48) {
+        ProfScope ps(PROF_ASM_APPLY, st);
+        if (ocmp_patch_apply_cta(npatch, bs, patch_dofs, inv_blocks, r, z, st)) return ocmp_check("ocmp_asm_apply");
+    }
     const int wpb = 8;
     const size_t smem = sizeof(double) * wpb * bs;
     long long blocks = (npatch + wpb - 1) / wpb;
@@ -426,7 +448,7 @@ struct Ctx {
                 k_had<<<grid_for(n), 256, 0, st>>>(n, sy->patch_weight, sy->freemask, z, z);
             }
         } else if (sy->pre_kind == 4) {
-            ocmp_spmv(sy->nrows, sy->inv_rowptr, sy->inv_colidx, sy->inv_vals, r, z, st);
+            spmv_cat(PROF_SPMV_MG, sy->nrows, sy->inv_rowptr, sy->inv_colidx, sy->inv_vals, r, z, st);
             if (sy->freemask) {
                 ProfScope ps(PROF_VEC, st);
                 k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, z, z);
@@ -447,25 +469,25 @@ struct Ctx {
         smooth(sy, st, b, x);
         ocmp_axpby(n, 0.0, x, lv.omega, x, st);
         for (int s = 1; s < lv.nu; ++s) {
-            ocmp_spmv(sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
+            spmv_cat(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
             k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
             smooth(sy, st, r, t);
             ocmp_axpby(n, lv.omega, t, 1.0, x, st);
         }
-        ocmp_spmv(sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
+        spmv_cat(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
         k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
         const ocmp_mg_level& lc = L[l - 1];
         const long long nc = lc.sys.nrows;
         double* xc = lc.work;
         double* bc = lc.work + nc;
-        ocmp_spmv((int)nc, lv.r_rowptr, lv.r_colidx, lv.r_vals, r, bc, st);
+        spmv_cat(PROF_SPMV_MG, (int)nc, lv.r_rowptr, lv.r_colidx, lv.r_vals, r, bc, st);
         if (lc.sys.freemask) k_had<<<grid_for(nc), 256, 0, st>>>(nc, nullptr, lc.sys.freemask, bc, bc);
         vcycle(L, l - 1, st, bc, xc);
-        ocmp_spmv(sy->nrows, lv.p_rowptr, lv.p_colidx, lv.p_vals, xc, t, st);
+        spmv_cat(PROF_SPMV_MG, sy->nrows, lv.p_rowptr, lv.p_colidx, lv.p_vals, xc, t, st);
         if (sy->freemask) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, t, t);
         ocmp_axpby(n, 1.0, t, 1.0, x, st);
         for (int s = 0; s < lv.nu; ++s) {
-            ocmp_spmv(sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
+            spmv_cat(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
             k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
             smooth(sy, st, r, t);
             ocmp_axpby(n, lv.omega, t, 1.0, x, st);

@@ -33,7 +33,7 @@ def _grad_avg(q):
 
 class INSTaylorGreen:
     def __init__(self, N: int, order: int = 3, dt: float = 1e-3, nu: float = 1.0, ipc: float = 10.0,
-                 linear_solver: str = 'GMRes', preconditioner: str = 'asm', linear_tolerance: float = 1e-10,
+                 linear_solver: str = 'GMRes', preconditioner: str = 'multigrid', linear_tolerance: float = 1e-10,
                  linear_max_iterations: int = 500, nonlinear_max_iterations: int = 3,
                  nonlinear_tolerance=(1e-4, 1e-6), mesh=None):
         if mesh is None and preconditioner == 'multigrid':
@@ -142,7 +142,8 @@ class INSTaylorGreen:
             self.gfu.vec.data += inv * r
         elif self.linear_solver == 'GMRes':
             ngs.solvers.GMRes(A=self.a.mat, b=self.L.vec, pre=self.pre, freedofs=self.fes.FreeDofs(),
-                              x=self.gfu.vec, tol=self.linear_tolerance, maxsteps=self.linear_max_iterations)
+                              x=self.gfu.vec, tol=self.linear_tolerance, maxsteps=self.linear_max_iterations,
+                              restart=100)
         else:
             raise ValueError(self.linear_solver)
         self.linear_iterations.append(getattr(be, 'last_iters', 0))
