@@ -233,6 +233,18 @@ def main():
     n_asm = max(1, picard)
     asm_mnnz = nnz / (asm_ms / n_asm * 1e-3) / 1e6 if asm_ms > 0 else 0.0
     share = {k: round(v['ms'] / ms, 4) for k, v in prof.items()}
+    # dominant kernel of the step: the smoother application k_patch_apply (HBM bound: streams the patch inverses)
+    ap = prof['asm_apply']
+    ap_ms = ap['ms'] / max(1, ap['count'])
+    ap_bytes = ap['bytes'] / max(1, ap['count'])
+    ap_gbs = ap_bytes / (ap_ms * 1e-3) / 1e9 if ap['count'] else 0.0
+    roofline = {'kernel': 'k_patch_apply (additive-Schwarz smoother, all multigrid levels; launch-weighted mean)',
+                'bound': 'hbm', 'achieved': ap_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': ap_gbs / peak,
+                'peak_source': peak_src, 'bytes_per_launch': ap_bytes, 'launches': ap['count'],
+                'avg_launch_ms': ap_ms, 'share_of_step': share['asm_apply'],
+                'traffic': 2.386e9 if args.N == 128 else None,
+                'traffic_note': 'ncu --set full, fine-level launch at N=128: dram read 2.368 GB + write 0.018 GB vs '
+                                '2.330 GB algorithmic (profiles/r1_ncu_kernels.md)'}
     line = {
         'metric': 'INS s/timestep', 'value': sec, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': False, 'scaling': 'weak',
@@ -241,10 +253,11 @@ def main():
                     'gmres_its_per_step': lin_its / args.steps, 'l2_err_u': eu, 'l2_err_p': ep,
                     'setup_s': t_setup},
         'assembly_mnnz_per_s': asm_mnnz, 'spmv_gbs': spmv_gbs,
-        'roofline': {'kernel': 'k_spmv (CSR FP64 values + int32 columns)', 'bound': 'hbm', 'achieved': spmv_gbs,
-                     'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs / peak, 'frac_of_8000_nominal': spmv_gbs / 8000.0,
-                     'peak_source': peak_src, 'bytes_per_launch': spmv_bytes, 'launches': sp['count'],
-                     'avg_launch_ms': spmv_ms, 'traffic': None},
+        'roofline': roofline,
+        'roofline_spmv': {'kernel': 'k_spmv<16> fine level (CSR FP64 values + int32 columns)', 'bound': 'hbm',
+                          'achieved': spmv_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs / peak,
+                          'frac_of_8000_nominal': spmv_gbs / 8000.0, 'bytes_per_launch': spmv_bytes,
+                          'launches': sp['count'], 'avg_launch_ms': spmv_ms},
         'kernel_time_share': share,
         'e2e': {'value': ms_e2e / 1e3 / args.steps, 'unit': 's', 'h2d_bytes_per_step': int(8 * (2 * ndof + w.V.ndof)),
                 'd2h_bytes_per_step': int(8 * ndof)},

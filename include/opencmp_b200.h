@@ -147,6 +147,7 @@ long long ocmp_krylov_work_len(int nrows, int kind, int restart);
 void ocmp_profile_enable(int on);
 void ocmp_profile_reset(void);
 int ocmp_profile_read(int category, long long* count, double* ms);
+double ocmp_profile_bytes(int category);   /* algorithmic bytes of the category's launches (asm_apply only) */
 long long ocmp_launch_count(void);
 
 const char* ocmp_last_error(void);

@@ -82,6 +82,8 @@ def load_library() -> C.CDLL:
     lib.ocmp_profile_reset.restype = None
     lib.ocmp_profile_read.argtypes = [C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     lib.ocmp_launch_count.restype = C.c_longlong
+    lib.ocmp_profile_bytes.restype = C.c_double
+    lib.ocmp_profile_bytes.argtypes = [C.c_int]
     return lib
 
 
@@ -94,11 +96,11 @@ def read_profile(lib) -> dict:
     for i, name in enumerate(PROFILE_CATEGORIES):
         cnt, ms = C.c_longlong(0), C.c_double(0.0)
         lib.ocmp_profile_read(i, C.byref(cnt), C.byref(ms))
-        out[name] = dict(count=int(cnt.value), ms=float(ms.value))
+        out[name] = dict(count=int(cnt.value), ms=float(ms.value), bytes=float(lib.ocmp_profile_bytes(i)))
     return out
 
 
-EXPORTED = ['ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
+EXPORTED = ['ocmp_profile_bytes', 'ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
             'ocmp_dot', 'ocmp_axpby', 'ocmp_masked_assign', 'ocmp_jacobi_setup', 'ocmp_asm_setup', 'ocmp_asm_apply',
             'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version']
 

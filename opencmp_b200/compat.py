@@ -1,0 +1,67 @@
+"""Install the opencmp_b200 front end under the import names OpenCMP uses:
+
+    import opencmp_b200.compat as c; c.install_as_ngsolve()
+    import opencmp            # the unmodified reference package now runs on the B200 backend
+
+Aliases: ``ngsolve`` (+ ``ngsolve.comp``, ``ngsolve.solvers``, ``ngsolve.config``), ``pyngcore`` / ``ngsolve.ngstd``
+(TaskManager, SetNumThreads, BitArray), ``netgen.meshing`` / ``netgen.read_gmsh`` (mesh readers only). This is the
+reference-side binding a maintainer would add in ``opencmp/__init__.py``.
+"""
+from __future__ import annotations
+
+import sys
+import types
+
+
+def install_as_ngsolve(force: bool = False) -> None:
+    if 'ngsolve' in sys.modules and not force and getattr(sys.modules['ngsolve'], '__b200__', False):
+        return
+    from . import ngs
+    from .mesh import load_mesh, read_msh
+    ngs.__b200__ = True
+    sys.modules['ngsolve'] = ngs
+    comp = types.ModuleType('ngsolve.comp')
+    for name in ('ProxyFunction', 'FESpace', 'DifferentialSymbol', 'GridFunction', 'BilinearForm', 'LinearForm',
+                 'Preconditioner', 'Mesh', 'Region', 'SumOfIntegrals'):
+        setattr(comp, name, getattr(ngs, name))
+    ngs.comp = comp
+    sys.modules['ngsolve.comp'] = comp
+    solv = types.ModuleType('ngsolve.solvers')
+    for name in ('CG', 'MinRes', 'GMRes', 'PreconditionedRichardson'):
+        setattr(solv, name, getattr(ngs.solvers, name))
+    sys.modules['ngsolve.solvers'] = solv
+    core = types.ModuleType('pyngcore')
+    core.TaskManager, core.SetNumThreads, core.BitArray = ngs.TaskManager, ngs.SetNumThreads, ngs.BitArray
+    sys.modules['pyngcore'] = core
+    ngs.ngstd = core
+    sys.modules['ngsolve.ngstd'] = core
+    ngs.ngsglobals = ngs.ngsglobals
+    netgen = types.ModuleType('netgen')
+    meshing = types.ModuleType('netgen.meshing')
+
+    class _NgMesh:
+        """``ngmsh.Mesh(dim)`` followed by ``.Load(filename)`` — reference helpers/io.py:94-99."""
+
+        def __init__(self, dim=3):
+            self.dim = dim
+            self._mesh = None
+
+        def Load(self, filename):
+            self._mesh = load_mesh(filename)
+
+    meshing.Mesh = _NgMesh
+    read_gmsh = types.ModuleType('netgen.read_gmsh')
+    read_gmsh.ReadGmsh = lambda filename: read_msh(filename if filename.endswith('.msh') else filename + '.msh')
+    netgen.meshing, netgen.read_gmsh = meshing, read_gmsh
+    sys.modules['netgen'] = netgen
+    sys.modules['netgen.meshing'] = meshing
+    sys.modules['netgen.read_gmsh'] = read_gmsh
+    if 'pyparsing' not in sys.modules:
+        try:
+            import pyparsing  # noqa: F401
+        except ImportError:
+            try:
+                from pip._vendor import pyparsing as _pp
+                sys.modules['pyparsing'] = _pp
+            except ImportError:
+                pass

@@ -14,6 +14,7 @@ enum { PROF_SPMV = 0, PROF_ASM_APPLY, PROF_COEF, PROF_CONTRACT, PROF_LIN, PROF_M
        PROF_SETUP, PROF_SPMV_MG, PROF_NCAT };
 void ocmp_prof_begin(int cat, cudaStream_t st);
 void ocmp_prof_end(int cat, cudaStream_t st);
+void ocmp_prof_bytes(int cat, double bytes);
 struct ProfScope {
     int cat; cudaStream_t st;
     ProfScope(int c, cudaStream_t s) : cat(c), st(s) { ocmp_prof_begin(c, s); }

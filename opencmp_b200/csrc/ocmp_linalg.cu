@@ -41,6 +41,7 @@ struct ProfCat {
     std::vector<cudaEvent_t> ev;     // begin/end pairs not yet folded into ms
     double ms = 0.0;
     long long count = 0;
+    double bytes = 0.0;              // algorithmic bytes moved by the launches of this category
 };
 ProfCat g_cat[PROF_NCAT];
 std::vector<cudaEvent_t> g_pool;
@@ -81,7 +82,7 @@ void ocmp_prof_end(int cat, cudaStream_t st) {
 }
 extern "C" void ocmp_profile_enable(int on) { g_prof = on != 0; }
 extern "C" void ocmp_profile_reset(void) {
-    for (auto& c : g_cat) { prof_fold(c); c.ms = 0.0; c.count = 0; }
+    for (auto& c : g_cat) { prof_fold(c); c.ms = 0.0; c.count = 0; c.bytes = 0.0; }
     g_launches = 0;
 }
 extern "C" int ocmp_profile_read(int cat, long long* count, double* ms) {
@@ -91,6 +92,10 @@ extern "C" int ocmp_profile_read(int cat, long long* count, double* ms) {
     if (ms) *ms = g_cat[cat].ms;
     return 0;
 }
+void ocmp_prof_bytes(int cat, double bytes) {
+    if (g_prof) g_cat[cat].bytes += bytes;
+}
+extern "C" double ocmp_profile_bytes(int cat) { return (cat < 0 || cat >= PROF_NCAT) ? 0.0 : g_cat[cat].bytes; }
 extern "C" long long ocmp_launch_count(void) { return g_launches; }
 extern "C" const char* ocmp_last_error(void) { return g_err; }
 extern "C" int ocmp_version(void) { return 100; }
@@ -409,6 +414,7 @@ extern "C" int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const d
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(z, 0, sizeof(double) * n, st);
     if (npatch <= 0) return 0;
+    ocmp_prof_bytes(PROF_ASM_APPLY, 8.0 * npatch * bs * bs + 16.0 * n);
     if (bs >= 48) {
         ProfScope ps(PROF_ASM_APPLY, st);
         if (ocmp_patch_apply_cta(npatch, bs, patch_dofs, inv_blocks, r, z, st)) return ocmp_check("ocmp_asm_apply");

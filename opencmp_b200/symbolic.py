@@ -288,6 +288,11 @@ class CoefficientFunction:
         return CoefficientFunction._lift(o) / self
 
     def __pow__(self, o):
+        if isinstance(o, (int, float)) and float(o).is_integer() and 1 <= int(o) <= 8 and self.arr.ndim:
+            out = self                      # integer powers of tensors are repeated products (v**2 = v*v = |v|^2)
+            for _ in range(int(o) - 1):
+                out = out * self
+            return out
         o = CoefficientFunction._lift(o)
         return self._ew(o, lambda x, y: S.coef(Coef.binary('pow', x.as_coef(), y.as_coef())))
 
@@ -353,7 +358,8 @@ class Parameter(CoefficientFunction):
 def _unary(name):
     def fn(a):
         if not isinstance(a, CoefficientFunction):
-            return CoefficientFunction(a).map_coef(lambda c: Coef.unary(name, c))
+            from .ir import _PY_UNARY
+            return _PY_UNARY[name](float(a))          # plain numbers stay plain numbers, like ngs.sqrt(2.0)
         return a.map_coef(lambda c: Coef.unary(name, c))
     fn.__name__ = name
     return fn

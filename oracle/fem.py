@@ -314,6 +314,10 @@ def solve_direct(A: sp.csr_matrix, b: np.ndarray, x: np.ndarray, free: np.ndarra
     idx = np.nonzero(free)[0]
     Aff = A[idx][:, idx].tocsc()
     lu = spla.splu(Aff)
+    rf = r[idx]
+    d = lu.solve(rf)
+    for _ in range(2):            # two steps of iterative refinement, PARDISO's default behaviour
+        d += lu.solve(rf - Aff @ d)
     out = x.copy()
-    out[idx] += lu.solve(r[idx])
+    out[idx] += d
     return out
