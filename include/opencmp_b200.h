@@ -96,7 +96,12 @@ int ocmp_jacobi_setup(int nrows, const int* diagpos, const double* vals, const d
 /* additive Schwarz over dof patches (patch_dofs: npatch x bs, padded with -1): gather the dense blocks from the CSR
  * matrix and invert them in shared memory (batched Gauss-Jordan with partial pivoting) */
 int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
-                   const double* vals, const double* freemask, double* inv_blocks, void* stream);
+                   const double* vals, const double* freemask, double* inv_blocks, const int* positions,
+                   void* stream);
+/* one-off: CSR positions of every (padded to a multiple of 16) patch entry, npatch x NP x NP int32, -1 = not in the
+ * pattern; NULL positions in ocmp_asm_setup selects the slower pivoted shared-memory kernel */
+int ocmp_patch_positions(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
+                         int* positions, void* stream);
 int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const double* inv_blocks, const double* r, double* z,
                    long long n, void* stream);
 

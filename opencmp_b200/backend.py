@@ -73,7 +73,8 @@ def load_library() -> C.CDLL:
     lib.ocmp_axpby.argtypes = [C.c_longlong, C.c_double, P, C.c_double, P, P]
     lib.ocmp_masked_assign.argtypes = [C.c_longlong, P, P, P, P, P]
     lib.ocmp_jacobi_setup.argtypes = [C.c_int, P, P, P, P, P]
-    lib.ocmp_asm_setup.argtypes = [C.c_int, C.c_int, P, P, P, P, P, P, P]
+    lib.ocmp_asm_setup.argtypes = [C.c_int, C.c_int, P, P, P, P, P, P, P, P]
+    lib.ocmp_patch_positions.argtypes = [C.c_int, C.c_int, P, P, P, P, P]
     lib.ocmp_asm_apply.argtypes = [C.c_int, C.c_int, P, P, P, P, C.c_longlong, P]
     lib.ocmp_krylov.argtypes = [C.POINTER(System), C.c_int, P, P, C.c_double, C.c_int, C.c_int, C.c_double, P,
                                 C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_double), P]
@@ -100,7 +101,7 @@ def read_profile(lib) -> dict:
     return out
 
 
-EXPORTED = ['ocmp_profile_bytes', 'ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
+EXPORTED = ['ocmp_patch_positions', 'ocmp_profile_bytes', 'ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
             'ocmp_dot', 'ocmp_axpby', 'ocmp_masked_assign', 'ocmp_jacobi_setup', 'ocmp_asm_setup', 'ocmp_asm_apply',
             'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version']
 
@@ -458,9 +459,14 @@ class CudaBackend:
             npatch, bs = pt['npatch'], pt['bs']
             if pt.get('inv') is None:
                 pt['inv'] = self.torch.empty(npatch * bs * bs, dtype=self.torch.float64, device=self.device)
+            if pt.get('pos') is None and bs <= 160:
+                npad = 16 * ((bs + 15) // 16)
+                pt['pos'] = self.torch.empty(npatch * npad * npad, dtype=self.torch.int32, device=self.device)
+                self._ck(self.lib.ocmp_patch_positions(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(),
+                                                       pd['colidx'].data_ptr(), pt['pos'].data_ptr(), st))
             self._ck(self.lib.ocmp_asm_setup(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(),
                                              pd['colidx'].data_ptr(), mat.values.data_ptr(), _ptr(fm),
-                                             pt['inv'].data_ptr(), st))
+                                             pt['inv'].data_ptr(), _ptr(pt.get('pos')), st))
             self.launches += 1
             return _Precond(2, inv=pt['inv'], npatch=npatch, bs=bs, pdofs=pt['dofs'], fm=fm, wgt=pt['wgt'])
         raise NotImplementedError('preconditioner type {}'.format(kind))

@@ -6,7 +6,7 @@ int ocmp_fail(int code, const char* msg);
 int ocmp_check(const char* where);
 int ocmp_sm_count();
 int ocmp_patch_invert_registers(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
-                                const double* fm, double* inv, int* flag_dev, cudaStream_t st);
+                                const double* fm, double* inv, int* flag_dev, const int* pos, cudaStream_t st);
 int ocmp_patch_apply_cta(int npatch, int bs, const int* pd, const double* inv, const double* r, double* z,
                          cudaStream_t st);
 // optional per-category device timing (CUDA events on the launching stream) and launch counting

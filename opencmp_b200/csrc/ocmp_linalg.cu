@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(256) k_asm_setup(int npatch, int bs, const int
 }
 
 extern "C" int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
-                              const double* vals, const double* freemask, double* inv_blocks, void* stream) {
+                              const double* vals, const double* freemask, double* inv_blocks, const int* positions,
+                              void* stream) {
     if (npatch <= 0) return 0;
     const size_t smem = sizeof(double) * ((size_t)bs * bs + bs) + sizeof(int) * bs;
     if (smem > 220 * 1024) return ocmp_fail(-3, "patch too large for shared memory");
@@ -370,8 +371,8 @@ extern "C" int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const i
         if (!flag_dev) cudaMalloc(&flag_dev, sizeof(int));
         cudaStream_t st = (cudaStream_t)stream;
         cudaMemsetAsync(flag_dev, 0, sizeof(int), st);
-        if (ocmp_patch_invert_registers(npatch, bs, patch_dofs, rowptr, colidx, vals, freemask, inv_blocks, flag_dev,
-                                        st)) {
+        if (positions && ocmp_patch_invert_registers(npatch, bs, patch_dofs, rowptr, colidx, vals, freemask, inv_blocks,
+                                                     flag_dev, positions, st)) {
             int flag = 0;
             cudaMemcpyAsync(&flag, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
             cudaStreamSynchronize(st);

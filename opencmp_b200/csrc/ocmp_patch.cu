@@ -22,46 +22,44 @@ __global__ void __launch_bounds__(256, 1) k_patch_invert(int npatch, int bs, con
                                                          const int* __restrict__ colidx,
                                                          const double* __restrict__ vals,
                                                          const double* __restrict__ fm, double* __restrict__ inv,
-                                                         int* __restrict__ flag) {
+                                                         int* __restrict__ flag, const int* __restrict__ pos) {
     constexpr int NP = 16 * T;
     __shared__ double rowk[2][NP];
     __shared__ double colk[2][NP];
+    __shared__ double pivr[2];            // reciprocal of the pivot, computed once by its owner
     __shared__ int sd[NP];
     __shared__ unsigned char sfree[NP];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     for (int p = blockIdx.x; p < npatch; p += gridDim.x) {
         __syncthreads();
-        for (int i = threadIdx.x; i < NP; i += 256) {
+        int mine = 0;
+        if (threadIdx.x < NP) {                   // NP <= 160 < 256: one entry per thread
+            const int i = threadIdx.x;
             const int d = i < bs ? __ldg(pdofs + (long long)p * bs + i) : -1;
             sd[i] = d;
             sfree[i] = (d >= 0 && (!fm || __ldg(fm + d) > 0.0)) ? 1 : 0;
+            mine = d >= 0;
         }
-        __syncthreads();
+        const int nvalid = __syncthreads_count(mine);   // padding (-1) sits at the end of the sorted dof list
+        // gather through the cached patch -> nnz positions (built once per pattern by k_patch_positions): T*T
+        // independent loads per thread, fully pipelined
         double M[T][T];
+        {
+            const int* pp = pos + (long long)p * NP * NP;
+            int q[T][T];
 #pragma unroll
-        for (int a = 0; a < T; ++a) {
-            const int i = ty + 16 * a;
-            const int di = sd[i];
-            const bool fi = sfree[i];
-            int lo0 = 0, hi0 = -1;
-            if (fi) { lo0 = __ldg(rowptr + di); hi0 = __ldg(rowptr + di + 1) - 1; }
+            for (int a = 0; a < T; ++a)
 #pragma unroll
-            for (int b = 0; b < T; ++b) {
-                const int j = tx + 16 * b;
-                double v = (i == j) ? 1.0 : 0.0;
-                if (fi && sfree[j]) {
-                    const int dj = sd[j];
-                    v = 0.0;
-                    int lo = lo0, hi = hi0;
-                    while (lo <= hi) {
-                        const int mid = (lo + hi) >> 1;
-                        const int c = __ldg(colidx + mid);
-                        if (c == dj) { v = __ldg(vals + mid); break; }
-                        if (c < dj) lo = mid + 1; else hi = mid - 1;
-                    }
+                for (int b = 0; b < T; ++b) q[a][b] = __ldg(pp + (ty + 16 * a) * NP + tx + 16 * b);
+#pragma unroll
+            for (int a = 0; a < T; ++a)
+#pragma unroll
+                for (int b = 0; b < T; ++b) {
+                    const int i = ty + 16 * a, j = tx + 16 * b;
+                    double v = (i == j) ? 1.0 : 0.0;
+                    if (sfree[i] && sfree[j]) v = q[a][b] >= 0 ? __ldg(vals + q[a][b]) : 0.0;
+                    M[a][b] = v;
                 }
-                M[a][b] = v;
-            }
         }
         bool bad = false;
 #pragma unroll
@@ -76,11 +74,14 @@ __global__ void __launch_bounds__(256, 1) k_patch_invert(int npatch, int bs, con
                 if (tx == kr) {
 #pragma unroll
                     for (int a = 0; a < T; ++a) colk[buf][ty + 16 * a] = M[a][ka];
+                    if (ty == kr) {
+                        const double d = M[ka][ka];
+                        if (!(fabs(d) > 1e-280)) bad = true;
+                        pivr[buf] = 1.0 / d;
+                    }
                 }
                 __syncthreads();
-                const double d = rowk[buf][k];
-                if (!(fabs(d) > 1e-280)) bad = true;
-                const double ip = 1.0 / d;
+                const double ip = pivr[buf];
                 double ci[T], rj[T];
 #pragma unroll
                 for (int a = 0; a < T; ++a) ci[a] = colk[buf][ty + 16 * a] * ip;
@@ -120,69 +121,147 @@ __global__ void __launch_bounds__(256, 1) k_patch_invert(int npatch, int bs, con
 
 template <int T>
 static void launch_invert(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
-                          const double* fm, double* inv, int* flag, cudaStream_t st) {
+                          const double* fm, double* inv, int* flag, const int* pos, cudaStream_t st) {
     const int cap = ocmp_sm_count();
-    k_patch_invert<T><<<npatch < cap ? npatch : cap, 256, 0, st>>>(npatch, bs, pd, rp, ci, vals, fm, inv, flag);
+    k_patch_invert<T><<<npatch < cap ? npatch : cap, 256, 0, st>>>(npatch, bs, pd, rp, ci, vals, fm, inv, flag, pos);
 }
 
 // returns 1 if handled (flag_dev is set to 1 on a vanishing pivot), 0 if the patch is too large for this kernel
+// positions of the (16T x 16T padded) patch entries in the CSR value array, -1 where the pair is not in the pattern
+__global__ void __launch_bounds__(256) k_patch_positions(int npatch, int bs, int NP, const int* __restrict__ pdofs,
+                                                         const int* __restrict__ rowptr,
+                                                         const int* __restrict__ colidx, int* __restrict__ pos) {
+    const long long total = (long long)npatch * NP * NP;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(idx / (NP * NP)), rem = (int)(idx % (NP * NP)), i = rem / NP, j = rem % NP;
+        int out = -1;
+        if (i < bs && j < bs) {
+            const int di = __ldg(pdofs + (long long)p * bs + i), dj = __ldg(pdofs + (long long)p * bs + j);
+            if (di >= 0 && dj >= 0) {
+                int lo = __ldg(rowptr + di), hi = __ldg(rowptr + di + 1) - 1;
+                while (lo <= hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int c = __ldg(colidx + mid);
+                    if (c == dj) { out = mid; break; }
+                    if (c < dj) lo = mid + 1; else hi = mid - 1;
+                }
+            }
+        }
+        pos[idx] = out;
+    }
+}
+
+extern "C" int ocmp_patch_positions(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
+                                    int* pos, void* stream) {
+    const int NP = 16 * ((bs + 15) / 16);
+    const long long total = (long long)npatch * NP * NP;
+    if (total <= 0) return 0;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)ocmp_sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    k_patch_positions<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(npatch, bs, NP, patch_dofs, rowptr, colidx, pos);
+    return ocmp_check("ocmp_patch_positions");
+}
+
 int ocmp_patch_invert_registers(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
-                                const double* fm, double* inv, int* flag_dev, cudaStream_t st) {
+                                const double* fm, double* inv, int* flag_dev, const int* pos, cudaStream_t st) {
     const int T = (bs + 15) / 16;
     switch (T) {
-        case 1: launch_invert<1>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, st); return 1;
-        case 2: launch_invert<2>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, st); return 1;
-        case 3: launch_invert<3>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, st); return 1;
-        case 4: launch_invert<4>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, st); return 1;
-        case 5: launch_invert<5>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, st); return 1;
-        case 6: launch_invert<6>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, st); return 1;
-        case 7: launch_invert<7>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, st); return 1;
-        case 8: launch_invert<8>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, st); return 1;
-        case 9: launch_invert<9>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, st); return 1;
-        case 10: launch_invert<10>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, st); return 1;
+        case 1: launch_invert<1>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 2: launch_invert<2>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 3: launch_invert<3>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 4: launch_invert<4>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 5: launch_invert<5>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 6: launch_invert<6>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 7: launch_invert<7>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 8: launch_invert<8>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 9: launch_invert<9>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 10: launch_invert<10>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
         default: return 0;
     }
 }
 
 // ---- application ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_patch_apply(int npatch, int bs, const int* __restrict__ pdofs,
+// One CTA per patch. Columns of the (transposed-stored) inverse are dealt round-robin to the 8 warps; within a column
+// every lane owns the row pairs (2*lane, 2*lane+1) + 64*m and streams them with 16-byte loads, two columns per
+// iteration, so a warp keeps up to 2*MR independent 512-byte requests in flight.
+template <int MR, int NW>
+__global__ void __launch_bounds__(NW * 32) k_patch_apply(int npatch, int bs, const int* __restrict__ pdofs,
                                                      const double* __restrict__ inv, const double* __restrict__ r,
                                                      double* __restrict__ z) {
-    extern __shared__ double sm[];         // r_loc[bs], partial[8][bs]
+    extern __shared__ double sm[];         // r_loc[bs], partial[NW][bs]
     double* rl = sm;
     double* part = sm + bs;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool even = (bs & 1) == 0;
     for (int p = blockIdx.x; p < npatch; p += gridDim.x) {
         const int* d = pdofs + (long long)p * bs;
         __syncthreads();
-        for (int j = threadIdx.x; j < bs; j += 256) {
+        for (int j = threadIdx.x; j < bs; j += NW * 32) {
             const int dj = __ldg(d + j);
             rl[j] = dj >= 0 ? __ldg(r + dj) : 0.0;
         }
         __syncthreads();
         const double* A = inv + (long long)p * bs * bs;
-        double s[8];
+        double s0[MR], s1[MR];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) s[m] = 0.0;
-        for (int j = warp; j < bs; j += 8) {
-            const double rj = rl[j];
-            const double* col = A + (long long)j * bs;
+        for (int m = 0; m < MR; ++m) { s0[m] = 0.0; s1[m] = 0.0; }
+        if (even) {
+            int j = warp;
+            for (; j + NW < bs; j += 2 * NW) {
+                const double ra = rl[j], rb = rl[j + NW];
+                const double2* ca = reinterpret_cast<const double2*>(A + (long long)j * bs);
+                const double2* cb = reinterpret_cast<const double2*>(A + (long long)(j + NW) * bs);
+                double2 va[MR], vb[MR];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int i = lane + 32 * m;
-                if (i < bs) s[m] = fma(__ldg(col + i), rj, s[m]);
+                for (int m = 0; m < MR; ++m) {
+                    const int i2 = lane + 32 * m;
+                    const bool ok = 2 * i2 < bs;
+                    va[m] = ok ? __ldg(ca + i2) : make_double2(0.0, 0.0);
+                    vb[m] = ok ? __ldg(cb + i2) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    s0[m] = fma(va[m].x, ra, s0[m]); s1[m] = fma(va[m].y, ra, s1[m]);
+                    s0[m] = fma(vb[m].x, rb, s0[m]); s1[m] = fma(vb[m].y, rb, s1[m]);
+                }
+            }
+            for (; j < bs; j += NW) {
+                const double ra = rl[j];
+                const double2* ca = reinterpret_cast<const double2*>(A + (long long)j * bs);
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    const int i2 = lane + 32 * m;
+                    if (2 * i2 < bs) {
+                        const double2 v = __ldg(ca + i2);
+                        s0[m] = fma(v.x, ra, s0[m]); s1[m] = fma(v.y, ra, s1[m]);
+                    }
+                }
+            }
+        } else {
+            for (int j = warp; j < bs; j += NW) {
+                const double ra = rl[j];
+                const double* ca = A + (long long)j * bs;
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    const int i = 2 * (lane + 32 * m);
+                    if (i < bs) s0[m] = fma(__ldg(ca + i), ra, s0[m]);
+                    if (i + 1 < bs) s1[m] = fma(__ldg(ca + i + 1), ra, s1[m]);
+                }
             }
         }
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int i = lane + 32 * m;
-            if (i < bs) part[warp * bs + i] = s[m];
+        for (int m = 0; m < MR; ++m) {
+            const int i = 2 * (lane + 32 * m);
+            if (i < bs) part[warp * bs + i] = s0[m];
+            if (i + 1 < bs) part[warp * bs + i + 1] = s1[m];
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < bs; i += 256) {
+        for (int i = threadIdx.x; i < bs; i += NW * 32) {
             double t = 0.0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) t += part[w * bs + i];
+            for (int w = 0; w < NW; ++w) t += part[w * bs + i];
             const int di = __ldg(d + i);
             if (di >= 0) atomicAdd(z + di, t);
         }
@@ -192,8 +271,13 @@ __global__ void __launch_bounds__(256) k_patch_apply(int npatch, int bs, const i
 int ocmp_patch_apply_cta(int npatch, int bs, const int* pd, const double* inv, const double* r, double* z,
                          cudaStream_t st) {
     if (bs > 256) return 0;
-    const size_t smem = sizeof(double) * 9 * bs;
-    const int cap = ocmp_sm_count() * 8;
-    k_patch_apply<<<npatch < cap ? npatch : cap, 256, smem, st>>>(npatch, bs, pd, inv, r, z);
+    constexpr int NW = 4;
+    const size_t smem = sizeof(double) * (NW + 1) * bs;
+    const int cap = ocmp_sm_count() * 16;
+    const int grid = npatch < cap ? npatch : cap;
+    if (bs <= 64) k_patch_apply<1, NW><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
+    else if (bs <= 128) k_patch_apply<2, NW><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
+    else if (bs <= 192) k_patch_apply<3, NW><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
+    else k_patch_apply<4, NW><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
     return 1;
 }
