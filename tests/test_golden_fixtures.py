@@ -1,0 +1,61 @@
+"""Golden fixtures produced by the UNMODIFIED reference package (tests/golden/make_golden.py: reference model and
+solver code -> opencmp_b200 front end -> oracle). They pin
+  * the restated weak forms of tests/cases.py to the reference's own forms (CPU, oracle backend), and
+  * the CUDA path to the reference's numbers at the tolerances of the north star (GPU).
+The recorded error norms coincide with the values the reference asserts in
+pytests/full_system/stokes/test_stokes.py:37,45 ([1e-10, 6e-12, 3e-11, 2e-12, ...])."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from opencmp_b200.mesh import Mesh
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _load(name):
+    z = np.load(os.path.join(HERE, name + '.npz'))
+    mesh = Mesh(2, 'tri', z['points'], z['cells'], z['bnd_facets'], z['bnd_region'], [str(s) for s in z['bnd_names']])
+    errs = dict(zip([str(s) for s in z['err_names']], z['err_vals']))
+    return mesh, z['vec'], errs
+
+
+def _solve(mesh, DG):
+    c = cases.stokes(mesh, 3, DG)
+    ngs = c['ngs']
+    c['gfu'].components[0].Set(c['uex'], definedon=c['mesh'].Boundaries(c['walls']))
+    c['a'].Assemble()
+    c['L'].Assemble()
+    sol = cases.direct_solve(c)
+    u = c['gfu'].components[0]
+    err = np.sqrt(ngs.Integrate(ngs.InnerProduct(u - c['uex'], u - c['uex']), c['mesh']))
+    return sol, err
+
+
+@pytest.mark.parametrize('name,DG', [('stokes_pipe_cg', False), ('stokes_pipe_dg', True)])
+def test_reference_error_norms_match_recorded_values(name, DG):
+    _, _, errs = _load(name)
+    expected = {'l2 norm in u': 1e-10, 'l2 norm in p': 6e-12, 'l1 norm in u': 3e-11, 'l1 norm in p': 2e-12,
+                'linfinity norm in p': 2e-11, 'divergence of u': 3e-10}
+    for k, e in expected.items():
+        assert np.isclose(errs[k], e, rtol=3, atol=1e-12), (k, errs[k], e)     # reference helpers/testing.py:82
+
+
+@pytest.mark.parametrize('name,DG', [('stokes_pipe_cg', False), ('stokes_pipe_dg', True)])
+def test_oracle_with_restated_forms_reproduces_reference_solution(oracle_backend, name, DG):
+    mesh, vec, errs = _load(name)
+    sol, err = _solve(mesh, DG)
+    assert sol.shape == vec.shape
+    assert np.abs(sol - vec).max() < 1e-9 * np.abs(vec).max()
+    assert np.isclose(err, errs['l2 norm in u'], rtol=0.5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,DG', [('stokes_pipe_cg', False), ('stokes_pipe_dg', True)])
+def test_gpu_reproduces_reference_solution(cuda_backend, name, DG):
+    mesh, vec, errs = _load(name)
+    sol, err = _solve(mesh, DG)
+    assert np.abs(sol - vec).max() < 1e-9 * np.abs(vec).max()
+    assert err < 4e-10
