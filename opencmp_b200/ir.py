@@ -33,7 +33,7 @@ BINARY = {'add': 'ADD', 'sub': 'SUB', 'mul': 'MUL', 'div': 'DIV', 'pow': 'POW', 
 MAX_REGS = 48
 
 _PY_UNARY = {'neg': lambda a: -a, 'abs': abs, 'sqrt': math.sqrt, 'sin': math.sin, 'cos': math.cos, 'tan': math.tan,
-             'exp': math.exp, 'log': math.log, 'tanh': math.tanh, 'erf': math.erf, 'floor': math.floor,
+             'exp': lambda a: math.exp(a) if a < 709.0 else float('inf'), 'log': math.log, 'tanh': math.tanh, 'erf': math.erf, 'floor': math.floor,
              'ceil': math.ceil, 'round': lambda a: float(np.round(a)), 'trunc': math.trunc,
              'sgn': lambda a: float((a > 0) - (a < 0)), 'atan': math.atan}
 _PY_BINARY = {'add': lambda a, b: a + b, 'sub': lambda a, b: a - b, 'mul': lambda a, b: a * b,

@@ -66,6 +66,20 @@ class Mesh(_Mesh):
     def ngmesh(self):
         return self
 
+    @property
+    def nface(self):
+        return self.ne if self.dim == 2 else self.nf
+
+    @property
+    def nfacet(self):
+        return self.nf
+
+    def GetCurveOrder(self):
+        return getattr(self, '_curve_order', 1)
+
+    def Curve(self, order):
+        self._curve_order = int(order)       # straight-sided cells: nothing to project onto (see mesh.Mesh.Curve)
+
     def __call__(self, *pt):
         return MeshPoint(self, pt)
 
@@ -73,6 +87,80 @@ class Mesh(_Mesh):
 class MeshPoint:
     def __init__(self, mesh, pt):
         self.mesh, self.pt = mesh, tuple(float(v) for v in pt)
+        self._loc = None
+
+    def locate(self):
+        """(cell, reference coordinates) of the point; brute force over the affine cells."""
+        if self._loc is None:
+            m = self.mesh
+            x = np.zeros(m.dim)
+            x[:len(self.pt[:m.dim])] = self.pt[:m.dim]
+            xi = np.einsum('eab,eb->ea', np.linalg.inv(m.jacobians()), x[None, :] - m.origins())
+            if m.cell_type in ('tri', 'tet'):
+                inside = np.minimum(xi.min(axis=1), 1.0 - xi.sum(axis=1))
+            else:
+                inside = np.minimum(xi.min(axis=1), (1.0 - xi).min(axis=1))
+            c = int(np.argmax(inside))
+            if inside[c] < -1e-10:
+                raise ValueError('point {} lies outside the mesh'.format(self.pt))
+            self._loc = (c, xi[c])
+        return self._loc
+
+
+def evaluate_at_point(cf, mip):
+    """Evaluate a coefficient function (constants, coordinates, parameters, functions, GridFunctions) at a MeshPoint."""
+    import math
+    from .ir import _PY_UNARY, _PY_BINARY
+    mesh = mip.mesh
+    cache = {}
+
+    def field(gf, blk, row):
+        c, xi = mip.locate()
+        fes = gf.space
+        b = fes.blocks[blk]
+        tab = b.basis.tabulate(xi[None, :])[0]                      # (nrows, nloc)
+        coef = np.asarray(gf.vec_numpy())[fes.cell_dofs[c, fes.loc_offsets[blk]:fes.loc_offsets[blk] + b.nloc]]
+        ref = tab @ coef
+        J = mesh.jacobians()[c]
+        Ji = np.linalg.inv(J)
+        d = mesh.dim
+        if b.kind == 'scalar':
+            phys = np.concatenate([[ref[0]], Ji.T @ ref[1:]])
+        else:
+            det = np.linalg.det(J)
+            val = J @ ref[:d] / det
+            g = J @ ref[d:].reshape(d, d) @ Ji / det
+            phys = np.concatenate([val, g.reshape(-1)])
+        return float(phys[row])
+
+    def ev(c):
+        if id(c) in cache:
+            return cache[id(c)]
+        if c.op == 'const':
+            v = c.val
+        elif c.op == 'param':
+            v = c.val.Get()
+        elif c.op == 'coord':
+            v = mip.pt[c.val] if c.val < len(mip.pt) else 0.0
+        elif c.op == 'field':
+            v = field(c.val[0], c.val[1], c.val[2])
+        elif c.op == 'ifpos':
+            v = ev(c.args[1]) if ev(c.args[0]) > 0 else ev(c.args[2])
+        elif c.op in _PY_UNARY:
+            v = _PY_UNARY[c.op](ev(c.args[0]))
+        elif c.op in _PY_BINARY:
+            v = _PY_BINARY[c.op](ev(c.args[0]), ev(c.args[1]))
+        elif c.op == 'piecewise':
+            v = ev(c.val[1][0])
+        else:
+            raise NotImplementedError('point evaluation of {}'.format(c.op))
+        cache[id(c)] = v
+        return v
+
+    vals = [ev(s.as_coef()) for s in cf.arr.reshape(-1)]
+    if cf.arr.ndim == 0:
+        return vals[0]
+    return tuple(vals)
 
 
 # ---- spaces ------------------------------------------------------------------------------------------------------------
@@ -240,13 +328,22 @@ class GridFunction(CoefficientFunction):
             self.vec = BaseVector(get_backend().zeros(n))
 
     def Save(self, filename, parallel=False):
-        np.save(_sol_path(filename), self.vec.NumPy())
+        """DOF dump under exactly the given name (``<model>_<time>.sol``, reference helpers/saving.py:74-93). The
+        payload is a NumPy array in OUR DOF order — not interchangeable with NGSolve's binary .sol files."""
+        with open(str(filename), 'wb') as fh:
+            np.save(fh, np.asarray(self.vec.NumPy()))
 
     def Load(self, filename, parallel=False):
-        self.vec.data = BaseVector(get_backend().from_numpy(np.load(_sol_path(filename))))
+        with open(str(filename), 'rb') as fh:
+            data = np.load(fh)
+        if data.shape[0] != len(self.vec):
+            raise ValueError('checkpoint {} holds {} DOFs, the GridFunction has {}'.format(filename, data.shape[0],
+                                                                                          len(self.vec)))
+        self.vec.data = BaseVector(get_backend().from_numpy(data))
 
-    def __call__(self, *a, **k):
-        raise NotImplementedError('point evaluation of a GridFunction')
+    def __call__(self, mip, *a, **k):
+        """Point evaluation ``gfu(mesh(x, y))`` (controllers / unit tests; host side, not on the hot path)."""
+        return evaluate_at_point(self, mip)
 
 
 def _sol_path(fn):

@@ -322,6 +322,11 @@ class CoefficientFunction:
                     kinds.add('test-function')
         return 'coef {} dims={}'.format(' '.join(sorted(kinds)) or 'function', self.dims)
 
+    def __call__(self, mip, *a, **k):
+        """``cf(mesh(x, y))`` point evaluation (reference pytests/helpers/test_math.py:44-72)."""
+        from .ngs import evaluate_at_point
+        return evaluate_at_point(self, mip)
+
     def map_coef(self, fn) -> 'CoefficientFunction':
         out = _obj(self.arr.shape)
         for idx in (np.ndindex(*self.arr.shape) if self.arr.shape else [()]):
