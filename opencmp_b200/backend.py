@@ -500,6 +500,12 @@ class CudaBackend:
             bs = int((big < np.iinfo(np.int32).max).sum(axis=1).max())
             dofs = big[:, :bs].copy()
             dofs[dofs == np.iinfo(np.int32).max] = -1
+        if dofs.shape[1] > 160 and kind != 'cell':
+            # vertex stars of irregular meshes can exceed what the register-tiled inversion holds (bs <= 160):
+            # fall back to cell patches for this space
+            out = self._patches(fes, 'cell')
+            sd[key] = out
+            return out
         dofs = np.ascontiguousarray(dofs, dtype=np.int32)
         mult = np.bincount(dofs[dofs >= 0].ravel(), minlength=fes.ndof).astype(np.float64)
         out = dict(npatch=dofs.shape[0], bs=dofs.shape[1], dofs=self._up(dofs),
@@ -564,4 +570,7 @@ class CudaBackend:
         p = _P()
         p.state = state
         out.zero_()
-        self.krylov('gmres', mat, r, out, p, free, 1e-13, 4000, False, False, restart=100)
+        # two passes: the second restarts from the first answer with a fresh residual (iterative refinement), which
+        # brings the result to the round-off level a sparse direct solver with refinement reaches
+        for _ in range(2):
+            self.krylov('gmres', mat, r, out, p, free, 1e-13, 4000, False, False, restart=100)

@@ -534,7 +534,8 @@ def delaunay_rectangle(n: int, seed: int = 0, size: Sequence[float] = (1.0, 1.0)
     pts = np.concatenate([bnd, inner]) * np.array([lx, ly])
     tri = Delaunay(pts).simplices
     P = pts[tri]
-    area = 0.5 * np.abs(np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]))
+    e1, e2 = P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]
+    area = 0.5 * np.abs(e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0])
     tri = tri[area > 1e-12 * lx * ly]
     tmp = Mesh(2, 'tri', pts, tri, np.zeros((0, 2), np.int64), np.zeros(0, np.int32), list(names))
     bf = tmp.facets[tmp.bnd_facets].astype(np.int64)

@@ -72,6 +72,10 @@ def main():
         'stokes_pipe_dg': ('pytests/full_system/stokes/stationary_pipe/config',
                            {('DG', 'DG'): 'True', ('FINITE ELEMENT SPACE', 'elements'): 'u -> HDiv\np -> L2'}),
         'stokes_pipe_cg': ('pytests/full_system/stokes/stationary_pipe/config', {}),
+        # pytests/full_system/ins/test_ins.py:79-87 (Oseen, implicit Euler, HDiv-DG), shortened to three time steps
+        'ins_sinusoidal_dg_3steps': ('pytests/full_system/ins/sinusoidal_transient/config',
+                                     {('DG', 'DG'): 'True', ('FINITE ELEMENT SPACE', 'elements'): 'u -> HDiv\np -> L2',
+                                      ('TRANSIENT', 'time_range'): '0.0, 0.003'}),
     }
     for name, (cfg, ov) in cases.items():
         solver, sol, errs = run_reference(cfg, ov)

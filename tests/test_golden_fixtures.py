@@ -59,3 +59,40 @@ def test_gpu_reproduces_reference_solution(cuda_backend, name, DG):
     sol, err = _solve(mesh, DG)
     assert np.abs(sol - vec).max() < 1e-9 * np.abs(vec).max()
     assert err < 4e-10
+
+
+def _ins_steps(mesh):
+    """examples/INS / pytests sinusoidal_transient restated (opencmp_b200/workloads.py), three implicit-Euler steps."""
+    from opencmp_b200.workloads import INSTaylorGreen
+    w = INSTaylorGreen(0, order=3, dt=1e-3, nu=1.0, ipc=10.0, linear_solver='direct', preconditioner=None,
+                       nonlinear_max_iterations=20, nonlinear_tolerance=(1e-4, 1e-8), mesh=mesh)
+    for _ in range(3):
+        w.step()
+    return w.gfu.vec.NumPy().copy(), w.errors()
+
+
+def _compare_ins(sol, vec):
+    # velocity block is determined uniquely; the pressure (all-Dirichlet velocity data, -1e-10 p q regularisation)
+    # only up to its mean, so compare the pressure after removing the mean DOF-wise difference of the constants
+    nu = 1308
+    assert np.abs(sol[:nu] - vec[:nu]).max() < 1e-9 * np.abs(vec[:nu]).max()
+    dp = sol[nu:] - vec[nu:]
+    const = dp[0::6]                     # first L2 mode of every cell is the constant
+    assert np.abs(const - const.mean()).max() < 1e-7 * np.abs(vec[nu:]).max()
+    rest = np.delete(dp, np.arange(0, dp.size, 6))
+    assert np.abs(rest).max() < 1e-7 * np.abs(vec[nu:]).max()
+
+
+def test_oracle_ins_workload_reproduces_reference_ins_model(oracle_backend):
+    mesh, vec, errs = _load('ins_sinusoidal_dg_3steps')
+    sol, (eu, ep) = _ins_steps(mesh)
+    _compare_ins(sol, vec)
+    assert np.isclose(eu, errs['l2 norm in u'], rtol=1e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_ins_workload_reproduces_reference_ins_model(cuda_backend):
+    mesh, vec, errs = _load('ins_sinusoidal_dg_3steps')
+    sol, (eu, ep) = _ins_steps(mesh)
+    _compare_ins(sol, vec)
+    assert np.isclose(eu, errs['l2 norm in u'], rtol=1e-6)
