@@ -137,3 +137,92 @@ def direct_solve(case, be_numpy=True):
     r.data = L.vec - a.mat * gfu.vec
     gfu.vec.data += inv * r
     return gfu.vec.NumPy().copy()
+
+
+def poisson_dim(mesh, order, DG=False):
+    """Diffuse-interface Poisson: reference opencmp/models/poisson_dim.py:33-160 — every integrand weighted by the
+    phase field phi, Nitsche terms on the diffuse boundary as volume terms with grad(phi), |grad(phi)| and a mask."""
+    ngs = _ngs()
+    m = ngs.Mesh(mesh)
+    fes = ngs.FESpace([ngs.H1(m, order=order, dgjumps=DG)], dgjumps=DG)
+    H = ngs.H1(m, order=order)
+    u, v = fes.TrialFunction()[0], fes.TestFunction()[0]
+    dt = ngs.Parameter(1.0)
+    dc = ngs.CoefficientFunction(0.7)
+    r2 = (ngs.x - 0.5) * (ngs.x - 0.5) + (ngs.y - 0.5) * (ngs.y - 0.5)
+    lam = 0.08
+    phi_cf = 0.5 * (1.0 + ngs.erf((0.3 - ngs.sqrt(r2 + 1e-12)) / lam))
+    phi, mag, mask = ngs.GridFunction(H), ngs.GridFunction(H), ngs.GridFunction(H)
+    phi.Set(phi_cf)
+    mask.Set(ngs.CoefficientFunction(1.0))
+    gphi = ngs.Grad(phi)
+    mag.Set(ngs.sqrt(gphi * gphi + 1e-14))
+    n, h, alpha = dg_funcs(ngs, m, 10.0 * order ** 2)
+    g = ngs.sin(ngs.x) + ngs.y
+    f = ngs.CoefficientFunction(1.0) + ngs.x * ngs.y
+    a = ngs.BilinearForm(fes)
+    a += dt * dc * ngs.InnerProduct(ngs.Grad(u), ngs.Grad(v)) * phi * ngs.dx
+    a += dt * alpha * u * v * (1.0 - phi) * ngs.dx                                  # poisson_dim.py:47
+    a += dt * dc * (ngs.Grad(u) * gphi * v + ngs.Grad(v) * gphi * u + alpha * u * v * mag) * mask * ngs.dx
+    if DG:
+        ju, jv = jump(u), jump(v)
+        a += dt * dc * (-ju * n * grad_avg(ngs, v) - grad_avg(ngs, u) * jv * n + alpha * ju * jv) * phi \
+            * ngs.dx(skeleton=True)
+    L = ngs.LinearForm(fes)
+    L += dt * f * v * phi * ngs.dx
+    L += dt * dc * (ngs.Grad(v) * gphi * g + alpha * g * v * mag) * mask * ngs.dx   # poisson_dim.py:130-136
+    gfu = ngs.GridFunction(fes)
+    return dict(ngs=ngs, mesh=m, fes=fes, a=a, L=L, gfu=gfu, noset=True, keep=(phi, mag, mask))
+
+
+def species(mesh, order, wind):
+    """Multi-component species transport, DG: reference opencmp/models/multi_component_ins.py:158-449 — diffusion SIP,
+    upwinded advection by a velocity field (IfPos max/min), cross-species linear reactions, outflow boundary terms."""
+    ngs = _ngs()
+    m = ngs.Mesh(mesh)
+    V = ngs.HDiv(m, order=order, dgjumps=True)
+    A, B = ngs.L2(m, order=order, dgjumps=True), ngs.L2(m, order=order, dgjumps=True)
+    fes = ngs.FESpace([A, B], dgjumps=True)
+    (ca, cb), (ra, rb) = fes.TrialFunction(), fes.TestFunction()
+    w = ngs.GridFunction(V)
+    w.vec.data = ngs.BaseVector(ngs.get_backend().from_numpy(wind(V.ndof)))
+    dt = ngs.Parameter(0.01)
+    n, h, alpha = dg_funcs(ngs, m, 10.0 * order ** 2)
+    a = ngs.BilinearForm(fes)
+    L = ngs.LinearForm(fes)
+    for c, r, D, k, src in ((ca, ra, 0.1, 0.5, 1.0 + ngs.x), (cb, rb, 0.02, -0.5, ngs.sin(ngs.y))):
+        a += c * r * ngs.dx                                                              # time derivative
+        a += dt * D * ngs.InnerProduct(ngs.Grad(c), ngs.Grad(r)) * ngs.dx              # :223-224
+        a += -dt * c * (w * ngs.Grad(r)) * ngs.dx                                       # :260
+        jc, jr = jump(c), jump(r)
+        a += dt * D * (alpha * jc * jr - grad_avg(ngs, c) * n * jr - grad_avg(ngs, r) * n * jc) * ngs.dx(skeleton=True)
+        wn = w * n
+        a += dt * jr * (c * ngs.IfPos(wn, wn, 0.0) + c.Other() * ngs.IfPos(wn, 0.0, wn)) * ngs.dx(skeleton=True)
+        a += dt * r * c * ngs.IfPos(wn, wn, 0.0) * ngs.ds(skeleton=True)                # :267-275
+        L += dt * src * r * ngs.dx
+    a += -dt * 0.5 * ca * rb * ngs.dx + dt * 0.25 * cb * ra * ngs.dx                    # cross-species reactions :245-256
+    gfu = ngs.GridFunction(fes)
+    return dict(ngs=ngs, mesh=m, fes=fes, a=a, L=L, gfu=gfu, noset=True, keep=(w,))
+
+
+def stokes_3d(cell, order, n=2):
+    """Taylor-Hood Stokes on a structured 3-D box (hex Q2/Q1 is the SURVEY 8(d) 3-D throughput configuration)."""
+    from opencmp_b200.mesh import structured_3d
+    ngs = _ngs()
+    m = ngs.Mesh(structured_3d([n, n, n], cell=cell))
+    V = ngs.VectorH1(m, order=order, dirichlet='back|left|bottom')
+    Q = ngs.H1(m, order=order - 1)
+    fes = ngs.FESpace([V, Q])
+    (u, p), (v, q) = fes.TrialFunction(), fes.TestFunction()
+    W = ngs.GridFunction(V)
+    W.vec.data = ngs.BaseVector(ngs.get_backend().from_numpy(random_wind(V.ndof, 9)))
+    a = ngs.BilinearForm(fes)
+    a += (0.1 * ngs.InnerProduct(ngs.Grad(u), ngs.Grad(v)) - ngs.div(u) * q - ngs.div(v) * p - 1e-10 * p * q) * ngs.dx
+    a += -ngs.InnerProduct(ngs.OuterProduct(u, W), ngs.Grad(v)) * ngs.dx
+    n3 = ngs.specialcf.normal(3)
+    a += v * (ngs.IfPos(W * n3, W * n3, 0.0) * u) * ngs.ds(definedon=m.Boundaries('front|top'))
+    L = ngs.LinearForm(fes)
+    L += v * ngs.CoefficientFunction((ngs.z, ngs.sin(ngs.x), ngs.y * ngs.y)) * ngs.dx
+    L += v * (-2.0 * n3) * ngs.ds(definedon=m.Boundaries('right'))
+    gfu = ngs.GridFunction(fes)
+    return dict(ngs=ngs, mesh=m, fes=fes, a=a, L=L, gfu=gfu, noset=True, keep=(W,))

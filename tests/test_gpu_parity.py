@@ -36,7 +36,9 @@ def _assembled(build):
         c = build()
         ngs = c['ngs']
         g = c['gfu']
-        if 'exact' in c:
+        if c.get('noset'):
+            pass
+        elif 'exact' in c:
             g.components[0].Set(c['exact'], definedon=c['mesh'].Boundaries(c['dnames']))
         else:
             g.components[0].Set(c['uex'], definedon=c['mesh'].Boundaries(c['walls']))
@@ -71,6 +73,11 @@ CASES = {
     'ins_hdiv_dg_p1_oseen': lambda: cases.stokes(cases.channel_mesh(), 1, True, wind=lambda n: cases.random_wind(n),
                                                   dt_val=0.01, mass=True),
     'poisson_quad_q2': lambda: cases.poisson(cases.structured_2d([5, 4], cell='quad'), 2, False),
+    'poisson_dim_h1_p2': lambda: cases.poisson_dim(cases.structured_2d([8, 8], cell='quad'), 2, False),
+    'poisson_dim_h1_p2_dg_tri': lambda: cases.poisson_dim(cases.square_mesh(6), 2, True),
+    'species_dg_p2': lambda: cases.species(cases.square_mesh(5), 2, lambda n: cases.random_wind(n, 11)),
+    'stokes_3d_hex_q2q1': lambda: cases.stokes_3d('hex', 2),
+    'stokes_3d_tet_p2p1': lambda: cases.stokes_3d('tet', 2),
 }
 
 
