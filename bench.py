@@ -35,6 +35,7 @@ def parse():
     ap.add_argument('--order', type=int, default=3)
     ap.add_argument('--cpu-N', type=int, default=20, help='mesh size of the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--dist-n', type=int, default=512, help='cells per direction and rank of the distributed leg')
     return ap.parse_args()
 
 
@@ -131,7 +132,8 @@ def workload_config(args, where):
             'N': args.N, 'order': args.order, 'linear_solver': 'GMRES(100) + geometric multigrid V(2,2), vertex-patch additive Schwarz smoother, tol 1e-10'
             if where == 'gpu' else 'direct (SuperLU)', 'nonlinear_max_iterations': 3,
             'l2': 'inputs larger than L2 (CSR matrix ~0.8 GB at N=128); no explicit flush',
-            'parallelism': 'replicas' if args.gpus > 1 else 'single'}
+            'parallelism': ('replicas of the INS step (one full problem per GPU) + element-partitioned Poisson leg '
+                            'reported under multi_gpu') if args.gpus > 1 else 'single'}
 
 
 def main():
@@ -209,6 +211,22 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     eu, ep = w.errors()
+    # ---- element-partitioned leg (N > 1): halo-exchange SpMV + all-reduced Jacobi-CG on a distributed Poisson problem
+    multi = None
+    if world > 1:
+        from opencmp_b200.dist_workload import DistributedPoisson
+        dp = DistributedPoisson(args.dist_n, 2, world, rank)
+        sp_ms = dp.time_spmv()
+        its, res, sec_cg, _ = dp.solve(maxit=100)
+        tt = torch.tensor([sp_ms, sec_cg / max(1, its) * 1e3], dtype=torch.float64, device='cuda')
+        bb = torch.tensor([float(dp.spmv_bytes_owned())], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(bb)
+        multi = {'workload': 'Poisson H1 order 2, structured {0}x{1}x2 triangles, one cell block per rank, one ghost '
+                             'layer'.format(args.dist_n, args.dist_n * world),
+                 'global_dofs': dp.nglobal, 'spmv_ms_max_over_ranks': float(tt[0]),
+                 'spmv_gbs_aggregate': float(bb[0]) / float(tt[0]) / 1e6, 'cg_ms_per_iteration': float(tt[1]),
+                 'collectives': 'halo exchange: batched isend/irecv (NCCL); dot products: all_reduce'}
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -263,6 +281,8 @@ def main():
                 'd2h_bytes_per_step': int(8 * ndof)},
         'gpu_launches': launches, 'clocks': clocks,
     }
+    if multi is not None:
+        line['multi_gpu'] = multi
     if not args.no_cpu and world == 1:
         try:
             per, cne, cnd, _ = cpu_step_seconds(args.cpu_N, args.order)
