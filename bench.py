@@ -129,7 +129,7 @@ def workload_config(args, where):
     return {'workload': 'INS Taylor-Green 2D, structured {0}x{0}x2 triangles on [0,pi]^2, HDiv-DG order {1} / L2 order {2}, '
                         'Oseen + implicit Euler, dt=1e-3, nu=1 (examples/INS scaled up)'.format(args.N, args.order,
                                                                                                args.order - 1),
-            'N': args.N, 'order': args.order, 'linear_solver': 'GMRES(100) + geometric multigrid V(2,2), vertex-patch additive Schwarz smoother, tol 1e-10'
+            'N': args.N, 'order': args.order, 'linear_solver': 'GMRES(100) + geometric multigrid V(1,1), vertex-patch additive Schwarz smoother (damping 0.7), tol 1e-10'
             if where == 'gpu' else 'direct (SuperLU)', 'nonlinear_max_iterations': 3,
             'l2': 'inputs larger than L2 (CSR matrix ~0.8 GB at N=128); no explicit flush',
             'parallelism': ('replicas of the INS step (one full problem per GPU) + element-partitioned Poisson leg '

@@ -442,7 +442,7 @@ class CudaBackend:
         if kind == 'multigrid':
             from .multigrid import MultigridState
             if state is None or getattr(state, 'kind', 0) != 3:
-                state = MultigridState(self, form, nu=int(os.environ.get('OCMP_MG_NU', '2')),
+                state = MultigridState(self, form, nu=int(os.environ.get('OCMP_MG_NU', '1')),
                                        omega=float(os.environ.get('OCMP_MG_OMEGA', '0.7')))
             return state.update(mat)
         if kind in ('local', 'jacobi'):
