@@ -84,6 +84,48 @@ def main():
                             err_names=np.array(list(errs.keys())), err_vals=np.array(list(errs.values())),
                             **mesh_arrays(m))
         print(name, len(sol.vec), errs)
+    # ---- lowered form programs of the reference's own model classes (replayed by tests/test_golden_programs.py) ---
+    from opencmp_b200.serialize import dump
+    from oracle import fem
+    dg_ins = {('DG', 'DG'): 'True', ('FINITE ELEMENT SPACE', 'elements'): 'u -> HDiv\np -> L2'}
+    short = {('TRANSIENT', 'time_range'): '0.0, 0.002'}
+    prog_cases = {
+        # INS (models/ins.py) — Oseen + Crank-Nicolson: Stokes terms, Oseen convection, DG facet upwinding, and the
+        # "bilinear form applied to a known field" right-hand side of time_integration_schemes.py:135-190
+        'prog_ins_dg_oseen_cn': ('pytests/full_system/ins/sinusoidal_transient/config',
+                                 {**dg_ins, **short, ('TRANSIENT', 'scheme'): 'crank nicolson'}),
+        # INS IMEX / CNLF (ins.py:300-321 explicit convection, schemes :249-304), Taylor-Hood CG
+        'prog_ins_cg_imex_cnlf': ('pytests/full_system/ins/sinusoidal_transient/config',
+                                  {**short, ('SOLVER', 'linearization_method'): 'IMEX', ('TRANSIENT', 'scheme'): 'CNLF',
+                                   ('TRANSIENT', 'time_range'): '0.0, 0.004'}),
+        # MultiComponentINS (models/multi_component_ins.py): HDiv-DG velocity + two L2 species, diffusion-convection
+        'prog_mcins_dg_diffusion_convection': ('pytests/full_system/mcins/diffusion_convection/config',
+                                               {('DG', 'DG'): 'True', ('FINITE ELEMENT SPACE', 'elements'):
+                                                'u -> HDiv\np -> L2\na -> L2\nb -> L2', **short}),
+        # MultiComponentINS CG with coupled first-order reactions (trial functions inside source terms, :245-256)
+        'prog_mcins_cg_1st_rxn_coupled': ('pytests/full_system/mcins/1st_rxn_coupled/config', dict(short)),
+        # Poisson DG transient (models/poisson.py:71-158 incl. interior-facet SIP and Nitsche boundary terms)
+        'prog_poisson_dg_transient': ('pytests/full_system/poisson/transient_coarse/config',
+                                      {('DG', 'DG'): 'True', **short}),
+        # stationary INS in a pipe, stress boundary conditions, Oseen + Anderson mixing (ins.py:208-223)
+        'prog_ins_cg_stationary_stress': ('pytests/full_system/ins/pressure_flow_in_pipe_stress/config', {}),
+    }
+    rng = np.random.default_rng(7)
+    for name, (cfg, ov) in prog_cases.items():
+        try:
+            solver, sol, errs = run_reference(cfg, ov)
+        except SystemExit:
+            pass
+        a, L = solver.a[0], solver.L[0]
+        a.Assemble()
+        L.Assemble()
+        A = fem.csr_matrix(a.space, a.mat.values)
+        X = rng.uniform(-1.0, 1.0, (3, a.space.ndof))
+        Y = np.stack([A @ x for x in X])
+        dump(os.path.join(here, name + '.npz'), {'a': a.program(), 'L': L.program()},
+             dict(X=X, Y=Y, rhs=np.asarray(L.vec.NumPy()), diag=A.diagonal(), absmax=np.abs(a.mat.values).max()))
+        print(name, a.space.ndof, A.nnz, [i.kind for i in a.program().integrals], os.path.getsize(
+            os.path.join(here, name + '.npz')))
     shutil.rmtree(work, ignore_errors=True)
 
 
