@@ -471,9 +471,11 @@ class CudaBackend:
             return _Precond(2, inv=pt['inv'], npatch=npatch, bs=bs, pdofs=pt['dofs'], fm=fm, wgt=pt['wgt'])
         raise NotImplementedError('preconditioner type {}'.format(kind))
 
-    def _patches(self, fes, kind: str) -> dict:
+    def _patches(self, fes, kind: str, vmask=None) -> dict:
+        """vmask: optional boolean mask over the mesh vertices — keep only the patches of those vertices (the
+        element-partitioned smoother applies the patches of the vertices a rank owns)."""
         sd = self.space_data(fes)
-        key = 'patch_' + kind
+        key = 'patch_' + kind + ('' if vmask is None else '_owned')
         if key in sd:
             return sd[key]
         cd = fes.cell_dofs
@@ -500,6 +502,8 @@ class CudaBackend:
             bs = int((big < np.iinfo(np.int32).max).sum(axis=1).max())
             dofs = big[:, :bs].copy()
             dofs[dofs == np.iinfo(np.int32).max] = -1
+            if vmask is not None:
+                dofs = dofs[np.asarray(vmask, dtype=bool)]
         if dofs.shape[1] > 160 and kind != 'cell':
             # vertex stars of irregular meshes can exceed what the register-tiled inversion holds (bs <= 160):
             # fall back to cell patches for this space
@@ -574,3 +578,67 @@ class CudaBackend:
         # brings the result to the round-off level a sparse direct solver with refinement reaches
         for _ in range(2):
             self.krylov('gmres', mat, r, out, p, free, 1e-13, 4000, False, False, restart=100)
+
+
+# ---- primitives used by the element-partitioned multigrid driver (dist_mg.py) -----------------------------------
+def _cuda_csr_handle(self, m):
+    m = m.tocsr()
+    m.sort_indices()
+    return dict(nrows=m.shape[0], rowptr=self._up(m.indptr.astype(np.int32)), colidx=self._up(m.indices.astype(np.int32)),
+                vals=self._up(m.data.astype(np.float64)))
+
+
+def _cuda_csr_mult(self, h, x, y):
+    self._ck(self.lib.ocmp_spmv(h['nrows'], h['rowptr'].data_ptr(), h['colidx'].data_ptr(), h['vals'].data_ptr(),
+                                x.data_ptr(), y.data_ptr(), self._stream()))
+
+
+def _cuda_patch_state(self, fes, vmask):
+    return self._patches(fes, 'vertex', vmask)
+
+
+def _cuda_patch_setup(self, mat, pt, fm):
+    pd = self.pattern_data(mat.space)
+    npatch, bs = pt['npatch'], pt['bs']
+    st = self._stream()
+    if pt.get('inv') is None:
+        pt['inv'] = self.torch.empty(npatch * bs * bs, dtype=self.torch.float64, device=self.device)
+    if pt.get('pos') is None and bs <= 160:
+        npad = 16 * ((bs + 15) // 16)
+        pt['pos'] = self.torch.empty(npatch * npad * npad, dtype=self.torch.int32, device=self.device)
+        self._ck(self.lib.ocmp_patch_positions(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(),
+                                               pd['colidx'].data_ptr(), pt['pos'].data_ptr(), st))
+    self._ck(self.lib.ocmp_asm_setup(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(),
+                                     pd['colidx'].data_ptr(), mat.values.data_ptr(), _ptr(fm), pt['inv'].data_ptr(),
+                                     _ptr(pt.get('pos')), st))
+
+
+def _cuda_patch_apply(self, pt, r, z):
+    self._ck(self.lib.ocmp_asm_apply(pt['npatch'], pt['bs'], pt['dofs'].data_ptr(), pt['inv'].data_ptr(),
+                                     r.data_ptr(), z.data_ptr(), z.numel(), self._stream()))
+
+
+def _cuda_patch_count(self, pt, n):
+    d = pt['dofs'].reshape(-1).to(self.torch.int64)
+    d = d[d >= 0]
+    return self.torch.bincount(d, minlength=n).to(self.torch.float64)
+
+
+def _cuda_dense_inverse(self, mat, fm):
+    t = self.torch
+    pat = mat.space.pattern()
+    n = mat.height
+    rows = self._up(np.repeat(np.arange(n), np.diff(pat.rowptr)).astype(np.int64))
+    cols = self._up(pat.colidx.astype(np.int64))
+    dense = t.zeros((n, n), dtype=t.float64, device=self.device)
+    dense[rows, cols] = mat.values
+    dense = dense * fm[:, None] * fm[None, :] + t.diag(1.0 - fm)
+    inv = t.linalg.inv(dense).contiguous()
+    return dict(nrows=n, rowptr=self._up((np.arange(n + 1, dtype=np.int64) * n).astype(np.int32)),
+                colidx=self._up(np.tile(np.arange(n, dtype=np.int32), n)), vals=inv.view(-1))
+
+
+for _name, _fn in (('csr_handle', _cuda_csr_handle), ('csr_mult', _cuda_csr_mult), ('patch_state', _cuda_patch_state),
+                   ('patch_setup', _cuda_patch_setup), ('patch_apply', _cuda_patch_apply),
+                   ('patch_count', _cuda_patch_count), ('dense_inverse', _cuda_dense_inverse)):
+    setattr(CudaBackend, _name, _fn)

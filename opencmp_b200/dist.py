@@ -28,19 +28,26 @@ from .mesh import Mesh
 class Partition:
     """Cell partition of a global mesh and the local (owned + ghost) mesh of one rank."""
 
-    def __init__(self, mesh: Mesh, nranks: int, rank: int, layers: int = 1):
+    def __init__(self, mesh: Mesh, nranks: int, rank: int, layers: Optional[int] = 1):
         self.mesh, self.nranks, self.rank = mesh, nranks, rank
         self._layers = layers
         ne = mesh.ne
         self.cell_rank = (np.arange(ne, dtype=np.int64) * nranks // ne).astype(np.int32)
         owned = self.cell_rank == rank
         local = owned.copy()
-        for _ in range(layers):                       # grow by vertex adjacency
+        if layers is None:                            # replicated level: every cell is local
+            local[:] = True
+        for _ in range(layers or 0):                  # grow by vertex adjacency
             vmask = np.zeros(mesh.nv, dtype=bool)
             vmask[mesh.cells[local].ravel()] = True
             local = vmask[mesh.cells].any(axis=1)
         self.local_cells = np.nonzero(local)[0]
         self.owned_local = owned[self.local_cells]    # mask over local cells
+        # vertex ownership (patch smoothers): rank of the lowest global cell containing the vertex
+        vowner = np.full(mesh.nv, nranks, dtype=np.int32)
+        order = np.arange(ne - 1, -1, -1)
+        vowner[mesh.cells[order].ravel()] = np.repeat(self.cell_rank[order], mesh.cells.shape[1])
+        self.vertex_owner = vowner
 
     def local_mesh(self) -> Mesh:
         """Sub-mesh in ascending global cell / vertex order (keeps the sorted-vertex convention); boundary facets of
@@ -157,7 +164,7 @@ class DofMap:
 
 
 def _layers_of(part: Partition) -> int:
-    return getattr(part, '_layers', 1)
+    return part._layers
 
 
 class DistributedOperator:

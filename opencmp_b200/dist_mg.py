@@ -1,0 +1,213 @@
+"""Element-partitioned geometric multigrid + GMRES on top of dist.py.
+
+Every level of the ``Mesh.Refine()`` hierarchy is partitioned with the same (nested) contiguous cell blocks; a rank
+holds, per level, a local mesh (owned cells + two vertex layers), the local operator assembled by the ordinary
+single-GPU kernels, the vertex-star patches of the vertices it owns, and the local prolongation. The coarsest level is
+replicated (every cell local) and solved redundantly with an explicit inverse. All vectors are local (owned + ghost)
+and kept *consistent*: ghost entries equal the owner's value.
+
+Communication per V-cycle and level: one halo exchange after each SpMV, ``reverse_add`` + exchange after each smoother
+application (patch corrections reach ghost DOFs) and after the restriction. Per GMRES iteration: the Gram-Schmidt
+coefficients are all-reduced as one small vector.
+
+The cycle is driven from Python in this round (the single-GPU cycle runs inside the C ABI); vector updates between
+the hand-written kernels (SpMV, patch inversion / application, assembly) use array expressions of the backend array
+type, and the Gram-Schmidt projections a library matrix-vector product.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+from .dist import DofMap, Partition
+from .multigrid import clone_space, mesh_levels, prolongation
+
+
+def _allreduce(vals, like):
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return np.asarray(vals, dtype=np.float64)
+    dev = like.device if isinstance(like, torch.Tensor) else 'cpu'
+    t = torch.as_tensor(np.asarray(vals, dtype=np.float64), device=dev)
+    dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
+class _Level:
+    pass
+
+
+class DistributedMultigrid:
+    """Levels [0 .. L]; level L is the space of the bilinear form ``bf`` (built on the rank's local finest mesh)."""
+
+    def __init__(self, be, bf, global_fine_mesh, part_fine: Partition, nu: int = 1, omega: float = 0.7):
+        from . import ngs
+        from .symbolic import lower_form
+        self.be, self.bf, self.nu, self.omega = be, bf, nu, omega
+        world, rank = part_fine.nranks, part_fine.rank
+        gmeshes = mesh_levels(global_fine_mesh)
+        L = len(gmeshes) - 1
+        self.levels: List[_Level] = []
+        for l, gm in enumerate(gmeshes):
+            lv = _Level()
+            if l == L:
+                lv.part = part_fine
+                lv.mesh = bf.space.mesh
+                lv.fes = bf.space
+            else:
+                lv.part = Partition(gm, world, rank, layers=None if l == 0 else part_fine._layers)
+                lv.mesh = ngs.Mesh(lv.part.local_mesh())
+                lv.fes = clone_space(bf.space, lv.mesh)
+            gfes = clone_space(bf.space, ngs.Mesh(gm))                       # global numbering only
+            lv.map = DofMap(lv.part, gfes, lv.fes)
+            lv.free = be.from_numpy(lv.fes.FreeDofs().astype(np.float64))
+            lv.owned = be.from_numpy(lv.map.owned.astype(np.float64))
+            lv.n = lv.fes.ndof
+            if l < L:
+                lv.program = lower_form(lv.fes, bf.integrals, 2, drop_fields=True)
+                lv.mat = ngs.Matrix(lv.fes)
+            if l > 0:
+                vown = lv.part.vertex_owner[lv.mesh.global_vertices] == rank
+                lv.patches = be.patch_state(lv.fes, vown)
+                cnt = be.patch_count(lv.patches, lv.n)
+                lv.map.exchange(cnt, reverse_add=True)
+                lv.map.exchange(cnt)
+                lv.wgt = lv.free / (cnt + (cnt == 0))
+                prev = self.levels[l - 1]
+                parent_global = lv.part.local_cells // 4
+                parent = np.searchsorted(prev.part.local_cells, parent_global)
+                assert (prev.part.local_cells[parent] == parent_global).all(), 'parent of a local cell is not local'
+                P = prolongation(prev.fes, lv.fes, parent)
+                lv.P = be.csr_handle(P)
+                lv.R = be.csr_handle(P.T.tocsr())
+            self.levels.append(lv)
+        self.inv0 = None
+
+    # ---- set-up after every assembly ---------------------------------------------------------------------------
+    def update(self):
+        be = self.be
+        for l, lv in enumerate(self.levels):
+            if l < len(self.levels) - 1:
+                be.assemble_matrix(lv.program, lv.mat)
+            else:
+                lv.mat = self.bf.mat
+            if l == 0:
+                self.inv0 = be.dense_inverse(lv.mat, lv.free)
+            else:
+                be.patch_setup(lv.mat, lv.patches, lv.free)
+        return self
+
+    # ---- level operators (all vectors consistent) ----------------------------------------------------------------
+    def mult(self, l, x):
+        lv = self.levels[l]
+        y = self.be.zeros(lv.n)
+        self.be.spmv(lv.mat, x, y)
+        lv.map.exchange(y)
+        return y
+
+    def smooth(self, l, r):
+        lv = self.levels[l]
+        z = self.be.zeros(lv.n)
+        self.be.patch_apply(lv.patches, r, z)
+        lv.map.exchange(z, reverse_add=True)
+        lv.map.exchange(z)
+        return z * lv.wgt
+
+    def vcycle(self, l, b):
+        lv = self.levels[l]
+        be = self.be
+        if l == 0:
+            x = be.zeros(lv.n)
+            be.csr_mult(self.inv0, b, x)
+            # every rank solved redundantly with ITS OWN copy of the (atomically assembled, hence round-off-different)
+            # coarse matrix; the regularised pressure mode amplifies such differences, so take the owners' values
+            lv.map.exchange(x)
+            return x * lv.free
+        x = self.omega * self.smooth(l, b)
+        for _ in range(1, self.nu):
+            x = x + self.omega * self.smooth(l, (b - self.mult(l, x)) * lv.free)
+        r = (b - self.mult(l, x)) * lv.free
+        prev = self.levels[l - 1]
+        bc = be.zeros(prev.n)
+        be.csr_mult(lv.R, r * lv.owned, bc)
+        prev.map.exchange(bc, reverse_add=True)
+        prev.map.exchange(bc)
+        xc = self.vcycle(l - 1, bc * prev.free)
+        t = be.zeros(lv.n)
+        be.csr_mult(lv.P, xc, t)
+        x = x + t * lv.free
+        for _ in range(self.nu):
+            x = x + self.omega * self.smooth(l, (b - self.mult(l, x)) * lv.free)
+        return x
+
+    def precond(self, r):
+        return self.vcycle(len(self.levels) - 1, r)
+
+    # ---- Krylov ------------------------------------------------------------------------------------------------
+    def dots(self, V, k, w):
+        """<V_j, w> over owned entries, j < k, one all-reduce."""
+        lv = self.levels[-1]
+        local = V[:k] @ (w * lv.owned)
+        loc = local.cpu().numpy() if hasattr(local, 'cpu') else np.asarray(local)
+        return _allreduce(loc, w)
+
+    def gmres(self, b, x, tol=1e-10, maxit=300, restart=50):
+        """Left-preconditioned restarted GMRES with CGS2 on the free DOFs; x (consistent) holds the initial guess and
+        the Dirichlet values. Same recurrence as ocmp_krylov kind 1."""
+        be = self.be
+        top = len(self.levels) - 1
+        lv = self.levels[top]
+        n = lv.n
+        V = be.zeros((restart + 1) * n).reshape(restart + 1, n)
+        it, beta0, res = 0, None, 0.0
+        done = False
+        while not done and it < maxit:
+            r = (b - self.mult(top, x)) * lv.free
+            z = self.precond(r)
+            beta = float(np.sqrt(self.dots(z.reshape(1, n), 1, z)[0]))
+            if beta0 is None:
+                beta0 = beta
+            res = beta
+            if beta == 0.0 or beta < tol * beta0:
+                break
+            V[0] = z / beta
+            H = np.zeros((restart + 1, restart))
+            cs, sn, g = np.zeros(restart), np.zeros(restart), np.zeros(restart + 1)
+            g[0] = beta
+            k = 0
+            while k < restart and it < maxit:
+                w = self.precond(self.mult(top, V[k]) * lv.free)
+                h = self.dots(V, k + 1, w)
+                w = w - self._lincomb(V, k + 1, h)
+                h2 = self.dots(V, k + 1, w)
+                w = w - self._lincomb(V, k + 1, h2)
+                h = h + h2
+                hn = float(np.sqrt(self.dots(w.reshape(1, n), 1, w)[0]))
+                H[:k + 1, k] = h
+                H[k + 1, k] = hn
+                for i in range(k):
+                    a_, b_ = H[i, k], H[i + 1, k]
+                    H[i, k], H[i + 1, k] = cs[i] * a_ + sn[i] * b_, -sn[i] * a_ + cs[i] * b_
+                den = np.hypot(H[k, k], H[k + 1, k])
+                cs[k], sn[k] = (1.0, 0.0) if den == 0 else (H[k, k] / den, H[k + 1, k] / den)
+                H[k, k] = cs[k] * H[k, k] + sn[k] * H[k + 1, k]
+                H[k + 1, k] = 0.0
+                g[k + 1] = -sn[k] * g[k]
+                g[k] = cs[k] * g[k]
+                it += 1
+                res = abs(g[k + 1])
+                if hn > 0:
+                    V[k + 1] = w / hn
+                k += 1
+                if res < tol * beta0 or hn == 0:
+                    done = True
+                    break
+            y = np.linalg.solve(np.triu(H[:k, :k]), g[:k]) if k else np.zeros(0)
+            x += self._lincomb(V, k, y)
+        return it, res
+
+    def _lincomb(self, V, k, coef):
+        c = self.be.from_numpy(np.asarray(coef, dtype=np.float64))
+        return c @ V[:k]

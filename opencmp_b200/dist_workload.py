@@ -69,3 +69,79 @@ class DistributedPoisson:
         its, res = self.op.cg(self.b, x, self.dinv, self.free, tol=tol, maxit=maxit)
         torch.cuda.synchronize()
         return its, res, time.perf_counter() - t0, x
+
+
+class DistributedINS:
+    """The INS Taylor-Green time step of workloads.INSTaylorGreen, element-partitioned: R ranks, rank r owns the
+    strip [0,pi] x [r pi, (r+1) pi] (n0 x n0 coarse squares refined k times), geometric multigrid + GMRES distributed
+    with dist_mg.DistributedMultigrid. Per-rank work is fixed as R grows (weak scaling)."""
+
+    def __init__(self, N: int, world: int, rank: int, order: int = 3, n0: int = 4, strips: int = None, **kw):
+        from .workloads import INSTaylorGreen
+        from .dist_mg import DistributedMultigrid
+        self.world, self.rank = world, rank
+        k, n = 0, N
+        while n % 2 == 0 and n > n0:
+            n //= 2
+            k += 1
+        strips = world if strips is None else strips          # domain [0,pi] x [0, strips*pi]
+        gmesh = structured_2d([n, n * strips], scale=(np.pi, np.pi * strips))
+        for _ in range(k):
+            gmesh.Refine()
+        self.gmesh = gmesh
+        self.part = Partition(gmesh, world, rank, layers=2)
+        outer = self
+
+        class _Local(INSTaylorGreen):
+            def _integrate(self, cf):
+                val = ngs.Integrate(cf, self.mesh, definedon=self.mesh.Materials('owned'))
+                import torch
+                import torch.distributed as dist
+                if dist.is_initialized() and dist.get_world_size() > 1:
+                    t = torch.tensor([val], dtype=torch.float64,
+                                     device='cuda' if ngs.get_backend().name == 'cuda' else 'cpu')
+                    dist.all_reduce(t)
+                    val = float(t[0])
+                return val
+
+            def apply_dirichlet_bcs(self):
+                super().apply_dirichlet_bcs()
+                outer.mg.levels[-1].map.exchange(self.gfu.vec.a)
+
+            def assemble(self):
+                self.a.Assemble()
+                self.L.Assemble()
+                outer.mg.levels[-1].map.exchange(self.L.vec.a)
+                outer.mg.update()
+
+            def linear_solve(self):
+                it, res = outer.mg.gmres(self.L.vec.a, self.gfu.vec.a, tol=self.linear_tolerance,
+                                         maxit=self.linear_max_iterations, restart=50)
+                self.linear_iterations.append(it)
+
+        self.w = _Local(N, order=order, mesh=self.part.local_mesh(), preconditioner=None, **kw)
+        self.mg = DistributedMultigrid(ngs.get_backend(), self.w.a, gmesh, self.part)
+        top = self.mg.levels[-1].map
+        for gf in (self.w.gfu, self.w.gfu_0):
+            top.exchange(gf.vec.a)
+        vmap = self._velocity_map()
+        vmap.exchange(self.w.W.vec.a)
+        self._vmap = vmap
+        step0 = self.w.step
+
+        def step():
+            out = step0()
+            vmap.exchange(self.w.W.vec.a)
+            return out
+        self.w.step = step
+
+    def _velocity_map(self):
+        gV = ngs.HDiv(ngs.Mesh(self.gmesh), order=self.w.order, dirichlet=self.w.dirichlet, dgjumps=True)
+        return DofMap(self.part, gV, self.w.V)
+
+    def step(self):
+        return self.w.step()
+
+    @property
+    def ndof_global(self):
+        return self.mg.levels[-1].map.nglobal

@@ -39,14 +39,18 @@ def clone_space(fes: FESpace, mesh) -> FESpace:
     return cls(mesh, order=fes.order, dirichlet=b.dirichlet or '', dgjumps=fes.dgjumps, family=fes.name)
 
 
-def prolongation(fes_c: FESpace, fes_f: FESpace) -> sp.csr_matrix:
-    """(ndof_f x ndof_c) embedding of the coarse space into the fine space; fine cell k has parent k // 4."""
+def prolongation(fes_c: FESpace, fes_f: FESpace, parent=None) -> sp.csr_matrix:
+    """(ndof_f x ndof_c) embedding of the coarse space into the fine space. ``parent[k]`` is the coarse cell containing
+    fine cell k (default: uniform refinement kept by Mesh.Refine(), parent k // 4; the element-partitioned layer passes
+    the parent map of its local sub-meshes)."""
     mc, mf = fes_c.mesh, fes_f.mesh
-    if mf.ne != 4 * mc.ne:
-        raise ValueError('prolongation needs a uniformly refined mesh')
+    if parent is None:
+        if mf.ne != 4 * mc.ne:
+            raise ValueError('prolongation needs a uniformly refined mesh')
+        parent = np.arange(mf.ne) // 4
+    parent = np.asarray(parent, dtype=np.int64)
     dim = mf.dim
     Jc, Jf = mc.jacobians(), mf.jacobians()
-    parent = np.arange(mf.ne) // 4
     Jci = np.linalg.inv(Jc)[parent]
     A = np.einsum('eab,ebc->eac', Jci, Jf)                              # xi_c = A xi_f + b
     b = np.einsum('eab,eb->ea', Jci, mf.origins() - mc.origins()[parent])

@@ -159,8 +159,8 @@ class INSTaylorGreen:
             self.assemble()
             self.linear_solve()
             diff = self.W - u_comp
-            err = float(np.sqrt(ngs.Integrate(ngs.InnerProduct(diff, diff), self.mesh)))
-            unorm = float(np.sqrt(ngs.Integrate(ngs.InnerProduct(u_comp, u_comp), self.mesh)))
+            err = float(np.sqrt(self._integrate(ngs.InnerProduct(diff, diff))))
+            unorm = float(np.sqrt(self._integrate(ngs.InnerProduct(u_comp, u_comp))))
             it += 1
             self.W.vec.data = u_comp.vec
             if err < self.abs_nonlinear_tolerance + self.rel_nonlinear_tolerance * unorm or \
@@ -170,13 +170,16 @@ class INSTaylorGreen:
         self.gfu_0.vec.data = self.gfu.vec
         return err
 
+    def _integrate(self, cf):
+        return ngs.Integrate(cf, self.mesh)
+
     def errors(self):
         """L2 errors against the reference solution (helpers/error.py:54-128); pressure compared up to its mean."""
         u, p = self.gfu.components
         du = u - self.u_ref
-        eu = float(np.sqrt(ngs.Integrate(ngs.InnerProduct(du, du), self.mesh)))
-        area = ngs.Integrate(ngs.CoefficientFunction(1.0), self.mesh)
-        pm = ngs.Integrate(p - self.p_ref, self.mesh) / area
+        eu = float(np.sqrt(self._integrate(ngs.InnerProduct(du, du))))
+        area = self._integrate(ngs.CoefficientFunction(1.0))
+        pm = self._integrate(p - self.p_ref) / area
         dp = p - self.p_ref - pm
-        ep = float(np.sqrt(ngs.Integrate(dp * dp, self.mesh)))
+        ep = float(np.sqrt(self._integrate(dp * dp)))
         return eu, ep

@@ -176,3 +176,59 @@ def gmres(A, b, x, P, proj, tol, maxit):
     for i in range(k_used):
         u += yk[i] * Q[i]
     return u
+
+
+# ---- primitives of the element-partitioned multigrid driver, NumPy versions (gloo tests) --------------------------
+def _vertex_patches(fes, vmask):
+    m = fes.mesh
+    v2c = [[] for _ in range(m.nv)]
+    for c in range(m.ne):
+        for v in m.cells[c]:
+            v2c[v].append(c)
+    keep = np.arange(m.nv) if vmask is None else np.nonzero(np.asarray(vmask, bool))[0]
+    return [np.unique(np.concatenate([fes.cell_dofs[c] for c in v2c[v]])) for v in keep]
+
+
+class _OraclePrimitives:
+    def csr_handle(self, m):
+        return m.tocsr()
+
+    def csr_mult(self, h, x, y):
+        y[:] = h @ x
+
+    def patch_state(self, fes, vmask):
+        return dict(dofs=_vertex_patches(fes, vmask), inv=None)
+
+    def patch_setup(self, mat, pt, fm):
+        A = self._csr(mat)
+        free = np.asarray(fm) > 0
+        inv = []
+        for d in pt['dofs']:
+            M = A[d][:, d].toarray()
+            f = free[d]
+            M[~f, :] = 0.0
+            M[:, ~f] = 0.0
+            M[~f, ~f] = 1.0
+            inv.append(np.linalg.inv(M))
+        pt['inv'] = inv
+
+    def patch_apply(self, pt, r, z):
+        z[:] = 0.0
+        for d, Ai in zip(pt['dofs'], pt['inv']):
+            z[d] += Ai @ r[d]
+
+    def patch_count(self, pt, n):
+        c = np.zeros(n)
+        for d in pt['dofs']:
+            c[d] += 1.0
+        return c
+
+    def dense_inverse(self, mat, fm):
+        A = self._csr(mat).toarray()
+        f = np.asarray(fm)
+        A = A * f[:, None] * f[None, :] + np.diag(1.0 - f)
+        return np.linalg.inv(A)
+
+
+for _n in ('csr_handle', 'csr_mult', 'patch_state', 'patch_setup', 'patch_apply', 'patch_count', 'dense_inverse'):
+    setattr(OracleBackend, _n, getattr(_OraclePrimitives, _n))
