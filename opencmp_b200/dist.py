@@ -99,6 +99,7 @@ class DofMap:
         # halo plan, identical on both sides because it is a pure function of the replicated global numbering
         self.recv: Dict[int, np.ndarray] = {}
         self.send: Dict[int, np.ndarray] = {}
+        self.shared: Dict[int, np.ndarray] = {}
         ghosts = np.nonzero(~self.owned)[0]
         for s in np.unique(self.owner_local[ghosts]):
             idx = ghosts[self.owner_local[ghosts] == s]
@@ -111,6 +112,9 @@ class DofMap:
             mine = theirs[owner[theirs] == me]          # ascending global id = their recv order
             if mine.size:
                 self.send[s] = g2l[mine]
+            both = theirs[g2l[theirs] >= 0]             # dofs local to both ranks, ascending global id on both sides
+            if both.size:
+                self.shared[s] = g2l[both]
         self._bufs = None
 
     # ---- communication -------------------------------------------------------------------------------------
@@ -141,6 +145,27 @@ class DofMap:
                 t.index_add_(0, it, buf)
             else:
                 t.index_copy_(0, it, buf)
+
+    def exchange_sum(self, x) -> None:
+        """x holds per-rank PARTIAL contributions (patch corrections, restricted residuals): afterwards every rank holds
+        the total on all its local entries — one round instead of reverse_add + exchange."""
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(x)
+        ops, staged = [], []
+        for s, idx in sorted(self.shared.items()):
+            it = self._index(idx, t.device)
+            ops.append(dist.P2POp(dist.isend, t.index_select(0, it).contiguous(), s))
+            buf = torch.empty(len(idx), dtype=t.dtype, device=t.device)
+            staged.append((it, buf))
+            ops.append(dist.P2POp(dist.irecv, buf, s))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for it, buf in staged:
+            t.index_add_(0, it, buf)
 
     def _index(self, idx, device):
         import torch

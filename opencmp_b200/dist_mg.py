@@ -35,6 +35,14 @@ def _allreduce(vals, like):
     return t.cpu().numpy()
 
 
+def _broadcast(x):
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(x)
+        dist.broadcast(t, src=0)
+
+
 class _Level:
     pass
 
@@ -42,7 +50,8 @@ class _Level:
 class DistributedMultigrid:
     """Levels [0 .. L]; level L is the space of the bilinear form ``bf`` (built on the rank's local finest mesh)."""
 
-    def __init__(self, be, bf, global_fine_mesh, part_fine: Partition, nu: int = 1, omega: float = 0.7):
+    def __init__(self, be, bf, global_fine_mesh, part_fine: Partition, nu: int = 1, omega: float = 0.7,
+                 replicate_below: int = 100000):
         from . import ngs
         from .symbolic import lower_form
         self.be, self.bf, self.nu, self.omega = be, bf, nu, omega
@@ -52,28 +61,30 @@ class DistributedMultigrid:
         self.levels: List[_Level] = []
         for l, gm in enumerate(gmeshes):
             lv = _Level()
+            gfes = clone_space(bf.space, ngs.Mesh(gm))                       # global numbering only
+            # small levels are replicated: every cell local, all work redundant, no communication inside the level
+            lv.replicated = l < L and (l == 0 or gfes.ndof < replicate_below)
             if l == L:
                 lv.part = part_fine
                 lv.mesh = bf.space.mesh
                 lv.fes = bf.space
             else:
-                lv.part = Partition(gm, world, rank, layers=None if l == 0 else part_fine._layers)
+                lv.part = Partition(gm, world, rank, layers=None if lv.replicated else part_fine._layers)
                 lv.mesh = ngs.Mesh(lv.part.local_mesh())
                 lv.fes = clone_space(bf.space, lv.mesh)
-            gfes = clone_space(bf.space, ngs.Mesh(gm))                       # global numbering only
             lv.map = DofMap(lv.part, gfes, lv.fes)
             lv.free = be.from_numpy(lv.fes.FreeDofs().astype(np.float64))
-            lv.owned = be.from_numpy(lv.map.owned.astype(np.float64))
+            lv.owned = be.from_numpy(np.ones(lv.fes.ndof) if lv.replicated else lv.map.owned.astype(np.float64))
             lv.n = lv.fes.ndof
             if l < L:
                 lv.program = lower_form(lv.fes, bf.integrals, 2, drop_fields=True)
                 lv.mat = ngs.Matrix(lv.fes)
             if l > 0:
-                vown = lv.part.vertex_owner[lv.mesh.global_vertices] == rank
+                vown = None if lv.replicated else lv.part.vertex_owner[lv.mesh.global_vertices] == rank
                 lv.patches = be.patch_state(lv.fes, vown)
                 cnt = be.patch_count(lv.patches, lv.n)
-                lv.map.exchange(cnt, reverse_add=True)
-                lv.map.exchange(cnt)
+                if not lv.replicated:
+                    lv.map.exchange_sum(cnt)
                 lv.wgt = lv.free / (cnt + (cnt == 0))
                 prev = self.levels[l - 1]
                 parent_global = lv.part.local_cells // 4
@@ -91,6 +102,11 @@ class DistributedMultigrid:
         for l, lv in enumerate(self.levels):
             if l < len(self.levels) - 1:
                 be.assemble_matrix(lv.program, lv.mat)
+                if lv.replicated:
+                    # redundant work must be bitwise identical on every rank: the scatter-add assembly is not
+                    # (atomic order), and the regularised pressure mode amplifies round-off differences of the
+                    # inverses — so all ranks take rank 0's coarse matrix values
+                    _broadcast(lv.mat.values)
             else:
                 lv.mat = self.bf.mat
             if l == 0:
@@ -104,15 +120,16 @@ class DistributedMultigrid:
         lv = self.levels[l]
         y = self.be.zeros(lv.n)
         self.be.spmv(lv.mat, x, y)
-        lv.map.exchange(y)
+        if not lv.replicated:
+            lv.map.exchange(y)
         return y
 
     def smooth(self, l, r):
         lv = self.levels[l]
         z = self.be.zeros(lv.n)
         self.be.patch_apply(lv.patches, r, z)
-        lv.map.exchange(z, reverse_add=True)
-        lv.map.exchange(z)
+        if not lv.replicated:
+            lv.map.exchange_sum(z)
         return z * lv.wgt
 
     def vcycle(self, l, b):
@@ -132,9 +149,11 @@ class DistributedMultigrid:
         prev = self.levels[l - 1]
         bc = be.zeros(prev.n)
         be.csr_mult(lv.R, r * lv.owned, bc)
-        prev.map.exchange(bc, reverse_add=True)
-        prev.map.exchange(bc)
+        if not lv.replicated:
+            prev.map.exchange_sum(bc)
         xc = self.vcycle(l - 1, bc * prev.free)
+        if prev.replicated and not lv.replicated:
+            prev.map.exchange(xc)          # redundant coarse work differs by (amplified) round-off: owners' values win
         t = be.zeros(lv.n)
         be.csr_mult(lv.P, xc, t)
         x = x + t * lv.free

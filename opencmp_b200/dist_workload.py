@@ -76,7 +76,8 @@ class DistributedINS:
     strip [0,pi] x [r pi, (r+1) pi] (n0 x n0 coarse squares refined k times), geometric multigrid + GMRES distributed
     with dist_mg.DistributedMultigrid. Per-rank work is fixed as R grows (weak scaling)."""
 
-    def __init__(self, N: int, world: int, rank: int, order: int = 3, n0: int = 4, strips: int = None, **kw):
+    def __init__(self, N: int, world: int, rank: int, order: int = 3, n0: int = 4, strips: int = None,
+                 replicate_below: int = 100000, **kw):
         from .workloads import INSTaylorGreen
         from .dist_mg import DistributedMultigrid
         self.world, self.rank = world, rank
@@ -120,7 +121,7 @@ class DistributedINS:
                 self.linear_iterations.append(it)
 
         self.w = _Local(N, order=order, mesh=self.part.local_mesh(), preconditioner=None, **kw)
-        self.mg = DistributedMultigrid(ngs.get_backend(), self.w.a, gmesh, self.part)
+        self.mg = DistributedMultigrid(ngs.get_backend(), self.w.a, gmesh, self.part, replicate_below=replicate_below)
         top = self.mg.levels[-1].map
         for gf in (self.w.gfu, self.w.gfu_0):
             top.exchange(gf.vec.a)

@@ -10,7 +10,7 @@ be = CudaBackend(local); ngs.set_backend(be)
 from opencmp_b200.dist_workload import DistributedINS
 from opencmp_b200.workloads import INSTaylorGreen
 N = int(sys.argv[1]); order = int(sys.argv[2])
-d = DistributedINS(N, world, rank, order=order, n0=4)
+d = DistributedINS(N, world, rank, order=order, n0=4, replicate_below=int(os.environ.get('REPL', '100000')))
 g = INSTaylorGreen(N, order=order, mesh=d.gmesh, preconditioner='multigrid')
 top = d.mg.levels[-1].map
 l2g = torch.from_numpy(top.l2g).cuda(); vl2g = torch.from_numpy(d._vmap.l2g).cuda()
