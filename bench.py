@@ -35,6 +35,7 @@ def parse():
     ap.add_argument('--order', type=int, default=3)
     ap.add_argument('--cpu-N', type=int, default=20, help='mesh size of the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--dist-poisson', action='store_true', help='also run the distributed Poisson CG leg')
     ap.add_argument('--dist-n', type=int, default=512, help='cells per direction and rank of the distributed leg')
     return ap.parse_args()
 
@@ -132,8 +133,9 @@ def workload_config(args, where):
             'N': args.N, 'order': args.order, 'linear_solver': 'GMRES(100) + geometric multigrid V(1,1), vertex-patch additive Schwarz smoother (damping 0.7), tol 1e-10'
             if where == 'gpu' else 'direct (SuperLU)', 'nonlinear_max_iterations': 3,
             'l2': 'inputs larger than L2 (CSR matrix ~0.8 GB at N=128); no explicit flush',
-            'parallelism': ('replicas of the INS step (one full problem per GPU) + element-partitioned Poisson leg '
-                            'reported under multi_gpu') if args.gpus > 1 else 'single'}
+            'parallelism': ('element-partitioned: one {0}x{0}x2 strip per GPU (domain [0,pi] x [0,{1} pi]), two ghost '
+                            'layers, halo exchange + all-reduce over NCCL, distributed multigrid-GMRES'
+                            .format(args.N, args.gpus)) if args.gpus > 1 else 'single'}
 
 
 def main():
@@ -156,7 +158,14 @@ def main():
     ngs.set_backend(be)
     lib = be.lib
     t_setup = time.perf_counter()
-    w = INSTaylorGreen(args.N, order=args.order)
+    if world > 1:
+        # element-partitioned INS step: rank r owns the strip [0,pi] x [r pi, (r+1) pi] at N x N x 2 triangles
+        from opencmp_b200.dist_workload import DistributedINS
+        dins = DistributedINS(args.N, world, rank, order=args.order)
+        w = dins.w
+    else:
+        dins = None
+        w = INSTaylorGreen(args.N, order=args.order)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
     ndof, nnz, ne = w.ndof, w.nnz, w.mesh.ne
@@ -213,7 +222,7 @@ def main():
     eu, ep = w.errors()
     # ---- element-partitioned leg (N > 1): halo-exchange SpMV + all-reduced Jacobi-CG on a distributed Poisson problem
     multi = None
-    if world > 1:
+    if world > 1 and args.dist_poisson:
         from opencmp_b200.dist_workload import DistributedPoisson
         dp = DistributedPoisson(args.dist_n, 2, world, rank)
         sp_ms = dp.time_spmv()
@@ -267,7 +276,8 @@ def main():
         'metric': 'INS s/timestep', 'value': sec, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': False, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, 'gpu'),
-        'problem': {'cells': ne, 'dofs': ndof, 'nnz': nnz, 'picard_per_step': picard / args.steps,
+        'problem': {'cells': ne, 'dofs': ndof, 'nnz': nnz, 'global_dofs': dins.ndof_global if dins else ndof,
+                    'ranks': world, 'picard_per_step': picard / args.steps,
                     'gmres_its_per_step': lin_its / args.steps, 'l2_err_u': eu, 'l2_err_p': ep,
                     'setup_s': t_setup},
         'assembly_mnnz_per_s': asm_mnnz, 'spmv_gbs': spmv_gbs,
