@@ -31,7 +31,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--N', type=int, default=128, help='cells per direction of the structured mesh')
+    ap.add_argument('--N', type=int, default=256, help='cells per direction of the structured mesh')
     ap.add_argument('--order', type=int, default=3)
     ap.add_argument('--cpu-N', type=int, default=20, help='mesh size of the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true')
@@ -132,7 +132,7 @@ def workload_config(args, where):
                                                                                                args.order - 1),
             'N': args.N, 'order': args.order, 'linear_solver': 'GMRES(100) + geometric multigrid V(1,1), vertex-patch additive Schwarz smoother (damping 0.7), tol 1e-10'
             if where == 'gpu' else 'direct (SuperLU)', 'nonlinear_max_iterations': 3,
-            'l2': 'inputs larger than L2 (CSR matrix ~0.8 GB at N=128); no explicit flush',
+            'l2': 'inputs larger than L2 (CSR matrix 3.3 GB, patch inverses 9 GB at N=256); no explicit flush',
             'parallelism': ('element-partitioned: one {0}x{0}x2 strip per GPU (domain [0,pi] x [0,{1} pi]), two ghost '
                             'layers, halo exchange + all-reduce over NCCL, distributed multigrid-GMRES'
                             .format(args.N, args.gpus)) if args.gpus > 1 else 'single'}
@@ -269,8 +269,8 @@ def main():
                 'bound': 'hbm', 'achieved': ap_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': ap_gbs / peak,
                 'peak_source': peak_src, 'bytes_per_launch': ap_bytes, 'launches': ap['count'],
                 'avg_launch_ms': ap_ms, 'share_of_step': share['asm_apply'],
-                'traffic': 2.386e9 if args.N == 128 else None,
-                'traffic_note': 'ncu --set full, fine-level launch at N=128: dram read 2.368 GB + write 0.018 GB vs '
+                'traffic': None,
+                'traffic_note': 'ncu --set full, fine-level launch at N=128 (16 641 patches): dram read 2.368 GB + write 0.018 GB vs '
                                 '2.330 GB algorithmic (profiles/r1_ncu_kernels.md)'}
     line = {
         'metric': 'INS s/timestep', 'value': sec, 'unit': 's', 'n_gpus': world, 'steps': args.steps,

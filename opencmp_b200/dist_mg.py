@@ -116,11 +116,13 @@ class DistributedMultigrid:
         return self
 
     # ---- level operators (all vectors consistent) ----------------------------------------------------------------
-    def mult(self, l, x):
+    def mult(self, l, x, owned_only: bool = False):
+        """y = A x with consistent ghosts; ``owned_only`` skips the halo exchange when only owned entries are used
+        afterwards (the residual that is restricted)."""
         lv = self.levels[l]
         y = self.be.zeros(lv.n)
         self.be.spmv(lv.mat, x, y)
-        if not lv.replicated:
+        if not lv.replicated and not owned_only:
             lv.map.exchange(y)
         return y
 
@@ -145,7 +147,7 @@ class DistributedMultigrid:
         x = self.omega * self.smooth(l, b)
         for _ in range(1, self.nu):
             x = x + self.omega * self.smooth(l, (b - self.mult(l, x)) * lv.free)
-        r = (b - self.mult(l, x)) * lv.free
+        r = (b - self.mult(l, x, owned_only=True)) * lv.free
         prev = self.levels[l - 1]
         bc = be.zeros(prev.n)
         be.csr_mult(lv.R, r * lv.owned, bc)
