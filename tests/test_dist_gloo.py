@@ -107,3 +107,46 @@ def test_partitioned_operator_matches_global(family, order, dg):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, family, order, dg, out), nprocs=world, join=True)
     assert len(out) == world
+
+
+def _mg_worker(rank, world, port, replicate_below, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import opencmp_b200.ngs as ngs
+        from oracle.backend import OracleBackend
+        ngs.set_backend(OracleBackend())
+        from opencmp_b200.dist_workload import DistributedINS
+        from opencmp_b200.workloads import INSTaylorGreen
+        d = DistributedINS(4, world, rank, order=2, n0=2, replicate_below=replicate_below)
+        g = INSTaylorGreen(4, order=2, mesh=d.gmesh, linear_solver='direct', preconditioner=None)
+        top = d.mg.levels[-1].map
+        d.w.gfu.vec.a[:] = g.gfu.vec.a[top.l2g]
+        d.w.gfu_0.vec.a[:] = g.gfu_0.vec.a[top.l2g]
+        d.w.W.vec.a[:] = g.W.vec.a[d._vmap.l2g]
+        d.step()
+        g.step()
+        nu = d.w.V.ndof
+        err = np.abs(d.w.gfu.vec.a - g.gfu.vec.a[top.l2g])[:nu].max() / np.abs(g.gfu.vec.a).max()
+        assert err < 1e-9, err
+        assert d.w.picard_iterations == g.picard_iterations
+        eu_d, _ = d.w.errors()
+        eu_g, _ = g.errors()
+        assert abs(eu_d - eu_g) < 1e-9 * eu_g + 1e-14          # all-reduced error norm equals the global one
+        out[rank] = (err, list(d.w.linear_iterations))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('replicate_below', [0, 100000])
+def test_partitioned_multigrid_ins_step_matches_global_solve(replicate_below):
+    """One INS time step (Picard loop, assembly, distributed geometric multigrid + GMRES with halo exchange,
+    reverse-add and all-reduces) on 2 ranks equals the single-process step with a sparse direct solve."""
+    world = 2
+    port = _free_port()
+    mgr = mp.get_context('spawn').Manager()
+    out = mgr.dict()
+    mp.spawn(_mg_worker, args=(world, port, replicate_below, out), nprocs=world, join=True)
+    assert len(out) == world
+    assert out[0][1] == out[1][1]                                 # same iteration counts on both ranks
