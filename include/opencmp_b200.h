@@ -148,12 +148,24 @@ long long ocmp_krylov_work_len(int nrows, int kind, int restart);
 
 /* ---- instrumentation: per-category device time from CUDA events recorded around every launch on its own stream.
  * categories: 0 spmv, 1 asm_apply, 2 coefficient eval, 3 matrix contraction, 4 vector contraction, 5 multi-dot,
- * 6 multi-axpy, 7 other vector kernels, 8 preconditioner setup, 9 SpMVs inside the multigrid cycle */
+ * 6 multi-axpy, 7 other vector kernels, 8 preconditioner setup, 9 SpMVs inside the multigrid cycle, 10 halo exchange */
 void ocmp_profile_enable(int on);
 void ocmp_profile_reset(void);
 int ocmp_profile_read(int category, long long* count, double* ms);
 double ocmp_profile_bytes(int category);   /* algorithmic bytes of the category's launches (asm_apply only) */
 long long ocmp_launch_count(void);
+
+/* ---- element-partitioned runs (no reference counterpart): NCCL halo exchange in one call -----------
+ * ocmp_comm_unique_id: rank 0 creates the 128-byte NCCL id (broadcast it with any transport), ocmp_comm_init: all ranks.
+ * ocmp_halo_plan: per neighbour `peers[i]` the counts of values sent / received and the concatenated device index lists
+ * into the local vector; returns a plan handle (>= 0). ocmp_halo_run: pack, grouped ncclSend/ncclRecv on `stream`,
+ * unpack — add = 0 overwrites (ghost refresh), add = 1 accumulates (partial contributions). */
+int ocmp_comm_unique_id(void* out128_host);
+int ocmp_comm_init(const void* id128_host, int nranks, int rank);
+int ocmp_halo_plan(int nnbr, const int* peers_host, const int* send_cnt_host, const int* recv_cnt_host,
+                   const int* send_idx_dev, const int* recv_idx_dev, double* sendbuf_dev, double* recvbuf_dev);
+int ocmp_halo_run(int plan, double* x, int add, void* stream);
+int ocmp_allreduce_sum(double* buf_dev, int n, void* stream);
 
 const char* ocmp_last_error(void);
 int ocmp_version(void);

@@ -78,6 +78,11 @@ def load_library() -> C.CDLL:
     lib.ocmp_asm_apply.argtypes = [C.c_int, C.c_int, P, P, P, P, C.c_longlong, P]
     lib.ocmp_krylov.argtypes = [C.POINTER(System), C.c_int, P, P, C.c_double, C.c_int, C.c_int, C.c_double, P,
                                 C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_double), P]
+    lib.ocmp_comm_unique_id.argtypes = [C.c_char_p]
+    lib.ocmp_comm_init.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    lib.ocmp_halo_plan.argtypes = [C.c_int, P, P, P, P, P, P, P]
+    lib.ocmp_halo_run.argtypes = [C.c_int, P, C.c_int, P]
+    lib.ocmp_allreduce_sum.argtypes = [P, C.c_int, P]
     lib.ocmp_profile_enable.argtypes = [C.c_int]
     lib.ocmp_profile_enable.restype = None
     lib.ocmp_profile_reset.restype = None
@@ -89,7 +94,7 @@ def load_library() -> C.CDLL:
 
 
 PROFILE_CATEGORIES = ['spmv', 'asm_apply', 'coef', 'contract_matrix', 'contract_vector', 'multi_dot', 'multi_axpy',
-                      'vector', 'precond_setup', 'spmv_multigrid']
+                      'vector', 'precond_setup', 'spmv_multigrid', 'halo_exchange']
 
 
 def read_profile(lib) -> dict:
@@ -101,7 +106,8 @@ def read_profile(lib) -> dict:
     return out
 
 
-EXPORTED = ['ocmp_patch_positions', 'ocmp_profile_bytes', 'ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
+EXPORTED = ['ocmp_comm_unique_id', 'ocmp_comm_init', 'ocmp_halo_plan', 'ocmp_halo_run', 'ocmp_allreduce_sum',
+            'ocmp_patch_positions', 'ocmp_profile_bytes', 'ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
             'ocmp_dot', 'ocmp_axpby', 'ocmp_masked_assign', 'ocmp_jacobi_setup', 'ocmp_asm_setup', 'ocmp_asm_apply',
             'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version']
 
@@ -137,6 +143,41 @@ class CudaBackend:
         self.chunk_bytes = 48 << 20
 
     # ---- helpers -----------------------------------------------------------------------------------------------
+    def comm_init(self) -> bool:
+        """Create the library's own NCCL communicator (id broadcast through torch.distributed). Idempotent."""
+        import torch.distributed as dist
+        if getattr(self, '_comm_ready', False):
+            return True
+        if not (dist.is_initialized() and dist.get_world_size() > 1):
+            return False
+        buf = C.create_string_buffer(128)
+        if dist.get_rank() == 0:
+            self._ck(self.lib.ocmp_comm_unique_id(buf))
+        t = self.torch.frombuffer(bytearray(buf.raw), dtype=self.torch.uint8).to(self.device)
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().numpy().tobytes())
+        self._ck(self.lib.ocmp_comm_init(raw, dist.get_world_size(), dist.get_rank()))
+        self._comm_ready = True
+        return True
+
+    def halo_plan(self, peers, send_lists, recv_lists):
+        """Build a C-side halo plan from per-neighbour local index arrays; returns (handle, keep-alive tensors)."""
+        t = self.torch
+        cat = lambda ls: np.concatenate(ls).astype(np.int32) if ls else np.zeros(0, np.int32)
+        si, ri = self._up(cat(send_lists)), self._up(cat(recv_lists))
+        sb = t.empty(max(1, si.numel()), dtype=t.float64, device=self.device)
+        rb = t.empty(max(1, ri.numel()), dtype=t.float64, device=self.device)
+        arr = lambda v: (C.c_int * len(v))(*[int(a) for a in v])
+        h = self.lib.ocmp_halo_plan(len(peers), arr(peers), arr([len(a) for a in send_lists]),
+                                    arr([len(a) for a in recv_lists]), si.data_ptr(), ri.data_ptr(), sb.data_ptr(),
+                                    rb.data_ptr())
+        if h < 0:
+            self._ck(h)
+        return h, (si, ri, sb, rb)
+
+    def halo_run(self, handle, x, add: bool):
+        self._ck(self.lib.ocmp_halo_run(handle, x.data_ptr(), 1 if add else 0, self._stream()))
+
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 

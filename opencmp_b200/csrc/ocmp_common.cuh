@@ -11,7 +11,7 @@ int ocmp_patch_apply_cta(int npatch, int bs, const int* pd, const double* inv, c
                          cudaStream_t st);
 // optional per-category device timing (CUDA events on the launching stream) and launch counting
 enum { PROF_SPMV = 0, PROF_ASM_APPLY, PROF_COEF, PROF_CONTRACT, PROF_LIN, PROF_MDOT, PROF_MAXPY, PROF_VEC,
-       PROF_SETUP, PROF_SPMV_MG, PROF_NCAT };
+       PROF_SETUP, PROF_SPMV_MG, PROF_HALO, PROF_NCAT };
 void ocmp_prof_begin(int cat, cudaStream_t st);
 void ocmp_prof_end(int cat, cudaStream_t st);
 void ocmp_prof_bytes(int cat, double bytes);

@@ -126,6 +126,8 @@ class DofMap:
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return
         t = x if isinstance(x, torch.Tensor) else torch.from_numpy(x)
+        if t.is_cuda and self._native('rev' if reverse_add else 'fwd', t, add=reverse_add):
+            return
         out_plan, in_plan = (self.recv, self.send) if reverse_add else (self.send, self.recv)
         ops, staged = [], []
         for s, idx in sorted(out_plan.items()):
@@ -154,6 +156,8 @@ class DofMap:
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return
         t = x if isinstance(x, torch.Tensor) else torch.from_numpy(x)
+        if t.is_cuda and self._native('sum', t, add=True):
+            return
         ops, staged = [], []
         for s, idx in sorted(self.shared.items()):
             it = self._index(idx, t.device)
@@ -166,6 +170,23 @@ class DofMap:
                 w.wait()
         for it, buf in staged:
             t.index_add_(0, it, buf)
+
+    def _native(self, kind: str, t, add: bool) -> bool:
+        """Halo exchange through the C ABI (ocmp_halo_run: pack + grouped NCCL send/recv + unpack in one call)."""
+        from . import ngs
+        be = ngs.get_backend()
+        if getattr(be, 'name', '') != 'cuda' or not be.comm_init():
+            return False
+        plans = self.__dict__.setdefault('_plans', {})
+        if kind not in plans:
+            out_plan, in_plan = {'fwd': (self.send, self.recv), 'rev': (self.recv, self.send),
+                                 'sum': (self.shared, self.shared)}[kind]
+            peers = sorted(set(out_plan) | set(in_plan))
+            empty = np.zeros(0, dtype=np.int64)
+            plans[kind] = be.halo_plan(peers, [out_plan.get(s, empty) for s in peers],
+                                       [in_plan.get(s, empty) for s in peers])
+        be.halo_run(plans[kind][0], t, add)
+        return True
 
     def _index(self, idx, device):
         import torch
