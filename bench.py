@@ -104,7 +104,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cells_full = 2 * args.N * args.N
+    cells_full = 2 * args.N * args.N * max(1, args.gpus)      # weak scaling: one N x N x 2 strip per GPU
     times = []
     ne = ndof = nnz = 0
     for _ in range(max(1, args.warmup // 3)):
@@ -115,7 +115,8 @@ def run_reference(args):
     per = sum(times) / len(times)
     scaled = per * cells_full / ne
     sample = ('one time step (2 Picard iterations: assemble + SciPy SuperLU) at N={} ({} cells, {} DOFs), '
-              'scaled linearly by cell count x{:.1f} to N={}'.format(args.cpu_N, ne, ndof, cells_full / ne, args.N))
+              'scaled linearly by cell count x{:.1f} to {} strip(s) of N={}'.format(args.cpu_N, ne, ndof, cells_full / ne,
+                                                                              max(1, args.gpus), args.N))
     line = {'impl': 'reference', 'metric': 'INS s/timestep', 'value': scaled, 'unit': 's', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': scaled * 1e3, 'higher_is_better': False,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
