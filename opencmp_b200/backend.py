@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -134,7 +135,7 @@ class CudaBackend:
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
         self._mesh_cache: Dict[int, dict] = {}
         self._space_cache: Dict[int, dict] = {}
-        self._plan_cache: Dict[int, list] = {}
+        self._plan_cache = weakref.WeakKeyDictionary()     # plans die with their FormProgram (Integrate builds one per call)
         self._dbuf = None
         self._scal = torch.zeros(64, dtype=torch.float64, device=self.device)
         self.launches = 0
@@ -414,12 +415,11 @@ class CudaBackend:
         return plan
 
     def _plans(self, program: FormProgram) -> list:
-        key = id(program)
-        hit = self._plan_cache.get(key)
-        if hit is None or hit[0] is not program:
-            hit = (program, [self._build_plans(program, integ) for integ in program.integrals])
-            self._plan_cache[key] = hit
-        return hit[1]
+        hit = self._plan_cache.get(program)
+        if hit is None:
+            hit = [self._build_plans(program, integ) for integ in program.integrals]
+            self._plan_cache[program] = hit
+        return hit
 
     def _run(self, program: FormProgram, out, mode: str):
         torch = self.torch

@@ -13,6 +13,7 @@ dual tables are tabulated once on the host like any other basis table.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Dict, Optional
 
 import numpy as np
@@ -133,6 +134,8 @@ def set_gridfunction(gf, cf: CoefficientFunction, definedon: Optional[Region]) -
         return
     key = (id(gf._root), tuple(blocks), bnd, None if definedon is None else definedon.ids, id(cf))
     hit = _cache.get(key)
+    if hit is not None and (hit[5]() is not gf._root or hit[6] is not be):
+        hit = None                                   # id() of a dead object was reused, or the backend changed
     if hit is None:
         order = max(root_space.blocks[b].order for b in blocks)
         deg = 2 * order
@@ -165,9 +168,12 @@ def set_gridfunction(gf, cf: CoefficientFunction, definedon: Optional[Region]) -
             np.add.at(count, cd[cells].ravel(), 1.0)
         mask = count > 0
         inv = np.where(mask, 1.0 / np.maximum(count, 1.0), 0.0)
-        hit = (prog, be.from_numpy(inv), be.from_numpy(mask.astype(np.float64)), be.zeros(pspace.ndof), cf)
+        hit = (prog, be.from_numpy(inv), be.from_numpy(mask.astype(np.float64)), be.zeros(pspace.ndof), cf,
+               weakref.ref(gf._root), be)
+        if len(_cache) >= 256:                       # bounded: models may rebuild their boundary data every step
+            _cache.pop(next(iter(_cache)))
         _cache[key] = hit
-    prog, inv, mask, work, _keep = hit
+    prog, inv, mask, work = hit[:4]
     be.assemble_vector(prog, work)
     be.masked_assign(gf.vec.a, work, inv, mask)
 
