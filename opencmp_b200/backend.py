@@ -35,11 +35,12 @@ class CoefPlan(C.Structure):
 class ContractPlan(C.Structure):
     _fields_ = [('dim', C.c_int), ('kind', C.c_int), ('nq', C.c_int), ('nside', C.c_int), ('nblk', C.c_int),
                 ('nloc', C.c_int), ('sbsz', C.c_int), ('zsz', C.c_int), ('nact', C.c_int), ('nslots', C.c_int),
-                ('eb', C.c_int),
+                ('eb', C.c_int), ('asz', C.c_int), ('nzd', C.c_int), ('nent', C.c_int), ('npairs', C.c_int),
+                ('nseg', C.c_int),
                 ('items', C.c_void_p), ('geo', C.c_void_p), ('facet_cells', C.c_void_p), ('facet_local', C.c_void_p),
                 ('blk', C.c_void_p), ('tab', C.c_void_p), ('zdesc', C.c_void_p), ('ent', C.c_void_p),
-                ('adesc', C.c_void_p), ('amap', C.c_void_p), ('seg', C.c_void_p), ('cell2nnz', C.c_void_p),
-                ('facet2nnz', C.c_void_p), ('cell_dofs', C.c_void_p)]
+                ('dofdesc', C.c_void_p), ('pairs', C.c_void_p), ('amap', C.c_void_p), ('seg', C.c_void_p),
+                ('cell2nnz', C.c_void_p), ('facet2nnz', C.c_void_p), ('cell_dofs', C.c_void_p)]
 
 
 class System(C.Structure):
@@ -357,7 +358,7 @@ class CudaBackend:
                 s, b, r = decode(tr)
                 ent.append([slot, ((s * nblk + b) << 8) | r])
             xp.ent = up(np.array(ent), np.int32).data_ptr()
-            xp.zsz = len(ent)
+            xp.nent = len(ent)
             xp.eb = 1
             plan['contract'] = xp
             return plan
@@ -368,46 +369,61 @@ class CudaBackend:
             st, bt, rt = decode(tr)
             su, bu, ru = decode(ur)
             segs.setdefault((st, bt, rt, su, bu), []).append((slot, ru))
+        pad4 = lambda v: (v + 3) // 4 * 4
+        # per (side, local dof): how to build its physical table column
+        dofdesc = []
+        for s_ in range(nside):
+            for bidx, b in enumerate(blocks):
+                for il in range(b.nloc):
+                    dofdesc.append([(0 if b.kind == 'scalar' else 1) | (b.basis.nrows << 8), b.nloc,
+                                    blk_tab[bidx][3] + il, sb_off[bidx] + il])
+        # Z rows: one (padded) segment per (test row, trial side-block)
         zdesc, ent, seg_z = [], [], {}
         zoff = 0
         for key in sorted(segs):
             st, bt, rt, su, bu = key
             k0 = len(ent)
-            ent += [[slot, ru] for slot, ru in segs[key]]
-            k1 = len(ent)
             nl = blocks[bu].nloc
+            ent += [[slot, ru * nl] for slot, ru in segs[key]]
+            k1 = len(ent)
             seg_z[key] = zoff
             for j in range(nl):
-                zdesc.append([k0, k1, su * sbsz + sb_off[bu] + j, nl])
-            zoff += nl
+                zdesc.append([k0, k1, su * sbsz + sb_off[bu] + j, zoff + j])
+            zoff += pad4(nl)
+        # active block pairs
         pairs: Dict[tuple, list] = {}
         for key in sorted(segs):
             st, bt, rt, su, bu = key
             pairs.setdefault((st, bt, su, bu), []).append((rt, seg_z[key]))
-        seg_arr, adesc, amap = [], [], []
+        pair_arr, seg_arr, amap = [], [], []
+        aoff = 0
         for (st, bt, su, bu), lst in sorted(pairs.items()):
+            ni, nj = blocks[bt].nloc, blocks[bu].nloc
+            njp = pad4(nj)
             s0 = len(seg_arr)
-            seg_arr += [[rt, z] for rt, z in lst]
-            ns = len(lst)
-            nlt, nlu = blocks[bt].nloc, blocks[bu].nloc
+            seg_arr += [[rt * ni, z] for rt, z in lst]
+            nj4 = njp // 4
+            magic = ((1 << 32) // nj4 + 1) & 0xffffffff if nj4 > 1 else 0
+            pair_arr.append([aoff, ni, nj4, st * sbsz + sb_off[bt], s0, len(lst), magic, 0])
             lot, lou = fes.loc_offsets[bt], fes.loc_offsets[bu]
-            for i in range(nlt):
-                for j in range(nlu):
-                    adesc.append([st * sbsz + sb_off[bt] + i, nlt, s0 | (ns << 24), j])
-                    amap.append((st << 30) | (su << 29) | ((lot + i) * fes.nloc + lou + j))
-        xp.zsz, xp.nact = zoff, len(adesc)
+            for i in range(ni):
+                for j in range(nj):
+                    amap.append([(st << 30) | (su << 29) | ((lot + i) * fes.nloc + lou + j), aoff + i * njp + j])
+            aoff += ni * njp
+        xp.zsz, xp.nact, xp.asz = zoff, len(amap), aoff
+        xp.nzd, xp.nent, xp.npairs, xp.nseg = len(zdesc), len(ent), len(pair_arr), len(seg_arr)
         xp.zdesc = up(np.array(zdesc), np.int32).data_ptr()
         xp.ent = up(np.array(ent), np.int32).data_ptr()
         xp.seg = up(np.array(seg_arr), np.int32).data_ptr()
-        xp.adesc = up(np.array(adesc), np.int32).data_ptr()
-        xp.amap = up(np.array(amap, dtype=np.int64).astype(np.uint32).view(np.int32), np.int32).data_ptr()
+        xp.dofdesc = up(np.array(dofdesc), np.int32).data_ptr()
+        xp.pairs = up(np.array(pair_arr, dtype=np.int64).astype(np.uint32).view(np.int32), np.int32).data_ptr()
+        xp.amap = up(np.array(amap, dtype=np.int64).astype(np.int32), np.int32).data_ptr()
         gs = dim + 2 * dim * dim + 1
+        nints = 4 * nside * fes.nloc + 4 * len(zdesc) + 2 * len(ent) + 8 * len(pair_arr) + 2 * len(seg_arr)
         eb_pick = 1
-        for eb in (16, 8, 4, 2, 1):
-            tpe = 256 // eb
-            need = -(-xp.nact // tpe)
-            smem = 8 * (eb * nside * sbsz + eb * zoff + eb * prog.nout + eb * nside * gs) + 16 * eb
-            if need <= 16 and smem <= 96 * 1024:
+        for eb in (8, 4, 2, 1):
+            smem = 8 * eb * (aoff + nside * sbsz + zoff + prog.nout + nside * gs) + 4 * (nints + 4 * eb) + 16
+            if smem <= 100 * 1024:
                 eb_pick = eb
                 break
         xp.eb = eb_pick

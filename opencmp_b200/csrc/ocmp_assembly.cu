@@ -232,23 +232,41 @@ __device__ __forceinline__ void dof_phys_rows(int kind, int nloc, int nrows, con
     phys_rows<DIM>(kind, R, g + DIM, g + DIM + DIM * DIM, g[GS - 1], PH);
 }
 
-template <int DIM, int NACC>
+// Contraction kernel. One CTA handles EB items; per quadrature point the physical tables (sB), the D values (sD) and
+// the rows Z_g = sum_k D_k B[trial row_k] (sZ) are staged in shared memory, then every *active block pair* (test block,
+// trial block) is updated as a small GEMM  A_p[i][j] += sum_g B[row_g][i] * Z_g[j]  with the accumulators in shared
+// memory and each thread owning 1 x 4 strips (one B load and two 16-byte Z loads per 4 FMAs). Pair widths are padded
+// to a multiple of 4 (Z padding stays zero). All descriptor tables are copied to shared memory once per CTA.
+template <int DIM>
 __global__ void __launch_bounds__(256) k_contract(const __grid_constant__ ocmp_contract_plan P, int item0, int nitems,
                                                   const double* __restrict__ dbuf, double* __restrict__ values) {
     constexpr int GS = GeoT<DIM>::GS;
     extern __shared__ double smem[];
     const int EB = P.eb, TPE = 256 / EB;
     const int nside = P.nside;
-    double* sB = smem;                                   // [EB][nside][sbsz]
-    double* sZ = sB + EB * nside * P.sbsz;               // [EB][zsz]
-    double* sD = sZ + EB * P.zsz;                        // [EB][nslots]
+    double* sA = smem;                                   // [EB][asz]
+    double* sZ = sA + EB * P.asz;                        // [EB][zsz]   (padded; sA and sZ stay 32-byte aligned)
+    double* sB = sZ + EB * P.zsz;                        // [EB][nside][sbsz]
+    double* sD = sB + EB * nside * P.sbsz;               // [EB][nslots]
     double* sG = sD + EB * P.nslots;                     // [EB][nside][GS]
     int* sI = reinterpret_cast<int*>(sG + EB * nside * GS);   // [EB][4]: cell0, cell1, lf0, lf1
+    int* tDof = sI + 4 * EB;                             // [nside*nloc][4]: kind | nr << 8, nl, tab offset, sB offset(+il)
+    int* tZ = tDof + 4 * nside * P.nloc;                 // [nzd][4]: entry k0, k1, sB base (incl. j), z index
+    int* tEnt = tZ + 4 * P.nzd;                          // [nent][2]: slot, row offset (row * stride)
+    int* tPair = tEnt + 2 * P.nent;                      // [npairs][8]
+    int* tSeg = tPair + 8 * P.npairs;                    // [nseg][2]: row offset (row * ni), z offset
     const int tid = threadIdx.x;
     const int e_own = tid / TPE, lane = tid % TPE;
     const long long dstride = (long long)nitems * P.nq;
     const int ngroups = (nitems + EB - 1) / EB;
     const int n2 = P.nloc * P.nloc;
+
+    for (int i = tid; i < 4 * nside * P.nloc; i += 256) tDof[i] = __ldg(P.dofdesc + i);
+    for (int i = tid; i < 4 * P.nzd; i += 256) tZ[i] = __ldg(P.zdesc + i);
+    for (int i = tid; i < 2 * P.nent; i += 256) tEnt[i] = __ldg(P.ent + i);
+    for (int i = tid; i < 8 * P.npairs; i += 256) tPair[i] = __ldg(P.pairs + i);
+    for (int i = tid; i < 2 * P.nseg; i += 256) tSeg[i] = __ldg(P.seg + i);
+    for (int i = tid; i < EB * P.zsz; i += 256) sZ[i] = 0.0;
 
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         __syncthreads();
@@ -265,92 +283,107 @@ __global__ void __launch_bounds__(256) k_contract(const __grid_constant__ ocmp_c
             }
             sI[4 * tid] = c0; sI[4 * tid + 1] = c1; sI[4 * tid + 2] = l0; sI[4 * tid + 3] = l1;
         }
+        for (int i = tid; i < EB * P.asz; i += 256) sA[i] = 0.0;
         __syncthreads();
         for (int idx = tid; idx < EB * nside * GS; idx += 256) {
             const int e = idx / (nside * GS), rem = idx % (nside * GS), s = rem / GS, k = rem % GS;
             const int c = sI[4 * e + s];
             sG[idx] = (c >= 0) ? __ldg(P.geo + (long long)c * GS + k) : (k == GS - 1 ? 1.0 : 0.0);
         }
-        double acc[NACC];
-#pragma unroll
-        for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+        const int it_own = grp * EB + e_own;
 
         for (int q = 0; q < P.nq; ++q) {
             __syncthreads();
-            for (int idx = tid; idx < EB * P.nslots; idx += 256) {
-                const int e = idx / P.nslots, k = idx % P.nslots, it = grp * EB + e;
-                sD[idx] = (it < nitems) ? __ldg(dbuf + (long long)k * dstride + (long long)it * P.nq + q) : 0.0;
-            }
-            for (int idx = tid; idx < EB * nside * P.nloc; idx += 256) {
-                const int e = idx / (nside * P.nloc), rem = idx % (nside * P.nloc), s = rem / P.nloc, i = rem % P.nloc;
-                int b = 0;
-                while (b + 1 < P.nblk && i >= __ldg(P.blk + 6 * (b + 1) + 4)) ++b;
-                const int* bd = P.blk + 6 * b;
-                const int kind = __ldg(bd), nl = __ldg(bd + 1), nr = __ldg(bd + 2), toff = __ldg(bd + 3),
-                          loff = __ldg(bd + 4), sboff = __ldg(bd + 5);
-                const int il = i - loff;
-                const int c = sI[4 * e + s];
-                double* out = sB + (e * nside + s) * P.sbsz + sboff + il;
+            // D values of this quadrature point
+            for (int k = lane; k < P.nslots; k += TPE)
+                sD[e_own * P.nslots + k] = (it_own < nitems)
+                    ? __ldg(dbuf + (long long)k * dstride + (long long)it_own * P.nq + q) : 0.0;
+            // physical basis tables of my item: one (side, dof) column per thread
+            for (int sd = lane; sd < nside * P.nloc; sd += TPE) {
+                const int4 dd = *reinterpret_cast<const int4*>(tDof + 4 * sd);
+                const int s = sd >= P.nloc ? 1 : 0;
+                const int kind = dd.x & 0xff, nr = dd.x >> 8, nl = dd.y;
+                const int c = sI[4 * e_own + s];
+                double* out = sB + (e_own * nside + s) * P.sbsz + dd.w;
                 if (c < 0) {
                     for (int r = 0; r < nr; ++r) out[r * nl] = 0.0;
                 } else {
-                    const int lfq = (P.kind == 0 ? 0 : sI[4 * e + 2 + s] * P.nq) + q;
-                    double PH[MAX_ROWS];
-                    dof_phys_rows<DIM>(kind, nl, nr, P.tab + toff + (long long)lfq * nr * nl, il,
-                                       sG + (e * nside + s) * GS, PH);
+                    const int lfq = (P.kind == 0 ? 0 : sI[4 * e_own + 2 + s] * P.nq) + q;
+                    const double* tq = P.tab + dd.z + (long long)lfq * nr * nl;      // dd.z includes the local dof
+                    const double* g = sG + (e_own * nside + s) * GS;
+                    if (kind == 0) {
+                        double R[1 + DIM], PH[MAX_ROWS];
 #pragma unroll
-                    for (int r = 0; r < MAX_ROWS; ++r)
-                        if (r < nr) out[r * nl] = PH[r];
+                        for (int r = 0; r < 1 + DIM; ++r) R[r] = __ldg(tq + r * nl);
+                        phys_rows<DIM>(0, R, g + DIM, g + DIM + DIM * DIM, g[GS - 1], PH);
+#pragma unroll
+                        for (int r = 0; r < 1 + DIM; ++r) out[r * nl] = PH[r];
+                    } else {
+                        double R[DIM + DIM * DIM], PH[MAX_ROWS];
+#pragma unroll
+                        for (int r = 0; r < DIM + DIM * DIM; ++r) R[r] = __ldg(tq + r * nl);
+                        phys_rows<DIM>(1, R, g + DIM, g + DIM + DIM * DIM, g[GS - 1], PH);
+#pragma unroll
+                        for (int r = 0; r < DIM + DIM * DIM; ++r) out[r * nl] = PH[r];
+                    }
                 }
             }
             __syncthreads();
-            for (int idx = tid; idx < EB * P.zsz; idx += 256) {
-                const int e = idx / P.zsz, z = idx % P.zsz;
-                const int4 zd = __ldg(reinterpret_cast<const int4*>(P.zdesc) + z);
-                const double* bb = sB + e * nside * P.sbsz + zd.z;
-                const double* dd = sD + e * P.nslots;
-                double s = 0.0;
-                for (int k = zd.x; k < zd.y; ++k) {
-                    const int2 en = __ldg(reinterpret_cast<const int2*>(P.ent) + k);
-                    s += dd[en.x] * bb[en.y * zd.w];
+            // Z rows
+            {
+                const double* bE = sB + e_own * nside * P.sbsz;
+                const double* dE = sD + e_own * P.nslots;
+                double* zE = sZ + e_own * P.zsz;
+                for (int z = lane; z < P.nzd; z += TPE) {
+                    const int4 zd = *reinterpret_cast<const int4*>(tZ + 4 * z);
+                    double s = 0.0;
+                    for (int k = zd.x; k < zd.y; ++k) s = fma(dE[tEnt[2 * k]], bE[zd.z + tEnt[2 * k + 1]], s);
+                    zE[zd.w] = s;
                 }
-                sZ[idx] = s;
             }
             __syncthreads();
+            // pair-wise update of the accumulators, 1 x 4 strips
             {
                 const double* bE = sB + e_own * nside * P.sbsz;
                 const double* zE = sZ + e_own * P.zsz;
-#pragma unroll
-                for (int a = 0; a < NACC; ++a) {
-                    const int ai = lane + a * TPE;
-                    if (ai < P.nact) {
-                        const int4 ad = __ldg(reinterpret_cast<const int4*>(P.adesc) + ai);
-                        const int s0 = ad.z & 0xffffff, ns = ad.z >> 24;
-                        double v = acc[a];
+                double* aE = sA + e_own * P.asz;
+                for (int p = 0; p < P.npairs; ++p) {
+                    const int* pd = tPair + 8 * p;
+                    const int aoff = pd[0], ni = pd[1], nj4 = pd[2], bbase = pd[3], s0 = pd[4], ns = pd[5];
+                    const unsigned magic = (unsigned)pd[6];
+                    const int nstrips = ni * nj4;
+                    for (int k = lane; k < nstrips; k += TPE) {
+                        const int i = nj4 == 1 ? k : (int)__umulhi((unsigned)k, magic);
+                        const int j4 = k - i * nj4;
+                        double* ap = aE + aoff + (i * nj4 + j4) * 4;
+                        double2 a0 = *reinterpret_cast<double2*>(ap), a1 = *reinterpret_cast<double2*>(ap + 2);
+                        const double* bp = bE + bbase + i;
+                        const double* zp = zE + 4 * j4;
                         for (int s = s0; s < s0 + ns; ++s) {
-                            const int2 sg = __ldg(reinterpret_cast<const int2*>(P.seg) + s);
-                            v = fma(bE[ad.x + sg.x * ad.y], zE[sg.y + ad.w], v);
+                            const double b = bp[tSeg[2 * s]];
+                            const double2 z0 = *reinterpret_cast<const double2*>(zp + tSeg[2 * s + 1]);
+                            const double2 z1 = *reinterpret_cast<const double2*>(zp + tSeg[2 * s + 1] + 2);
+                            a0.x = fma(b, z0.x, a0.x); a0.y = fma(b, z0.y, a0.y);
+                            a1.x = fma(b, z1.x, a1.x); a1.y = fma(b, z1.y, a1.y);
                         }
-                        acc[a] = v;
+                        *reinterpret_cast<double2*>(ap) = a0;
+                        *reinterpret_cast<double2*>(ap + 2) = a1;
                     }
                 }
             }
         }
+        __syncthreads();
         // ---- scatter-add through the element -> nnz map ------------------------------------------------------
-        const int it = grp * EB + e_own;
-        if (it < nitems) {
+        if (it_own < nitems) {
             const int c0 = sI[4 * e_own], c1 = sI[4 * e_own + 1];
-#pragma unroll
-            for (int a = 0; a < NACC; ++a) {
-                const int ai = lane + a * TPE;
-                if (ai < P.nact) {
-                    const int m = __ldg(P.amap + ai);
-                    const int st = (m >> 30) & 1, su = (m >> 29) & 1, ij = m & 0x1fffffff;
-                    int pos;
-                    if (st == su) pos = __ldg(P.cell2nnz + (long long)(st ? c1 : c0) * n2 + ij);
-                    else pos = __ldg(P.facet2nnz + ((long long)(item0 + it) * 2 + st) * n2 + ij);
-                    atomicAdd(values + pos, acc[a]);
-                }
+            const double* aE = sA + e_own * P.asz;
+            for (int ai = lane; ai < P.nact; ai += TPE) {
+                const int2 m = __ldg(reinterpret_cast<const int2*>(P.amap) + ai);
+                const int st = (m.x >> 30) & 1, su = (m.x >> 29) & 1, ij = m.x & 0x1fffffff;
+                int pos;
+                if (st == su) pos = __ldg(P.cell2nnz + (long long)(st ? c1 : c0) * n2 + ij);
+                else pos = __ldg(P.facet2nnz + ((long long)(item0 + it_own) * 2 + st) * n2 + ij);
+                atomicAdd(values + pos, aE[m.y]);
             }
         }
     }
@@ -377,7 +410,7 @@ __global__ void __launch_bounds__(128) k_lin(const __grid_constant__ ocmp_contra
     const int kind = bd[0], nl = bd[1], nr = bd[2], toff = bd[3], loff = bd[4];
     const int il = i - loff, sbk = s * P.nblk + b;
     // does any entry test against this side-block?
-    const int nent = P.zsz;
+    const int nent = P.nent;
     bool any = false;
     for (int k = 0; k < nent; ++k) any |= ((P.ent[2 * k + 1] >> 8) == sbk);
     if (!any) return;
@@ -428,28 +461,31 @@ extern "C" int ocmp_eval_coefficients(const ocmp_coef_plan* plan, int item0, int
 
 static size_t contract_smem(const ocmp_contract_plan* p) {
     const int gs = p->dim + 2 * p->dim * p->dim + 1;
-    return sizeof(double) * ((size_t)p->eb * p->nside * p->sbsz + (size_t)p->eb * p->zsz + (size_t)p->eb * p->nslots +
-                             (size_t)p->eb * p->nside * gs) + sizeof(int) * 4 * p->eb;
+    const size_t dbl = (size_t)p->eb * p->asz + (size_t)p->eb * p->nside * p->sbsz + (size_t)p->eb * p->zsz +
+                       (size_t)p->eb * p->nslots + (size_t)p->eb * p->nside * gs;
+    const size_t ints = 4 * (size_t)p->eb + 4 * (size_t)p->nside * p->nloc + 4 * (size_t)p->nzd + 2 * (size_t)p->nent +
+                        8 * (size_t)p->npairs + 2 * (size_t)p->nseg;
+    return sizeof(double) * dbl + sizeof(int) * ints + 16;
 }
 
-template <int DIM, int NACC>
+template <int DIM>
 static int launch_contract(const ocmp_contract_plan* plan, int item0, int nitems, const double* dbuf, double* values,
                            cudaStream_t st) {
     const size_t smem = contract_smem(plan);
     if (smem > 220 * 1024) return ocmp_fail(-3, "contraction plan needs more than 220 KB of shared memory");
     static size_t configured = 0;
     if (smem > configured) {
-        cudaFuncSetAttribute(k_contract<DIM, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_contract<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     const int ngroups = (nitems + plan->eb - 1) / plan->eb;
     int sms = ocmp_sm_count();
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contract<DIM, NACC>, 256, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contract<DIM>, 256, smem);
     if (per_sm < 1) per_sm = 1;
     const int grid = ngroups < sms * per_sm ? ngroups : sms * per_sm;
     ProfScope ps(PROF_CONTRACT, st);
-    k_contract<DIM, NACC><<<grid, 256, smem, st>>>(*plan, item0, nitems, dbuf, values);
+    k_contract<DIM><<<grid, 256, smem, st>>>(*plan, item0, nitems, dbuf, values);
     return ocmp_check("ocmp_contract_matrix");
 }
 
@@ -459,16 +495,9 @@ extern "C" int ocmp_contract_matrix(const ocmp_contract_plan* plan, int item0, i
     cudaStream_t st = (cudaStream_t)stream;
     const int eb = plan->eb;
     if (eb < 1 || eb > 16 || (eb & (eb - 1))) return ocmp_fail(-1, "eb must be a power of two <= 16");
-    const int tpe = 256 / eb;
-    const int need = (plan->nact + tpe - 1) / tpe;
-    if (plan->dim == 2) {
-        if (need <= 16) return launch_contract<2, 16>(plan, item0, nitems, dbuf, values, st);
-        if (need <= 32) return launch_contract<2, 32>(plan, item0, nitems, dbuf, values, st);
-    } else if (plan->dim == 3) {
-        if (need <= 16) return launch_contract<3, 16>(plan, item0, nitems, dbuf, values, st);
-        if (need <= 32) return launch_contract<3, 32>(plan, item0, nitems, dbuf, values, st);
-    } else return ocmp_fail(-1, "dim must be 2 or 3");
-    return ocmp_fail(-3, "local matrix too large for the register-accumulator kernel");
+    if (plan->dim == 2) return launch_contract<2>(plan, item0, nitems, dbuf, values, st);
+    if (plan->dim == 3) return launch_contract<3>(plan, item0, nitems, dbuf, values, st);
+    return ocmp_fail(-1, "dim must be 2 or 3");
 }
 
 extern "C" int ocmp_contract_vector(const ocmp_contract_plan* plan, int item0, int nitems, const double* dbuf,
