@@ -130,6 +130,12 @@ typedef struct ocmp_system {
     const int* inv_rowptr;   /* pre_kind 4 */
     const int* inv_colidx;
     const double* inv_vals;
+    /* element-partitioned runs; all zero / NULL on a single GPU. Vectors are local (owned + ghost)
+     * and kept consistent: ghost entries equal the owner's value. Plan fields hold ocmp_halo_plan handle + 1. */
+    const double* owned;     /* 1.0 on the entries this rank owns: dot products (followed by one ncclAllReduce) and
+                                restriction only see those; NULL = not distributed */
+    int halo_fwd;            /* refresh ghost entries after an SpMV / after the coarsest-level solve (0: none) */
+    int halo_sum;            /* sum the neighbours' partial patch corrections after the smoother (0: none) */
 } ocmp_system;
 
 /* One multigrid level: operator + smoother (sys), transfer from the next coarser level, work space.
@@ -142,6 +148,9 @@ typedef struct ocmp_mg_level {
     double* work;            /* 4 * nrows doubles: x, b, r, t */
     int nu;                  /* pre- and post-smoothing sweeps */
     double omega;            /* smoother damping */
+    int restrict_sum;        /* plan + 1 on the COARSE level: sum the partial restricted residuals (0: none) */
+    int handover;            /* plan + 1 on the COARSE level: a replicated coarse level hands the owners' correction up
+                                to a distributed one (redundant solves differ by round-off) (0: none) */
 } ocmp_mg_level;
 
 /* kind: 0 CG, 1 GMRES(restart), 2 Richardson. x holds the initial guess (and Dirichlet values) on entry.

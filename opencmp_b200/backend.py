@@ -48,13 +48,14 @@ class System(C.Structure):
                 ('freemask', C.c_void_p), ('pre_kind', C.c_int), ('dinv', C.c_void_p), ('npatch', C.c_int),
                 ('bs', C.c_int), ('patch_dofs', C.c_void_p), ('inv_blocks', C.c_void_p), ('patch_weight', C.c_void_p),
                 ('nlevels', C.c_int), ('levels', C.c_void_p), ('inv_rowptr', C.c_void_p), ('inv_colidx', C.c_void_p),
-                ('inv_vals', C.c_void_p)]
+                ('inv_vals', C.c_void_p), ('owned', C.c_void_p), ('halo_fwd', C.c_int), ('halo_sum', C.c_int)]
 
 
 class MGLevel(C.Structure):
     _fields_ = [('sys', System), ('ncoarse', C.c_int), ('p_rowptr', C.c_void_p), ('p_colidx', C.c_void_p),
                 ('p_vals', C.c_void_p), ('r_rowptr', C.c_void_p), ('r_colidx', C.c_void_p), ('r_vals', C.c_void_p),
-                ('work', C.c_void_p), ('nu', C.c_int), ('omega', C.c_double)]
+                ('work', C.c_void_p), ('nu', C.c_int), ('omega', C.c_double), ('restrict_sum', C.c_int),
+                ('handover', C.c_int)]
 
 
 def load_library() -> C.CDLL:

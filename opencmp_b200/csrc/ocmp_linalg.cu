@@ -138,10 +138,10 @@ static int spmv_cat(int cat, int nrows, const int* rowptr, const int* colidx, co
 
 // ---- level-1 ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dot(long long n, const double* __restrict__ x, const double* __restrict__ y,
-                                             double* __restrict__ out) {
+                                             double* __restrict__ out, const double* __restrict__ m = nullptr) {
     double s = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        s = fma(x[i], y[i], s);
+        s = fma(m ? x[i] * m[i] : x[i], y[i], s);
     s = block_reduce_sum(s);
     if (threadIdx.x == 0) atomicAdd(out, s);
 }
@@ -185,13 +185,14 @@ __global__ void __launch_bounds__(256) k_resid(long long n, const double* __rest
 // out[j] += <V_j, w>, j < k <= 8 ; V_j = V + j*ld
 template <int K>
 __global__ void __launch_bounds__(256) k_mdot(long long n, const double* __restrict__ V, long long ld, int k,
-                                              const double* __restrict__ w, double* __restrict__ out) {
+                                              const double* __restrict__ w, double* __restrict__ out,
+                                              const double* __restrict__ m = nullptr) {
     double s[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) s[j] = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
-        const double wi = w[i];
+        const double wi = m ? w[i] * m[i] : w[i];
 #pragma unroll
         for (int j = 0; j < K; ++j)
             if (j < k) s[j] = fma(V[j * ld + i], wi, s[j]);
@@ -439,8 +440,10 @@ struct Ctx {
     double* dscal;      // device scratch scalars (>= 64)
     double hscal[64];
 
+    // y = A x; element-partitioned: followed by the ghost refresh, so y is consistent like x
     void A(const double* x, double* y) const {
         ocmp_spmv(s->nrows, s->rowptr, s->colidx, s->vals, x, y, st);
+        if (s->halo_fwd) ocmp_halo_run(s->halo_fwd - 1, y, 0, st);
     }
     // one application of the smoother / local preconditioner of system `sy`: z = S r (r masked, result masked)
     static void smooth(const ocmp_system* sy, cudaStream_t st, const double* r, double* z) {
@@ -450,12 +453,16 @@ struct Ctx {
             k_had<<<grid_for(n), 256, 0, st>>>(n, sy->dinv, nullptr, r, z);
         } else if (sy->pre_kind == 2 || sy->pre_kind == 3) {
             ocmp_asm_apply(sy->npatch, sy->bs, sy->patch_dofs, sy->inv_blocks, r, z, n, st);
+            // a rank applies the patches of the vertices it owns; DOFs shared with a neighbour get the sum
+            if (sy->halo_sum) ocmp_halo_run(sy->halo_sum - 1, z, 1, st);
             if (sy->freemask || sy->patch_weight) {
                 ProfScope ps(PROF_VEC, st);
                 k_had<<<grid_for(n), 256, 0, st>>>(n, sy->patch_weight, sy->freemask, z, z);
             }
         } else if (sy->pre_kind == 4) {
             spmv_cat(PROF_SPMV_MG, sy->nrows, sy->inv_rowptr, sy->inv_colidx, sy->inv_vals, r, z, st);
+            // replicated coarsest level: every rank solved with its own (round-off different) copy; owners' values win
+            if (sy->halo_fwd) ocmp_halo_run(sy->halo_fwd - 1, z, 0, st);
             if (sy->freemask) {
                 ProfScope ps(PROF_VEC, st);
                 k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, z, z);
@@ -477,24 +484,30 @@ struct Ctx {
         ocmp_axpby(n, 0.0, x, lv.omega, x, st);
         for (int s = 1; s < lv.nu; ++s) {
             spmv_cat(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
+            if (sy->halo_fwd) ocmp_halo_run(sy->halo_fwd - 1, r, 0, st);
             k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
             smooth(sy, st, r, t);
             ocmp_axpby(n, lv.omega, t, 1.0, x, st);
         }
+        // residual to restrict: only the owned entries are used, so no ghost refresh after this SpMV
         spmv_cat(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
         k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
+        if (sy->owned) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->owned, r, r);
         const ocmp_mg_level& lc = L[l - 1];
         const long long nc = lc.sys.nrows;
         double* xc = lc.work;
         double* bc = lc.work + nc;
         spmv_cat(PROF_SPMV_MG, (int)nc, lv.r_rowptr, lv.r_colidx, lv.r_vals, r, bc, st);
+        if (lv.restrict_sum) ocmp_halo_run(lv.restrict_sum - 1, bc, 1, st);
         if (lc.sys.freemask) k_had<<<grid_for(nc), 256, 0, st>>>(nc, nullptr, lc.sys.freemask, bc, bc);
         vcycle(L, l - 1, st, bc, xc);
+        if (lv.handover) ocmp_halo_run(lv.handover - 1, xc, 0, st);
         spmv_cat(PROF_SPMV_MG, sy->nrows, lv.p_rowptr, lv.p_colidx, lv.p_vals, xc, t, st);
         if (sy->freemask) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, t, t);
         ocmp_axpby(n, 1.0, t, 1.0, x, st);
         for (int s = 0; s < lv.nu; ++s) {
             spmv_cat(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
+            if (sy->halo_fwd) ocmp_halo_run(sy->halo_fwd - 1, r, 0, st);
             k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
             smooth(sy, st, r, t);
             ocmp_axpby(n, lv.omega, t, 1.0, x, st);
@@ -509,8 +522,14 @@ struct Ctx {
         ProfScope ps(PROF_VEC, st);
         if (s->freemask) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, s->freemask, v, v);
     }
+    // <x, y> over the owned entries, summed over the ranks (one FP64 all-reduce) when element-partitioned
     double dot(const double* x, const double* y) {
-        ocmp_dot(n, x, y, dscal, st);
+        cudaMemsetAsync(dscal, 0, sizeof(double), st);
+        {
+            ProfScope ps(PROF_VEC, st);
+            if (n > 0) k_dot<<<grid_for(n), 256, 0, st>>>(n, x, y, dscal, s->owned);
+        }
+        if (s->owned) ocmp_allreduce_sum(dscal, 1, st);
         cudaMemcpyAsync(hscal, dscal, sizeof(double), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         return hscal[0];
@@ -521,9 +540,10 @@ struct Ctx {
         cudaMemsetAsync(dscal, 0, sizeof(double) * k, st);
         for (int j0 = 0; j0 < k; j0 += 8) {
             const int kk = (k - j0) < 8 ? (k - j0) : 8;
-            k_mdot<8><<<grid_for(n), 256, 0, st>>>(n, V + (long long)j0 * n, n, kk, w, dscal + j0);
+            k_mdot<8><<<grid_for(n), 256, 0, st>>>(n, V + (long long)j0 * n, n, kk, w, dscal + j0, s->owned);
         }
         ocmp_prof_end(PROF_MDOT, st);
+        if (s->owned) ocmp_allreduce_sum(dscal, k, st);
         cudaMemcpyAsync(hout, dscal, sizeof(double) * k, cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
     }

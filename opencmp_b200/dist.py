@@ -177,6 +177,11 @@ class DofMap:
         be = ngs.get_backend()
         if getattr(be, 'name', '') != 'cuda' or not be.comm_init():
             return False
+        be.halo_run(self.plan_handle(be, kind), t, add)
+        return True
+
+    def plan_handle(self, be, kind: str) -> int:
+        """C-side halo plan ('fwd' ghost refresh, 'rev' reverse add, 'sum' partial sums) of this map; built once."""
         plans = self.__dict__.setdefault('_plans', {})
         if kind not in plans:
             out_plan, in_plan = {'fwd': (self.send, self.recv), 'rev': (self.recv, self.send),
@@ -185,8 +190,7 @@ class DofMap:
             empty = np.zeros(0, dtype=np.int64)
             plans[kind] = be.halo_plan(peers, [out_plan.get(s, empty) for s in peers],
                                        [in_plan.get(s, empty) for s in peers])
-        be.halo_run(plans[kind][0], t, add)
-        return True
+        return plans[kind][0]
 
     def _index(self, idx, device):
         import torch

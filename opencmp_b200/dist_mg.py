@@ -10,12 +10,14 @@ Communication per V-cycle and level: one halo exchange after each SpMV, ``revers
 application (patch corrections reach ghost DOFs) and after the restriction. Per GMRES iteration: the Gram-Schmidt
 coefficients are all-reduced as one small vector.
 
-The cycle is driven from Python in this round (the single-GPU cycle runs inside the C ABI); vector updates between
-the hand-written kernels (SpMV, patch inversion / application, assembly) use array expressions of the backend array
-type, and the Gram-Schmidt projections a library matrix-vector product.
+On the GPU the whole GMRES + V-cycle runs inside the C ABI (ocmp_krylov with the element-partitioned fields of
+ocmp_system / ocmp_mg_level): exchanges and all-reduces are issued from the C driver on the kernels' stream. The Python
+cycle below is the same algorithm written with array expressions; it is what the gloo tests run on CPU and the
+reference the native driver is checked against (OCMP_DIST_NATIVE=0 selects it on the GPU).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -86,6 +88,7 @@ class DistributedMultigrid:
                 if not lv.replicated:
                     lv.map.exchange_sum(cnt)
                 lv.wgt = lv.free / (cnt + (cnt == 0))
+                lv.pw = 1.0 / (cnt + (cnt == 0))
                 prev = self.levels[l - 1]
                 parent_global = lv.part.local_cells // 4
                 parent = np.searchsorted(prev.part.local_cells, parent_global)
@@ -95,6 +98,8 @@ class DistributedMultigrid:
                 lv.R = be.csr_handle(P.T.tocsr())
             self.levels.append(lv)
         self.inv0 = None
+        self._native = None
+        self._work = None
 
     # ---- set-up after every assembly ---------------------------------------------------------------------------
     def update(self):
@@ -113,7 +118,71 @@ class DistributedMultigrid:
                 self.inv0 = be.dense_inverse(lv.mat, lv.free)
             else:
                 be.patch_setup(lv.mat, lv.patches, lv.free)
+        self._native = None
+        if getattr(be, 'name', '') == 'cuda' and os.environ.get('OCMP_DIST_NATIVE', '1') != '0':
+            self._native = self._native_levels()
         return self
+
+    def _native_levels(self):
+        """Level array for the C ABI driver (ocmp_krylov, pre_kind 3) with the element-partitioned fields filled in:
+        the whole GMRES + V-cycle then runs inside one C call per solve — halo exchanges (ocmp_halo_run) and the
+        all-reduces of the Gram-Schmidt coefficients are issued from there, on the same stream as the kernels."""
+        import ctypes as C
+        from .backend import MGLevel, System
+        be = self.be
+        dist_on = be.comm_init()
+        nl = len(self.levels)
+        arr = (MGLevel * nl)()
+        for l, lv in enumerate(self.levels):
+            s = arr[l].sys
+            pd = be.pattern_data(lv.fes)
+            s.nrows = lv.n
+            s.rowptr, s.colidx, s.vals = pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(), lv.mat.values.data_ptr()
+            s.freemask = lv.free.data_ptr()
+            distributed = dist_on and not lv.replicated
+            s.owned = lv.owned.data_ptr() if distributed else None
+            if not hasattr(lv, 'work'):
+                lv.work = be.zeros(4 * lv.n)
+            arr[l].work = lv.work.data_ptr()
+            arr[l].nu, arr[l].omega = self.nu, self.omega
+            if l == 0:
+                s.pre_kind = 4
+                s.inv_rowptr, s.inv_colidx = self.inv0['rowptr'].data_ptr(), self.inv0['colidx'].data_ptr()
+                s.inv_vals = self.inv0['vals'].data_ptr()
+                s.halo_fwd = lv.map.plan_handle(be, 'fwd') + 1 if dist_on else 0
+                continue
+            pt = lv.patches
+            s.pre_kind = 2
+            s.npatch, s.bs = pt['npatch'], pt['bs']
+            s.patch_dofs, s.inv_blocks = pt['dofs'].data_ptr(), pt['inv'].data_ptr()
+            s.patch_weight = lv.pw.data_ptr()
+            prev = self.levels[l - 1]
+            arr[l].ncoarse = prev.n
+            arr[l].p_rowptr, arr[l].p_colidx, arr[l].p_vals = (lv.P[k].data_ptr() for k in ('rowptr', 'colidx', 'vals'))
+            arr[l].r_rowptr, arr[l].r_colidx, arr[l].r_vals = (lv.R[k].data_ptr() for k in ('rowptr', 'colidx', 'vals'))
+            if distributed:
+                s.halo_fwd = lv.map.plan_handle(be, 'fwd') + 1
+                s.halo_sum = lv.map.plan_handle(be, 'sum') + 1
+                arr[l].restrict_sum = prev.map.plan_handle(be, 'sum') + 1
+                if prev.replicated:
+                    arr[l].handover = prev.map.plan_handle(be, 'fwd') + 1
+        top = System.from_buffer_copy(arr[nl - 1].sys)
+        top.pre_kind = 3
+        top.nlevels = nl
+        top.levels = C.addressof(arr)
+        return top, arr
+
+    def _gmres_native(self, b, x, tol, maxit, restart):
+        import ctypes as C
+        be = self.be
+        top, _ = self._native
+        wl = be.lib.ocmp_krylov_work_len(top.nrows, 1, restart)
+        if self._work is None or self._work.numel() < wl:
+            self._work = be.torch.empty(wl, dtype=be.torch.float64, device=be.device)
+        it, res = C.c_int(0), C.c_double(0.0)
+        be._ck(be.lib.ocmp_krylov(C.byref(top), 1, b.data_ptr(), x.data_ptr(), float(tol), int(maxit), int(restart),
+                                  1.0, self._work.data_ptr(), wl, C.byref(it), C.byref(res), be._stream()))
+        return it.value, res.value
 
     # ---- level operators (all vectors consistent) ----------------------------------------------------------------
     def mult(self, l, x, owned_only: bool = False):
@@ -177,6 +246,8 @@ class DistributedMultigrid:
     def gmres(self, b, x, tol=1e-10, maxit=300, restart=50):
         """Left-preconditioned restarted GMRES with CGS2 on the free DOFs; x (consistent) holds the initial guess and
         the Dirichlet values. Same recurrence as ocmp_krylov kind 1."""
+        if self._native is not None:
+            return self._gmres_native(b, x, tol, maxit, restart)
         be = self.be
         top = len(self.levels) - 1
         lv = self.levels[top]

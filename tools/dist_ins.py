@@ -25,6 +25,7 @@ torch.cuda.synchronize()
 if world > 1: dist.barrier()
 sec = (time.time() - t0) / K
 eu, ep = d.w.errors()
+chk = float(np.sqrt(d.w._integrate(ngs.InnerProduct(d.w.gfu.components[0], d.w.gfu.components[0]))))
 if rank == 0:
-    print(json.dumps({'world': world, 'N_per_rank': N, 'global_dofs': d.ndof_global, 'local_dofs': d.w.ndof, 's_per_step': sec, 'gmres_its_per_step': its / K, 'picard': d.w.picard_iterations, 'err_u': eu, 'err_p': ep, 'setup_s': ts}))
+    print(json.dumps({'world': world, 'N_per_rank': N, 'global_dofs': d.ndof_global, 'local_dofs': d.w.ndof, 's_per_step': sec, 'gmres_its_per_step': its / K, 'picard': d.w.picard_iterations, 'err_u': eu, 'err_p': ep, 'u_norm': repr(chk), 'native': os.environ.get('OCMP_DIST_NATIVE', '1'), 'setup_s': ts}))
 if world > 1: dist.destroy_process_group()
