@@ -539,6 +539,9 @@ class CudaBackend:
         cd = fes.cell_dofs
         if kind == 'cell':
             dofs = cd
+        elif kind in ('star', 'vanka'):
+            from .patches import vertex_patch_dofs
+            dofs = vertex_patch_dofs(fes, kind, vmask)
         else:
             m = fes.mesh
             ne, nvc = m.cells.shape
@@ -552,6 +555,11 @@ class CudaBackend:
             star = -np.ones((m.nv, maxc), dtype=np.int64)
             pos = np.arange(len(vsorted)) - start[vsorted]
             star[vsorted, pos] = cell_of
+            vbig = int(np.argmax(cnt))                 # largest closed star: skip the full table if it cannot fit
+            if len(np.unique(cd[star[vbig, :cnt[vbig]]])) > 160:
+                out = self._patches(fes, 'star', vmask)
+                sd[key] = out
+                return out
             big = np.where(star[:, :, None] >= 0, cd[np.maximum(star, 0)], np.iinfo(np.int32).max)
             big = np.sort(big.reshape(m.nv, -1), axis=1)
             dup = np.concatenate([np.zeros((m.nv, 1), bool), big[:, 1:] == big[:, :-1]], axis=1)
@@ -563,9 +571,10 @@ class CudaBackend:
             if vmask is not None:
                 dofs = dofs[np.asarray(vmask, dtype=bool)]
         if dofs.shape[1] > 160 and kind != 'cell':
-            # vertex stars of irregular meshes can exceed what the register-tiled inversion holds (bs <= 160):
-            # fall back to cell patches for this space
-            out = self._patches(fes, 'cell')
+            # closed vertex stars can exceed what the register-tiled inversion holds (bs <= 160) — always in 3-D
+            # (Q2/Q1 Taylor-Hood: 402 DOFs): take the open star (82-89 DOFs there), and cell patches if even that
+            # is too large
+            out = self._patches(fes, 'star' if kind == 'vertex' else 'cell', vmask if kind == 'vertex' else None)
             sd[key] = out
             return out
         dofs = np.ascontiguousarray(dofs, dtype=np.int32)
@@ -652,7 +661,7 @@ def _cuda_csr_mult(self, h, x, y):
 
 
 def _cuda_patch_state(self, fes, vmask):
-    return self._patches(fes, 'vertex', vmask)
+    return self._patches(fes, os.environ.get('OCMP_PATCH', 'vertex'), vmask)
 
 
 def _cuda_patch_setup(self, mat, pt, fm):

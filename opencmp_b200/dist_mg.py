@@ -23,7 +23,7 @@ from typing import List, Optional
 import numpy as np
 
 from .dist import DofMap, Partition
-from .multigrid import clone_space, mesh_levels, prolongation
+from .multigrid import clone_space, coefficient_fields, mesh_levels, prolongation, restrict_field
 
 
 def _allreduce(vals, like):
@@ -61,6 +61,7 @@ class DistributedMultigrid:
         gmeshes = mesh_levels(global_fine_mesh)
         L = len(gmeshes) - 1
         self.levels: List[_Level] = []
+        cfields = coefficient_fields(bf)
         for l, gm in enumerate(gmeshes):
             lv = _Level()
             gfes = clone_space(bf.space, ngs.Mesh(gm))                       # global numbering only
@@ -79,7 +80,6 @@ class DistributedMultigrid:
             lv.owned = be.from_numpy(np.ones(lv.fes.ndof) if lv.replicated else lv.map.owned.astype(np.float64))
             lv.n = lv.fes.ndof
             if l < L:
-                lv.program = lower_form(lv.fes, bf.integrals, 2, drop_fields=True)
                 lv.mat = ngs.Matrix(lv.fes)
             if l > 0:
                 vown = None if lv.replicated else lv.part.vertex_owner[lv.mesh.global_vertices] == rank
@@ -90,13 +90,23 @@ class DistributedMultigrid:
                 lv.wgt = lv.free / (cnt + (cnt == 0))
                 lv.pw = 1.0 / (cnt + (cnt == 0))
                 prev = self.levels[l - 1]
-                parent_global = lv.part.local_cells // 4
+                parent_global = lv.part.local_cells // (2 ** lv.mesh.dim)
                 parent = np.searchsorted(prev.part.local_cells, parent_global)
                 assert (prev.part.local_cells[parent] == parent_global).all(), 'parent of a local cell is not local'
                 P = prolongation(prev.fes, lv.fes, parent)
                 lv.P = be.csr_handle(P)
                 lv.R = be.csr_handle(P.T.tocsr())
             self.levels.append(lv)
+        # coefficient fields (DIM phase field, masks) get a stand-in on every coarse level, finest to coarsest
+        cur = {id(gf): gf for gf in cfields}
+        for l in range(L - 1, -1, -1):
+            lv, up = self.levels[l], self.levels[l + 1]
+            parent_global = up.part.local_cells // (2 ** up.mesh.dim)
+            parent = np.searchsorted(lv.part.local_cells, parent_global)
+            lv.field_map = {k: restrict_field(g, lv.mesh, parent) for k, g in cur.items()}
+            cur = dict(lv.field_map)
+            fmap = {id(gf): lv.field_map[id(gf)] for gf in cfields}
+            lv.program = lower_form(lv.fes, bf.integrals, 2, drop_fields=True, field_map=fmap)
         self.inv0 = None
         self._native = None
         self._work = None

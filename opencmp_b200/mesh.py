@@ -107,8 +107,10 @@ class Mesh:
         cf = self.cells.astype(np.int64)[:, lf]                  # (ne, nfc, nfv)
         key_src = np.sort(cf, axis=2).reshape(ne * nfc, nfv)
         base = np.int64(self.nv)
+        # a quadrilateral face is identified by its three lowest vertices (keeps the key inside int64 for large meshes)
+        nkey = min(nfv, 3)
         key = np.zeros(ne * nfc, dtype=np.int64)
-        for k in range(nfv):
+        for k in range(nkey):
             key = key * base + key_src[:, k]
         # unique facets ordered by key (deterministic), remember first occurrence for vertex order
         ukey, first, inv = np.unique(key, return_index=True, return_inverse=True)
@@ -139,7 +141,7 @@ class Mesh:
         if bnd_elems.size:
             bk = np.zeros(bnd_elems.shape[0], dtype=np.int64)
             bs = np.sort(bnd_elems, axis=1)
-            for k in range(nfv):
+            for k in range(nkey):
                 bk = bk * base + bs[:, k]
             pos = np.searchsorted(ukey, bk)
             ok = (pos < nf) & (ukey[np.minimum(pos, nf - 1)] == bk)
@@ -206,9 +208,78 @@ class Mesh:
             raise ValueError('quad/hex cells must be affine (parallelograms / parallelepipeds)')
 
     # ---- uniform refinement (reference: post_processing/error_analysis.py:83-86 calls mesh.Refine()) ---------
+    def _refine_tensor(self) -> 'Mesh':
+        """Uniform refinement of a quad / hex mesh: every cell is cut into 2^d children on its 3^d lattice. New vertices
+        are keyed by the set of parent vertices they average (edge midpoints, face centres, cell centres), so shared
+        ones are created once. Children of cell e are the fine cells 2^d e .. 2^d e + 2^d - 1."""
+        import itertools
+        d = self.dim
+        nvc = 2 ** d
+        S = [(0,), (0, 1), (1,)]
+
+        def lattice_sets(dd):
+            out = []
+            for idx in itertools.product(range(3), repeat=dd):          # idx = (i_{dd-1}, ..., i_0), i_0 fastest
+                axes = idx[::-1]
+                out.append([sum(b << a for a, b in enumerate(bits))
+                            for bits in itertools.product(*[S[i] for i in axes])])
+            return out
+
+        def lattice_ids(elems, dd, table):
+            """(n, 3^dd) global vertex ids of the lattice points of each element (corner ids for corners, new ids from
+            ``table`` — a dict filled on the fly — otherwise)."""
+            n = elems.shape[0]
+            sets = lattice_sets(dd)
+            keys = -np.ones((n, len(sets), nvc), dtype=np.int64)
+            for l, sub in enumerate(sets):
+                keys[:, l, :len(sub)] = elems[:, sub]
+            keys = np.sort(keys, axis=2)
+            return keys
+
+        c = self.cells.astype(np.int64)
+        ck = lattice_ids(c, d, None)                                      # (ne, 3^d, nvc)
+        bf = self.facets[self.bnd_facets].astype(np.int64)
+        bk = lattice_ids(bf, d - 1, None)                                 # (nb, 3^(d-1), nvc)
+        allk = np.concatenate([ck.reshape(-1, nvc), bk.reshape(-1, nvc)], axis=0)
+        corner = allk[:, -2] < 0                                          # exactly one parent vertex
+        uk, inv = np.unique(allk[~corner], axis=0, return_inverse=True)
+        ids = np.empty(allk.shape[0], dtype=np.int64)
+        ids[corner] = allk[corner, -1]
+        ids[~corner] = self.nv + inv.reshape(-1)
+        cnt = (uk >= 0).sum(axis=1)
+        newP = np.where(uk[:, :, None] >= 0, self.points[np.maximum(uk, 0)], 0.0).sum(axis=1) / cnt[:, None]
+        P = np.vstack([self.points, newP])
+        cl = ids[:ck.shape[0] * ck.shape[1]].reshape(self.ne, -1)        # (ne, 3^d)
+        bl = ids[ck.shape[0] * ck.shape[1]:].reshape(len(bf), -1)        # (nb, 3^(d-1))
+
+        def children(lat, dd):
+            out = []
+            for off in itertools.product(range(2), repeat=dd):            # child offset (o_{dd-1}, ..., o_0)
+                o = off[::-1]
+                verts = []
+                for bits in itertools.product(range(2), repeat=dd):
+                    bt = bits[::-1]
+                    verts.append(sum((o[a] + bt[a]) * 3 ** a for a in range(dd)))
+                out.append(lat[:, verts])
+            return np.stack(out, axis=1)                                   # (n, 2^dd, 2^dd)
+
+        cells = children(cl, d).reshape(-1, nvc)
+        bnd = children(bl, d - 1).reshape(-1, 2 ** (d - 1))
+        bidx = np.repeat(self.bnd_region, 2 ** (d - 1))
+        return Mesh(d, self.cell_type, P, cells, bnd, bidx, self.bnd_names, np.repeat(self.cell_mat, nvc),
+                    self.mat_names)
+
     def Refine(self) -> 'Mesh':
+        if self.cell_type in ('quad', 'hex'):
+            fine = self._refine_tensor()
+            coarse = Mesh.__new__(Mesh)
+            coarse.__dict__.update({k: v for k, v in self.__dict__.items() if k != '_b200_scalar_space'})
+            self.__dict__.update(fine.__dict__)
+            self.__dict__.pop('_b200_scalar_space', None)
+            self.coarse = coarse
+            return self
         if self.cell_type != 'tri':
-            raise NotImplementedError('Refine is implemented for triangle meshes')
+            raise NotImplementedError('Refine is implemented for triangle, quadrilateral and hexahedral meshes')
         P = self.points
         mid = 0.5 * (P[self.facets[:, 0]] + P[self.facets[:, 1]])
         newP = np.vstack([P, mid])

@@ -45,9 +45,10 @@ def prolongation(fes_c: FESpace, fes_f: FESpace, parent=None) -> sp.csr_matrix:
     the parent map of its local sub-meshes)."""
     mc, mf = fes_c.mesh, fes_f.mesh
     if parent is None:
-        if mf.ne != 4 * mc.ne:
+        nch = 2 ** mf.dim                      # children per cell: red refinement of triangles, 2^d for quads / hexes
+        if mf.ne != nch * mc.ne:
             raise ValueError('prolongation needs a uniformly refined mesh')
-        parent = np.arange(mf.ne) // 4
+        parent = np.arange(mf.ne) // nch
     parent = np.asarray(parent, dtype=np.int64)
     dim = mf.dim
     Jc, Jf = mc.jacobians(), mf.jacobians()
@@ -91,6 +92,54 @@ def prolongation(fes_c: FESpace, fes_f: FESpace, parent=None) -> sp.csr_matrix:
     return P
 
 
+def coefficient_fields(bf) -> list:
+    """GridFunctions the bilinear form is weighted with that do NOT live on (a component of) its own space: coefficient
+    fields such as the DIM phase field / masks (reference diffuse_interface/dim.py:390-445), which every level of the
+    hierarchy has to see. Fields on the form's own spaces (Oseen wind, previous iterates) are linearisation data and
+    only act on the finest level. ``gf.mg_static`` overrides the rule."""
+    from .ir import coef_leaves
+    fes = bf.space
+    own = [fes] + list(fes.components)
+    out, seen = [], set()
+    for cf, _ in bf.integrals.items:
+        s = cf.arr.reshape(())[()]
+        for lf in coef_leaves(list(s.t.values()), 'field'):
+            gf = lf.val[0]
+            if id(gf) in seen:
+                continue
+            seen.add(id(gf))
+            static = getattr(gf, 'mg_static', None)
+            if static is None:
+                static = not any(gf.space is o for o in own)
+            if static:
+                out.append(gf)
+    return out
+
+
+def restrict_field(gf, mesh_c, parent=None):
+    """Coarse-level stand-in of a coefficient field: re-evaluated from the expression it was ``Set`` from when that is
+    known, otherwise the least-squares restriction min ||P c - f|| through the exact prolongation of its space. Clipped
+    to the range of the fine DOF vector (mirrors the reference's clamp of phi, dim.py:434-435)."""
+    from . import ngs
+    import scipy.sparse.linalg as spla
+    be = ngs.get_backend()
+    fes_c = clone_space(gf.space, mesh_c)
+    out = ngs.GridFunction(fes_c)
+    fine = be.to_numpy(gf.vec.a)
+    src = getattr(gf, '_set_source', None)
+    if src is not None:
+        out.Set(src)
+        vals = be.to_numpy(out.vec.a)
+    else:
+        P = prolongation(fes_c, gf.space, parent)
+        vals, _ = spla.cg(P.T @ P, P.T @ fine, rtol=1e-12, maxiter=2000)
+    if fine.size:
+        vals = np.clip(vals, fine.min(), fine.max())
+    out.vec.data = ngs.BaseVector(be.from_numpy(vals))
+    out._set_source = src
+    return out
+
+
 # ---- device side: level hierarchy handed to the C ABI (pre_kind = 3) ---------------------------------------------
 class MultigridState:
     """Built by ``CudaBackend.precond_setup(..., 'multigrid')``; refreshed on every ``Preconditioner.Update()``."""
@@ -108,7 +157,17 @@ class MultigridState:
         if self.nlevels < 2:
             raise ValueError("Preconditioner type 'multigrid' needs a mesh refined with Mesh.Refine()")
         self.spaces = [clone_space(fes, m) for m in meshes[:-1]] + [fes]
-        self.programs = [lower_form(s, bf.integrals, 2, drop_fields=True) for s in self.spaces[:-1]]
+        # coefficient fields (DIM phase field, masks) get a stand-in on every coarse level, finest to coarsest
+        self.field_maps = [dict() for _ in meshes[:-1]]
+        self._coarse_fields = []
+        for gf in coefficient_fields(bf):
+            cur = gf
+            for l in range(self.nlevels - 2, -1, -1):
+                cur = restrict_field(cur, self.spaces[l].mesh)
+                self.field_maps[l][id(gf)] = cur
+                self._coarse_fields.append(cur)
+        self.programs = [lower_form(s, bf.integrals, 2, drop_fields=True, field_map=fm)
+                         for s, fm in zip(self.spaces[:-1], self.field_maps)]
         self.mats = [ngs.Matrix(s) for s in self.spaces[:-1]]
         self.transfers = []
         for lo, hi in zip(self.spaces[:-1], self.spaces[1:]):

@@ -320,7 +320,11 @@ class GridFunction(CoefficientFunction):
 
     def Set(self, cf, definedon=None, VOL_or_BND=None, **kw):
         from .project import set_gridfunction
-        set_gridfunction(self, CoefficientFunction._lift(cf), definedon)
+        cf = CoefficientFunction._lift(cf)
+        set_gridfunction(self, cf, definedon)
+        # remembered so that geometric multigrid can re-evaluate coefficient fields (e.g. the DIM phase field) on its
+        # coarse levels; a later direct write to .vec (clamping) is mimicked there by clipping to the fine range
+        self._set_source = cf if definedon is None else None
 
     def Update(self):
         n = self.space.ndof

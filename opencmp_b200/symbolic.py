@@ -117,6 +117,30 @@ def _other_coef(c: Coef, memo: Optional[dict] = None) -> Coef:
     return out
 
 
+def substitute_fields(c: Coef, mapping: dict, memo: Optional[dict] = None) -> Coef:
+    """Replace the GridFunction of every 'field' leaf by ``mapping[id(gf)]`` (same block / row / side)."""
+    memo = {} if memo is None else memo
+    if id(c) in memo:
+        return memo[id(c)]
+    if c.op == 'field':
+        gf, blk, row, side = c.val
+        out = Coef('field', (), (mapping[id(gf)], blk, row, side)) if id(gf) in mapping else c
+    elif not c.args:
+        out = c
+    else:
+        new = tuple(substitute_fields(a, mapping, memo) for a in c.args)
+        if all(n is o for n, o in zip(new, c.args)):
+            out = c
+        elif c.op == 'ifpos':
+            out = Coef.ifpos(*new)
+        elif len(new) == 1:
+            out = Coef.unary(c.op, new[0])
+        else:
+            out = Coef.binary(c.op, new[0], new[1])
+    memo[id(c)] = out
+    return out
+
+
 _S0 = S()
 
 
@@ -625,8 +649,11 @@ class SumOfIntegrals:
 
 # ---- lowering ------------------------------------------------------------------------------------------------------
 def lower_form(fes, integrals: SumOfIntegrals, arity: int, intorder: Optional[int] = None,
-               drop_fields: bool = False) -> FormProgram:
-    """Group the entries of all integrals by (kind, region) and compile one bytecode per group."""
+               drop_fields: bool = False, field_map: Optional[dict] = None) -> FormProgram:
+    """Group the entries of all integrals by (kind, region) and compile one bytecode per group.
+
+    ``drop_fields`` (coarse multigrid levels): terms weighted by a DOF vector are dropped, except when every field in
+    them has a coarse-level stand-in in ``field_map`` ({id(fine GridFunction): coarse GridFunction})."""
     mesh = fes.mesh
     nrows = fes.nrows
     groups: Dict[tuple, Dict[Tuple[Key, Key], Coef]] = {}
@@ -635,7 +662,14 @@ def lower_form(fes, integrals: SumOfIntegrals, arity: int, intorder: Optional[in
             raise ValueError('integrand must be scalar, got dims {}'.format(cf.dims))
         s: S = cf.arr.reshape(())[()]
         if drop_fields:       # coarse multigrid levels keep only the DOF-vector independent part of the form
-            s = S({k: c for k, c in s.t.items() if not coef_leaves([c], 'field')})
+            kept, memo = {}, {}
+            for k, c in s.t.items():
+                leaves = coef_leaves([c], 'field')
+                if not leaves:
+                    kept[k] = c
+                elif field_map and all(id(lf.val[0]) in field_map for lf in leaves):
+                    kept[k] = substitute_fields(c, field_map, memo)
+            s = S(kept)
         if m.kind == 'vol' and not m.skeleton:
             kind, rkind = 'cell', 'mat'
             nreg = len(mesh.mat_names)

@@ -183,3 +183,142 @@ class INSTaylorGreen:
         dp = p - self.p_ref - pm
         ep = float(np.sqrt(self._integrate(dp * dp)))
         return eu, ep
+
+
+class INSSphereDIM3D:
+    """3-D incompressible Navier-Stokes with the diffuse-interface method (BASELINE config 5).
+
+    Restates what the reference executes per time step for its ``INSDIM`` model with Oseen linearisation and the
+    implicit-Euler scheme, conforming (CG) Taylor-Hood Q2/Q1 on the structured hexahedral box [-1,1]^3 of the DIM mesh
+    generator (``quad_mesh = True``):
+
+      forms      opencmp/models/ins_dim.py:33-196 (phi-weighted stress / convection / incompressibility, penalisation
+                 alpha u v (1-phi) and -p div v (1-phi), Nitsche terms on the diffuse boundary with grad(phi),
+                 |grad(phi)| and the mask, their right-hand-side analogues)
+      DIM fields opencmp/diffuse_interface/dim.py:390-445 (phi as an H1 GridFunction of the interpolant order clamped
+                 to [1e-10, 1]; grad(phi) and |grad(phi)| evaluated from it; mask = 1)
+      phi        erf profile of the signed distance, opencmp/diffuse_interface/interface.py:173-178, here of a sphere
+                 of radius R computed analytically instead of through the STL -> EDT pipeline (out of scope)
+      scheme / time step / Picard / solve: as INSTaylorGreen above.
+
+    Physical set-up: fluid inside the sphere, whose (diffuse) wall rotates rigidly about the z axis: DIM Dirichlet
+    data g = omega e_z x r. Rigid rotation is the exact Navier-Stokes solution in the sphere, which the workload starts
+    from, so ``errors()`` measures how well the DIM step preserves it. Homogeneous conformal Dirichlet data on the box.
+    """
+
+    def __init__(self, N: int, order: int = 2, dt: float = 1e-2, nu: float = 0.1, ipc: float = 10.0,
+                 radius: float = 0.5, lam_cells: float = 2.0, omega_rot: float = 1.0,
+                 preconditioner: str = 'multigrid', linear_tolerance: float = 1e-8, linear_max_iterations: int = 400,
+                 nonlinear_max_iterations: int = 3, nonlinear_tolerance=(1e-4, 1e-6), n0: int = 2, mesh=None):
+        from .mesh import structured_3d
+        if mesh is None:
+            nc = N
+            while preconditioner == 'multigrid' and nc % 2 == 0 and nc > n0:
+                nc //= 2
+            mesh = structured_3d([nc] * 3, scale=(2.0,) * 3, offset=(1.0,) * 3)
+            while nc < N:
+                mesh.Refine()
+                nc *= 2
+        self.mesh = ngs.Mesh(mesh)
+        m = self.mesh
+        k = order
+        self.order = k
+        self.preconditioner = preconditioner
+        self.linear_tolerance, self.linear_max_iterations = linear_tolerance, linear_max_iterations
+        self.nonlinear_max_iters = nonlinear_max_iterations
+        self.rel_nonlinear_tolerance, self.abs_nonlinear_tolerance = nonlinear_tolerance
+        dnames = 'back|left|front|right|bottom|top'
+        self.dirichlet = dnames
+        # models/ins.py:95-128 with DG = False: Taylor-Hood
+        self.V = ngs.VectorH1(m, order=k, dirichlet=dnames)
+        self.Q = ngs.H1(m, order=k - 1)
+        self.fes = ngs.FESpace([self.V, self.Q])
+        (u, p), (v, q) = self.fes.TrialFunction(), self.fes.TestFunction()
+        self.t, self.dt = ngs.Parameter(0.0), ngs.Parameter(dt)
+        dtp = self.dt
+        x, y, z = ngs.x, ngs.y, ngs.z
+        kv = ngs.CoefficientFunction(nu)
+        h = ngs.specialcf.mesh_size
+        alpha = (ipc * k ** 2) / h                          # base_model.py:150, helpers/ngsolve_.py:67
+        # ---- diffuse-interface fields (dim.py:390-445) ----
+        hcell = 2.0 / N
+        self.lam = lam_cells * hcell
+        H = ngs.H1(m, order=k)
+        self.fes_phi = H
+        r = ngs.sqrt(x * x + y * y + z * z + 1e-30)
+        phi_cf = 0.5 * (1.0 + ngs.erf((radius - r) / self.lam))
+        self.phi = ngs.GridFunction(H)
+        self.phi.Set(phi_cf)
+        be = ngs.get_backend()
+        pv = be.to_numpy(self.phi.vec.a)
+        self.phi.vec.data = ngs.BaseVector(be.from_numpy(np.clip(pv, 1e-10, 1.0)))      # dim.py:434-435
+        self.mask = ngs.GridFunction(H)
+        self.mask.Set(ngs.CoefficientFunction(1.0))
+        phi, mask = self.phi, self.mask
+        gphi = ngs.Grad(phi)
+        mag = ngs.Norm(gphi)
+        self.u_ref = ngs.CoefficientFunction((-omega_rot * y, omega_rot * x, 0.0 * x))
+        self.p_ref = 0.5 * omega_rot ** 2 * (x * x + y * y)
+        g = self.u_ref
+        f = ngs.CoefficientFunction((0.0, 0.0, 0.0))
+        self.gfu, self.gfu_0 = ngs.GridFunction(self.fes), ngs.GridFunction(self.fes)
+        self.W = ngs.GridFunction(self.V)                    # Oseen wind, models/ins.py:130-134
+        w = self.W
+        a = ngs.BilinearForm(self.fes)
+        # construct_bilinear_time_coefficient, ins_dim.py:106-146 (no rigid body motion)
+        a += dtp * (-ngs.div(u) * q - ngs.div(v) * p - 1e-10 * p * q) * phi * ngs.dx
+        a += -dtp * p * ngs.div(v) * (1.0 - phi) * ngs.dx
+        # construct_bilinear_time_ODE, ins_dim.py:33-104
+        a += dtp * (kv * ngs.InnerProduct(ngs.Grad(u), ngs.Grad(v))) * phi * ngs.dx
+        a += -dtp * ngs.InnerProduct(ngs.OuterProduct(u, w), ngs.Grad(v)) * phi * ngs.dx
+        a += dtp * alpha * u * v * (1.0 - phi) * ngs.dx
+        a += dtp * (kv * ngs.InnerProduct(ngs.Grad(u), ngs.OuterProduct(v, gphi))
+                    + kv * ngs.InnerProduct(ngs.Grad(v), ngs.OuterProduct(u, gphi))
+                    + kv * alpha * u * v * mag) * mask * ngs.dx
+        a += dtp * (v * (0.5 * w * (-gphi) * u + 0.5 * ngs.Norm(w * (-gphi)) * u)) * mask * ngs.dx
+        # time derivative, base_model.py:418-497 with the DIM weight
+        a += (u * v) * phi * ngs.dx
+        L = ngs.LinearForm(self.fes)
+        # construct_linear, ins_dim.py:148-206
+        L += dtp * v * f * phi * ngs.dx
+        L += dtp * (kv * ngs.InnerProduct(ngs.Grad(v), ngs.OuterProduct(g, gphi))
+                    + kv * alpha * g * v * mag) * mask * ngs.dx
+        L += dtp * v * (0.5 * w * gphi * g + 0.5 * ngs.Norm(w * (-gphi)) * g) * mask * ngs.dx
+        L += (self.gfu_0.components[0] * v) * phi * ngs.dx
+        self.a, self.L = a, L
+        self.pre = ngs.Preconditioner(a, preconditioner) if preconditioner is not None else None
+        # start from the rigid rotation inside the sphere (zero on the box boundary)
+        cut = 0.5 * (1.0 + ngs.erf((0.9 - r) / 0.05))
+        self.gfu.components[0].Set(self.u_ref * cut)
+        self.gfu.components[1].Set(self.p_ref * cut)
+        self.apply_dirichlet_bcs()
+        self.gfu_0.vec.data = self.gfu.vec
+        self.W.vec.data = self.gfu.components[0].vec
+        self.picard_iterations = 0
+        self.linear_iterations = []
+
+    ndof = INSTaylorGreen.ndof
+    nnz = INSTaylorGreen.nnz
+    assemble = INSTaylorGreen.assemble
+    step = INSTaylorGreen.step
+    _integrate = INSTaylorGreen._integrate
+
+    def apply_dirichlet_bcs(self):
+        """base_model.py:321-341 — homogeneous data on the box faces"""
+        self.gfu.components[0].Set(ngs.CoefficientFunction((0.0, 0.0, 0.0)),
+                                   definedon=self.mesh.Boundaries(self.dirichlet))
+
+    def linear_solve(self):
+        """base_model.py:886-947, linear_solver = GMRes"""
+        be = ngs.get_backend()
+        ngs.solvers.GMRes(A=self.a.mat, b=self.L.vec, pre=self.pre, freedofs=self.fes.FreeDofs(), x=self.gfu.vec,
+                          tol=self.linear_tolerance, maxsteps=self.linear_max_iterations, restart=100)
+        self.linear_iterations.append(getattr(be, 'last_iters', 0))
+
+    def errors(self):
+        """phi-weighted L2 deviation from the rigid rotation, relative to its phi-weighted norm."""
+        u = self.gfu.components[0]
+        du = u - self.u_ref
+        eu = float(np.sqrt(self._integrate(ngs.InnerProduct(du, du) * self.phi)))
+        un = float(np.sqrt(self._integrate(ngs.InnerProduct(self.u_ref, self.u_ref) * self.phi)))
+        return eu / un, un

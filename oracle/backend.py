@@ -197,7 +197,18 @@ class _OraclePrimitives:
         y[:] = h @ x
 
     def patch_state(self, fes, vmask):
-        return dict(dofs=_vertex_patches(fes, vmask), inv=None)
+        import os
+        kind = os.environ.get('OCMP_PATCH', 'vertex')
+        if kind != 'vertex':
+            # open-star / Vanka patch layouts are host logic of the product (opencmp_b200/patches.py); the oracle only
+            # restates the arithmetic done on them
+            from opencmp_b200.patches import vertex_patch_dofs
+            return dict(dofs=[d[d >= 0] for d in vertex_patch_dofs(fes, kind, vmask)], inv=None)
+        dofs = _vertex_patches(fes, vmask)
+        if max(len(d) for d in dofs) > 160:          # same size rule as CudaBackend._patches
+            from opencmp_b200.patches import vertex_patch_dofs
+            dofs = [d[d >= 0] for d in vertex_patch_dofs(fes, 'star', vmask)]
+        return dict(dofs=dofs, inv=None)
 
     def patch_setup(self, mat, pt, fm):
         A = self._csr(mat)
