@@ -31,13 +31,22 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--N', type=int, default=256, help='cells per direction of the structured mesh')
-    ap.add_argument('--order', type=int, default=3)
-    ap.add_argument('--cpu-N', type=int, default=20, help='mesh size of the bounded CPU sample')
+    ap.add_argument('--workload', default='ins2d', choices=['ins2d', 'ins3d_dim'],
+                    help='ins2d: 2-D INS Taylor-Green, HDiv-DG order 3 (BASELINE configs[2] scaled up, the default); '
+                         'ins3d_dim: 3-D INS with a diffuse-interface sphere, Taylor-Hood Q2/Q1 hexes (configs[4])')
+    ap.add_argument('--N', type=int, default=None, help='cells per direction of the structured mesh '
+                                                        '(default 256 for ins2d, 32 for ins3d_dim)')
+    ap.add_argument('--order', type=int, default=None)
+    ap.add_argument('--cpu-N', type=int, default=None, help='mesh size of the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--dist-poisson', action='store_true', help='also run the distributed Poisson CG leg')
     ap.add_argument('--dist-n', type=int, default=512, help='cells per direction and rank of the distributed leg')
-    return ap.parse_args()
+    a = ap.parse_args()
+    d = {'ins2d': (256, 3, 20), 'ins3d_dim': (32, 2, 8)}[a.workload]
+    a.N = d[0] if a.N is None else a.N
+    a.order = d[1] if a.order is None else a.order
+    a.cpu_N = d[2] if a.cpu_N is None else a.cpu_N
+    return a
 
 
 class ClockSampler:
@@ -81,15 +90,26 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def cpu_step_seconds(N, order, steps=1):
+def cpu_step_seconds(N, order, steps=1, workload='ins2d'):
     """Oracle (CPU restatement, NumPy/SciPy; NOT NGSolve) timed on one Picard-iterated time step."""
     import opencmp_b200.ngs as ngs
     from oracle.backend import OracleBackend
-    from opencmp_b200.workloads import INSTaylorGreen
+    from opencmp_b200.workloads import INSTaylorGreen, INSSphereDIM3D
     old = ngs._backend
     ngs.set_backend(OracleBackend())
     try:
-        w = INSTaylorGreen(N, order=order, linear_solver='direct', preconditioner=None)
+        if workload == 'ins3d_dim':
+            w = INSSphereDIM3D(N, order=order, preconditioner=None, nu=1.0)
+
+            def direct():                       # the reference's default linear_solver = direct (base_model.py:918-922)
+                inv = w.a.mat.Inverse(w.fes.FreeDofs())
+                r = w.L.vec.CreateVector()
+                r.data = w.L.vec - w.a.mat * w.gfu.vec
+                w.gfu.vec.data += inv * r
+                w.linear_iterations.append(0)
+            w.linear_solve = direct
+        else:
+            w = INSTaylorGreen(N, order=order, linear_solver='direct', preconditioner=None)
         w.step()                          # warm-up (lowering, tabulation caches)
         t0 = time.perf_counter()
         for _ in range(steps):
@@ -104,13 +124,14 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cells_full = 2 * args.N * args.N * max(1, args.gpus)      # weak scaling: one N x N x 2 strip per GPU
+    # weak scaling: one N x N x 2 strip (2-D) / one N^3 brick (3-D) per GPU
+    cells_full = (args.N ** 3 if args.workload == 'ins3d_dim' else 2 * args.N * args.N) * max(1, args.gpus)
     times = []
     ne = ndof = nnz = 0
     for _ in range(max(1, args.warmup // 3)):
-        cpu_step_seconds(args.cpu_N, args.order)
+        cpu_step_seconds(args.cpu_N, args.order, workload=args.workload)
     for _ in range(args.steps):
-        dt, ne, ndof, nnz = cpu_step_seconds(args.cpu_N, args.order)
+        dt, ne, ndof, nnz = cpu_step_seconds(args.cpu_N, args.order, workload=args.workload)
         times.append(dt)
     per = sum(times) / len(times)
     scaled = per * cells_full / ne
@@ -128,6 +149,17 @@ def run_reference(args):
 
 
 def workload_config(args, where):
+    if args.workload == 'ins3d_dim':
+        return {'workload': 'INS-DIM 3D (BASELINE configs[4]): structured {0}^3 hexes on [-1,1]^3, Taylor-Hood Q{1}/Q{2}, '
+                            'diffuse-interface sphere R=0.5 (erf profile, lambda = 2h, phi clamped to [1e-10,1]), rotating '
+                            'wall as DIM Dirichlet data, Oseen + implicit Euler, dt=1e-2, nu=1 '
+                            '(reference models/ins_dim.py forms)'.format(args.N, args.order, args.order - 1),
+                'N': args.N, 'order': args.order,
+                'linear_solver': 'GMRES(100) + geometric multigrid V(1,1) on the hex hierarchy, open-star vertex-patch '
+                                 'additive Schwarz smoother (damping 0.7), coarse-level phase field, tol 1e-12'
+                if where == 'gpu' else 'direct (SuperLU)', 'nonlinear_max_iterations': 3,
+                'l2': 'inputs larger than L2 (CSR matrix and patch inverses are GBs); no explicit flush',
+                'parallelism': 'single'}
     return {'workload': 'INS Taylor-Green 2D, structured {0}x{0}x2 triangles on [0,pi]^2, HDiv-DG order {1} / L2 order {2}, '
                         'Oseen + implicit Euler, dt=1e-3, nu=1 (examples/INS scaled up)'.format(args.N, args.order,
                                                                                                args.order - 1),
@@ -159,11 +191,17 @@ def main():
     ngs.set_backend(be)
     lib = be.lib
     t_setup = time.perf_counter()
+    if world > 1 and args.workload != 'ins2d':
+        raise SystemExit('bench.py: --workload {} runs on one GPU in this round'.format(args.workload))
     if world > 1:
         # element-partitioned INS step: rank r owns the strip [0,pi] x [r pi, (r+1) pi] at N x N x 2 triangles
         from opencmp_b200.dist_workload import DistributedINS
         dins = DistributedINS(args.N, world, rank, order=args.order)
         w = dins.w
+    elif args.workload == 'ins3d_dim':
+        from opencmp_b200.workloads import INSSphereDIM3D
+        dins = None
+        w = INSSphereDIM3D(args.N, order=args.order, nu=1.0, linear_tolerance=1e-12)
     else:
         dins = None
         w = INSTaylorGreen(args.N, order=args.order)
@@ -270,9 +308,12 @@ def main():
                 'bound': 'hbm', 'achieved': ap_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': ap_gbs / peak,
                 'peak_source': peak_src, 'bytes_per_launch': ap_bytes, 'launches': ap['count'],
                 'avg_launch_ms': ap_ms, 'share_of_step': share['asm_apply'],
-                'traffic': None,
-                'traffic_note': 'ncu --set full, fine-level launch at N=128 (16 641 patches): dram read 2.368 GB + write 0.018 GB vs '
-                                '2.330 GB algorithmic (profiles/r1_ncu_kernels.md)'}
+                # ncu --set full of the fine-level launch at N=128 (16 641 patches, 2.330 GB algorithmic): dram read
+                # 2.368 GB + write 0.018 GB (profiles/r1_ncu_kernels.md) — 1.024 x the algorithmic bytes, scaled here
+                'traffic': 1.024 * ap_bytes if args.workload == 'ins2d' else None,
+                'traffic_note': 'per launch, from the measured dram/algorithmic ratio 1.024 of the ncu --set full capture '
+                                'at N=128 (dram read 2.368 GB + write 0.018 GB vs 2.330 GB algorithmic, '
+                                'profiles/r1_ncu_kernels.md)'}
     line = {
         'metric': 'INS s/timestep', 'value': sec, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': False, 'scaling': 'weak',
@@ -296,7 +337,7 @@ def main():
         line['multi_gpu'] = multi
     if not args.no_cpu and world == 1:
         try:
-            per, cne, cnd, _ = cpu_step_seconds(args.cpu_N, args.order)
+            per, cne, cnd, _ = cpu_step_seconds(args.cpu_N, args.order, workload=args.workload)
             line['cpu_baseline'] = {
                 'value': per * ne / cne, 'unit': 's', 'cores': 1, 'kind': 'port',
                 'sample': 'CPU restatement (NumPy/SciPy, not NGSolve): one time step at N={} ({} cells, {} DOFs) took '

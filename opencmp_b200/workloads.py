@@ -206,9 +206,9 @@ class INSSphereDIM3D:
     from, so ``errors()`` measures how well the DIM step preserves it. Homogeneous conformal Dirichlet data on the box.
     """
 
-    def __init__(self, N: int, order: int = 2, dt: float = 1e-2, nu: float = 0.1, ipc: float = 10.0,
+    def __init__(self, N: int, order: int = 2, dt: float = 1e-2, nu: float = 1.0, ipc: float = 10.0,
                  radius: float = 0.5, lam_cells: float = 2.0, omega_rot: float = 1.0,
-                 preconditioner: str = 'multigrid', linear_tolerance: float = 1e-8, linear_max_iterations: int = 400,
+                 preconditioner: str = 'multigrid', linear_tolerance: float = 1e-12, linear_max_iterations: int = 400,
                  nonlinear_max_iterations: int = 3, nonlinear_tolerance=(1e-4, 1e-6), n0: int = 2, mesh=None):
         from .mesh import structured_3d
         if mesh is None:

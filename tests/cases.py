@@ -226,3 +226,20 @@ def stokes_3d(cell, order, n=2):
     L += v * (-2.0 * n3) * ngs.ds(definedon=m.Boundaries('right'))
     gfu = ngs.GridFunction(fes)
     return dict(ngs=ngs, mesh=m, fes=fes, a=a, L=L, gfu=gfu, noset=True, keep=(W,))
+
+
+def ins_dim_3d(n=4, n0=2, **kw):
+    """BASELINE config 5 at test size: INS with the diffuse-interface method (reference models/ins_dim.py) on the
+    structured hex box, Taylor-Hood Q2/Q1, phase field of a sphere — the workload bench.py --workload ins3d_dim runs."""
+    from opencmp_b200.mesh import structured_3d
+    from opencmp_b200.workloads import INSSphereDIM3D
+    ngs = _ngs()
+    mesh = structured_3d([n0] * 3, scale=(2.0,) * 3, offset=(1.0,) * 3)
+    k = n0
+    while k < n:
+        mesh.Refine()
+        k *= 2
+    w = INSSphereDIM3D(n, mesh=mesh, **kw)
+    w.W.vec.data = ngs.BaseVector(ngs.get_backend().from_numpy(
+        ngs.get_backend().to_numpy(w.W.vec.a) + random_wind(w.V.ndof, 13, 0.1) * w.V.FreeDofs()))
+    return dict(ngs=ngs, mesh=w.mesh, fes=w.fes, a=w.a, L=w.L, gfu=w.gfu, noset=True, keep=(w,), workload=w)

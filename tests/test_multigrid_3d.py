@@ -1,0 +1,126 @@
+"""Host logic of the 3-D path (CPU, oracle backend): hex refinement, exact prolongation on the hex hierarchy,
+open-star / Vanka vertex patches, coarse-level stand-ins of coefficient fields, and the geometric-multigrid GMRES on the
+3-D INS-DIM workload compared with the sparse direct solve."""
+import numpy as np
+import pytest
+
+import cases
+
+
+@pytest.fixture()
+def ngs():
+    import opencmp_b200.ngs as ngs
+    from oracle.backend import OracleBackend
+    old = ngs._backend
+    ngs.set_backend(OracleBackend())
+    yield ngs
+    ngs.set_backend(old)
+
+
+@pytest.mark.parametrize('cell', ['quad', 'hex'])
+def test_tensor_refine(cell):
+    from opencmp_b200.mesh import structured_2d, structured_3d
+    if cell == 'quad':
+        m, ref = structured_2d([3, 2], cell='quad'), structured_2d([6, 4], cell='quad')
+    else:
+        m, ref = structured_3d([2, 3, 2]), structured_3d([4, 6, 4])
+    ne0 = m.ne
+    pc = m.points[m.cells].mean(axis=1)
+    m.Refine()
+    nch = 2 ** m.dim
+    assert m.ne == nch * ne0 == ref.ne and m.nv == ref.nv and m.nf == ref.nf
+    m.check_affine()
+    assert np.allclose(np.linalg.det(m.jacobians()), np.linalg.det(ref.jacobians())[0])
+    # children 2^d e .. 2^d e + 2^d - 1 tile their parent
+    cent = m.points[m.cells].mean(axis=1).reshape(ne0, nch, m.dim).mean(axis=1)
+    assert np.abs(cent - pc).max() < 1e-14
+    assert m.coarse.ne == ne0
+    for r in range(len(m.bnd_names)):
+        assert (m.bnd_region == r).sum() == (ref.bnd_region == r).sum()
+    # same point set as the directly generated fine mesh
+    a = np.unique(np.round(m.points, 12), axis=0)
+    b = np.unique(np.round(ref.points, 12), axis=0)
+    assert np.abs(a - b).max() < 1e-12
+
+
+def test_hex_prolongation_is_exact(ngs):
+    from opencmp_b200.mesh import structured_3d
+    from opencmp_b200.multigrid import clone_space, prolongation
+    mesh = structured_3d([2, 2, 2])
+    mesh.Refine()
+    mf = ngs.Mesh(mesh)
+    fine = ngs.FESpace([ngs.VectorH1(mf, order=2), ngs.H1(mf, order=1)])
+    coarse = clone_space(fine, mesh.coarse)
+    P = prolongation(coarse, fine)
+    x, y, z = ngs.x, ngs.y, ngs.z
+    u = ngs.CoefficientFunction((x * y + z * z, 1.0 - 2.0 * x * z, y * y * x))     # in Q2^3
+    p = 1.0 + x - 2.0 * y + 3.0 * z + x * y * z                                     # in Q1
+    gc, gf = ngs.GridFunction(coarse), ngs.GridFunction(fine)
+    for g in (gc, gf):
+        g.components[0].Set(u)
+        g.components[1].Set(p)
+    assert np.abs(P @ gc.vec.NumPy() - gf.vec.NumPy()).max() < 1e-10
+
+
+def test_star_and_vanka_patches(ngs):
+    from opencmp_b200.mesh import structured_3d
+    from opencmp_b200.patches import vertex_patch_dofs
+    from oracle.backend import _vertex_patches
+    m = ngs.Mesh(structured_3d([4, 4, 4]))
+    V = ngs.VectorH1(m, order=2, dirichlet='back|left|front|right|bottom|top')
+    fes = ngs.FESpace([V, ngs.H1(m, order=1)])
+    closed = vertex_patch_dofs(fes, 'vertex', drop_constrained=False)
+    ref = _vertex_patches(fes, None)
+    assert all(np.array_equal(r, g[g >= 0]) for r, g in zip(ref, closed))
+    star = vertex_patch_dofs(fes, 'star')
+    vanka = vertex_patch_dofs(fes, 'vanka')
+    centre = int(np.argmin(np.abs(m.points - 0.5).sum(axis=1)))
+    assert (star[centre] >= 0).sum() == 3 * 27 + 1            # interior Q2 nodes of the 2x2x2 star + its own pressure
+    assert (vanka[centre] >= 0).sum() == 3 * 27 + 27
+    assert star.shape[1] <= 160 and closed.shape[1] == 3 * 125 + 27
+    free = fes.FreeDofs()
+    for tab in (star, vanka):
+        d = tab[tab >= 0]
+        assert free[d].all()                                   # constrained DOFs dropped
+        assert np.array_equal(np.unique(d), np.nonzero(free)[0])   # every free DOF is covered
+    for v in range(m.nv):
+        assert set(star[v][star[v] >= 0]) <= set(vanka[v][vanka[v] >= 0]) <= set(closed[v][closed[v] >= 0])
+
+
+def test_coarse_phase_field_and_multigrid_solve(ngs):
+    """3-D INS-DIM, 4^3 hexes refined from 2^3: the coarse level sees a restricted phase field (non-singular coarse
+    operator) and multigrid-GMRES reproduces the direct solve. Tolerance: see tests/test_gpu_parity.py
+    ::test_ins_dim_3d_multigrid_step (condition number > 1e10 from the reference's phi >= 1e-10 clamp)."""
+    from opencmp_b200.dist import Partition
+    from opencmp_b200.dist_mg import DistributedMultigrid
+    from opencmp_b200.mesh import structured_3d
+    from opencmp_b200.multigrid import coefficient_fields
+    from opencmp_b200.workloads import INSSphereDIM3D
+    import scipy.sparse.linalg as spla
+    be = ngs.get_backend()
+    gm = structured_3d([2, 2, 2], scale=(2.0,) * 3, offset=(1.0,) * 3)
+    gm.Refine()
+    part = Partition(gm, 1, 0, layers=2)
+    w = INSSphereDIM3D(4, preconditioner=None, mesh=part.local_mesh(), nu=1.0)
+    fields = coefficient_fields(w.a)
+    assert {id(g) for g in fields} == {id(w.phi), id(w.mask)}       # the Oseen wind is not a coefficient field
+    mg = DistributedMultigrid(be, w.a, gm, part, replicate_below=0)
+    w.t.Set(w.dt.Get())
+    w.a.Assemble()
+    w.L.Assemble()
+    mg.update()
+    phi_c = mg.levels[0].field_map[id(w.phi)]
+    pc = phi_c.vec.NumPy()
+    assert pc.min() >= 1e-10 and pc.max() <= 1.0 and pc.max() > 0.5
+    A0 = be._csr(mg.levels[0].mat)
+    assert abs(A0).sum() > 0                                         # all-field-weighted form survived on the coarse level
+    A, b = be._csr(w.a.mat), w.L.vec.NumPy().copy()
+    idx = np.nonzero(np.asarray(w.fes.FreeDofs(), bool))[0]
+    x0 = w.gfu.vec.NumPy().copy()
+    it, res = mg.gmres(w.L.vec.a, w.gfu.vec.a, tol=1e-13, maxit=200, restart=100)
+    xd = x0.copy()
+    xd[idx] += spla.splu(A[idx][:, idx].tocsc()).solve((b - A @ x0)[idx])
+    nv = w.V.ndof
+    got = w.gfu.vec.NumPy()
+    assert it < 60
+    assert np.linalg.norm((got - xd)[:nv]) < 1e-6 * np.linalg.norm(xd[:nv])
