@@ -151,7 +151,7 @@ def run_reference(args):
 def workload_config(args, where):
     if args.workload == 'ins3d_dim':
         return {'workload': 'INS-DIM 3D (BASELINE configs[4]): structured {0}^3 hexes on [-1,1]^3, Taylor-Hood Q{1}/Q{2}, '
-                            'diffuse-interface sphere R=0.5 (erf profile, lambda = 2h, phi clamped to [1e-10,1]), rotating '
+                            'diffuse-interface sphere R=0.5 (erf profile, lambda = 0.25, phi clamped to [1e-10,1]), rotating '
                             'wall as DIM Dirichlet data, Oseen + implicit Euler, dt=1e-2, nu=1 '
                             '(reference models/ins_dim.py forms)'.format(args.N, args.order, args.order - 1),
                 'N': args.N, 'order': args.order,
@@ -159,7 +159,10 @@ def workload_config(args, where):
                                  'additive Schwarz smoother (damping 0.7), coarse-level phase field, tol 1e-12'
                 if where == 'gpu' else 'direct (SuperLU)', 'nonlinear_max_iterations': 3,
                 'l2': 'inputs larger than L2 (CSR matrix and patch inverses are GBs); no explicit flush',
-                'parallelism': 'single'}
+                'parallelism': ('element-partitioned: one {0}^3 brick with its own sphere per GPU (domain [-1,{1}] x '
+                                '[-1,1]^2), two ghost layers, halo exchange + all-reduce over NCCL issued by the C ABI '
+                                'Krylov driver, distributed multigrid-GMRES'.format(args.N, 2 * args.gpus - 1))
+                if args.gpus > 1 else 'single'}
     return {'workload': 'INS Taylor-Green 2D, structured {0}x{0}x2 triangles on [0,pi]^2, HDiv-DG order {1} / L2 order {2}, '
                         'Oseen + implicit Euler, dt=1e-3, nu=1 (examples/INS scaled up)'.format(args.N, args.order,
                                                                                                args.order - 1),
@@ -167,7 +170,8 @@ def workload_config(args, where):
             if where == 'gpu' else 'direct (SuperLU)', 'nonlinear_max_iterations': 3,
             'l2': 'inputs larger than L2 (CSR matrix 3.3 GB, patch inverses 9 GB at N=256); no explicit flush',
             'parallelism': ('element-partitioned: one {0}x{0}x2 strip per GPU (domain [0,pi] x [0,{1} pi]), two ghost '
-                            'layers, halo exchange + all-reduce over NCCL, distributed multigrid-GMRES'
+                            'layers, halo exchange + all-reduce over NCCL issued by the C ABI Krylov driver, distributed '
+                            'multigrid-GMRES'
                             .format(args.N, args.gpus)) if args.gpus > 1 else 'single'}
 
 
@@ -191,9 +195,12 @@ def main():
     ngs.set_backend(be)
     lib = be.lib
     t_setup = time.perf_counter()
-    if world > 1 and args.workload != 'ins2d':
-        raise SystemExit('bench.py: --workload {} runs on one GPU in this round'.format(args.workload))
-    if world > 1:
+    if world > 1 and args.workload == 'ins3d_dim':
+        # element-partitioned 3-D INS-DIM step: rank r owns the brick [-1 + 2r, 1 + 2r] x [-1,1]^2 at N^3 hexes
+        from opencmp_b200.dist_workload import DistributedINSDIM3D
+        dins = DistributedINSDIM3D(args.N, world, rank, order=args.order)
+        w = dins.w
+    elif world > 1:
         # element-partitioned INS step: rank r owns the strip [0,pi] x [r pi, (r+1) pi] at N x N x 2 triangles
         from opencmp_b200.dist_workload import DistributedINS
         dins = DistributedINS(args.N, world, rank, order=args.order)

@@ -158,6 +158,10 @@ typedef struct ocmp_mg_level {
 int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, double* x, double tol, int maxit, int restart,
                 double damp, double* work, long long work_len, int* iters, double* resid, void* stream);
 long long ocmp_krylov_work_len(int nrows, int kind, int restart);
+/* Relative preconditioned residual after every iteration of the last ocmp_krylov call (CG, GMRES); returns the number
+ * of iterations recorded and copies at most `cap` of them. NGSolve's solvers print these with printrates=True
+ * (reference base_model.py:925-943 passes printrates=self.verbose). */
+int ocmp_krylov_history(double* out_host, int cap);
 
 /* ---- instrumentation: per-category device time from CUDA events recorded around every launch on its own stream.
  * categories: 0 spmv, 1 asm_apply, 2 coefficient eval, 3 matrix contraction, 4 vector contraction, 5 multi-dot,

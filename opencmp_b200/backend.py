@@ -81,6 +81,7 @@ def load_library() -> C.CDLL:
     lib.ocmp_asm_apply.argtypes = [C.c_int, C.c_int, P, P, P, P, C.c_longlong, P]
     lib.ocmp_krylov.argtypes = [C.POINTER(System), C.c_int, P, P, C.c_double, C.c_int, C.c_int, C.c_double, P,
                                 C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_double), P]
+    lib.ocmp_krylov_history.argtypes = [C.POINTER(C.c_double), C.c_int]
     lib.ocmp_comm_unique_id.argtypes = [C.c_char_p]
     lib.ocmp_comm_init.argtypes = [C.c_char_p, C.c_int, C.c_int]
     lib.ocmp_halo_plan.argtypes = [C.c_int, P, P, P, P, P, P, P]
@@ -109,7 +110,7 @@ def read_profile(lib) -> dict:
     return out
 
 
-EXPORTED = ['ocmp_comm_unique_id', 'ocmp_comm_init', 'ocmp_halo_plan', 'ocmp_halo_run', 'ocmp_allreduce_sum',
+EXPORTED = ['ocmp_krylov_history', 'ocmp_comm_unique_id', 'ocmp_comm_init', 'ocmp_halo_plan', 'ocmp_halo_run', 'ocmp_allreduce_sum',
             'ocmp_patch_positions', 'ocmp_profile_bytes', 'ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
             'ocmp_dot', 'ocmp_axpby', 'ocmp_masked_assign', 'ocmp_jacobi_setup', 'ocmp_asm_setup', 'ocmp_asm_apply',
             'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version']
@@ -630,6 +631,12 @@ class CudaBackend:
         self.last_iters, self.last_resid = it.value, res.value
         if printrates:
             print('{}: {} iterations, residual {:.3e}'.format(kind, it.value, res.value))
+
+    def krylov_history(self, cap: int = 4096):
+        """Relative preconditioned residuals of the last Krylov solve (one per iteration)."""
+        buf = (C.c_double * cap)()
+        n = self.lib.ocmp_krylov_history(buf, cap)
+        return [buf[i] for i in range(min(n, cap))]
 
     def solve_free(self, mat, r, out, freedofs):
         """Stand-in for ``mat.Inverse(freedofs) * r``: GMRES + cell-patch additive Schwarz driven to 1e-13."""

@@ -555,6 +555,14 @@ struct Ctx {
 };
 }  // namespace
 
+// relative (preconditioned) residual after every iteration of the last ocmp_krylov call
+static std::vector<double> g_history;
+extern "C" int ocmp_krylov_history(double* out, int cap) {
+    const int n = (int)g_history.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = g_history[i];
+    return n;
+}
+
 extern "C" long long ocmp_krylov_work_len(int nrows, int kind, int restart) {
     const long long n = nrows;
     if (kind == 0) return 4 * n + 64;
@@ -571,6 +579,7 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
     c.s = sys; c.st = (cudaStream_t)stream; c.n = n;
     int it = 0;
     double res = 0.0;
+    g_history.clear();
     if (kind == 0) {                       // preconditioned CG on the free dofs
         double *r = work, *z = work + n, *p = work + 2 * n, *Ap = work + 3 * n;
         c.dscal = work + 4 * n;
@@ -594,6 +603,7 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
                 c.axpby(1.0, z, rzn / rz, p);
                 ++it;
                 res = sqrt(fabs(rzn));
+                g_history.push_back(res / err0);
                 rz = rzn;
                 if (res < tol * err0 || rzn == 0.0) break;
             }
@@ -647,6 +657,7 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
                 g[k] = cs[k] * g[k];
                 ++it;
                 res = fabs(g[k + 1]);
+                g_history.push_back(res / beta0);
                 if (hn > 0.0) {
                     double* vn = V + (long long)(k + 1) * n;
                     c.axpby(1.0 / hn, w, 0.0, vn);

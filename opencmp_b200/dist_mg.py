@@ -263,6 +263,7 @@ class DistributedMultigrid:
         lv = self.levels[top]
         n = lv.n
         V = be.zeros((restart + 1) * n).reshape(restart + 1, n)
+        self.history = []                  # relative preconditioned residual per iteration (diagnostics)
         it, beta0, res = 0, None, 0.0
         done = False
         while not done and it < maxit:
@@ -300,6 +301,7 @@ class DistributedMultigrid:
                 g[k] = cs[k] * g[k]
                 it += 1
                 res = abs(g[k + 1])
+                self.history.append(res / beta0)
                 if hn > 0:
                     V[k + 1] = w / hn
                 k += 1

@@ -146,3 +146,84 @@ class DistributedINS:
     @property
     def ndof_global(self):
         return self.mg.levels[-1].map.nglobal
+
+
+class DistributedINSDIM3D:
+    """The 3-D INS-DIM time step of workloads.INSSphereDIM3D, element-partitioned: R ranks, rank r owns the brick
+    [-1 + 2r, 1 + 2r] x [-1,1]^2 (n0^3 coarse hexes refined k times) with its own diffuse-interface sphere; geometric
+    multigrid + GMRES distributed with dist_mg.DistributedMultigrid (the phase field gets a stand-in on every local
+    coarse level). Per-rank work is fixed as R grows (weak scaling)."""
+
+    def __init__(self, N: int, world: int, rank: int, order: int = 2, n0: int = 2, bricks: int = None,
+                 replicate_below: int = 100000, **kw):
+        from .mesh import structured_3d
+        from .workloads import INSSphereDIM3D
+        from .dist_mg import DistributedMultigrid
+        self.world, self.rank = world, rank
+        k, n = 0, N
+        while n % 2 == 0 and n > n0:
+            n //= 2
+            k += 1
+        bricks = world if bricks is None else bricks
+        gmesh = structured_3d([n * bricks, n, n], scale=(2.0 * bricks, 2.0, 2.0), offset=(1.0, 1.0, 1.0))
+        for _ in range(k):
+            gmesh.Refine()
+        self.gmesh = gmesh
+        self.part = Partition(gmesh, world, rank, layers=2)
+        outer = self
+
+        def integrate(cf):
+            w = outer.w
+            val = ngs.Integrate(cf, w.mesh, definedon=w.mesh.Materials('owned'))
+            import torch
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                t = torch.tensor([val], dtype=torch.float64,
+                                 device='cuda' if ngs.get_backend().name == 'cuda' else 'cpu')
+                dist.all_reduce(t)
+                val = float(t[0])
+            return val
+
+        class _Local(INSSphereDIM3D):
+            def apply_dirichlet_bcs(self):
+                super().apply_dirichlet_bcs()
+                if getattr(outer, 'mg', None) is not None:
+                    outer.mg.levels[-1].map.exchange(self.gfu.vec.a)
+
+            def assemble(self):
+                self.a.Assemble()
+                self.L.Assemble()
+                outer.mg.levels[-1].map.exchange(self.L.vec.a)
+                outer.mg.update()
+
+            def linear_solve(self):
+                it, res = outer.mg.gmres(self.L.vec.a, self.gfu.vec.a, tol=self.linear_tolerance,
+                                         maxit=self.linear_max_iterations, restart=100)
+                self.linear_iterations.append(it)
+
+        self.mg = None
+        self.w = None
+        w = _Local.__new__(_Local)
+        self.w = w
+        _Local.__init__(w, N, order=order, mesh=self.part.local_mesh(), preconditioner=None, integrate=integrate, **kw)
+        self.mg = DistributedMultigrid(ngs.get_backend(), w.a, gmesh, self.part, replicate_below=replicate_below)
+        top = self.mg.levels[-1].map
+        for gf in (w.gfu, w.gfu_0):
+            top.exchange(gf.vec.a)
+        gV = ngs.VectorH1(ngs.Mesh(gmesh), order=order, dirichlet=w.dirichlet)
+        self._vmap = DofMap(self.part, gV, w.V)
+        self._vmap.exchange(w.W.vec.a)
+        step0 = w.step
+
+        def step():
+            out = step0()
+            self._vmap.exchange(w.W.vec.a)
+            return out
+        w.step = step
+
+    def step(self):
+        return self.w.step()
+
+    @property
+    def ndof_global(self):
+        return self.mg.levels[-1].map.nglobal

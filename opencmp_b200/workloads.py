@@ -207,10 +207,13 @@ class INSSphereDIM3D:
     """
 
     def __init__(self, N: int, order: int = 2, dt: float = 1e-2, nu: float = 1.0, ipc: float = 10.0,
-                 radius: float = 0.5, lam_cells: float = 2.0, omega_rot: float = 1.0,
+                 radius: float = 0.5, lam: float = 0.25, lam_cells: float = None, omega_rot: float = 1.0,
                  preconditioner: str = 'multigrid', linear_tolerance: float = 1e-12, linear_max_iterations: int = 400,
-                 nonlinear_max_iterations: int = 3, nonlinear_tolerance=(1e-4, 1e-6), n0: int = 2, mesh=None):
+                 nonlinear_max_iterations: int = 3, nonlinear_tolerance=(1e-4, 1e-6), n0: int = 2, mesh=None,
+                 integrate=None):
         from .mesh import structured_3d
+        if integrate is not None:              # element-partitioned runs: owned cells + all-reduce
+            self._integrate = integrate
         if mesh is None:
             nc = N
             while preconditioner == 'multigrid' and nc % 2 == 0 and nc > n0:
@@ -241,11 +244,16 @@ class INSSphereDIM3D:
         h = ngs.specialcf.mesh_size
         alpha = (ipc * k ** 2) / h                          # base_model.py:150, helpers/ngsolve_.py:67
         # ---- diffuse-interface fields (dim.py:390-445) ----
-        hcell = 2.0 / N
-        self.lam = lam_cells * hcell
+        # interface width: a physical length (default R/2), or ``lam_cells`` mesh widths. The reference clamps phi at
+        # 1e-10, which leaves the pressure outside the fluid determined only through 1e-10-scaled rows; once a large
+        # part of the box is clamped (lam <~ 0.15 here) the discrete system is numerically singular — two refinement
+        # passes of a sparse LU disagree by O(1) — so no solver, direct or Krylov, has a meaningful answer there.
+        self.lam = lam if lam_cells is None else lam_cells * 2.0 / N
         H = ngs.H1(m, order=k)
         self.fes_phi = H
-        r = ngs.sqrt(x * x + y * y + z * z + 1e-30)
+        # one sphere per [-1,1]^3 brick: the element-partitioned run lines R bricks up along x (weak scaling)
+        xl = (x + 1.0) - 2.0 * ngs.floor(0.5 * (x + 1.0)) - 1.0
+        r = ngs.sqrt(xl * xl + y * y + z * z + 1e-30)
         phi_cf = 0.5 * (1.0 + ngs.erf((radius - r) / self.lam))
         self.phi = ngs.GridFunction(H)
         self.phi.Set(phi_cf)
@@ -257,8 +265,8 @@ class INSSphereDIM3D:
         phi, mask = self.phi, self.mask
         gphi = ngs.Grad(phi)
         mag = ngs.Norm(gphi)
-        self.u_ref = ngs.CoefficientFunction((-omega_rot * y, omega_rot * x, 0.0 * x))
-        self.p_ref = 0.5 * omega_rot ** 2 * (x * x + y * y)
+        self.u_ref = ngs.CoefficientFunction((-omega_rot * y, omega_rot * xl, 0.0 * x))
+        self.p_ref = 0.5 * omega_rot ** 2 * (xl * xl + y * y)
         g = self.u_ref
         f = ngs.CoefficientFunction((0.0, 0.0, 0.0))
         self.gfu, self.gfu_0 = ngs.GridFunction(self.fes), ngs.GridFunction(self.fes)

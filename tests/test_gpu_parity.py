@@ -78,7 +78,7 @@ CASES = {
     'species_dg_p2': lambda: cases.species(cases.square_mesh(5), 2, lambda n: cases.random_wind(n, 11)),
     'stokes_3d_hex_q2q1': lambda: cases.stokes_3d('hex', 2),
     'stokes_3d_tet_p2p1': lambda: cases.stokes_3d('tet', 2),
-    'ins_dim_3d_hex_q2q1': lambda: cases.ins_dim_3d(4, preconditioner=None),
+    'ins_dim_3d_hex_q2q1': lambda: cases.ins_dim_3d(4, preconditioner=None, lam=1.0),
 }
 
 
@@ -168,7 +168,8 @@ def test_ins_dim_3d_multigrid_step():
     velocity, not 1e-9 (matrix and right-hand side of this case are compared at 1e-12 in test_assembly_matches_oracle).
     """
     def run(pre):
-        c = cases.ins_dim_3d(4, preconditioner=pre, nonlinear_max_iterations=2, nonlinear_tolerance=(0.0, 0.0))
+        c = cases.ins_dim_3d(4, preconditioner=pre, lam=1.0, nonlinear_max_iterations=2,
+                              nonlinear_tolerance=(0.0, 0.0))
         w = c['workload']
         ngs = c['ngs']
         if pre is None:

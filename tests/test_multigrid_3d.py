@@ -101,7 +101,7 @@ def test_coarse_phase_field_and_multigrid_solve(ngs):
     gm = structured_3d([2, 2, 2], scale=(2.0,) * 3, offset=(1.0,) * 3)
     gm.Refine()
     part = Partition(gm, 1, 0, layers=2)
-    w = INSSphereDIM3D(4, preconditioner=None, mesh=part.local_mesh(), nu=1.0)
+    w = INSSphereDIM3D(4, preconditioner=None, mesh=part.local_mesh(), lam=1.0)
     fields = coefficient_fields(w.a)
     assert {id(g) for g in fields} == {id(w.phi), id(w.mask)}       # the Oseen wind is not a coefficient field
     mg = DistributedMultigrid(be, w.a, gm, part, replicate_below=0)
