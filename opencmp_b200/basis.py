@@ -406,24 +406,49 @@ class L2Tensor(_TensorScalarBasis):
         self.entity_dofs = [('cell', 0, self.ndof, 'c')]
 
 
-# ---- HDiv (BDM_k) on triangles --------------------------------------------------------------------------------
+# ---- HDiv (BDM_k, RT_k) on triangles --------------------------------------------------------------------------
 class HDivTri(Basis):
+    """BDM_k = [P_k]^2 (NGSolve's default HDiv) or, with ``RT=True`` (reference models/ins.py:114-117),
+    RT_k = [P_k]^2 + x P~_k (P~_k homogeneous of degree k): same k+1 normal moments per edge, interior moments against
+    [P_{k-1}]^2 instead of grad P_{k-1} + curl(b P_{k-2}). Basis = dual basis of those functionals."""
     kind = 'hdiv'
 
     def __init__(self, cell_type: str, order: int, RT: bool = False):
         if cell_type != 'tri':
             raise NotImplementedError('HDiv is implemented on triangles')
-        if RT:
-            raise NotImplementedError('HDiv(RT=True) is not implemented yet')
         if order < 1:
             raise ValueError('HDiv needs order >= 1')
         super().__init__(cell_type, order)
         k = order
+        self.RT = bool(RT)
         lam = _barycentric(2)
         scal = _dubiner_tri(k, lam[0], lam[1], lam[2])           # expansion basis of P_k
         ns = len(scal)
-        nd = 2 * ns
-        # expansion functions e_m = (scal, 0) for m < ns, (0, scal) otherwise
+        # expansion functions e_m = (scal, 0) for m < ns, (0, scal) for m < 2 ns, then (x q, y q), q in P~_k (RT only)
+        X, Y = Poly.var(2, 0), Poly.var(2, 1)
+        extra = []
+        if RT:
+            for a in range(k + 1):
+                q = Poly.const(2, 1.0)
+                for _ in range(a):
+                    q = q * X
+                for _ in range(k - a):
+                    q = q * Y
+                extra.append((X * q, Y * q))
+        nd = 2 * ns + len(extra)
+        self._extra = extra
+        self._egrad = [[[c.diff(a) for a in range(2)] for c in e] for e in extra]
+
+        def expand(pts):
+            """(npts, 2, nd): both components of every expansion function."""
+            sv_ = np.stack([q(pts) for q in scal], axis=1)
+            out_ = np.zeros((pts.shape[0], 2, nd))
+            out_[:, 0, :ns] = sv_
+            out_[:, 1, ns:2 * ns] = sv_
+            for j, (ex, ey) in enumerate(extra):
+                out_[:, 0, 2 * ns + j] = ex(pts)
+                out_[:, 1, 2 * ns + j] = ey(pts)
+            return out_
         loc = local_topology('tri')
         ref = loc['ref']
         rows = []
@@ -435,11 +460,10 @@ class HDivTri(Basis):
             t = ref[b] - ref[a]
             n = np.array([t[1], -t[0]])
             pts = ref[a][None, :] + s[:, None] * t[None, :]
-            sv = np.stack([q(pts) for q in scal], axis=1)          # (nq, ns)
+            ev = expand(pts)                                       # (nq, 2, nd)
             for l in range(k + 1):
                 ql = eval_legendre(l, 2 * s - 1) * w
-                r = np.concatenate([n[0] * (ql @ sv), n[1] * (ql @ sv)])
-                edge_rows[(le, l)] = r
+                edge_rows[(le, l)] = ql @ (n[0] * ev[:, 0, :] + n[1] * ev[:, 1, :])
         for le in range(3):
             rows.append(edge_rows[(le, 0)])
             ent_lo.append(('facet', le, 1, 'lo'))
@@ -449,16 +473,22 @@ class HDivTri(Basis):
             ent_hi.append(('facet', le, k, 'hi'))
         # interior moments: against grad(P_{k-1} \ const) and curl(bubble * P_{k-2})
         cp, cw = cell_rule('tri', 2 * k + 2)
-        sv = np.stack([q(cp) for q in scal], axis=1)
+        ev = expand(cp)
         tests = []
-        for q in _dubiner_tri(k - 1, lam[0], lam[1], lam[2])[1:]:
-            tests.append((q.diff(0), q.diff(1)))
-        bub = lam[0] * lam[1] * lam[2]
-        for q in _dubiner_tri(k - 2, lam[0], lam[1], lam[2]):
-            f = bub * q
-            tests.append((f.diff(1), -f.diff(0)))
+        if RT:
+            zero = Poly.const(2, 0.0)
+            for q in _dubiner_tri(k - 1, lam[0], lam[1], lam[2]):
+                tests.append((q, zero))
+                tests.append((zero, q))
+        else:
+            for q in _dubiner_tri(k - 1, lam[0], lam[1], lam[2])[1:]:
+                tests.append((q.diff(0), q.diff(1)))
+            bub = lam[0] * lam[1] * lam[2]
+            for q in _dubiner_tri(k - 2, lam[0], lam[1], lam[2]):
+                f = bub * q
+                tests.append((f.diff(1), -f.diff(0)))
         for tx, ty in tests:
-            rows.append(np.concatenate([(cw * tx(cp)) @ sv, (cw * ty(cp)) @ sv]))
+            rows.append((cw * tx(cp)) @ ev[:, 0, :] + (cw * ty(cp)) @ ev[:, 1, :])
         nint = len(tests)
         V = np.stack(rows, axis=0)
         assert V.shape == (nd, nd), V.shape
@@ -480,6 +510,12 @@ class HDivTri(Basis):
             out[:, c, :] = sv @ Cc
             for a in range(2):
                 out[:, 2 + c * 2 + a, :] = sg[:, a, :] @ Cc
+        for j, (e, g) in enumerate(zip(self._extra, self._egrad)):       # RT: the x P~_k part
+            Cj = C[2 * ns + j, :]
+            for c in range(2):
+                out[:, c, :] += np.outer(e[c](pts), Cj)
+                for a in range(2):
+                    out[:, 2 + c * 2 + a, :] += np.outer(g[c][a](pts), Cj)
         return out
 
 

@@ -36,7 +36,8 @@ def clone_space(fes: FESpace, mesh) -> FESpace:
     if fes.components:
         return cls([clone_space(c, mesh) for c in fes.components], dgjumps=fes.dgjumps)
     b = fes.blocks[0]
-    return cls(mesh, order=fes.order, dirichlet=b.dirichlet or '', dgjumps=fes.dgjumps, family=fes.name)
+    return cls(mesh, order=fes.order, dirichlet=b.dirichlet or '', dgjumps=fes.dgjumps, family=fes.name,
+               RT=getattr(fes, 'RT', False))
 
 
 def prolongation(fes_c: FESpace, fes_f: FESpace, parent=None) -> sp.csr_matrix:

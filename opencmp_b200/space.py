@@ -146,6 +146,7 @@ class FESpace:
         else:
             self.mesh = spaces_or_mesh
             self.name = family
+            self.RT = bool(RT)
             self.order = int(order)
             self.dgjumps = bool(dgjumps)
             self.components = []

@@ -65,13 +65,13 @@ def poisson(mesh, order, DG, family='H1', transient_dt=None):
     return dict(ngs=ngs, mesh=m, fes=fes, a=a, L=L, gfu=gfu, exact=exact, dnames=dnames, params=(dt, t))
 
 
-def stokes(mesh, order, DG, wind=None, dt_val=1.0, mass=False, walls='wall', nu=1e-3):
+def stokes(mesh, order, DG, wind=None, dt_val=1.0, mass=False, walls='wall', nu=1e-3, RT=False):
     """Stokes / Oseen forms: reference opencmp/models/stokes.py:43-129 and models/ins.py:178-321."""
     ngs = _ngs()
     m = ngs.Mesh(mesh)
     if DG:
-        V = ngs.HDiv(m, order=order, dirichlet=walls, dgjumps=True)
-        Q = ngs.L2(m, order=order - 1, dgjumps=True)
+        V = ngs.HDiv(m, order=order, dirichlet=walls, dgjumps=True, RT=RT)        # models/ins.py:114-117
+        Q = ngs.L2(m, order=order - (0 if RT else 1), dgjumps=True)
     else:
         V = ngs.VectorH1(m, order=order, dirichlet=walls)
         Q = ngs.H1(m, order=order - 1)

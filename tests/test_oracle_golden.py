@@ -127,3 +127,24 @@ def test_transient_poisson_mass_term(oracle_backend):
     # decay rate of the first eigenmode exp(-2 pi^2 t) within discretisation error of implicit Euler
     ratio = energy[-1] / energy[-2]
     assert abs(ratio - (1.0 / (1 + 0.05 * 2 * np.pi ** 2)) ** 2) < 0.05
+
+
+def test_stokes_poiseuille_raviart_thomas(oracle_backend):
+    """``HDiv(..., RT=True)`` (reference models/ins.py:114-117): the Poiseuille solution of
+    pytests/full_system/stokes is representable in RT_2 / P_2 as well, so it is reproduced to round-off and the
+    velocity is pointwise divergence free."""
+    ngs = oracle_backend
+    c = cases.stokes(_channel(), 2, True, RT=True)
+    assert c['V'].ndof > cases.stokes(_channel(), 2, True)['V'].ndof          # RT_k is richer than BDM_k
+    c['gfu'].components[0].Set(c['uex'], definedon=c['mesh'].Boundaries(c['walls']))
+    c['a'].Assemble()
+    c['L'].Assemble()
+    cases.direct_solve(c)
+    u, p = c['gfu'].components
+    m = c['mesh']
+    du = u - c['uex']
+    area = ngs.Integrate(ngs.CoefficientFunction(1.0), m)
+    dp = p - c['pex'] - ngs.Integrate(p - c['pex'], m) / area
+    assert np.sqrt(ngs.Integrate(ngs.InnerProduct(du, du), m)) < 4e-9
+    assert np.sqrt(ngs.Integrate(dp * dp, m)) < 1e-9
+    assert np.sqrt(ngs.Integrate(ngs.div(u) ** 2, m)) < 1e-6
