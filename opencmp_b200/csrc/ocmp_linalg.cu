@@ -240,6 +240,28 @@ extern "C" int ocmp_axpby(long long n, double a, const double* x, double b, doub
     if (n > 0) k_axpby<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, a, x, b, y);
     return ocmp_check("ocmp_axpby");
 }
+// out[j] = <V_j, w>, j < k (V_j = V + j*ld), out on the device; w += sum_j coef[j] V_j (coef on the device).
+// Building blocks of the Krylov drivers below, exported for the nonlinear mixers (opencmp_b200/mixing.py).
+extern "C" int ocmp_mdot(long long n, const double* V, long long ld, int k, const double* w, double* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k <= 0) return 0;
+    cudaMemsetAsync(out, 0, sizeof(double) * k, st);
+    ocmp_prof_begin(PROF_MDOT, st);
+    for (int j0 = 0; j0 < k && n > 0; j0 += 8) {
+        const int kk = (k - j0) < 8 ? (k - j0) : 8;
+        k_mdot<8><<<grid_for(n), 256, 0, st>>>(n, V + (long long)j0 * ld, ld, kk, w, out + j0);
+    }
+    ocmp_prof_end(PROF_MDOT, st);
+    return ocmp_check("ocmp_mdot");
+}
+extern "C" int ocmp_maxpy(long long n, const double* V, long long ld, int k, const double* coef, double* w,
+                          void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k <= 0 || n <= 0) return 0;
+    ProfScope ps(PROF_MAXPY, st);
+    k_maxpy<<<grid_for(n), 256, sizeof(double) * k, st>>>(n, V, ld, k, coef, w);
+    return ocmp_check("ocmp_maxpy");
+}
 extern "C" int ocmp_masked_assign(long long n, double* dst, const double* src, const double* inv, const double* mask,
                                   void* stream) {
     ProfScope ps(PROF_VEC, (cudaStream_t)stream);

@@ -104,9 +104,7 @@ class DofMap:
         for s in np.unique(self.owner_local[ghosts]):
             idx = ghosts[self.owner_local[ghosts] == s]
             self.recv[int(s)] = idx[np.argsort(l2g[idx])]
-        for s in range(R):
-            if s == me:
-                continue
+        for s in _candidate_peers(part):
             other = Partition(part.mesh, R, s, layers=_layers_of(part))
             theirs = np.unique(gcd[other.local_cells].ravel())
             mine = theirs[owner[theirs] == me]          # ascending global id = their recv order
@@ -211,6 +209,23 @@ class DofMap:
             dist.all_reduce(t)
             local = float(t[0])
         return local
+
+
+def _candidate_peers(part: Partition) -> List[int]:
+    """Ranks whose local (owned + ghost) cells can intersect this rank's: those owning a cell within twice the ghost
+    depth of this rank's owned cells (every rank on a replicated level). Keeps the halo-plan construction from
+    rebuilding the partition of all R ranks when only the geometric neighbours matter."""
+    R, me = part.nranks, part.rank
+    layers = _layers_of(part)
+    if layers is None:
+        return [s for s in range(R) if s != me]
+    mesh = part.mesh
+    near = part.cell_rank == me
+    for _ in range(2 * layers):
+        vmask = np.zeros(mesh.nv, dtype=bool)
+        vmask[mesh.cells[near].ravel()] = True
+        near = vmask[mesh.cells].any(axis=1)
+    return [int(s) for s in np.unique(part.cell_rank[near]) if s != me]
 
 
 def _layers_of(part: Partition) -> int:
