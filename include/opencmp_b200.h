@@ -91,6 +91,11 @@ int ocmp_dot(long long n, const double* x, const double* y, double* out, void* s
 int ocmp_axpby(long long n, double a, const double* x, double b, double* y, void* stream);   /* y = a x + b y */
 int ocmp_masked_assign(long long n, double* dst, const double* src, const double* inv, const double* mask,
                        void* stream);
+/* Batched level-1 building blocks of the Krylov drivers, also used by the stationary nonlinear mixers that stand in for
+ * reference opencmp/solvers/nonlinear_mixing.py:19-141 (Anderson / DiagBroyden / linear mixing on the DOF vector):
+ * out_dev[j] = <V_j, w>, j < k, V_j = V + j*ld;   w += sum_j coef_dev[j] V_j. */
+int ocmp_mdot(long long n, const double* V, long long ld, int k, const double* w, double* out_dev, void* stream);
+int ocmp_maxpy(long long n, const double* V, long long ld, int k, const double* coef_dev, double* w, void* stream);
 
 /* ---- preconditioners: stand in for ngs.Preconditioner(a, type) + .Update() (reference
  *      opencmp/models/base_model.py:365-383, opencmp/solvers/base_solver.py:711-719) -------------------------- */

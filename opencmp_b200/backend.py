@@ -75,6 +75,8 @@ def load_library() -> C.CDLL:
     lib.ocmp_dot.argtypes = [C.c_longlong, P, P, P, P]
     lib.ocmp_axpby.argtypes = [C.c_longlong, C.c_double, P, C.c_double, P, P]
     lib.ocmp_masked_assign.argtypes = [C.c_longlong, P, P, P, P, P]
+    lib.ocmp_mdot.argtypes = [C.c_longlong, P, C.c_longlong, C.c_int, P, P, P]
+    lib.ocmp_maxpy.argtypes = [C.c_longlong, P, C.c_longlong, C.c_int, P, P, P]
     lib.ocmp_jacobi_setup.argtypes = [C.c_int, P, P, P, P, P]
     lib.ocmp_asm_setup.argtypes = [C.c_int, C.c_int, P, P, P, P, P, P, P, P]
     lib.ocmp_patch_positions.argtypes = [C.c_int, C.c_int, P, P, P, P, P]
@@ -110,7 +112,7 @@ def read_profile(lib) -> dict:
     return out
 
 
-EXPORTED = ['ocmp_krylov_history', 'ocmp_comm_unique_id', 'ocmp_comm_init', 'ocmp_halo_plan', 'ocmp_halo_run', 'ocmp_allreduce_sum',
+EXPORTED = ['ocmp_mdot', 'ocmp_maxpy', 'ocmp_krylov_history', 'ocmp_comm_unique_id', 'ocmp_comm_init', 'ocmp_halo_plan', 'ocmp_halo_run', 'ocmp_allreduce_sum',
             'ocmp_patch_positions', 'ocmp_profile_bytes', 'ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
             'ocmp_dot', 'ocmp_axpby', 'ocmp_masked_assign', 'ocmp_jacobi_setup', 'ocmp_asm_setup', 'ocmp_asm_apply',
             'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version']
@@ -206,7 +208,24 @@ class CudaBackend:
         return a.detach().cpu().numpy()
 
     def copy_into(self, dst, src):
+        if isinstance(src, np.ndarray):        # e.g. the reference's host-side mixers hand back NumPy arrays
+            src = self.torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64))
         dst.copy_(src)
+
+    def mdot(self, V, w):
+        """Host array of <V_j, w> for the rows of the 2-D device array V (one batched launch + one read-back)."""
+        k, n = V.shape
+        self._ck(self.lib.ocmp_mdot(n, V.data_ptr(), V.stride(0), k, w.data_ptr(), self._scal.data_ptr(),
+                                    self._stream()))
+        self.launches += 1
+        return self._scal[:k].cpu().numpy()
+
+    def maxpy(self, V, coef, w):
+        """w += sum_j coef[j] V_j (coef: host array)."""
+        k, n = V.shape
+        c = self._up(np.asarray(coef, dtype=np.float64))
+        self._ck(self.lib.ocmp_maxpy(n, V.data_ptr(), V.stride(0), k, c.data_ptr(), w.data_ptr(), self._stream()))
+        self.launches += 1
 
     def dot(self, a, b):
         self._ck(self.lib.ocmp_dot(a.numel(), a.data_ptr(), b.data_ptr(), self._scal.data_ptr(), self._stream()))

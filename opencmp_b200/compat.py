@@ -13,7 +13,12 @@ import sys
 import types
 
 
-def install_as_ngsolve(force: bool = False) -> None:
+def install_as_ngsolve(force: bool = False, device_mixing: bool = False) -> None:
+    """``device_mixing``: also register opencmp_b200.mixing as ``opencmp.solvers.nonlinear_mixing`` (same interface as
+    the reference module, history vectors kept on the device). Must happen before ``import opencmp``."""
+    if device_mixing:
+        from . import mixing
+        sys.modules['opencmp.solvers.nonlinear_mixing'] = mixing
     if 'ngsolve' in sys.modules and not force and getattr(sys.modules['ngsolve'], '__b200__', False):
         return
     from . import ngs

@@ -40,6 +40,12 @@ class OracleBackend:
     def dot(self, a, b):
         return float(np.dot(a, b))
 
+    def mdot(self, V, w):
+        return np.asarray(V) @ np.asarray(w)
+
+    def maxpy(self, V, coef, w):
+        w += np.asarray(coef, dtype=np.float64) @ np.asarray(V)
+
     def masked_assign(self, dst, src, inv, mask):
         m = mask > 0
         dst[m] = src[m] * inv[m]
