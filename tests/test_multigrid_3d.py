@@ -124,3 +124,32 @@ def test_coarse_phase_field_and_multigrid_solve(ngs):
     got = w.gfu.vec.NumPy()
     assert it < 60
     assert np.linalg.norm((got - xd)[:nv]) < 1e-6 * np.linalg.norm(xd[:nv])
+
+
+def test_cuda_backend_patch_tables_host_logic(ngs):
+    """CudaBackend._patches is host code (NumPy) feeding the smoother kernels: closed stars in 2-D (identical to the
+    oracle's), automatic switch to open stars with an even stride in 3-D, owned-vertex subsets for partitioned runs."""
+    from opencmp_b200.backend import CudaBackend
+    from opencmp_b200.mesh import structured_2d, structured_3d
+    from oracle.backend import _vertex_patches
+    be = CudaBackend.__new__(CudaBackend)                    # no device needed for the table construction
+    cache = {}
+    be.space_data = lambda fes: cache.setdefault(id(fes), {})
+    be._up = lambda a, dtype=None: np.asarray(a)
+    m = ngs.Mesh(structured_2d([6, 6], scale=(np.pi, np.pi)))
+    fes = ngs.FESpace([ngs.HDiv(m, order=3, dirichlet='top|bottom|left|right', dgjumps=True),
+                       ngs.L2(m, order=2, dgjumps=True)], dgjumps=True)
+    vm = np.zeros(m.nv, bool)
+    vm[::3] = True
+    for mask in (None, vm):
+        pt = be._patches(fes, 'vertex', mask)
+        ref = _vertex_patches(fes, mask)
+        assert pt['bs'] == 132 and pt['npatch'] == len(ref)
+        assert all(np.array_equal(r, d[d >= 0]) for r, d in zip(ref, pt['dofs']))
+    m3 = ngs.Mesh(structured_3d([4, 4, 4]))
+    f3 = ngs.FESpace([ngs.VectorH1(m3, order=2, dirichlet='back|left|front|right|bottom|top'), ngs.H1(m3, order=1)])
+    p3 = be._patches(f3, 'vertex')
+    assert p3['npatch'] == m3.nv and p3['bs'] == 90 and (p3['dofs'][:, -1] == -1).all()
+    assert p3['dofs'].dtype == np.int32 and p3['wgt'].min() > 0
+    covered = np.unique(p3['dofs'][p3['dofs'] >= 0])
+    assert np.array_equal(covered, np.nonzero(f3.FreeDofs())[0])
