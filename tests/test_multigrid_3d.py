@@ -62,6 +62,24 @@ def test_hex_prolongation_is_exact(ngs):
     assert np.abs(P @ gc.vec.NumPy() - gf.vec.NumPy()).max() < 1e-10
 
 
+def test_quad_prolongation_is_exact(ngs):
+    """2-D quadrilateral hierarchy (the reference's DIM meshes default to quads, expanded_config_parser.py:79)."""
+    from opencmp_b200.mesh import structured_2d
+    from opencmp_b200.multigrid import clone_space, prolongation
+    mesh = structured_2d([3, 2], cell='quad')
+    mesh.Refine()
+    mf = ngs.Mesh(mesh)
+    fine = ngs.FESpace([ngs.H1(mf, order=3), ngs.L2(mf, order=2)])
+    coarse = clone_space(fine, mesh.coarse)
+    P = prolongation(coarse, fine)
+    x, y = ngs.x, ngs.y
+    gc, gf = ngs.GridFunction(coarse), ngs.GridFunction(fine)
+    for g in (gc, gf):
+        g.components[0].Set(x * x * x * y * y - 2.0 * x * y * y * y + 1.0)
+        g.components[1].Set(x * x * y * y - x + 3.0 * y)
+    assert np.abs(P @ gc.vec.NumPy() - gf.vec.NumPy()).max() < 1e-10
+
+
 def test_star_and_vanka_patches(ngs):
     from opencmp_b200.mesh import structured_3d
     from opencmp_b200.patches import vertex_patch_dofs
