@@ -55,6 +55,11 @@ class Coef:
         Coef._table[key] = self
         return self
 
+    def __reduce__(self):
+        # pickling (the reference's post-processing hands GridFunctions to a multiprocessing.Pool,
+        # post_processing/output_conversions.py:192-199) must go through __new__ again to keep the hash-consing
+        return (Coef, (self.op, self.args, self.val))
+
     # constructors with constant folding -------------------------------------------------------------------------
     @staticmethod
     def const(v) -> 'Coef':

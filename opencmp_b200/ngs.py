@@ -203,6 +203,15 @@ class BaseVector:
     def __len__(self):
         return int(self.a.shape[0])
 
+    def __getstate__(self):
+        # pickled as a host array: the reference's .vtu conversion ships GridFunctions to worker processes
+        # (post_processing/output_conversions.py:192-199), which must not touch the device
+        a = self.a
+        return {'a': a if isinstance(a, np.ndarray) else get_backend().to_numpy(a)}
+
+    def __setstate__(self, state):
+        self.a = state['a']
+
     @property
     def size(self):
         return len(self)
@@ -305,8 +314,9 @@ class GridFunction(CoefficientFunction):
         self._g = g
 
     def vec_numpy(self):
-        """Host copy of the ROOT dof vector (used by the test oracle only)."""
-        return get_backend().to_numpy(self._root.vec.a)
+        """Host copy of the ROOT dof vector (test oracle, point evaluation, .vtu export)."""
+        a = self._root.vec.a
+        return a if isinstance(a, np.ndarray) else get_backend().to_numpy(a)
 
     def _grad_cf(self):
         return CoefficientFunction(_arr=self._g)
@@ -343,7 +353,10 @@ class GridFunction(CoefficientFunction):
         if data.shape[0] != len(self.vec):
             raise ValueError('checkpoint {} holds {} DOFs, the GridFunction has {}'.format(filename, data.shape[0],
                                                                                           len(self.vec)))
-        self.vec.data = BaseVector(get_backend().from_numpy(data))
+        if isinstance(self.vec.a, np.ndarray):          # host storage (oracle backend, or an unpickled copy in a worker)
+            self.vec.a[:] = data
+        else:
+            self.vec.data = BaseVector(get_backend().from_numpy(data))
 
     def __call__(self, mip, *a, **k):
         """Point evaluation ``gfu(mesh(x, y))`` (controllers / unit tests; host side, not on the hot path)."""
@@ -572,9 +585,7 @@ class BitArray:
 
 
 # ---- names OpenCMP imports but the hot path never touches (post-processing, DIM pre-processing) -------------------
-class VTKOutput:
-    def __init__(self, *a, **k):
-        raise NotImplementedError('VTKOutput: .vtu export is outside the hot path (SURVEY 8(f) N3)')
+from .vtk import VTKOutput  # noqa: E402  (.vtu export of the reference's post-processing)
 
 
 def VoxelCoefficient(*a, **k):

@@ -70,3 +70,32 @@ def test_reference_poisson_example_h_convergence(ref_tree):
     rows = [ln.split() for ln in r.stdout.splitlines() if ln.startswith('1/')]
     rates = [float(x[-1]) for x in rows]
     assert len(rates) == 5 and all(abs(x - 4.0) < 0.1 for x in rates[1:]), r.stdout[-1500:]
+
+
+def test_reference_vtu_post_processing_through_the_boundary(ref_tree):
+    """`save_type = .vtu`: the reference's own post-processing (post_processing/output_conversions.py — a
+    multiprocessing.Pool of workers loading every .sol file and calling VTKOutput(...).Do(), then writing the .pvd
+    collection) runs unmodified on our GridFunction / VTKOutput."""
+    case = ref_tree / 'pytests' / 'full_system' / 'restart' / 'transient_poisson'
+    cfg = (case / 'config').read_text()
+    cfg = cfg.replace('save_type = .sol', 'save_type = .vtu').replace('time_range = 0.0, 0.1', 'time_range = 0.0, 0.03')
+    cfg = cfg.replace('run_dir = .', 'run_dir = pytests/full_system/restart/transient_poisson')
+    (case / 'config_vtu').write_text(cfg)
+    script = textwrap.dedent('''
+        import sys
+        sys.path.insert(0, {root!r}); sys.path.insert(0, {tree!r})
+        import conftest
+        from opencmp.run import run
+        run('pytests/full_system/restart/transient_poisson/config_vtu')
+    ''').format(root=ROOT, tree=str(ref_tree))
+    r = subprocess.run([sys.executable, '-c', script], cwd=ref_tree, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = case / 'output'
+    vtus = sorted((out / 'poisson_vtu').glob('*.vtu'))
+    assert len(vtus) == 4                                   # t = 0, 0.01, 0.02, 0.03
+    pvd = (out / 'poisson_transient.pvd').read_text()
+    assert pvd.count('<DataSet') == 4 and 'poisson_vtu/poisson_0.01.vtu' in pvd
+    import xml.etree.ElementTree as ET
+    piece = ET.parse(vtus[1]).getroot().find('UnstructuredGrid/Piece')
+    names = [d.get('Name') for d in piece.findall('PointData/DataArray')]
+    assert names == ['u'] and int(piece.get('NumberOfCells')) > 0
