@@ -349,7 +349,9 @@ class GridFunction(CoefficientFunction):
 
     def Load(self, filename, parallel=False):
         with open(str(filename), 'rb') as fh:
-            data = np.load(fh)
+            magic = fh.read(6)
+            fh.seek(0)
+            data = np.load(fh) if magic == b'\x93NUMPY' else self._from_ngsolve_binary(fh.read(), str(filename))
         if data.shape[0] != len(self.vec):
             raise ValueError('checkpoint {} holds {} DOFs, the GridFunction has {}'.format(filename, data.shape[0],
                                                                                           len(self.vec)))
@@ -357,6 +359,30 @@ class GridFunction(CoefficientFunction):
             self.vec.a[:] = data
         else:
             self.vec.data = BaseVector(get_backend().from_numpy(data))
+
+    def _from_ngsolve_binary(self, raw: bytes, filename: str):
+        """A .sol file written by NGSolve itself (``GridFunction.Save``: the DOF values as raw doubles, by node type —
+        vertices, edges, faces, cells). For an H1 space the vertex DOFs are the nodal values in mesh-vertex order in
+        NGSolve's basis and in ours; the edge / face / cell DOFs belong to NGSolve's integrated-Legendre functions,
+        whose scaling and orientation conventions cannot be checked without NGSolve. Such a file is therefore accepted
+        exactly when its high-order part vanishes — true for the phase fields and masks the reference's DIM generator
+        writes on the simulation mesh (piecewise multilinear voxel data, e.g. pytests/full_system/dim/dim_poisson_2) —
+        and refused otherwise."""
+        fes = self.space
+        blocks = fes.blocks
+        if len(raw) != 8 * fes.ndof or len(blocks) != 1 or blocks[0].family != 'H1':
+            raise ValueError('{}: not a checkpoint of this package, and not an NGSolve H1 DOF dump of {} values'
+                             .format(filename, fes.ndof))
+        vals = np.frombuffer(raw, dtype=np.float64)
+        nv = fes.mesh.nv
+        scale = max(np.abs(vals[:nv]).max(), 1e-300)
+        if vals.size > nv and np.abs(vals[nv:]).max() > 1e-9 * scale:
+            raise NotImplementedError('{}: NGSolve-binary .sol with a non-zero high-order part (max {:.2e}); NGSolve\'s '
+                                      'high-order basis conventions are not available here'
+                                      .format(filename, np.abs(vals[nv:]).max()))
+        out = np.zeros(fes.ndof)
+        out[:nv] = vals[:nv]
+        return out
 
     def __call__(self, mip, *a, **k):
         """Point evaluation ``gfu(mesh(x, y))`` (controllers / unit tests; host side, not on the hot path)."""

@@ -78,6 +78,8 @@ def main():
                                       ('TRANSIENT', 'time_range'): '0.0, 0.003'}),
     }
     for name, (cfg, ov) in cases.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         solver, sol, errs = run_reference(cfg, ov)
         m = solver.model.mesh
         np.savez_compressed(os.path.join(here, name + '.npz'), vec=np.asarray(sol.vec.NumPy()),
@@ -109,7 +111,14 @@ def main():
                                       {('DG', 'DG'): 'True', **short}),
         # stationary INS in a pipe, stress boundary conditions, Oseen + Anderson mixing (ins.py:208-223)
         'prog_ins_cg_stationary_stress': ('pytests/full_system/ins/pressure_flow_in_pipe_stress/config', {}),
+        # PoissonDIM (models/poisson_dim.py) with the phase field and the two boundary masks the reference ships as
+        # NGSolve-binary .sol files (pytests/full_system/dim/dim_poisson_2: 39 x 39 quads, H1 order 3, DIM Dirichlet
+        # data on 'top' / 'bottom' of a diffuse disc) — DIM.get_DIM_gridfunctions load_method = file (dim.py:348-378)
+        'prog_poisson_dim_2': ('pytests/full_system/dim/dim_poisson_2/config', {}),
     }
+    only = set(sys.argv[1:])
+    if only:
+        prog_cases = {k: v for k, v in prog_cases.items() if k in only}
     rng = np.random.default_rng(7)
     for name, (cfg, ov) in prog_cases.items():
         try:

@@ -99,3 +99,58 @@ def test_reference_vtu_post_processing_through_the_boundary(ref_tree):
     piece = ET.parse(vtus[1]).getroot().find('UnstructuredGrid/Piece')
     names = [d.get('Name') for d in piece.findall('PointData/DataArray')]
     assert names == ['u'] and int(piece.get('NumberOfCells')) > 0
+
+
+def test_reference_dim_poisson_with_shipped_phase_field(ref_tree):
+    """pytests/full_system/dim/test_dim.py::test_DIM_poisson_2 — the reference's DIM class loads the phase field and
+    the two boundary masks it ships as NGSolve-binary .sol files (H1 order 3 on 39 x 39 quads; their high-order part
+    vanishes, so the vertex values determine them, see GridFunction._from_ngsolve_binary), PoissonDIM builds the
+    phi-weighted forms (models/poisson_dim.py) and the stationary solver runs. Then the phi-weighted L2 error against
+    the manufactured solution of its ref_sol_config is measured: 1.1e-3 relative."""
+    r = _pytest(ref_tree, 'pytests/full_system/dim/test_dim.py', '-k', 'poisson_2')
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert '1 passed' in r.stdout
+    script = textwrap.dedent('''
+        import sys
+        sys.path.insert(0, {root!r}); sys.path.insert(0, {tree!r})
+        import conftest
+        import numpy as np
+        import opencmp_b200.ngs as ngs
+        from opencmp.config_functions import ConfigParser
+        from opencmp.models import get_model_class
+        from opencmp.solvers import get_solver_class
+        cfg = ConfigParser('pytests/full_system/dim/dim_poisson_2/config')
+        solver = get_solver_class(cfg)(get_model_class('Poisson', True), cfg)
+        sol = solver.solve()
+        m = solver.model
+        phi = m.DIM_solver.phi_gfu
+        u = sol.components[0] if sol.components else sol
+        ref = ngs.sin(np.pi * ngs.x) * ngs.cos(np.pi * ngs.y)
+        err = np.sqrt(ngs.Integrate((u - ref) * (u - ref) * phi, m.mesh))
+        nrm = np.sqrt(ngs.Integrate(ref * ref * phi, m.mesh))
+        print('RESULT', type(m).__name__, sorted(m.DIM_solver.mask_gfu_dict), err / nrm, ngs.Integrate(phi, m.mesh))
+    ''').format(root=ROOT, tree=str(ref_tree))
+    r = subprocess.run([sys.executable, '-c', script], cwd=ref_tree, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith('RESULT')][0].split()
+    assert line[1] == 'PoissonDIM' and "'bottom'," in line[2] + line[3]
+    assert float(line[-2]) < 3e-3                    # phi-weighted relative L2 error
+    assert abs(float(line[-1]) - 2.865) < 0.01       # area of the diffuse disc
+
+
+def test_ngsolve_binary_sol_with_high_order_part_is_refused(ref_tree):
+    """dim_stokes_2/phi.sol carries non-zero edge / cell DOFs in NGSolve's basis: refused loudly, not misread."""
+    script = textwrap.dedent('''
+        import sys
+        sys.path.insert(0, {root!r}); sys.path.insert(0, {tree!r})
+        import conftest
+        import opencmp_b200.ngs as ngs
+        m = ngs.Mesh('pytests/full_system/dim/dim_stokes_2/dim_dir/mesh.vol')
+        g = ngs.GridFunction(ngs.H1(m, order=2))
+        try:
+            g.Load('pytests/full_system/dim/dim_stokes_2/dim_dir/phi.sol')
+        except NotImplementedError as e:
+            print('REFUSED', e)
+    ''').format(root=ROOT, tree=str(ref_tree))
+    r = subprocess.run([sys.executable, '-c', script], cwd=ref_tree, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'REFUSED' in r.stdout, r.stdout + r.stderr[-2000:]
