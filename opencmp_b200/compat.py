@@ -43,20 +43,20 @@ def install_as_ngsolve(force: bool = False, device_mixing: bool = False) -> None
     ngs.ngsglobals = ngs.ngsglobals
     netgen = types.ModuleType('netgen')
     meshing = types.ModuleType('netgen.meshing')
-
-    class _NgMesh:
-        """``ngmsh.Mesh(dim)`` followed by ``.Load(filename)`` — reference helpers/io.py:94-99."""
-
-        def __init__(self, dim=3):
-            self.dim = dim
-            self._mesh = None
-
-        def Load(self, filename):
-            self._mesh = load_mesh(filename)
-
-    meshing.Mesh = _NgMesh
+    # ``ngmsh.Mesh(dim)`` + ``.Load(filename)`` (reference helpers/io.py:94-99) and the builder calls of
+    # diffuse_interface/mesh_helpers.py:494-690
+    from . import netgen_shim
+    for name in ('Mesh', 'MeshPoint', 'Pnt', 'Element1D', 'Element2D', 'Element3D', 'FaceDescriptor', 'PointId'):
+        setattr(meshing, name, getattr(netgen_shim, name))
     read_gmsh = types.ModuleType('netgen.read_gmsh')
     read_gmsh.ReadGmsh = lambda filename: read_msh(filename if filename.endswith('.msh') else filename + '.msh')
+    if 'edt' not in sys.modules:
+        try:
+            import edt  # noqa: F401
+        except ImportError:
+            edt_mod = types.ModuleType('edt')
+            edt_mod.edt = netgen_shim.edt
+            sys.modules['edt'] = edt_mod
     netgen.meshing, netgen.read_gmsh = meshing, read_gmsh
     sys.modules['netgen'] = netgen
     sys.modules['netgen.meshing'] = meshing

@@ -330,7 +330,13 @@ class GridFunction(CoefficientFunction):
 
     def Set(self, cf, definedon=None, VOL_or_BND=None, **kw):
         from .project import set_gridfunction
+        if isinstance(cf, VoxelCoefficient):
+            return cf.set_into(self, definedon)
         cf = CoefficientFunction._lift(cf)
+        from .hostproject import foreign_fields, set_from_points
+        if foreign_fields(cf, self.space.mesh):
+            # data living on another mesh (DIM: phase field generated on a finer grid, dim.py:393-409)
+            return set_from_points(self, cf, definedon)
         set_gridfunction(self, cf, definedon)
         # remembered so that geometric multigrid can re-evaluate coefficient fields (e.g. the DIM phase field) on its
         # coarse levels; a later direct write to .vec (clamping) is mimicked there by clipping to the fine range
@@ -614,8 +620,56 @@ class BitArray:
 from .vtk import VTKOutput  # noqa: E402  (.vtu export of the reference's post-processing)
 
 
-def VoxelCoefficient(*a, **k):
-    raise NotImplementedError('VoxelCoefficient: diffuse-interface pre-processing is outside the hot path')
+class VoxelCoefficient:
+    """``ngs.VoxelCoefficient(start, end, values, linear=True)``: node data on a regular grid spanning [start, end],
+    interpolated multilinearly — how the reference turns phase-field / mask arrays into GridFunctions
+    (helpers/ngsolve_.py:170-192 ``numpy_to_ngsolve``, :260, :288; values indexed [z][y][x]).
+
+    Supported use: ``GridFunction.Set(VoxelCoefficient(...))`` on an H1 space of a quadrilateral / hexahedral mesh whose
+    vertices are grid nodes (the reference's default ``N == N_mesh``, ``quad_mesh = True``). The data are then exactly
+    the multilinear part of the space: vertex DOFs = node values, higher-order DOFs = 0 — which is also what NGSolve
+    produces (the high-order part of the .sol files it wrote for pytests/full_system/dim/dim_poisson_2 is 6e-12)."""
+
+    def __init__(self, start, end, values, linear: bool = True, **_):
+        if not linear:
+            raise NotImplementedError('VoxelCoefficient(linear=False)')
+        self.start = np.asarray(start, dtype=np.float64)
+        self.end = np.asarray(end, dtype=np.float64)
+        self.values = np.asarray(values, dtype=np.float64)
+        if self.values.ndim != len(self.start):
+            raise ValueError('VoxelCoefficient: {}-d data for a {}-d box'.format(self.values.ndim, len(self.start)))
+
+    def vertex_values(self, mesh) -> np.ndarray:
+        d = mesh.dim
+        shape = self.values.shape[::-1]                                 # (nx, ny[, nz])
+        idx = []
+        for a in range(d):
+            h = (self.end[a] - self.start[a]) / max(shape[a] - 1, 1)
+            t = (mesh.points[:, a] - self.start[a]) / h
+            k = np.rint(t)
+            if np.abs(t - k).max() > 1e-8 or k.min() < 0 or k.max() > shape[a] - 1:
+                raise NotImplementedError('VoxelCoefficient: the mesh vertices are not nodes of the voxel grid '
+                                          '(phase field generated on a different resolution than the mesh)')
+            idx.append(k.astype(np.int64))
+        return self.values[tuple(idx[::-1])]
+
+    def set_into(self, gf, definedon=None) -> None:
+        fes = gf.space
+        exact = definedon is None and len(fes.blocks) == 1 and fes.blocks[0].family == 'H1' \
+            and fes.mesh.cell_type in ('quad', 'hex') and gf._root is gf
+        if exact:
+            try:
+                vals = self.vertex_values(fes.mesh)
+            except NotImplementedError:
+                exact = False
+        if not exact:
+            # other grids / cell types / spaces: local L2 projection of the interpolated data on the host
+            from .hostproject import set_from_points
+            return set_from_points(gf, self, definedon)
+        out = np.zeros(fes.ndof)
+        out[:fes.mesh.nv] = vals
+        gf.vec.data = BaseVector(get_backend().from_numpy(out))
+        gf._set_source = None
 
 
 def BoundaryFromVolumeCF(cf):

@@ -154,3 +154,14 @@ def test_ngsolve_binary_sol_with_high_order_part_is_refused(ref_tree):
     ''').format(root=ROOT, tree=str(ref_tree))
     r = subprocess.run([sys.executable, '-c', script], cwd=ref_tree, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'REFUSED' in r.stdout, r.stdout + r.stderr[-2000:]
+
+
+def test_reference_dim_generation_pipeline_through_the_boundary(ref_tree):
+    """pytests/full_system/dim/test_dim.py, the `load_method = generate` cases: the reference's own DIM pre-processing
+    (structured mesh built through the netgen.meshing builder calls of mesh_helpers.get_Netgen_nonconformal, STL
+    boundary -> ray tracing -> Euclidean distance transform (`edt`) -> erf profile -> VoxelCoefficient ->
+    GridFunction, boundary masks, and — dim_poisson_5 — a phase field generated on a 59 x 59 grid projected onto the
+    19 x 19 simulation mesh) followed by the PoissonDIM solve, all unmodified."""
+    r = _pytest(ref_tree, 'pytests/full_system/dim/test_dim.py', '-k', 'poisson')
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert '6 passed' in r.stdout
