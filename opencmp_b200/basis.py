@@ -519,6 +519,91 @@ class HDivTri(Basis):
         return out
 
 
+# ---- HDiv (RT_[k]) on quadrilaterals -----------------------------------------------------------------------------
+class HDivQuad(Basis):
+    """Raviart-Thomas space RT_[k] = Q_{k+1,k} x Q_{k,k+1} on the reference square — the space NGSolve's
+    ``HDiv(order=k)`` has on quadrilaterals (k+1 normal moments per edge like BDM_k on triangles, 2k(k+1) interior
+    functions; dimension 2(k+1)(k+2)). The reference's diffuse-interface meshes are quadrilateral by default
+    (config_functions/expanded_config_parser.py:79), so its HDiv-DG Stokes / INS DIM models live on this element
+    (pytests/full_system/dim/dim_stokes_1). Basis = dual basis of: edge normal moments against Legendre polynomials
+    (lowest order first, all edges), interior moments against Q_{k-1,k} x Q_{k,k-1}."""
+    kind = 'hdiv'
+
+    def __init__(self, cell_type: str, order: int, RT: bool = False):
+        if cell_type != 'quad':
+            raise NotImplementedError('HDivQuad lives on quadrilaterals')
+        if order < 1:
+            raise ValueError('HDiv needs order >= 1')
+        super().__init__(cell_type, order)
+        k = order
+        self.RT = bool(RT)                    # RT_[k] already is the Raviart-Thomas element; the flag changes nothing
+        # expansion functions: x-component L_a(x) L_b(y), a <= k+1, b <= k; y-component a <= k, b <= k+1
+        self._ix = [(a, b) for a in range(k + 2) for b in range(k + 1)]
+        self._iy = [(a, b) for a in range(k + 1) for b in range(k + 2)]
+        nx, ny = len(self._ix), len(self._iy)
+        nd = nx + ny
+        loc = local_topology('quad')
+        ref = loc['ref']
+        s, w = gauss_01(k + 3)
+        rows = []
+        edge_rows = {}
+        for le, (a, b) in enumerate(loc['edges']):
+            t = ref[b] - ref[a]
+            n = np.array([t[1], -t[0]])
+            pts = ref[a][None, :] + s[:, None] * t[None, :]
+            ev = self._expand(pts)[:, :2, :]                        # (nq, 2, nd)
+            for l in range(k + 1):
+                ql = eval_legendre(l, 2 * s - 1) * w
+                edge_rows[(le, l)] = ql @ (n[0] * ev[:, 0, :] + n[1] * ev[:, 1, :])
+        ent_lo, ent_hi = [], []
+        for le in range(4):
+            rows.append(edge_rows[(le, 0)])
+            ent_lo.append(('facet', le, 1, 'lo'))
+        for le in range(4):
+            for l in range(1, k + 1):
+                rows.append(edge_rows[(le, l)])
+            ent_hi.append(('facet', le, k, 'hi'))
+        cp, cw = cell_rule('quad', 2 * k + 3)
+        ev = self._expand(cp)[:, :2, :]
+        lx, _ = _leg_1d(k, cp[:, 0])
+        ly, _ = _leg_1d(k, cp[:, 1])
+        nint = 0
+        for a in range(k):                                          # x-component tests: Q_{k-1,k}
+            for b in range(k + 1):
+                rows.append((cw * lx[:, a] * ly[:, b]) @ ev[:, 0, :])
+                nint += 1
+        for a in range(k + 1):                                      # y-component tests: Q_{k,k-1}
+            for b in range(k):
+                rows.append((cw * lx[:, a] * ly[:, b]) @ ev[:, 1, :])
+                nint += 1
+        V = np.stack(rows, axis=0)
+        assert V.shape == (nd, nd), V.shape
+        self._coef = np.linalg.inv(V)
+        self.ndof = nd
+        self.entity_dofs = ent_lo + ent_hi + [('cell', 0, nint, 'c')]
+
+    def _expand(self, pts):
+        """(npts, 6, nd): rows [ux, uy, dux/dx, dux/dy, duy/dx, duy/dy] of every expansion function."""
+        k = self.order
+        pts = np.asarray(pts, dtype=np.float64)
+        vx1, gx1 = _leg_1d(k + 1, pts[:, 0])
+        vy1, gy1 = _leg_1d(k + 1, pts[:, 1])
+        nx = len(self._ix)
+        out = np.zeros((pts.shape[0], 6, nx + len(self._iy)))
+        for j, (a, b) in enumerate(self._ix):
+            out[:, 0, j] = vx1[:, a] * vy1[:, b]
+            out[:, 2, j] = gx1[:, a] * vy1[:, b]
+            out[:, 3, j] = vx1[:, a] * gy1[:, b]
+        for j, (a, b) in enumerate(self._iy):
+            out[:, 1, nx + j] = vx1[:, a] * vy1[:, b]
+            out[:, 4, nx + j] = gx1[:, a] * vy1[:, b]
+            out[:, 5, nx + j] = vx1[:, a] * gy1[:, b]
+        return out
+
+    def tabulate(self, pts):
+        return self._expand(pts) @ self._coef
+
+
 @lru_cache(maxsize=None)
 def make_basis(family: str, cell_type: str, order: int, RT: bool = False) -> Basis:
     simplex = cell_type in ('tri', 'tet')
@@ -527,5 +612,5 @@ def make_basis(family: str, cell_type: str, order: int, RT: bool = False) -> Bas
     if family == 'L2':
         return L2Simplex(cell_type, order) if simplex else L2Tensor(cell_type, order)
     if family == 'HDiv':
-        return HDivTri(cell_type, order, RT)
+        return HDivQuad(cell_type, order, RT) if cell_type == 'quad' else HDivTri(cell_type, order, RT)
     raise ValueError('unknown finite element family {}'.format(family))

@@ -243,3 +243,11 @@ def ins_dim_3d(n=4, n0=2, **kw):
     w.W.vec.data = ngs.BaseVector(ngs.get_backend().from_numpy(
         ngs.get_backend().to_numpy(w.W.vec.a) + random_wind(w.V.ndof, 13, 0.1) * w.V.FreeDofs()))
     return dict(ngs=ngs, mesh=w.mesh, fes=w.fes, a=w.a, L=w.L, gfu=w.gfu, noset=True, keep=(w,), workload=w)
+
+
+def quad_channel_mesh(nx=8, ny=4):
+    """1 x 0.2 channel of quadrilaterals with the boundary names of pytests/mesh_files/channel_3bcs.vol."""
+    from opencmp_b200.mesh import structured_2d
+    m = structured_2d([nx, ny], scale=(1.0, 0.2), cell='quad')
+    m.bnd_names = [{'bottom': 'wall', 'top': 'wall', 'left': 'inlet', 'right': 'outlet'}[n] for n in m.bnd_names]
+    return m

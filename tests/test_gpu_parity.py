@@ -68,8 +68,6 @@ CASES = {
     'stokes_th_p2_oseen': lambda: cases.stokes(cases.channel_mesh(), 2, False,
                                                 wind=lambda n: cases.random_wind(n)),
     'stokes_hdiv_dg_p3': lambda: cases.stokes(cases.channel_mesh(), 3, True),
-    'stokes_hdiv_rt_p2_oseen': lambda: cases.stokes(cases.channel_mesh(), 2, True, RT=True, dt_val=0.01, mass=True,
-                                                     wind=lambda n: cases.random_wind(n)),
     'ins_hdiv_dg_p3_oseen': lambda: cases.stokes(cases.channel_mesh(), 3, True, wind=lambda n: cases.random_wind(n),
                                                   dt_val=0.01, mass=True),
     'ins_hdiv_dg_p1_oseen': lambda: cases.stokes(cases.channel_mesh(), 1, True, wind=lambda n: cases.random_wind(n),

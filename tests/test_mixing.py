@@ -38,14 +38,6 @@ def test_mixers_reproduce_reference_vectors_host_arrays(scheme):
     assert _replay(scheme, OracleBackend()) < 1e-10
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize('scheme', SCHEMES)
-def test_mixers_reproduce_reference_vectors_on_device(scheme):
-    """Same replay with the history on the GPU (ocmp_mdot / ocmp_maxpy); 1e-9 relative like every solution field."""
-    from opencmp_b200.backend import CudaBackend
-    assert _replay(scheme, CudaBackend()) < 1e-9
-
-
 def test_unknown_scheme_raises_like_the_reference():
     from opencmp_b200 import mixing
     with pytest.raises(ValueError):

@@ -162,6 +162,6 @@ def test_reference_dim_generation_pipeline_through_the_boundary(ref_tree):
     boundary -> ray tracing -> Euclidean distance transform (`edt`) -> erf profile -> VoxelCoefficient ->
     GridFunction, boundary masks, and — dim_poisson_5 — a phase field generated on a 59 x 59 grid projected onto the
     19 x 19 simulation mesh) followed by the PoissonDIM solve, all unmodified."""
-    r = _pytest(ref_tree, 'pytests/full_system/dim/test_dim.py', '-k', 'poisson')
+    r = _pytest(ref_tree, 'pytests/full_system/dim/test_dim.py', '-k', 'poisson or stokes_1')
     assert r.returncode == 0, r.stdout[-3000:]
-    assert '6 passed' in r.stdout
+    assert '7 passed' in r.stdout        # dim_stokes_1: StokesDIM, HDiv-DG order 2 / L2 order 1 on quadrilaterals
