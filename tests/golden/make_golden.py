@@ -116,6 +116,24 @@ def main():
         # data on 'top' / 'bottom' of a diffuse disc) — DIM.get_DIM_gridfunctions load_method = file (dim.py:348-378)
         'prog_poisson_dim_2': ('pytests/full_system/dim/dim_poisson_2/config', {}),
     }
+    # INSDIM (models/ins_dim.py: the form set of BASELINE configs[4]) — the reference ships no INS-DIM case, so its
+    # StokesDIM test (pytests/full_system/dim/dim_stokes_1: HDiv-DG order 2 / L2 order 1 on 29 x 29 quadrilaterals,
+    # diffuse circle generated from circle_nd.stl by the reference's own pre-processing) is switched to the INS model:
+    # Oseen linearisation, implicit Euler, two time steps, nu = 0.1
+    src, dst = 'pytests/full_system/dim/dim_stokes_1', 'pytests/full_system/dim/dim_ins_1'
+    if not os.path.isdir(dst):
+        shutil.copytree(src, dst)
+        cfg_txt = open(dst + '/config').read().replace('dim_stokes_1', 'dim_ins_1').replace('model = Stokes', 'model = INS')
+        cfg_txt = cfg_txt.replace('transient = False', 'transient = True\nscheme = implicit euler\n'
+                                  'time_range = 0.0, 0.02\ndt = 1e-2')
+        cfg_txt = cfg_txt.replace('[SOLVER]', '[SOLVER]\nlinearization_method = Oseen\nnonlinear_max_iterations = 3\n'
+                                  'nonlinear_tolerance = relative -> 1e-6\n                      absolute -> 1e-8')
+        open(dst + '/config', 'w').write(cfg_txt)
+        mc = open(dst + '/model_dir/model_config').read().replace('all -> 0.001', 'all -> 0.1')
+        open(dst + '/model_dir/model_config', 'w').write(mc)
+        ic = open(dst + '/ic_dir/ic_config').read().replace('[STOKES]', '[INS]')
+        open(dst + '/ic_dir/ic_config', 'w').write(ic)
+    prog_cases['prog_ins_dim_dg_quad'] = (dst + '/config', {})
     only = set(sys.argv[1:])
     if only:
         prog_cases = {k: v for k, v in prog_cases.items() if k in only}
