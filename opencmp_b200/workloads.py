@@ -185,6 +185,40 @@ class INSTaylorGreen:
         return eu, ep
 
 
+def ins_dim_cg_forms(fes, phi, gphi, mag, mask, w, gfu_0, g, f, kv, alpha, dtp):
+    """Bilinear and linear form of one implicit-Euler / Oseen step of the reference's ``INSDIM`` model on a conforming
+    (Taylor-Hood) space, no rigid-body motion, one DIM Dirichlet marker — a restatement of
+
+      construct_bilinear_time_coefficient   opencmp/models/ins_dim.py:106-146
+      construct_bilinear_time_ODE           opencmp/models/ins_dim.py:33-104
+      construct_linear                      opencmp/models/ins_dim.py:148-206
+      time-derivative terms x phi           solvers/time_integration_schemes.py:663-685, models/base_model.py:418-497
+
+    checked entry by entry against the matrix / right-hand side the reference class itself assembles
+    (tests/test_reference_models.py::test_workload_forms_equal_reference_insdim). ``gphi`` / ``mag`` are the DIM
+    solver's grad(phi) and |grad(phi)|: expressions of phi when it was generated on the simulation mesh
+    (diffuse_interface/dim.py:391-392), separately projected GridFunctions otherwise (:393-409)."""
+    (u, p), (v, q) = fes.TrialFunction(), fes.TestFunction()
+    a = ngs.BilinearForm(fes)
+    a += dtp * (-ngs.div(u) * q - ngs.div(v) * p - 1e-10 * p * q) * phi * ngs.dx
+    a += -dtp * p * ngs.div(v) * (1.0 - phi) * ngs.dx
+    a += dtp * (kv * ngs.InnerProduct(ngs.Grad(u), ngs.Grad(v))) * phi * ngs.dx
+    a += -dtp * ngs.InnerProduct(ngs.OuterProduct(u, w), ngs.Grad(v)) * phi * ngs.dx
+    a += dtp * alpha * u * v * (1.0 - phi) * ngs.dx
+    a += dtp * (kv * ngs.InnerProduct(ngs.Grad(u), ngs.OuterProduct(v, gphi))
+                + kv * ngs.InnerProduct(ngs.Grad(v), ngs.OuterProduct(u, gphi))
+                + kv * alpha * u * v * mag) * mask * ngs.dx
+    a += dtp * (v * (0.5 * w * (-gphi) * u + 0.5 * ngs.Norm(w * (-gphi)) * u)) * mask * ngs.dx
+    a += (u * v) * phi * ngs.dx
+    L = ngs.LinearForm(fes)
+    L += dtp * v * f * phi * ngs.dx
+    L += dtp * (kv * ngs.InnerProduct(ngs.Grad(v), ngs.OuterProduct(g, gphi))
+                + kv * alpha * g * v * mag) * mask * ngs.dx
+    L += dtp * v * (0.5 * w * gphi * g + 0.5 * ngs.Norm(w * (-gphi)) * g) * mask * ngs.dx
+    L += (gfu_0.components[0] * v) * phi * ngs.dx
+    return a, L
+
+
 class INSSphereDIM3D:
     """3-D incompressible Navier-Stokes with the diffuse-interface method (BASELINE config 5).
 
@@ -236,7 +270,6 @@ class INSSphereDIM3D:
         self.V = ngs.VectorH1(m, order=k, dirichlet=dnames)
         self.Q = ngs.H1(m, order=k - 1)
         self.fes = ngs.FESpace([self.V, self.Q])
-        (u, p), (v, q) = self.fes.TrialFunction(), self.fes.TestFunction()
         self.t, self.dt = ngs.Parameter(0.0), ngs.Parameter(dt)
         dtp = self.dt
         x, y, z = ngs.x, ngs.y, ngs.z
@@ -263,8 +296,6 @@ class INSSphereDIM3D:
         self.mask = ngs.GridFunction(H)
         self.mask.Set(ngs.CoefficientFunction(1.0))
         phi, mask = self.phi, self.mask
-        gphi = ngs.Grad(phi)
-        mag = ngs.Norm(gphi)
         self.u_ref = ngs.CoefficientFunction((-omega_rot * y, omega_rot * xl, 0.0 * x))
         self.p_ref = 0.5 * omega_rot ** 2 * (xl * xl + y * y)
         g = self.u_ref
@@ -272,28 +303,9 @@ class INSSphereDIM3D:
         self.gfu, self.gfu_0 = ngs.GridFunction(self.fes), ngs.GridFunction(self.fes)
         self.W = ngs.GridFunction(self.V)                    # Oseen wind, models/ins.py:130-134
         w = self.W
-        a = ngs.BilinearForm(self.fes)
-        # construct_bilinear_time_coefficient, ins_dim.py:106-146 (no rigid body motion)
-        a += dtp * (-ngs.div(u) * q - ngs.div(v) * p - 1e-10 * p * q) * phi * ngs.dx
-        a += -dtp * p * ngs.div(v) * (1.0 - phi) * ngs.dx
-        # construct_bilinear_time_ODE, ins_dim.py:33-104
-        a += dtp * (kv * ngs.InnerProduct(ngs.Grad(u), ngs.Grad(v))) * phi * ngs.dx
-        a += -dtp * ngs.InnerProduct(ngs.OuterProduct(u, w), ngs.Grad(v)) * phi * ngs.dx
-        a += dtp * alpha * u * v * (1.0 - phi) * ngs.dx
-        a += dtp * (kv * ngs.InnerProduct(ngs.Grad(u), ngs.OuterProduct(v, gphi))
-                    + kv * ngs.InnerProduct(ngs.Grad(v), ngs.OuterProduct(u, gphi))
-                    + kv * alpha * u * v * mag) * mask * ngs.dx
-        a += dtp * (v * (0.5 * w * (-gphi) * u + 0.5 * ngs.Norm(w * (-gphi)) * u)) * mask * ngs.dx
-        # time derivative, base_model.py:418-497 with the DIM weight
-        a += (u * v) * phi * ngs.dx
-        L = ngs.LinearForm(self.fes)
-        # construct_linear, ins_dim.py:148-206
-        L += dtp * v * f * phi * ngs.dx
-        L += dtp * (kv * ngs.InnerProduct(ngs.Grad(v), ngs.OuterProduct(g, gphi))
-                    + kv * alpha * g * v * mag) * mask * ngs.dx
-        L += dtp * v * (0.5 * w * gphi * g + 0.5 * ngs.Norm(w * (-gphi)) * g) * mask * ngs.dx
-        L += (self.gfu_0.components[0] * v) * phi * ngs.dx
-        self.a, self.L = a, L
+        gphi = ngs.Grad(phi)                                 # dim.py:391-392 (phi lives on the simulation mesh)
+        self.a, self.L = ins_dim_cg_forms(self.fes, phi, gphi, ngs.Norm(gphi), mask, w, self.gfu_0, g, f, kv, alpha,
+                                          dtp)
         self.pre = ngs.Preconditioner(a, preconditioner) if preconditioner is not None else None
         # start from the rigid rotation inside the sphere (zero on the box boundary)
         cut = 0.5 * (1.0 + ngs.erf((0.9 - r) / 0.05))

@@ -165,3 +165,68 @@ def test_reference_dim_generation_pipeline_through_the_boundary(ref_tree):
     r = _pytest(ref_tree, 'pytests/full_system/dim/test_dim.py', '-k', 'poisson or stokes_1')
     assert r.returncode == 0, r.stdout[-3000:]
     assert '7 passed' in r.stdout        # dim_stokes_1: StokesDIM, HDiv-DG order 2 / L2 order 1 on quadrilaterals
+
+
+def test_workload_forms_equal_reference_insdim(ref_tree):
+    """The bench workload of BASELINE configs[4] restates the INSDIM forms (opencmp_b200/workloads.ins_dim_cg_forms).
+    Here the reference's own INSDIM class — conforming Taylor-Hood elements on the quadrilateral DIM mesh, circle from
+    circle_nd.stl, Oseen + implicit Euler, non-zero DIM Dirichlet data — assembles its system for the second time step,
+    and the restated forms, given the same mesh, phase field, mask, wind and previous solution, must give the same
+    matrix and right-hand side entry by entry (1e-12 of the largest entry)."""
+    import re
+    src = ref_tree / 'pytests' / 'full_system' / 'dim' / 'dim_stokes_1'
+    dst = ref_tree / 'pytests' / 'full_system' / 'dim' / 'dim_ins_cg'
+    if not dst.exists():
+        shutil.copytree(src, dst)
+        cfg = (dst / 'config').read_text().replace('dim_stokes_1', 'dim_ins_cg').replace('model = Stokes', 'model = INS')
+        cfg = cfg.replace('u -> HDiv', 'u -> VectorH1').replace('p -> L2', 'p -> H1').replace('DG = True', 'DG = False')
+        cfg = cfg.replace('transient = False', 'transient = True\nscheme = implicit euler\ntime_range = 0.0, 0.02\n'
+                          'dt = 1e-2')
+        cfg = cfg.replace('[SOLVER]', '[SOLVER]\nlinearization_method = Oseen\nnonlinear_max_iterations = 2\n'
+                          'nonlinear_tolerance = relative -> 1e-6\n                      absolute -> 1e-8')
+        (dst / 'config').write_text(cfg)
+        mc = (dst / 'model_dir' / 'model_config').read_text().replace('all -> 0.001', 'all -> 0.1')
+        (dst / 'model_dir' / 'model_config').write_text(mc)
+        (dst / 'ic_dir' / 'ic_config').write_text((dst / 'ic_dir' / 'ic_config').read_text().replace('[STOKES]', '[INS]'))
+        bc = (dst / 'dim_dir' / 'bc_dir' / 'dim_bc_config').read_text()
+        (dst / 'dim_dir' / 'bc_dir' / 'dim_bc_config').write_text(bc.replace('[0.0, 0.0]', '[0.3*y, -0.3*x]'))
+    script = textwrap.dedent('''
+        import sys
+        sys.path.insert(0, {root!r}); sys.path.insert(0, {tree!r})
+        import conftest
+        import numpy as np
+        import opencmp_b200.ngs as ngs
+        from opencmp_b200.workloads import ins_dim_cg_forms
+        from opencmp.config_functions import ConfigParser
+        from opencmp.models import get_model_class
+        from opencmp.solvers import get_solver_class
+        cfg = ConfigParser('pytests/full_system/dim/dim_ins_cg/config')
+        solver = get_solver_class(cfg)(get_model_class('INS', True), cfg)
+        solver.solve()
+        m = solver.model
+        assert type(m).__name__ == 'INSDIM' and m.mesh.cell_type == 'quad'
+        a_ref, L_ref = solver.a[0], solver.L[0]
+        a_ref.Assemble(); L_ref.Assemble()
+        k = m.interp_ord
+        x, y = ngs.x, ngs.y
+        phi, mask = m.DIM_solver.phi_gfu, m.DIM_solver.mask_gfu_dict['all']
+        w = m.W[0] if isinstance(m.W, (list, tuple)) else m.W
+        gfu_0 = solver.gfu_0_list[0] if hasattr(solver, 'gfu_0_list') else solver.gfu_0
+        h = ngs.specialcf.mesh_size
+        alpha = (10.0 * k ** 2) / h
+        dt = solver.dt_param[0] if hasattr(solver, 'dt_param') else ngs.Parameter(1e-2)
+        D = m.DIM_solver
+        a, L = ins_dim_cg_forms(m.fes, phi, D.grad_phi_gfu, D.mag_grad_phi_gfu, mask, w, gfu_0,
+                                ngs.CoefficientFunction((0.3 * y, -0.3 * x)),
+                                ngs.CoefficientFunction((0.0, 0.0)), ngs.CoefficientFunction(0.1), alpha, dt)
+        a.Assemble(); L.Assemble()
+        A, B = np.asarray(a.mat.values), np.asarray(a_ref.mat.values)
+        print('RESULT', m.fes.ndof, len(A), np.abs(A - B).max() / np.abs(B).max(),
+              np.abs(L.vec.NumPy() - L_ref.vec.NumPy()).max() / np.abs(L_ref.vec.NumPy()).max(),
+              float(np.abs(w.vec.NumPy()).max()))
+    ''').format(root=ROOT, tree=str(ref_tree))
+    r = subprocess.run([sys.executable, '-c', script], cwd=ref_tree, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith('RESULT')][0].split()
+    assert float(line[3]) < 1e-12 and float(line[4]) < 1e-12, line
+    assert float(line[5]) > 1e-3          # the Oseen wind is not trivially zero
