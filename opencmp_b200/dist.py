@@ -13,8 +13,10 @@ The reference has no distributed code at all ("MPI = future work"); th
   gloo in the CPU tests), per Krylov iteration one all-reduce per dot product over the owned entries (``dot``);
   contributions computed for ghost entries (restriction, patch corrections) go back with ``reverse_add``.
 
-Round-1 status: distributed SpMV, dots and Jacobi-preconditioned CG run on this layer (tests/test_dist_gloo.py with
-world_size 2 on CPU; bench.py --gpus N reports them); the multigrid-preconditioned INS step still runs as replicas.
+On this layer run: distributed SpMV, dots and Jacobi-preconditioned CG (``DistributedOperator``), and the distributed
+geometric multigrid + GMRES of dist_mg.py that bench.py --gpus N uses for the 2-D INS and 3-D INS-DIM time steps (on
+the GPU driven by the C ABI, which issues the halo exchanges and all-reduces itself). tests/test_dist_gloo.py covers
+all of it with world_size 2 on CPU.
 """
 from __future__ import annotations
 
