@@ -249,7 +249,9 @@ __global__ void __launch_bounds__(256) k_contract(const __grid_constant__ ocmp_c
     double* sB = sZ + EB * P.zsz;                        // [EB][nside][sbsz]
     double* sD = sB + EB * nside * P.sbsz;               // [EB][nslots]
     double* sG = sD + EB * P.nslots;                     // [EB][nside][GS]
-    int* sI = reinterpret_cast<int*>(sG + EB * nside * GS);   // [EB][4]: cell0, cell1, lf0, lf1
+    // [EB][4]: cell0, cell1, lf0, lf1 — rounded up to 16 bytes (an odd number of doubles precedes it for some EB = 1
+    // plans; the descriptor tables behind it are read with int4 loads; contract_smem() reserves the slack)
+    int* sI = reinterpret_cast<int*>((reinterpret_cast<size_t>(sG + EB * nside * GS) + 15) & ~(size_t)15);
     int* tDof = sI + 4 * EB;                             // [nside*nloc][4]: kind | nr << 8, nl, tab offset, sB offset(+il)
     int* tZ = tDof + 4 * nside * P.nloc;                 // [nzd][4]: entry k0, k1, sB base (incl. j), z index
     int* tEnt = tZ + 4 * P.nzd;                          // [nent][2]: slot, row offset (row * stride)

@@ -1,0 +1,140 @@
+"""Host-side check of the launch plans the CUDA backend builds (no GPU needed): for every GPU parity case the plan
+builder runs with host tensors standing in for device buffers, and the compile-time limits and alignment assumptions
+of the kernels in csrc/ocmp_assembly.cu are checked on the resulting structs — shared-memory budget of k_contract,
+MAX_ROWS / MAX_FSLOTS / OCMP_MAX_REGS, the bit packing of the scatter map, 16-byte alignment of the descriptor
+tables read with int4 loads. The numbers are computed by the oracle backend; only the plan construction of
+``CudaBackend`` runs (it is pure host logic)."""
+import weakref
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle.backend import OracleBackend
+from opencmp_b200.backend import CudaBackend
+
+MAX_ROWS, MAX_FSLOTS, MAX_REGS = 12, 40, 48          # csrc/ocmp_assembly.cu, include/opencmp_b200.h
+
+
+def _dry_cuda_backend():
+    be = object.__new__(CudaBackend)
+    be.torch = torch
+    be.device = torch.device('cpu')
+    be._mesh_cache, be._space_cache = {}, {}
+    be._plan_cache = weakref.WeakKeyDictionary()
+    return be
+
+
+class PlanProbe(OracleBackend):
+    """Oracle backend that also builds (and inspects) the CUDA launch plans of everything it assembles."""
+
+    def __init__(self):
+        self.dry = _dry_cuda_backend()
+        self.seen = []
+
+    def _probe(self, program):
+        for integ, plan in zip(program.integrals, self.dry._plans(program)):
+            self.seen.append(check_plan(program, integ, plan))
+
+    def assemble_matrix(self, program, mat):
+        self._probe(program)
+        return super().assemble_matrix(program, mat)
+
+    def assemble_vector(self, program, out):
+        self._probe(program)
+        return super().assemble_vector(program, out)
+
+    def integrate(self, program):
+        self._probe(program)
+        return super().integrate(program)
+
+
+def contract_smem(xp, dim):
+    """Mirror of contract_smem() in csrc/ocmp_assembly.cu."""
+    gs = dim + 2 * dim * dim + 1
+    dbl = xp.eb * (xp.asz + xp.nside * xp.sbsz + xp.zsz + xp.nslots + xp.nside * gs)
+    ints = 4 * xp.eb + 4 * xp.nside * xp.nloc + 4 * xp.nzd + 2 * xp.nent + 8 * xp.npairs + 2 * xp.nseg
+    return 8 * dbl + 4 * ints + 16, dbl
+
+
+def check_plan(program, integ, plan):
+    cp = plan['coef']
+    assert cp.nfslots <= MAX_FSLOTS
+    assert cp.nreg <= MAX_REGS
+    for (gf, blk, row, side) in integ.prog.fields:
+        assert gf.space.blocks[blk].basis.nrows <= MAX_ROWS
+        assert row < gf.space.blocks[blk].basis.nrows
+    xp = plan['contract']
+    if xp is None:
+        return 0
+    fes = program.fes
+    for b in fes.blocks:
+        assert b.basis.nrows <= MAX_ROWS and b.basis.nrows < 256          # row index packed in 8 bits
+    if program.arity == 1:
+        return 0
+    smem, dbl = contract_smem(xp, cp.dim)
+    assert smem <= 220 * 1024, 'k_contract needs {} bytes of shared memory'.format(smem)
+    assert xp.eb in (1, 2, 4, 8, 16)
+    assert xp.asz % 4 == 0 and xp.zsz % 4 == 0                              # sA / sZ strips read as double2 pairs
+    # sI (and the int4-read descriptor tables behind it) start after `dbl` doubles of the 16-byte aligned base
+    assert dbl % 2 == 0, 'descriptor tables of k_contract would be 8- but not 16-byte aligned'
+    assert fes.nloc * fes.nloc < (1 << 29)                                   # amap packs i * nloc + j in 29 bits
+    return smem
+
+
+def _programs(build, assemble=True):
+    import opencmp_b200.ngs as ngs
+    be = PlanProbe()
+    old = ngs._backend
+    ngs.set_backend(be)
+    try:
+        c = build()
+        g = c['gfu']
+        if c.get('noset'):
+            pass
+        elif 'exact' in c:
+            g.components[0].Set(c['exact'], definedon=c['mesh'].Boundaries(c['dnames']))
+        else:
+            g.components[0].Set(c['uex'], definedon=c['mesh'].Boundaries(c['walls']))
+        c['a'].Assemble()
+        c['L'].Assemble()
+    finally:
+        ngs.set_backend(old)
+    return be.seen
+
+
+def _all_cases():
+    from test_gpu_parity import CASES as established
+    from test_zz_gpu_late_additions import CASES as late
+    out = dict(established)
+    out.update(late)
+    return out
+
+
+ALL = _all_cases()
+# the 3-D cases take a while on the oracle; one hex and one tet case are enough for the plan limits
+SLOW = {'ins_dim_3d_hex_q2q1'}
+
+
+@pytest.mark.parametrize('name', sorted(n for n in ALL if n not in SLOW))
+def test_launch_plans_respect_kernel_limits(name):
+    seen = _programs(ALL[name])
+    assert len(seen) > 0
+    assert max(seen) > 0                 # at least one bilinear contraction plan was built and checked
+
+
+def test_golden_program_plans_respect_kernel_limits():
+    """The replayed reference-model programs (tests/golden/prog_*.npz) go through the same plan builder."""
+    import test_golden_programs as tg
+    import opencmp_b200.ngs as ngs
+    assert set(tg.LATE) <= set(tg.FIXTURES)
+    for name in tg.FIXTURES:
+        be = PlanProbe()
+        old = ngs._backend
+        ngs.set_backend(be)
+        try:
+            tg._replay(ngs, name)
+        finally:
+            ngs.set_backend(old)
+        assert be.seen, name
