@@ -104,7 +104,7 @@ class INSTaylorGreen:
         L += dtp * v * (-0.5 * w * n * g + 0.5 * ngs.Norm(w * n) * g) * ds_d
         L += (self.gfu_0.components[0] * v) * ngs.dx
         self.a, self.L = a, L
-        self.pre = ngs.Preconditioner(a, preconditioner) if preconditioner is not None else None
+        self.pre = ngs.Preconditioner(self.a, preconditioner) if preconditioner is not None else None
         # initial condition (examples/INS/ic_dir/ic_config) and wind
         self.gfu.components[0].Set(self.u_ref)
         self.gfu.components[1].Set(self.p_ref)
@@ -306,7 +306,7 @@ class INSSphereDIM3D:
         gphi = ngs.Grad(phi)                                 # dim.py:391-392 (phi lives on the simulation mesh)
         self.a, self.L = ins_dim_cg_forms(self.fes, phi, gphi, ngs.Norm(gphi), mask, w, self.gfu_0, g, f, kv, alpha,
                                           dtp)
-        self.pre = ngs.Preconditioner(a, preconditioner) if preconditioner is not None else None
+        self.pre = ngs.Preconditioner(self.a, preconditioner) if preconditioner is not None else None
         # start from the rigid rotation inside the sphere (zero on the box boundary)
         cut = 0.5 * (1.0 + ngs.erf((0.9 - r) / 0.05))
         self.gfu.components[0].Set(self.u_ref * cut)
