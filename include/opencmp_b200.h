@@ -113,6 +113,14 @@ int ocmp_patch_positions(int npatch, int bs, const int* patch_dofs, const int* r
                          int* positions, void* stream);
 int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const double* inv_blocks, const double* r, double* z,
                    long long n, void* stream);
+/* The same smoother with the patch inverses STORED in FP32 (inverted and applied in FP64 arithmetic): its application
+ * is bound by streaming the inverses from HBM, so this halves the bytes of the dominant kernel; as a preconditioner
+ * inside FP64 GMRES it leaves iteration counts and solutions unchanged. bs must be a multiple of 4. */
+int ocmp_asm_setup_f32(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
+                       const double* vals, const double* freemask, float* inv_blocks, const int* positions,
+                       void* stream);
+int ocmp_asm_apply_f32(int npatch, int bs, const int* patch_dofs, const float* inv_blocks, const double* r, double* z,
+                       long long n, void* stream);
 
 /* ---- Krylov: stand in for ngs.solvers.CG / GMRes / PreconditionedRichardson and for mat.Inverse applied to a
  *      residual (reference opencmp/models/base_model.py:886-947) ---------------------------------------------- */
@@ -128,7 +136,7 @@ typedef struct ocmp_system {
     const double* dinv;
     int npatch, bs;
     const int* patch_dofs;
-    const double* inv_blocks;
+    const void* inv_blocks;  /* npatch x bs x bs, transposed per patch; double, or float when inv_fp32 is set */
     const double* patch_weight; /* optional per-dof weight applied after the additive patch solves (restricted / averaged AS) */
     int nlevels;             /* pre_kind 3: levels[0] coarsest ... levels[nlevels-1] = this system */
     const struct ocmp_mg_level* levels;
@@ -141,6 +149,7 @@ typedef struct ocmp_system {
                                 restriction only see those; NULL = not distributed */
     int halo_fwd;            /* refresh ghost entries after an SpMV / after the coarsest-level solve (0: none) */
     int halo_sum;            /* sum the neighbours' partial patch corrections after the smoother (0: none) */
+    int inv_fp32;            /* 1: inv_blocks holds floats (ocmp_asm_setup_f32); 0: doubles */
 } ocmp_system;
 
 /* One multigrid level: operator + smoother (sys), transfer from the next coarser level, work space.

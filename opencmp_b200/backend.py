@@ -48,7 +48,8 @@ class System(C.Structure):
                 ('freemask', C.c_void_p), ('pre_kind', C.c_int), ('dinv', C.c_void_p), ('npatch', C.c_int),
                 ('bs', C.c_int), ('patch_dofs', C.c_void_p), ('inv_blocks', C.c_void_p), ('patch_weight', C.c_void_p),
                 ('nlevels', C.c_int), ('levels', C.c_void_p), ('inv_rowptr', C.c_void_p), ('inv_colidx', C.c_void_p),
-                ('inv_vals', C.c_void_p), ('owned', C.c_void_p), ('halo_fwd', C.c_int), ('halo_sum', C.c_int)]
+                ('inv_vals', C.c_void_p), ('owned', C.c_void_p), ('halo_fwd', C.c_int), ('halo_sum', C.c_int),
+                ('inv_fp32', C.c_int)]
 
 
 class MGLevel(C.Structure):
@@ -81,6 +82,8 @@ def load_library() -> C.CDLL:
     lib.ocmp_asm_setup.argtypes = [C.c_int, C.c_int, P, P, P, P, P, P, P, P]
     lib.ocmp_patch_positions.argtypes = [C.c_int, C.c_int, P, P, P, P, P]
     lib.ocmp_asm_apply.argtypes = [C.c_int, C.c_int, P, P, P, P, C.c_longlong, P]
+    lib.ocmp_asm_setup_f32.argtypes = lib.ocmp_asm_setup.argtypes
+    lib.ocmp_asm_apply_f32.argtypes = lib.ocmp_asm_apply.argtypes
     lib.ocmp_krylov.argtypes = [C.POINTER(System), C.c_int, P, P, C.c_double, C.c_int, C.c_int, C.c_double, P,
                                 C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_double), P]
     lib.ocmp_krylov_history.argtypes = [C.POINTER(C.c_double), C.c_int]
@@ -115,6 +118,7 @@ def read_profile(lib) -> dict:
 EXPORTED = ['ocmp_mdot', 'ocmp_maxpy', 'ocmp_krylov_history', 'ocmp_comm_unique_id', 'ocmp_comm_init', 'ocmp_halo_plan', 'ocmp_halo_run', 'ocmp_allreduce_sum',
             'ocmp_patch_positions', 'ocmp_profile_bytes', 'ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
             'ocmp_dot', 'ocmp_axpby', 'ocmp_masked_assign', 'ocmp_jacobi_setup', 'ocmp_asm_setup', 'ocmp_asm_apply',
+            'ocmp_asm_setup_f32', 'ocmp_asm_apply_f32',
             'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version']
 
 
@@ -534,20 +538,28 @@ class CudaBackend:
             # cell patches for kind 'asm_cell'; averaged by the patch multiplicity of every dof
             fes = mat.space
             pt = self._patches(fes, 'cell' if kind == 'asm_cell' else os.environ.get('OCMP_PATCH', 'vertex'))
-            npatch, bs = pt['npatch'], pt['bs']
-            if pt.get('inv') is None:
-                pt['inv'] = self.torch.empty(npatch * bs * bs, dtype=self.torch.float64, device=self.device)
-            if pt.get('pos') is None and bs <= 160:
-                npad = 16 * ((bs + 15) // 16)
-                pt['pos'] = self.torch.empty(npatch * npad * npad, dtype=self.torch.int32, device=self.device)
-                self._ck(self.lib.ocmp_patch_positions(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(),
-                                                       pd['colidx'].data_ptr(), pt['pos'].data_ptr(), st))
-            self._ck(self.lib.ocmp_asm_setup(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(),
-                                             pd['colidx'].data_ptr(), mat.values.data_ptr(), _ptr(fm),
-                                             pt['inv'].data_ptr(), _ptr(pt.get('pos')), st))
+            self._invert_patches(pt, pd, mat, fm)
             self.launches += 1
-            return _Precond(2, inv=pt['inv'], npatch=npatch, bs=bs, pdofs=pt['dofs'], fm=fm, wgt=pt['wgt'])
+            return _Precond(2, inv=pt['inv'], npatch=pt['npatch'], bs=pt['bs'], pdofs=pt['dofs'], fm=fm,
+                            wgt=pt['wgt'], fp32=pt['fp32'])
         raise NotImplementedError('preconditioner type {}'.format(kind))
+
+    def _invert_patches(self, pt, pd, mat, fm) -> None:
+        """(Re)compute the stored patch inverses of the patch table ``pt`` for the current matrix values. With
+        ``pt['fp32']`` (OCMP_PATCH_FP32=1) they are stored in FP32 — inverted and applied in FP64 arithmetic."""
+        t = self.torch
+        npatch, bs = pt['npatch'], pt['bs']
+        st = self._stream()
+        if pt.get('inv') is None:
+            pt['inv'] = t.empty(npatch * bs * bs, dtype=t.float32 if pt['fp32'] else t.float64, device=self.device)
+        if pt.get('pos') is None and bs <= 160:
+            npad = 16 * ((bs + 15) // 16)
+            pt['pos'] = t.empty(npatch * npad * npad, dtype=t.int32, device=self.device)
+            self._ck(self.lib.ocmp_patch_positions(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(),
+                                                   pd['colidx'].data_ptr(), pt['pos'].data_ptr(), st))
+        setup = self.lib.ocmp_asm_setup_f32 if pt['fp32'] else self.lib.ocmp_asm_setup
+        self._ck(setup(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(),
+                       mat.values.data_ptr(), _ptr(fm), pt['inv'].data_ptr(), _ptr(pt.get('pos')), st))
 
     def _patches(self, fes, kind: str, vmask=None) -> dict:
         """vmask: optional boolean mask over the mesh vertices — keep only the patches of those vertices (the
@@ -597,14 +609,18 @@ class CudaBackend:
             out = self._patches(fes, 'star' if kind == 'vertex' else 'cell', vmask if kind == 'vertex' else None)
             sd[key] = out
             return out
-        if dofs.shape[1] % 2 and kind != 'cell':
-            # even patch stride: the columns of the stored inverses stay 16-byte aligned, which k_patch_apply needs
-            # for its double2 loads (an odd stride falls back to 8-byte loads at ~15 % lower bandwidth)
-            dofs = np.concatenate([dofs, -np.ones((dofs.shape[0], 1), dtype=dofs.dtype)], axis=1)
+        fp32 = os.environ.get('OCMP_PATCH_FP32', '0') == '1'
+        align = 4 if fp32 else 2
+        if dofs.shape[1] % align and (kind != 'cell' or fp32):
+            # patch stride padded so that the columns of the stored inverses stay 16-byte aligned, which k_patch_apply
+            # needs for its 16-byte loads (double2: even stride, an odd one falls back to 8-byte loads at ~15 % lower
+            # bandwidth; float4 for FP32-stored inverses: multiple of 4, required)
+            npad = -dofs.shape[1] % align
+            dofs = np.concatenate([dofs, -np.ones((dofs.shape[0], npad), dtype=dofs.dtype)], axis=1)
         dofs = np.ascontiguousarray(dofs, dtype=np.int32)
         mult = np.bincount(dofs[dofs >= 0].ravel(), minlength=fes.ndof).astype(np.float64)
         out = dict(npatch=dofs.shape[0], bs=dofs.shape[1], dofs=self._up(dofs),
-                   wgt=self._up(1.0 / np.maximum(mult, 1.0)), inv=None)
+                   wgt=self._up(1.0 / np.maximum(mult, 1.0)), inv=None, fp32=fp32)
         sd[key] = out
         return out
 
@@ -621,7 +637,7 @@ class CudaBackend:
                 s.dinv = pre.dinv.data_ptr()
             elif pre.kind == 3:
                 top = pre.levels[pre.nlevels - 1].sys
-                for name in ('npatch', 'bs', 'patch_dofs', 'inv_blocks', 'patch_weight'):
+                for name in ('npatch', 'bs', 'patch_dofs', 'inv_blocks', 'patch_weight', 'inv_fp32'):
                     setattr(s, name, getattr(top, name))
                 s.nlevels = pre.nlevels
                 s.levels = C.addressof(pre.levels)
@@ -629,6 +645,7 @@ class CudaBackend:
                 s.npatch, s.bs = pre.npatch, pre.bs
                 s.patch_dofs, s.inv_blocks = pre.pdofs.data_ptr(), pre.inv.data_ptr()
                 s.patch_weight = _ptr(pre.wgt)
+                s.inv_fp32 = 1 if getattr(pre, 'fp32', False) else 0
         return s
 
     def krylov(self, kind, mat, b, x, pre, freedofs, tol, maxit, initialize, printrates, damp=1.0, restart=None):
@@ -695,24 +712,13 @@ def _cuda_patch_state(self, fes, vmask):
 
 
 def _cuda_patch_setup(self, mat, pt, fm):
-    pd = self.pattern_data(mat.space)
-    npatch, bs = pt['npatch'], pt['bs']
-    st = self._stream()
-    if pt.get('inv') is None:
-        pt['inv'] = self.torch.empty(npatch * bs * bs, dtype=self.torch.float64, device=self.device)
-    if pt.get('pos') is None and bs <= 160:
-        npad = 16 * ((bs + 15) // 16)
-        pt['pos'] = self.torch.empty(npatch * npad * npad, dtype=self.torch.int32, device=self.device)
-        self._ck(self.lib.ocmp_patch_positions(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(),
-                                               pd['colidx'].data_ptr(), pt['pos'].data_ptr(), st))
-    self._ck(self.lib.ocmp_asm_setup(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(),
-                                     pd['colidx'].data_ptr(), mat.values.data_ptr(), _ptr(fm), pt['inv'].data_ptr(),
-                                     _ptr(pt.get('pos')), st))
+    self._invert_patches(pt, self.pattern_data(mat.space), mat, fm)
 
 
 def _cuda_patch_apply(self, pt, r, z):
-    self._ck(self.lib.ocmp_asm_apply(pt['npatch'], pt['bs'], pt['dofs'].data_ptr(), pt['inv'].data_ptr(),
-                                     r.data_ptr(), z.data_ptr(), z.numel(), self._stream()))
+    apply = self.lib.ocmp_asm_apply_f32 if pt['fp32'] else self.lib.ocmp_asm_apply
+    self._ck(apply(pt['npatch'], pt['bs'], pt['dofs'].data_ptr(), pt['inv'].data_ptr(), r.data_ptr(), z.data_ptr(),
+                   z.numel(), self._stream()))
 
 
 def _cuda_patch_count(self, pt, n):

@@ -9,6 +9,12 @@ int ocmp_patch_invert_registers(int npatch, int bs, const int* pd, const int* rp
                                 const double* fm, double* inv, int* flag_dev, const int* pos, cudaStream_t st);
 int ocmp_patch_apply_cta(int npatch, int bs, const int* pd, const double* inv, const double* r, double* z,
                          cudaStream_t st);
+// FP32-stored inverses (ocmp_system.inv_fp32): same arithmetic in FP64, half the bytes streamed per application
+int ocmp_patch_invert_registers_f32(int npatch, int bs, const int* pd, const int* rp, const int* ci,
+                                    const double* vals, const double* fm, float* inv, int* flag_dev, const int* pos,
+                                    cudaStream_t st);
+int ocmp_patch_apply_cta_f32(int npatch, int bs, const int* pd, const float* inv, const double* r, double* z,
+                             cudaStream_t st);
 // optional per-category device timing (CUDA events on the launching stream) and launch counting
 enum { PROF_SPMV = 0, PROF_ASM_APPLY, PROF_COEF, PROF_CONTRACT, PROF_LIN, PROF_MDOT, PROF_MAXPY, PROF_VEC,
        PROF_SETUP, PROF_SPMV_MG, PROF_HALO, PROF_NCAT };

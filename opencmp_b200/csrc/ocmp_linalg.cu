@@ -291,10 +291,11 @@ extern "C" int ocmp_jacobi_setup(int nrows, const int* diagpos, const double* va
 // One CTA per patch: gather the dense block straight from the CSR matrix (binary search of each column in its row),
 // impose identity rows/cols on constrained or padded dofs, invert it IN PLACE by Gauss-Jordan with partial pivoting
 // in shared memory and store the inverse transposed (inv[j*bs + i] = (A^-1)_{ij}) for coalesced application.
+template <typename OutT>
 __global__ void __launch_bounds__(256) k_asm_setup(int npatch, int bs, const int* __restrict__ pdofs,
                                                    const int* __restrict__ rowptr, const int* __restrict__ colidx,
                                                    const double* __restrict__ vals, const double* __restrict__ fm,
-                                                   double* __restrict__ inv) {
+                                                   OutT* __restrict__ inv) {
     extern __shared__ double M[];          // bs x bs, then fcol[bs], then piv[bs] (int)
     double* fcol = M + bs * bs;
     int* piv = reinterpret_cast<int*>(fcol + bs);
@@ -371,20 +372,30 @@ __global__ void __launch_bounds__(256) k_asm_setup(int npatch, int bs, const int
         }
         for (int idx = threadIdx.x; idx < bs * bs; idx += blockDim.x) {
             const int j = idx / bs, i = idx % bs;
-            inv[(long long)p * bs * bs + idx] = M[i * bs + j];
+            inv[(long long)p * bs * bs + idx] = (OutT)M[i * bs + j];
         }
     }
 }
 
-extern "C" int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
-                              const double* vals, const double* freemask, double* inv_blocks, const int* positions,
-                              void* stream) {
+static int invert_dispatch(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
+                           const double* fm, double* inv, int* flag, const int* pos, cudaStream_t st) {
+    return ocmp_patch_invert_registers(npatch, bs, pd, rp, ci, vals, fm, inv, flag, pos, st);
+}
+static int invert_dispatch(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
+                           const double* fm, float* inv, int* flag, const int* pos, cudaStream_t st) {
+    return ocmp_patch_invert_registers_f32(npatch, bs, pd, rp, ci, vals, fm, inv, flag, pos, st);
+}
+
+template <typename OutT>
+static int asm_setup(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
+                     const double* vals, const double* freemask, OutT* inv_blocks, const int* positions,
+                     void* stream) {
     if (npatch <= 0) return 0;
     const size_t smem = sizeof(double) * ((size_t)bs * bs + bs) + sizeof(int) * bs;
     if (smem > 220 * 1024) return ocmp_fail(-3, "patch too large for shared memory");
     static size_t configured = 0;
     if (smem > configured) {
-        cudaFuncSetAttribute(k_asm_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_asm_setup<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     const int cap = ocmp_sm_count() * 4;
@@ -394,23 +405,37 @@ extern "C" int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const i
         if (!flag_dev) cudaMalloc(&flag_dev, sizeof(int));
         cudaStream_t st = (cudaStream_t)stream;
         cudaMemsetAsync(flag_dev, 0, sizeof(int), st);
-        if (positions && ocmp_patch_invert_registers(npatch, bs, patch_dofs, rowptr, colidx, vals, freemask, inv_blocks,
-                                                     flag_dev, positions, st)) {
+        if (positions && invert_dispatch(npatch, bs, patch_dofs, rowptr, colidx, vals, freemask, inv_blocks, flag_dev,
+                                         positions, st)) {
             int flag = 0;
             cudaMemcpyAsync(&flag, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
             cudaStreamSynchronize(st);
             if (!flag) return ocmp_check("ocmp_asm_setup");
         }
     }
-    k_asm_setup<<<npatch < cap ? npatch : cap, 256, smem, (cudaStream_t)stream>>>(npatch, bs, patch_dofs, rowptr, colidx,
-                                                                                  vals, freemask, inv_blocks);
+    k_asm_setup<OutT><<<npatch < cap ? npatch : cap, 256, smem, (cudaStream_t)stream>>>(npatch, bs, patch_dofs, rowptr,
+                                                                                        colidx, vals, freemask,
+                                                                                        inv_blocks);
     return ocmp_check("ocmp_asm_setup");
+}
+
+extern "C" int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
+                              const double* vals, const double* freemask, double* inv_blocks, const int* positions,
+                              void* stream) {
+    return asm_setup<double>(npatch, bs, patch_dofs, rowptr, colidx, vals, freemask, inv_blocks, positions, stream);
+}
+
+extern "C" int ocmp_asm_setup_f32(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
+                                  const double* vals, const double* freemask, float* inv_blocks, const int* positions,
+                                  void* stream) {
+    return asm_setup<float>(npatch, bs, patch_dofs, rowptr, colidx, vals, freemask, inv_blocks, positions, stream);
 }
 
 
 // one warp per patch: z[dofs] += A_p^-1 r[dofs]
+template <typename InT>
 __global__ void __launch_bounds__(256) k_asm_apply(int npatch, int bs, const int* __restrict__ pdofs,
-                                                   const double* __restrict__ inv, const double* __restrict__ r,
+                                                   const InT* __restrict__ inv, const double* __restrict__ r,
                                                    double* __restrict__ z) {
     extern __shared__ double sr[];         // [warps][bs]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -423,25 +448,35 @@ __global__ void __launch_bounds__(256) k_asm_apply(int npatch, int bs, const int
             rr[j] = dj >= 0 ? __ldg(r + dj) : 0.0;
         }
         __syncwarp();
-        const double* A = inv + p * bs * bs;
+        const InT* A = inv + p * bs * bs;
         for (int i = lane; i < bs; i += 32) {
             double s = 0.0;
-            for (int j = 0; j < bs; ++j) s = fma(__ldg(A + j * bs + i), rr[j], s);
+            for (int j = 0; j < bs; ++j) s = fma((double)__ldg(A + j * bs + i), rr[j], s);
             const int di = __ldg(d + i);
             if (di >= 0) atomicAdd(z + di, s);
         }
     }
 }
 
-extern "C" int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const double* inv_blocks, const double* r,
-                              double* z, long long n, void* stream) {
+static int apply_cta(int npatch, int bs, const int* pd, const double* inv, const double* r, double* z,
+                     cudaStream_t st) {
+    return ocmp_patch_apply_cta(npatch, bs, pd, inv, r, z, st);
+}
+static int apply_cta(int npatch, int bs, const int* pd, const float* inv, const double* r, double* z,
+                     cudaStream_t st) {
+    return ocmp_patch_apply_cta_f32(npatch, bs, pd, inv, r, z, st);
+}
+
+template <typename InT>
+static int asm_apply(int npatch, int bs, const int* patch_dofs, const InT* inv_blocks, const double* r, double* z,
+                     long long n, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(z, 0, sizeof(double) * n, st);
     if (npatch <= 0) return 0;
-    ocmp_prof_bytes(PROF_ASM_APPLY, 8.0 * npatch * bs * bs + 16.0 * n);
+    ocmp_prof_bytes(PROF_ASM_APPLY, (double)sizeof(InT) * npatch * bs * bs + 16.0 * n);
     if (bs >= 48) {
         ProfScope ps(PROF_ASM_APPLY, st);
-        if (ocmp_patch_apply_cta(npatch, bs, patch_dofs, inv_blocks, r, z, st)) return ocmp_check("ocmp_asm_apply");
+        if (apply_cta(npatch, bs, patch_dofs, inv_blocks, r, z, st)) return ocmp_check("ocmp_asm_apply");
     }
     const int wpb = 8;
     const size_t smem = sizeof(double) * wpb * bs;
@@ -449,8 +484,18 @@ extern "C" int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const d
     const long long cap = (long long)ocmp_sm_count() * 8;
     if (blocks > cap) blocks = cap;
     ProfScope ps(PROF_ASM_APPLY, st);
-    k_asm_apply<<<(unsigned)blocks, wpb * 32, smem, st>>>(npatch, bs, patch_dofs, inv_blocks, r, z);
+    k_asm_apply<InT><<<(unsigned)blocks, wpb * 32, smem, st>>>(npatch, bs, patch_dofs, inv_blocks, r, z);
     return ocmp_check("ocmp_asm_apply");
+}
+
+extern "C" int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const double* inv_blocks, const double* r,
+                              double* z, long long n, void* stream) {
+    return asm_apply<double>(npatch, bs, patch_dofs, inv_blocks, r, z, n, stream);
+}
+
+extern "C" int ocmp_asm_apply_f32(int npatch, int bs, const int* patch_dofs, const float* inv_blocks, const double* r,
+                                  double* z, long long n, void* stream) {
+    return asm_apply<float>(npatch, bs, patch_dofs, inv_blocks, r, z, n, stream);
 }
 
 // ---- Krylov drivers ---------------------------------------------------------------------------------------------
@@ -474,7 +519,10 @@ struct Ctx {
             ProfScope ps(PROF_VEC, st);
             k_had<<<grid_for(n), 256, 0, st>>>(n, sy->dinv, nullptr, r, z);
         } else if (sy->pre_kind == 2 || sy->pre_kind == 3) {
-            ocmp_asm_apply(sy->npatch, sy->bs, sy->patch_dofs, sy->inv_blocks, r, z, n, st);
+            if (sy->inv_fp32)
+                ocmp_asm_apply_f32(sy->npatch, sy->bs, sy->patch_dofs, (const float*)sy->inv_blocks, r, z, n, st);
+            else
+                ocmp_asm_apply(sy->npatch, sy->bs, sy->patch_dofs, (const double*)sy->inv_blocks, r, z, n, st);
             // a rank applies the patches of the vertices it owns; DOFs shared with a neighbour get the sum
             if (sy->halo_sum) ocmp_halo_run(sy->halo_sum - 1, z, 1, st);
             if (sy->freemask || sy->patch_weight) {

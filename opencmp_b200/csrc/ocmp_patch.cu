@@ -16,12 +16,12 @@
 #include "../../include/opencmp_b200.h"
 #include "ocmp_common.cuh"
 
-template <int T>
+template <int T, typename OutT = double>
 __global__ void __launch_bounds__(256, 1) k_patch_invert(int npatch, int bs, const int* __restrict__ pdofs,
                                                          const int* __restrict__ rowptr,
                                                          const int* __restrict__ colidx,
                                                          const double* __restrict__ vals,
-                                                         const double* __restrict__ fm, double* __restrict__ inv,
+                                                         const double* __restrict__ fm, OutT* __restrict__ inv,
                                                          int* __restrict__ flag, const int* __restrict__ pos) {
     constexpr int NP = 16 * T;
     __shared__ double rowk[2][NP];
@@ -106,24 +106,25 @@ __global__ void __launch_bounds__(256, 1) k_patch_invert(int npatch, int bs, con
             }
         }
         if (bad) *flag = 1;
-        double* out = inv + (long long)p * bs * bs;
+        OutT* out = inv + (long long)p * bs * bs;
 #pragma unroll
         for (int a = 0; a < T; ++a) {
             const int i = ty + 16 * a;
 #pragma unroll
             for (int b = 0; b < T; ++b) {
                 const int j = tx + 16 * b;
-                if (i < bs && j < bs) out[(long long)j * bs + i] = M[a][b];
+                if (i < bs && j < bs) out[(long long)j * bs + i] = (OutT)M[a][b];
             }
         }
     }
 }
 
-template <int T>
+template <int T, typename OutT>
 static void launch_invert(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
-                          const double* fm, double* inv, int* flag, const int* pos, cudaStream_t st) {
+                          const double* fm, OutT* inv, int* flag, const int* pos, cudaStream_t st) {
     const int cap = ocmp_sm_count();
-    k_patch_invert<T><<<npatch < cap ? npatch : cap, 256, 0, st>>>(npatch, bs, pd, rp, ci, vals, fm, inv, flag, pos);
+    k_patch_invert<T, OutT><<<npatch < cap ? npatch : cap, 256, 0, st>>>(npatch, bs, pd, rp, ci, vals, fm, inv, flag,
+                                                                         pos);
 }
 
 // returns 1 if handled (flag_dev is set to 1 on a vanishing pivot), 0 if the patch is too large for this kernel
@@ -164,22 +165,36 @@ extern "C" int ocmp_patch_positions(int npatch, int bs, const int* patch_dofs, c
     return ocmp_check("ocmp_patch_positions");
 }
 
-int ocmp_patch_invert_registers(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
-                                const double* fm, double* inv, int* flag_dev, const int* pos, cudaStream_t st) {
+template <typename OutT>
+static int invert_registers(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
+                            const double* fm, OutT* inv, int* flag_dev, const int* pos, cudaStream_t st) {
     const int T = (bs + 15) / 16;
     switch (T) {
-        case 1: launch_invert<1>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
-        case 2: launch_invert<2>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
-        case 3: launch_invert<3>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
-        case 4: launch_invert<4>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
-        case 5: launch_invert<5>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
-        case 6: launch_invert<6>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
-        case 7: launch_invert<7>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
-        case 8: launch_invert<8>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
-        case 9: launch_invert<9>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
-        case 10: launch_invert<10>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 1: launch_invert<1, OutT>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 2: launch_invert<2, OutT>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 3: launch_invert<3, OutT>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 4: launch_invert<4, OutT>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 5: launch_invert<5, OutT>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 6: launch_invert<6, OutT>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 7: launch_invert<7, OutT>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 8: launch_invert<8, OutT>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 9: launch_invert<9, OutT>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
+        case 10: launch_invert<10, OutT>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st); return 1;
         default: return 0;
     }
+}
+
+int ocmp_patch_invert_registers(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
+                                const double* fm, double* inv, int* flag_dev, const int* pos, cudaStream_t st) {
+    return invert_registers<double>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st);
+}
+
+// the same inversion (FP64 arithmetic in registers), inverse stored in FP32: the smoother only preconditions, and its
+// application is bound by streaming the stored inverses from HBM — half the bytes, same GMRES iteration counts
+int ocmp_patch_invert_registers_f32(int npatch, int bs, const int* pd, const int* rp, const int* ci,
+                                    const double* vals, const double* fm, float* inv, int* flag_dev, const int* pos,
+                                    cudaStream_t st) {
+    return invert_registers<float>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st);
 }
 
 // ---- application ------------------------------------------------------------------------------------------------
@@ -279,5 +294,100 @@ int ocmp_patch_apply_cta(int npatch, int bs, const int* pd, const double* inv, c
     else if (bs <= 128) k_patch_apply<2, NW><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
     else if (bs <= 192) k_patch_apply<3, NW><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
     else k_patch_apply<4, NW><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
+    return 1;
+}
+
+// FP32-stored inverses (bs a multiple of 4 so that every column starts 16-byte aligned): the same column-per-warp
+// scheme, every lane owns the rows 4*lane .. 4*lane+3 (+ 128*m) and streams them with 16-byte loads, UC columns per
+// iteration in flight; products and sums in FP64.
+template <int MR, int NW, int UC>
+__global__ void __launch_bounds__(NW * 32) k_patch_apply_f32(int npatch, int bs, const int* __restrict__ pdofs,
+                                                             const float* __restrict__ inv,
+                                                             const double* __restrict__ r, double* __restrict__ z) {
+    extern __shared__ double sm[];         // r_loc[bs], partial[NW][bs]
+    double* rl = sm;
+    double* part = sm + bs;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = blockIdx.x; p < npatch; p += gridDim.x) {
+        const int* d = pdofs + (long long)p * bs;
+        __syncthreads();
+        for (int j = threadIdx.x; j < bs; j += NW * 32) {
+            const int dj = __ldg(d + j);
+            rl[j] = dj >= 0 ? __ldg(r + dj) : 0.0;
+        }
+        __syncthreads();
+        const float* A = inv + (long long)p * bs * bs;
+        double s[MR][4];
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[m][c] = 0.0;
+        int j = warp;
+        for (; j + (UC - 1) * NW < bs; j += UC * NW) {
+            float4 v[UC][MR];
+            double rj[UC];
+#pragma unroll
+            for (int u = 0; u < UC; ++u) {
+                rj[u] = rl[j + u * NW];
+                const float4* col = reinterpret_cast<const float4*>(A + (long long)(j + u * NW) * bs);
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    const int i4 = lane + 32 * m;
+                    v[u][m] = (4 * i4 < bs) ? __ldg(col + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UC; ++u)
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    s[m][0] = fma((double)v[u][m].x, rj[u], s[m][0]);
+                    s[m][1] = fma((double)v[u][m].y, rj[u], s[m][1]);
+                    s[m][2] = fma((double)v[u][m].z, rj[u], s[m][2]);
+                    s[m][3] = fma((double)v[u][m].w, rj[u], s[m][3]);
+                }
+        }
+        for (; j < bs; j += NW) {
+            const double rj = rl[j];
+            const float4* col = reinterpret_cast<const float4*>(A + (long long)j * bs);
+#pragma unroll
+            for (int m = 0; m < MR; ++m) {
+                const int i4 = lane + 32 * m;
+                if (4 * i4 < bs) {
+                    const float4 v = __ldg(col + i4);
+                    s[m][0] = fma((double)v.x, rj, s[m][0]);
+                    s[m][1] = fma((double)v.y, rj, s[m][1]);
+                    s[m][2] = fma((double)v.z, rj, s[m][2]);
+                    s[m][3] = fma((double)v.w, rj, s[m][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            const int i = 4 * (lane + 32 * m);
+            if (i < bs) {                      // bs % 4 == 0: all four rows exist
+#pragma unroll
+                for (int c = 0; c < 4; ++c) part[warp * bs + i + c] = s[m][c];
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < bs; i += NW * 32) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) t += part[w * bs + i];
+            const int di = __ldg(d + i);
+            if (di >= 0) atomicAdd(z + di, t);
+        }
+    }
+}
+
+int ocmp_patch_apply_cta_f32(int npatch, int bs, const int* pd, const float* inv, const double* r, double* z,
+                             cudaStream_t st) {
+    if (bs > 256 || (bs & 3)) return 0;
+    constexpr int NW = 4;
+    const size_t smem = sizeof(double) * (NW + 1) * bs;
+    const int cap = ocmp_sm_count() * 16;
+    const int grid = npatch < cap ? npatch : cap;
+    if (bs <= 128) k_patch_apply_f32<1, NW, 4><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
+    else k_patch_apply_f32<2, NW, 2><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
     return 1;
 }

@@ -165,6 +165,7 @@ class DistributedMultigrid:
             s.pre_kind = 2
             s.npatch, s.bs = pt['npatch'], pt['bs']
             s.patch_dofs, s.inv_blocks = pt['dofs'].data_ptr(), pt['inv'].data_ptr()
+            s.inv_fp32 = 1 if pt.get('fp32') else 0
             s.patch_weight = lv.pw.data_ptr()
             prev = self.levels[l - 1]
             arr[l].ncoarse = prev.n

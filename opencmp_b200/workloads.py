@@ -244,7 +244,7 @@ class INSSphereDIM3D:
                  radius: float = 0.5, lam: float = 0.25, lam_cells: float = None, omega_rot: float = 1.0,
                  preconditioner: str = 'multigrid', linear_tolerance: float = 1e-12, linear_max_iterations: int = 400,
                  nonlinear_max_iterations: int = 3, nonlinear_tolerance=(1e-4, 1e-6), n0: int = 2, mesh=None,
-                 integrate=None):
+                 integrate=None, periodic=(True, False, False)):
         from .mesh import structured_3d
         if integrate is not None:              # element-partitioned runs: owned cells + all-reduce
             self._integrate = integrate
@@ -284,9 +284,13 @@ class INSSphereDIM3D:
         self.lam = lam if lam_cells is None else lam_cells * 2.0 / N
         H = ngs.H1(m, order=k)
         self.fes_phi = H
-        # one sphere per [-1,1]^3 brick: the element-partitioned run lines R bricks up along x (weak scaling)
-        xl = (x + 1.0) - 2.0 * ngs.floor(0.5 * (x + 1.0)) - 1.0
-        r = ngs.sqrt(xl * xl + y * y + z * z + 1e-30)
+        # one sphere per [-1,1]^3 brick: the element-partitioned run tiles the domain with bricks along the
+        # ``periodic`` directions (weak scaling); local coordinates = position inside the brick
+        wrap = lambda c: (c + 1.0) - 2.0 * ngs.floor(0.5 * (c + 1.0)) - 1.0
+        xl = wrap(x) if periodic[0] else x
+        yl = wrap(y) if periodic[1] else y
+        zl = wrap(z) if periodic[2] else z
+        r = ngs.sqrt(xl * xl + yl * yl + zl * zl + 1e-30)
         phi_cf = 0.5 * (1.0 + ngs.erf((radius - r) / self.lam))
         self.phi = ngs.GridFunction(H)
         self.phi.Set(phi_cf)
@@ -296,8 +300,8 @@ class INSSphereDIM3D:
         self.mask = ngs.GridFunction(H)
         self.mask.Set(ngs.CoefficientFunction(1.0))
         phi, mask = self.phi, self.mask
-        self.u_ref = ngs.CoefficientFunction((-omega_rot * y, omega_rot * xl, 0.0 * x))
-        self.p_ref = 0.5 * omega_rot ** 2 * (xl * xl + y * y)
+        self.u_ref = ngs.CoefficientFunction((-omega_rot * yl, omega_rot * xl, 0.0 * x))
+        self.p_ref = 0.5 * omega_rot ** 2 * (xl * xl + yl * yl)
         g = self.u_ref
         f = ngs.CoefficientFunction((0.0, 0.0, 0.0))
         self.gfu, self.gfu_0 = ngs.GridFunction(self.fes), ngs.GridFunction(self.fes)

@@ -171,3 +171,23 @@ def test_cuda_backend_patch_tables_host_logic(ngs):
     assert p3['dofs'].dtype == np.int32 and p3['wgt'].min() > 0
     covered = np.unique(p3['dofs'][p3['dofs'] >= 0])
     assert np.array_equal(covered, np.nonzero(f3.FreeDofs())[0])
+
+
+def test_cuda_backend_patch_tables_fp32_stride(ngs, monkeypatch):
+    """OCMP_PATCH_FP32=1 (patch inverses stored in FP32): the patch stride is padded to a multiple of 4 so that every
+    stored column starts 16-byte aligned for the float4 loads of k_patch_apply_f32; the DOF content is unchanged."""
+    from opencmp_b200.backend import CudaBackend
+    from opencmp_b200.mesh import structured_3d
+    be = CudaBackend.__new__(CudaBackend)
+    be._up = lambda a, dtype=None: np.asarray(a)
+    m3 = ngs.Mesh(structured_3d([4, 4, 4]))
+    f3 = ngs.FESpace([ngs.VectorH1(m3, order=2, dirichlet='back|left|front|right|bottom|top'), ngs.H1(m3, order=1)])
+    cache = {}
+    be.space_data = lambda fes: cache.setdefault(id(fes), {})
+    p64 = be._patches(f3, 'vertex')
+    assert p64['bs'] == 90 and not p64['fp32']
+    monkeypatch.setenv('OCMP_PATCH_FP32', '1')
+    cache.clear()
+    p32 = be._patches(f3, 'vertex')
+    assert p32['fp32'] and p32['bs'] == 92 and p32['bs'] % 4 == 0
+    assert (p32['dofs'][:, 90:] == -1).all() and np.array_equal(p32['dofs'][:, :90], p64['dofs'])
