@@ -155,7 +155,7 @@ def workload_config(args, where):
                             'wall as DIM Dirichlet data, Oseen + implicit Euler, dt=1e-2, nu=1 '
                             '(reference models/ins_dim.py forms)'.format(args.N, args.order, args.order - 1),
                 'N': args.N, 'order': args.order,
-                'linear_solver': 'GMRES(100) + geometric multigrid V(1,1) on the hex hierarchy, open-star vertex-patch '
+                'linear_solver': 'GMRES(200) + geometric multigrid V(1,1) on the hex hierarchy, open-star vertex-patch '
                                  'additive Schwarz smoother (damping 0.7), coarse-level phase field, tol 1e-12'
                 if where == 'gpu' else 'direct (SuperLU)', 'nonlinear_max_iterations': 3,
                 'l2': 'inputs larger than L2 (CSR matrix and patch inverses are GBs); no explicit flush',

@@ -91,6 +91,7 @@ int ocmp_dot(long long n, const double* x, const double* y, double* out, void* s
 int ocmp_axpby(long long n, double a, const double* x, double b, double* y, void* stream);   /* y = a x + b y */
 int ocmp_masked_assign(long long n, double* dst, const double* src, const double* inv, const double* mask,
                        void* stream);
+int ocmp_to_f32(long long n, const double* src, float* dst, void* stream);   /* dst[i] = (float) src[i] */
 /* Batched level-1 building blocks of the Krylov drivers, also used by the stationary nonlinear mixers that stand in for
  * reference opencmp/solvers/nonlinear_mixing.py:19-141 (Anderson / DiagBroyden / linear mixing on the DOF vector):
  * out_dev[j] = <V_j, w>, j < k, V_j = V + j*ld;   w += sum_j coef_dev[j] V_j. */
@@ -150,6 +151,8 @@ typedef struct ocmp_system {
     int halo_fwd;            /* refresh ghost entries after an SpMV / after the coarsest-level solve (0: none) */
     int halo_sum;            /* sum the neighbours' partial patch corrections after the smoother (0: none) */
     int inv_fp32;            /* 1: inv_blocks holds floats (ocmp_asm_setup_f32); 0: doubles */
+    const float* vals32;     /* optional FP32 copy of vals (ocmp_to_f32): used for the operator applications inside
+                                the multigrid cycle only — the Krylov method around it always applies `vals` */
 } ocmp_system;
 
 /* One multigrid level: operator + smoother (sys), transfer from the next coarser level, work space.

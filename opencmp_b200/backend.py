@@ -49,7 +49,7 @@ class System(C.Structure):
                 ('bs', C.c_int), ('patch_dofs', C.c_void_p), ('inv_blocks', C.c_void_p), ('patch_weight', C.c_void_p),
                 ('nlevels', C.c_int), ('levels', C.c_void_p), ('inv_rowptr', C.c_void_p), ('inv_colidx', C.c_void_p),
                 ('inv_vals', C.c_void_p), ('owned', C.c_void_p), ('halo_fwd', C.c_int), ('halo_sum', C.c_int),
-                ('inv_fp32', C.c_int)]
+                ('inv_fp32', C.c_int), ('vals32', C.c_void_p)]
 
 
 class MGLevel(C.Structure):
@@ -83,6 +83,7 @@ def load_library() -> C.CDLL:
     lib.ocmp_patch_positions.argtypes = [C.c_int, C.c_int, P, P, P, P, P]
     lib.ocmp_asm_apply.argtypes = [C.c_int, C.c_int, P, P, P, P, C.c_longlong, P]
     lib.ocmp_asm_setup_f32.argtypes = lib.ocmp_asm_setup.argtypes
+    lib.ocmp_to_f32.argtypes = [C.c_longlong, P, P, P]
     lib.ocmp_asm_apply_f32.argtypes = lib.ocmp_asm_apply.argtypes
     lib.ocmp_krylov.argtypes = [C.POINTER(System), C.c_int, P, P, C.c_double, C.c_int, C.c_int, C.c_double, P,
                                 C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_double), P]
@@ -118,7 +119,7 @@ def read_profile(lib) -> dict:
 EXPORTED = ['ocmp_mdot', 'ocmp_maxpy', 'ocmp_krylov_history', 'ocmp_comm_unique_id', 'ocmp_comm_init', 'ocmp_halo_plan', 'ocmp_halo_run', 'ocmp_allreduce_sum',
             'ocmp_patch_positions', 'ocmp_profile_bytes', 'ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
             'ocmp_dot', 'ocmp_axpby', 'ocmp_masked_assign', 'ocmp_jacobi_setup', 'ocmp_asm_setup', 'ocmp_asm_apply',
-            'ocmp_asm_setup_f32', 'ocmp_asm_apply_f32',
+            'ocmp_asm_setup_f32', 'ocmp_asm_apply_f32', 'ocmp_to_f32',
             'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version']
 
 
@@ -561,6 +562,16 @@ class CudaBackend:
         self._ck(setup(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(),
                        mat.values.data_ptr(), _ptr(fm), pt['inv'].data_ptr(), _ptr(pt.get('pos')), st))
 
+    def fp32_copy(self, values, buf=None):
+        """FP32 copy of a matrix value array for the operator applications inside the multigrid cycle
+        (OCMP_SPMV_FP32=1); ``buf`` is reused when it fits."""
+        t = self.torch
+        if buf is None or buf.numel() != values.numel():
+            buf = t.empty(values.numel(), dtype=t.float32, device=self.device)
+        self._ck(self.lib.ocmp_to_f32(values.numel(), values.data_ptr(), buf.data_ptr(), self._stream()))
+        self.launches += 1
+        return buf
+
     def _patches(self, fes, kind: str, vmask=None) -> dict:
         """vmask: optional boolean mask over the mesh vertices — keep only the patches of those vertices (the
         element-partitioned smoother applies the patches of the vertices a rank owns)."""
@@ -637,7 +648,7 @@ class CudaBackend:
                 s.dinv = pre.dinv.data_ptr()
             elif pre.kind == 3:
                 top = pre.levels[pre.nlevels - 1].sys
-                for name in ('npatch', 'bs', 'patch_dofs', 'inv_blocks', 'patch_weight', 'inv_fp32'):
+                for name in ('npatch', 'bs', 'patch_dofs', 'inv_blocks', 'patch_weight', 'inv_fp32', 'vals32'):
                     setattr(s, name, getattr(top, name))
                 s.nlevels = pre.nlevels
                 s.levels = C.addressof(pre.levels)

@@ -118,6 +118,30 @@ __global__ void __launch_bounds__(256) k_spmv(int nrows, const int* __restrict__
     }
 }
 
+// the same with the matrix values stored in FP32 (products and sums in FP64): used for the operator applications
+// INSIDE the multigrid cycle when ocmp_system.vals32 is set — 8 instead of 12 bytes per non-zero
+template <int LPR>
+__global__ void __launch_bounds__(256) k_spmv_f32(int nrows, const int* __restrict__ rowptr,
+                                                  const int* __restrict__ col, const float* __restrict__ val,
+                                                  const double* __restrict__ x, double* __restrict__ y) {
+    const int lane = threadIdx.x % LPR;
+    const long long row0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    const long long stride = (long long)gridDim.x * blockDim.x / LPR;
+    for (long long row = row0; row < nrows; row += stride) {
+        const int a = __ldg(rowptr + row), b = __ldg(rowptr + row + 1);
+        double s = 0.0;
+        for (int k = a + lane; k < b; k += LPR) s = fma((double)__ldg(val + k), __ldg(x + __ldg(col + k)), s);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LPR);
+        if (lane == 0) y[row] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_to_f32(long long n, const double* __restrict__ src, float* __restrict__ dst) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = (float)src[i];
+}
+
 static int spmv_cat(int cat, int nrows, const int* rowptr, const int* colidx, const double* vals, const double* x,
                     double* y, cudaStream_t st);
 extern "C" int ocmp_spmv(int nrows, const int* rowptr, const int* colidx, const double* vals, const double* x,
@@ -134,6 +158,28 @@ static int spmv_cat(int cat, int nrows, const int* rowptr, const int* colidx, co
     ProfScope ps(cat, st);
     k_spmv<16><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, vals, x, y);
     return ocmp_check("ocmp_spmv");
+}
+
+static int spmv_cat_f32(int cat, int nrows, const int* rowptr, const int* colidx, const float* vals, const double* x,
+                        double* y, cudaStream_t st) {
+    if (nrows <= 0) return 0;
+    const int threads = 256;
+    const long long want = ((long long)nrows * 16 + threads - 1) / threads;
+    const long long cap = (long long)ocmp_sm_count() * 64;
+    const unsigned blocks = (unsigned)(want < cap ? want : cap);
+    ProfScope ps(cat, st);
+    k_spmv_f32<16><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, vals, x, y);
+    return ocmp_check("ocmp_spmv_f32");
+}
+
+extern "C" int ocmp_to_f32(long long n, const double* src, float* dst, void* stream) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)ocmp_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    ProfScope ps(PROF_SETUP, (cudaStream_t)stream);
+    k_to_f32<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, src, dst);
+    return ocmp_check("ocmp_to_f32");
 }
 
 // ---- level-1 ---------------------------------------------------------------------------------------------------
@@ -542,6 +588,11 @@ struct Ctx {
             k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, r, z);
         }
     }
+    // operator application inside the cycle: FP32-stored copy of the level matrix when the host provided one
+    static void level_spmv(const ocmp_system* sy, const double* x, double* y, cudaStream_t st) {
+        if (sy->vals32) spmv_cat_f32(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals32, x, y, st);
+        else spmv_cat(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, y, st);
+    }
     // V-cycle on level l: x = MG(b); b is masked on entry, x is masked on exit
     static void vcycle(const ocmp_mg_level* L, int l, cudaStream_t st, const double* b, double* x) {
         const ocmp_mg_level& lv = L[l];
@@ -553,14 +604,14 @@ struct Ctx {
         smooth(sy, st, b, x);
         ocmp_axpby(n, 0.0, x, lv.omega, x, st);
         for (int s = 1; s < lv.nu; ++s) {
-            spmv_cat(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
+            level_spmv(sy, x, r, st);
             if (sy->halo_fwd) ocmp_halo_run(sy->halo_fwd - 1, r, 0, st);
             k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
             smooth(sy, st, r, t);
             ocmp_axpby(n, lv.omega, t, 1.0, x, st);
         }
         // residual to restrict: only the owned entries are used, so no ghost refresh after this SpMV
-        spmv_cat(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
+        level_spmv(sy, x, r, st);
         k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
         if (sy->owned) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->owned, r, r);
         const ocmp_mg_level& lc = L[l - 1];
@@ -576,7 +627,7 @@ struct Ctx {
         if (sy->freemask) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, t, t);
         ocmp_axpby(n, 1.0, t, 1.0, x, st);
         for (int s = 0; s < lv.nu; ++s) {
-            spmv_cat(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, r, st);
+            level_spmv(sy, x, r, st);
             if (sy->halo_fwd) ocmp_halo_run(sy->halo_fwd - 1, r, 0, st);
             k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
             smooth(sy, st, r, t);

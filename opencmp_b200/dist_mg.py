@@ -166,6 +166,9 @@ class DistributedMultigrid:
             s.npatch, s.bs = pt['npatch'], pt['bs']
             s.patch_dofs, s.inv_blocks = pt['dofs'].data_ptr(), pt['inv'].data_ptr()
             s.inv_fp32 = 1 if pt.get('fp32') else 0
+            if os.environ.get('OCMP_SPMV_FP32', '0') == '1':
+                lv.vals32 = be.fp32_copy(lv.mat.values, getattr(lv, 'vals32', None))
+                s.vals32 = lv.vals32.data_ptr()
             s.patch_weight = lv.pw.data_ptr()
             prev = self.levels[l - 1]
             arr[l].ncoarse = prev.n

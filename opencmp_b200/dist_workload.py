@@ -198,7 +198,7 @@ class DistributedINSDIM3D:
 
             def linear_solve(self):
                 it, res = outer.mg.gmres(self.L.vec.a, self.gfu.vec.a, tol=self.linear_tolerance,
-                                         maxit=self.linear_max_iterations, restart=100)
+                                         maxit=self.linear_max_iterations, restart=self.gmres_restart)
                 self.linear_iterations.append(it)
 
         self.mg = None

@@ -192,6 +192,10 @@ class MultigridState:
         self.nu, self.omega = nu, omega
         self.fm = self.masks[-1]
         self.smoothers = [None] * self.nlevels
+        # OCMP_SPMV_FP32=1: the cycle applies FP32-stored copies of the level matrices (the Krylov method keeps FP64)
+        import os
+        self.spmv_fp32 = os.environ.get('OCMP_SPMV_FP32', '0') == '1'
+        self.vals32 = [None] * self.nlevels
 
     def update(self, fine_mat):
         be = self.be
@@ -217,6 +221,9 @@ class MultigridState:
                 sm = be.precond_setup(mat, 'asm', self.spaces[l].FreeDofs(), mask=self.masks[l])
                 self.smoothers[l] = sm
                 sys_ = be._system(mat, self.masks[l], sm)
+                if self.spmv_fp32:
+                    self.vals32[l] = be.fp32_copy(mat.values, self.vals32[l])
+                    sys_.vals32 = self.vals32[l].data_ptr()
                 P = self.transfers[l - 1]
                 lv.ncoarse = self.spaces[l - 1].ndof
                 lv.p_rowptr, lv.p_colidx, lv.p_vals = (a.data_ptr() for a in P[:3])

@@ -321,6 +321,12 @@ class INSSphereDIM3D:
         self.picard_iterations = 0
         self.linear_iterations = []
 
+    # GMRES restart length. The solves of this workload need 40-60 iterations on one brick but 100+ on a row of
+    # bricks (one nearly undetermined pressure mode per sphere); a restart in the middle of a solve throws the Krylov
+    # space away and costs 15-25 % more iterations (measured on the CPU restatement, profiles/r1_solver_convergence.md),
+    # so the basis is allowed to grow to 200 vectors (4.6 GB at 2.9 M DOFs per GPU).
+    gmres_restart = 200
+
     ndof = INSTaylorGreen.ndof
     nnz = INSTaylorGreen.nnz
     assemble = INSTaylorGreen.assemble
@@ -336,7 +342,7 @@ class INSSphereDIM3D:
         """base_model.py:886-947, linear_solver = GMRes"""
         be = ngs.get_backend()
         ngs.solvers.GMRes(A=self.a.mat, b=self.L.vec, pre=self.pre, freedofs=self.fes.FreeDofs(), x=self.gfu.vec,
-                          tol=self.linear_tolerance, maxsteps=self.linear_max_iterations, restart=100)
+                          tol=self.linear_tolerance, maxsteps=self.linear_max_iterations, restart=self.gmres_restart)
         self.linear_iterations.append(getattr(be, 'last_iters', 0))
 
     def errors(self):

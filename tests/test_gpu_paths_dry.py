@@ -238,6 +238,7 @@ def test_partitioned_workloads_execute_on_a_null_device(dry, monkeypatch, which,
     import opencmp_b200.ngs as ngs
     from opencmp_b200.dist_workload import DistributedINS, DistributedINSDIM3D
     monkeypatch.setenv('OCMP_PATCH_FP32', fp32)
+    monkeypatch.setenv('OCMP_SPMV_FP32', fp32)
     be = DryCudaBackend()
     old = ngs._backend
     ngs.set_backend(be)
@@ -247,7 +248,32 @@ def test_partitioned_workloads_execute_on_a_null_device(dry, monkeypatch, which,
         top, arr = d.mg._native
         assert top.pre_kind == 3 and top.nlevels == len(d.mg.levels) >= 2
         assert top.inv_fp32 == int(fp32) and arr[top.nlevels - 1].sys.inv_fp32 == int(fp32)
+        assert bool(arr[top.nlevels - 1].sys.vals32) == (fp32 == '1') and not arr[0].sys.vals32
         assert 'ocmp_krylov' in be.lib.calls
         assert ('ocmp_asm_setup_f32' in be.lib.calls) == (fp32 == '1')
+        assert ('ocmp_to_f32' in be.lib.calls) == (fp32 == '1')
+    finally:
+        ngs.set_backend(old)
+
+
+@pytest.mark.parametrize('fp32', ['0', '1'])
+def test_single_gpu_multigrid_state_on_a_null_device(dry, monkeypatch, fp32):
+    """MultigridState (ngs.Preconditioner(a, 'multigrid') on one GPU): level array incl. the FP32 options."""
+    import opencmp_b200.ngs as ngs
+    from opencmp_b200.workloads import INSTaylorGreen
+    monkeypatch.setenv('OCMP_PATCH_FP32', fp32)
+    monkeypatch.setenv('OCMP_SPMV_FP32', fp32)
+    be = DryCudaBackend()
+    old = ngs._backend
+    ngs.set_backend(be)
+    try:
+        w = INSTaylorGreen(8)
+        w.step()
+        st = w.pre.state
+        assert st.kind == 3 and st.nlevels >= 2
+        top = st.levels[st.nlevels - 1].sys
+        assert top.inv_fp32 == int(fp32) and bool(top.vals32) == (fp32 == '1') and not st.levels[0].sys.vals32
+        sys_ = be._system(w.a.mat, st.fm, st)
+        assert sys_.pre_kind == 3 and sys_.inv_fp32 == int(fp32) and bool(sys_.vals32) == (fp32 == '1')
     finally:
         ngs.set_backend(old)
