@@ -39,6 +39,10 @@ def parse():
     ap.add_argument('--order', type=int, default=None)
     ap.add_argument('--cpu-N', type=int, default=None, help='mesh size of the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--precond-storage', default='fp64', choices=['fp64', 'fp32'],
+                    help='storage of the multigrid data (patch inverses, level matrices inside the cycle); arithmetic '
+                         'and the Krylov method stay FP64. fp32 = OCMP_PATCH_FP32=1 OCMP_SPMV_FP32=1 (opt-in until it '
+                         'has been measured on a B200)')
     ap.add_argument('--dist-poisson', action='store_true', help='also run the distributed Poisson CG leg')
     ap.add_argument('--dist-n', type=int, default=512, help='cells per direction and rank of the distributed leg')
     a = ap.parse_args()
@@ -179,6 +183,8 @@ def main():
     args = parse()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.precond_storage == 'fp32':
+        os.environ['OCMP_PATCH_FP32'] = os.environ['OCMP_SPMV_FP32'] = '1'
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -317,14 +323,17 @@ def main():
                 'avg_launch_ms': ap_ms, 'share_of_step': share['asm_apply'],
                 # ncu --set full of the fine-level launch at N=128 (16 641 patches, 2.330 GB algorithmic): dram read
                 # 2.368 GB + write 0.018 GB (profiles/r1_ncu_kernels.md) — 1.024 x the algorithmic bytes, scaled here
-                'traffic': 1.024 * ap_bytes if args.workload == 'ins2d' else None,
+                'traffic': 1.024 * ap_bytes if args.workload == 'ins2d' and args.precond_storage == 'fp64' else None,
                 'traffic_note': 'per launch, from the measured dram/algorithmic ratio 1.024 of the ncu --set full capture '
                                 'at N=128 (dram read 2.368 GB + write 0.018 GB vs 2.330 GB algorithmic, '
                                 'profiles/r1_ncu_kernels.md)'}
     line = {
         'metric': 'INS s/timestep', 'value': sec, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': False, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, 'gpu'),
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': dict(workload_config(args, 'gpu'), precond_storage={
+            'patch_inverses': 'fp32' if os.environ.get('OCMP_PATCH_FP32', '0') == '1' else 'fp64',
+            'level_matrices_in_cycle': 'fp32' if os.environ.get('OCMP_SPMV_FP32', '0') == '1' else 'fp64'}),
         'problem': {'cells': ne, 'dofs': ndof, 'nnz': nnz, 'global_dofs': dins.ndof_global if dins else ndof,
                     'ranks': world, 'picard_per_step': picard / args.steps,
                     'gmres_its_per_step': lin_its / args.steps, 'l2_err_u': eu, 'l2_err_p': ep,

@@ -197,6 +197,7 @@ class _FakeStream:
 
 
 @pytest.mark.parametrize('argv', [['--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu'],
+                                  ['--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu', '--precond-storage', 'fp32'],
                                   ['--workload', 'ins3d_dim', '--N', '4', '--steps', '1', '--warmup', '1', '--no-cpu']])
 def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
     """bench.py's own arm, start to JSON line, with the CUDA runtime calls stubbed: the line must carry every key of
@@ -213,6 +214,8 @@ def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
     monkeypatch.setattr(torch, 'tensor', lambda data, **kw: real_tensor(data, **{k: v for k, v in kw.items()
                                                                                   if k != 'device'}))
     monkeypatch.setattr(sys, 'argv', ['bench.py'] + argv)
+    for k in ('OCMP_PATCH_FP32', 'OCMP_SPMV_FP32'):          # bench sets them for --precond-storage fp32; restored after
+        monkeypatch.setenv(k, '0')
     for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'):
         monkeypatch.delenv(k, raising=False)
     try:
@@ -224,6 +227,8 @@ def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
                 'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'e2e', 'gpu_launches', 'clocks'):
         assert key in line, key
     assert line['config']['workload'] and line['dtype'] == 'f64' and line['higher_is_better'] is False
+    want = 'fp32' if 'fp32' in argv else 'fp64'
+    assert line['config']['precond_storage'] == {'patch_inverses': want, 'level_matrices_in_cycle': want}
     for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
         assert key in line['roofline'], key
     for key in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'):
