@@ -39,6 +39,11 @@ def parse():
     ap.add_argument('--order', type=int, default=None)
     ap.add_argument('--cpu-N', type=int, default=None, help='mesh size of the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--full-mg-setup', action='store_true',
+                    help='re-assemble and re-invert the coarse multigrid levels on every Preconditioner.Update() '
+                         '(OCMP_MG_REUSE_COARSE=0); default: they are rebuilt only when a Parameter they read (dt, t) '
+                         'changes — their operators do not see the Oseen wind — while the finest level (the assembled '
+                         'system) is always set up again')
     ap.add_argument('--precond-storage', default='fp64', choices=['fp64', 'fp32'],
                     help='storage of the multigrid data (patch inverses, level matrices inside the cycle); arithmetic '
                          'and the Krylov method stay FP64. fp32 = OCMP_PATCH_FP32=1 OCMP_SPMV_FP32=1 (opt-in until it '
@@ -185,6 +190,8 @@ def main():
         return run_reference(args)
     if args.precond_storage == 'fp32':
         os.environ['OCMP_PATCH_FP32'] = os.environ['OCMP_SPMV_FP32'] = '1'
+    if args.full_mg_setup:
+        os.environ['OCMP_MG_REUSE_COARSE'] = '0'
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -331,7 +338,10 @@ def main():
         'metric': 'INS s/timestep', 'value': sec, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': False, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': dict(workload_config(args, 'gpu'), precond_storage={
+        'config': dict(workload_config(args, 'gpu'), coarse_levels=(
+            'rebuilt on every update' if os.environ.get('OCMP_MG_REUSE_COARSE', '1') == '0' else
+            'rebuilt when a Parameter they read changes (constant dt: once); finest level on every update'),
+            precond_storage={
             'patch_inverses': 'fp32' if os.environ.get('OCMP_PATCH_FP32', '0') == '1' else 'fp64',
             'level_matrices_in_cycle': 'fp32' if os.environ.get('OCMP_SPMV_FP32', '0') == '1' else 'fp64'}),
         'problem': {'cells': ne, 'dofs': ndof, 'nnz': nnz, 'global_dofs': dins.ndof_global if dins else ndof,

@@ -23,7 +23,8 @@ from typing import List, Optional
 import numpy as np
 
 from .dist import DofMap, Partition
-from .multigrid import clone_space, coefficient_fields, mesh_levels, prolongation, restrict_field
+from .multigrid import (clone_space, coarse_state_key, coefficient_fields, mesh_levels, prolongation, restrict_field,
+                        reuse_coarse_enabled)
 
 
 def _allreduce(vals, like):
@@ -110,12 +111,21 @@ class DistributedMultigrid:
         self.inv0 = None
         self._native = None
         self._work = None
+        self._coarse_key = None
+        self._fresh_coarse = True
+        self.coarse_setups = 0
 
     # ---- set-up after every assembly ---------------------------------------------------------------------------
     def update(self):
         be = self.be
+        # coarse levels only depend on the Parameters their programs read (multigrid.coarse_state_key): while those are
+        # unchanged, only the finest level (the operator that actually changed) is set up again
+        key = coarse_state_key([lv.program for lv in self.levels[:-1]])
+        reuse = reuse_coarse_enabled() and key == self._coarse_key and self.inv0 is not None
         for l, lv in enumerate(self.levels):
             if l < len(self.levels) - 1:
+                if reuse:
+                    continue
                 be.assemble_matrix(lv.program, lv.mat)
                 if lv.replicated:
                     # redundant work must be bitwise identical on every rank: the scatter-add assembly is not
@@ -128,6 +138,10 @@ class DistributedMultigrid:
                 self.inv0 = be.dense_inverse(lv.mat, lv.free)
             else:
                 be.patch_setup(lv.mat, lv.patches, lv.free)
+        if not reuse:
+            self._coarse_key = key
+            self.coarse_setups += 1
+        self._fresh_coarse = not reuse
         self._native = None
         if getattr(be, 'name', '') == 'cuda' and os.environ.get('OCMP_DIST_NATIVE', '1') != '0':
             self._native = self._native_levels()
@@ -167,7 +181,8 @@ class DistributedMultigrid:
             s.patch_dofs, s.inv_blocks = pt['dofs'].data_ptr(), pt['inv'].data_ptr()
             s.inv_fp32 = 1 if pt.get('fp32') else 0
             if os.environ.get('OCMP_SPMV_FP32', '0') == '1':
-                lv.vals32 = be.fp32_copy(lv.mat.values, getattr(lv, 'vals32', None))
+                if self._fresh_coarse or l == nl - 1 or getattr(lv, 'vals32', None) is None:
+                    lv.vals32 = be.fp32_copy(lv.mat.values, getattr(lv, 'vals32', None))
                 s.vals32 = lv.vals32.data_ptr()
             s.patch_weight = lv.pw.data_ptr()
             prev = self.levels[l - 1]

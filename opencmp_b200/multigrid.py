@@ -141,6 +141,21 @@ def restrict_field(gf, mesh_c, parent=None):
     return out
 
 
+def coarse_state_key(programs) -> tuple:
+    """Everything the re-discretised coarse-level operators depend on at run time: the values of the Parameters their
+    coefficient programs read (dt, t, ...). Their coefficient *fields* are the static stand-ins built once
+    (``restrict_field``); linearisation data (Oseen wind, previous iterates) only act on the finest level. While the key
+    is unchanged the coarse matrices, their patch inverses and the coarsest-level inverse are still valid — NGSolve's
+    own multigrid likewise keeps the coarse-level matrices it assembled earlier. ``OCMP_MG_REUSE_COARSE=0`` forces the
+    full set-up on every ``Update()``."""
+    return tuple(tuple(prog.param_values(integ).tolist()) for prog in programs for integ in prog.integrals)
+
+
+def reuse_coarse_enabled() -> bool:
+    import os
+    return os.environ.get('OCMP_MG_REUSE_COARSE', '1') != '0'
+
+
 # ---- device side: level hierarchy handed to the C ABI (pre_kind = 3) ---------------------------------------------
 class MultigridState:
     """Built by ``CudaBackend.precond_setup(..., 'multigrid')``; refreshed on every ``Preconditioner.Update()``."""
@@ -196,19 +211,28 @@ class MultigridState:
         import os
         self.spmv_fp32 = os.environ.get('OCMP_SPMV_FP32', '0') == '1'
         self.vals32 = [None] * self.nlevels
+        self._coarse_key = None
+        self.coarse_setups = 0                 # how often the coarse levels were (re)built — diagnostics / tests
+        self.updates = 0
 
     def update(self, fine_mat):
         be = self.be
         t = be.torch
-        for l in range(self.nlevels - 1):
-            be.assemble_matrix(self.programs[l], self.mats[l])
-        # coarsest level: explicit inverse of the free-free block (identity on constrained dofs)
-        n0 = self.spaces[0].ndof
-        dense = t.zeros((n0, n0), dtype=t.float64, device=be.device)
-        dense[self.rows0, self.cols0] = self.mats[0].values
-        m = self.masks[0]
-        dense = dense * m[:, None] * m[None, :] + t.diag(1.0 - m)
-        self.inv_vals = t.linalg.inv(dense).contiguous().view(-1)
+        self.updates += 1
+        key = coarse_state_key(self.programs)
+        reuse = reuse_coarse_enabled() and key == self._coarse_key and self.inv_vals is not None
+        if not reuse:
+            for l in range(self.nlevels - 1):
+                be.assemble_matrix(self.programs[l], self.mats[l])
+            # coarsest level: explicit inverse of the free-free block (identity on constrained dofs)
+            n0 = self.spaces[0].ndof
+            dense = t.zeros((n0, n0), dtype=t.float64, device=be.device)
+            dense[self.rows0, self.cols0] = self.mats[0].values
+            m = self.masks[0]
+            dense = dense * m[:, None] * m[None, :] + t.diag(1.0 - m)
+            self.inv_vals = t.linalg.inv(dense).contiguous().view(-1)
+            self._coarse_key = key
+            self.coarse_setups += 1
         for l in range(self.nlevels):
             mat = fine_mat if l == self.nlevels - 1 else self.mats[l]
             lv = self.levels[l]
@@ -218,11 +242,14 @@ class MultigridState:
                 sys_.inv_rowptr, sys_.inv_colidx = self.inv_rowptr.data_ptr(), self.inv_colidx.data_ptr()
                 sys_.inv_vals = self.inv_vals.data_ptr()
             else:
-                sm = be.precond_setup(mat, 'asm', self.spaces[l].FreeDofs(), mask=self.masks[l])
-                self.smoothers[l] = sm
+                fresh = not (reuse and l < self.nlevels - 1 and self.smoothers[l] is not None)
+                if fresh:
+                    self.smoothers[l] = be.precond_setup(mat, 'asm', self.spaces[l].FreeDofs(), mask=self.masks[l])
+                sm = self.smoothers[l]
                 sys_ = be._system(mat, self.masks[l], sm)
                 if self.spmv_fp32:
-                    self.vals32[l] = be.fp32_copy(mat.values, self.vals32[l])
+                    if fresh or self.vals32[l] is None:
+                        self.vals32[l] = be.fp32_copy(mat.values, self.vals32[l])
                     sys_.vals32 = self.vals32[l].data_ptr()
                 P = self.transfers[l - 1]
                 lv.ncoarse = self.spaces[l - 1].ndof

@@ -197,7 +197,8 @@ class _FakeStream:
 
 
 @pytest.mark.parametrize('argv', [['--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu'],
-                                  ['--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu', '--precond-storage', 'fp32'],
+                                  ['--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu', '--precond-storage', 'fp32',
+                                   '--full-mg-setup'],
                                   ['--workload', 'ins3d_dim', '--N', '4', '--steps', '1', '--warmup', '1', '--no-cpu']])
 def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
     """bench.py's own arm, start to JSON line, with the CUDA runtime calls stubbed: the line must carry every key of
@@ -216,6 +217,7 @@ def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
     monkeypatch.setattr(sys, 'argv', ['bench.py'] + argv)
     for k in ('OCMP_PATCH_FP32', 'OCMP_SPMV_FP32'):          # bench sets them for --precond-storage fp32; restored after
         monkeypatch.setenv(k, '0')
+    monkeypatch.setenv('OCMP_MG_REUSE_COARSE', '1')
     for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'):
         monkeypatch.delenv(k, raising=False)
     try:
@@ -272,9 +274,14 @@ def test_single_gpu_multigrid_state_on_a_null_device(dry, monkeypatch, fp32):
     old = ngs._backend
     ngs.set_backend(be)
     try:
-        w = INSTaylorGreen(8)
+        w = INSTaylorGreen(16)
+        w.step()
         w.step()
         st = w.pre.state
+        # coarse levels are set up once (their operators only depend on dt); the finest level on every Update()
+        setup = 'ocmp_asm_setup_f32' if fp32 == '1' else 'ocmp_asm_setup'
+        assert st.nlevels == 3 and st.coarse_setups == 1 and st.updates >= 2
+        assert be.lib.calls.count(setup) == st.updates + (st.nlevels - 2)
         assert st.kind == 3 and st.nlevels >= 2
         top = st.levels[st.nlevels - 1].sys
         assert top.inv_fp32 == int(fp32) and bool(top.vals32) == (fp32 == '1') and not st.levels[0].sys.vals32

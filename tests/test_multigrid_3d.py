@@ -191,3 +191,28 @@ def test_cuda_backend_patch_tables_fp32_stride(ngs, monkeypatch):
     p32 = be._patches(f3, 'vertex')
     assert p32['fp32'] and p32['bs'] == 92 and p32['bs'] % 4 == 0
     assert (p32['dofs'][:, 90:] == -1).all() and np.array_equal(p32['dofs'][:, :90], p64['dofs'])
+
+
+def test_coarse_levels_are_reused_until_a_parameter_changes(ngs, monkeypatch):
+    """The coarse-level operators of the multigrid hierarchy depend only on the Parameters their programs read (the
+    Oseen wind acts on the finest level only): two time steps with reuse give the same iterates and iteration counts as
+    with a full set-up on every update, the coarse levels are built once, and a changed dt rebuilds them."""
+    from opencmp_b200.dist_workload import DistributedINS
+
+    def run(reuse, change_dt=False):
+        monkeypatch.setenv('OCMP_MG_REUSE_COARSE', '1' if reuse else '0')
+        d = DistributedINS(8, 1, 0)
+        its = []
+        for k in range(2):
+            if change_dt and k == 1:
+                d.w.dt.Set(2.0 * d.w.dt.Get())
+            d.w.linear_iterations = []
+            d.step()
+            its += d.w.linear_iterations
+        return d.w.gfu.vec.NumPy().copy(), its, d.mg.coarse_setups
+    u_full, its_full, n_full = run(False)
+    u_reuse, its_reuse, n_reuse = run(True)
+    assert its_reuse == its_full and n_reuse == 1 and n_full == len(its_full)
+    assert np.abs(u_reuse - u_full).max() <= 1e-13 * np.abs(u_full).max()
+    _, its_dt, n_dt = run(True, change_dt=True)
+    assert n_dt == 2
