@@ -289,3 +289,61 @@ def test_single_gpu_multigrid_state_on_a_null_device(dry, monkeypatch, fp32):
         assert sys_.pre_kind == 3 and sys_.inv_fp32 == int(fp32) and bool(sys_.vals32) == (fp32 == '1')
     finally:
         ngs.set_backend(old)
+
+
+def test_smoke_executes_on_a_null_device(dry):
+    """__graft_entry__.smoke(): the host path runs to the comparison with the oracle (which cannot hold here)."""
+    import __graft_entry__ as g
+    with pytest.raises(AssertionError):
+        g.smoke()
+
+
+def _bench_rank(rank, world, port, argv, out):
+    """One rank of ``torchrun ... bench.py --gpus 2`` on a null device: gloo instead of NCCL, CUDA runtime stubbed."""
+    import json
+    import os
+    import sys
+    import io
+    import contextlib
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    backend_mod.CudaBackend = DryCudaBackend
+    torch.linalg.inv = lambda a: a.clone()
+    real_tensor, real_init = torch.tensor, dist.init_process_group
+    torch.cuda.set_device = lambda *a: None
+    torch.cuda.synchronize = lambda *a: None
+    torch.cuda.Event = _FakeEvent
+    torch.cuda.current_stream = lambda *a: _FakeStream()
+    torch.Tensor.pin_memory = lambda self: self
+    torch.tensor = lambda data, **kw: real_tensor(data, **{k: v for k, v in kw.items() if k != 'device'})
+    dist.init_process_group = lambda backend=None, **kw: real_init('gloo', rank=rank, world_size=world)
+    sys.argv = ['bench.py'] + argv
+    import bench
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        bench.main()
+    if rank == 0:
+        out['line'] = json.loads(buf.getvalue().strip().splitlines()[-1])
+    else:
+        out['other'] = buf.getvalue().strip()
+
+
+@pytest.mark.parametrize('argv', [['--gpus', '2', '--N', '8', '--steps', '1', '--warmup', '1'],
+                                  ['--gpus', '2', '--workload', 'ins3d_dim', '--N', '4', '--steps', '1', '--warmup', '1']])
+def test_bench_two_ranks_execute_on_a_null_device(argv):
+    """The multi-GPU arm of bench.py (element-partitioned workload, communicator set-up through the C ABI, halo plans,
+    level array of the distributed C driver, max-over-ranks timing, rank 0 prints) with two gloo ranks."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = mp.Manager().dict()
+    mp.spawn(_bench_rank, args=(2, port, argv, out), nprocs=2, join=True)
+    line = out['line']
+    assert out.get('other', '') == ''                       # only rank 0 prints
+    assert line['n_gpus'] == 2 and line['scaling'] == 'weak' and line['problem']['ranks'] == 2
+    assert line['problem']['global_dofs'] > line['problem']['dofs'] * 1.2
+    assert 'element-partitioned' in line['config']['parallelism']
