@@ -39,6 +39,11 @@ def parse():
     ap.add_argument('--order', type=int, default=None)
     ap.add_argument('--cpu-N', type=int, default=None, help='mesh size of the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--layout', default='bricks', choices=['bricks', 'sphere'],
+                    help='ins3d_dim on several GPUs. bricks: one N^3 brick with its own sphere per GPU, lined up along x '
+                         '(weak scaling, the default); sphere: ONE sphere in [-1,1]^3 meshed with N^3 hexes in total, '
+                         'cells split between the GPUs (BASELINE configs[4] as written; use N = 96 on 8 GPUs for the '
+                         'per-GPU size of N = 48 on one)')
     ap.add_argument('--full-mg-setup', action='store_true',
                     help='re-assemble and re-invert the coarse multigrid levels on every Preconditioner.Update() '
                          '(OCMP_MG_REUSE_COARSE=0); default: they are rebuilt only when a Parameter they read (dt, t) '
@@ -134,7 +139,8 @@ def run_reference(args):
     if rank != 0:
         return
     # weak scaling: one N x N x 2 strip (2-D) / one N^3 brick (3-D) per GPU
-    cells_full = (args.N ** 3 if args.workload == 'ins3d_dim' else 2 * args.N * args.N) * max(1, args.gpus)
+    cells_full = (args.N ** 3 if args.workload == 'ins3d_dim' else 2 * args.N * args.N) * \
+        (1 if args.workload == 'ins3d_dim' and args.layout == 'sphere' else max(1, args.gpus))
     times = []
     ne = ndof = nnz = 0
     for _ in range(max(1, args.warmup // 3)):
@@ -168,10 +174,14 @@ def workload_config(args, where):
                                  'additive Schwarz smoother (damping 0.7), coarse-level phase field, tol 1e-12'
                 if where == 'gpu' else 'direct (SuperLU)', 'nonlinear_max_iterations': 3,
                 'l2': 'inputs larger than L2 (CSR matrix and patch inverses are GBs); no explicit flush',
-                'parallelism': ('element-partitioned: one {0}^3 brick with its own sphere per GPU (domain [-1,{1}] x '
+                'parallelism': ('single' if args.gpus <= 1 else
+                                'element-partitioned: ONE sphere in [-1,1]^3, the {0}^3 hexes split into {1} contiguous '
+                                'blocks of the refinement-tree cell order, two ghost layers, halo exchange + all-reduce '
+                                'over NCCL issued by the C ABI Krylov driver, distributed multigrid-GMRES'
+                                .format(args.N, args.gpus) if args.layout == 'sphere' else
+                                'element-partitioned: one {0}^3 brick with its own sphere per GPU (domain [-1,{1}] x '
                                 '[-1,1]^2), two ghost layers, halo exchange + all-reduce over NCCL issued by the C ABI '
-                                'Krylov driver, distributed multigrid-GMRES'.format(args.N, 2 * args.gpus - 1))
-                if args.gpus > 1 else 'single'}
+                                'Krylov driver, distributed multigrid-GMRES'.format(args.N, 2 * args.gpus - 1))}
     return {'workload': 'INS Taylor-Green 2D, structured {0}x{0}x2 triangles on [0,pi]^2, HDiv-DG order {1} / L2 order {2}, '
                         'Oseen + implicit Euler, dt=1e-3, nu=1 (examples/INS scaled up)'.format(args.N, args.order,
                                                                                                args.order - 1),
@@ -211,7 +221,8 @@ def main():
     if world > 1 and args.workload == 'ins3d_dim':
         # element-partitioned 3-D INS-DIM step: rank r owns the brick [-1 + 2r, 1 + 2r] x [-1,1]^2 at N^3 hexes
         from opencmp_b200.dist_workload import DistributedINSDIM3D
-        dins = DistributedINSDIM3D(args.N, world, rank, order=args.order)
+        dins = DistributedINSDIM3D(args.N, world, rank, order=args.order,
+                                   bricks=1 if args.layout == 'sphere' else None)
         w = dins.w
     elif world > 1:
         # element-partitioned INS step: rank r owns the strip [0,pi] x [r pi, (r+1) pi] at N x N x 2 triangles

@@ -152,7 +152,7 @@ def test_partitioned_multigrid_ins_step_matches_global_solve(replicate_below):
     assert out[0][1] == out[1][1]                                 # same iteration counts on both ranks
 
 
-def _mg3d_worker(rank, world, port, out):
+def _mg3d_worker(rank, world, port, bricks, out):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -163,7 +163,7 @@ def _mg3d_worker(rank, world, port, out):
         from opencmp_b200.dist_workload import DistributedINSDIM3D
         from opencmp_b200.workloads import INSSphereDIM3D
         kw = dict(nonlinear_max_iterations=1, linear_tolerance=1e-13, lam=1.0)
-        d = DistributedINSDIM3D(4, world, rank, n0=2, replicate_below=0, **kw)
+        d = DistributedINSDIM3D(4, world, rank, n0=2, replicate_below=0, bricks=bricks, **kw)
         g = INSSphereDIM3D(4, mesh=d.gmesh, preconditioner=None, **kw)
 
         def direct():
@@ -196,13 +196,16 @@ def DofMapOf(d, g):
     return DofMap(d.part, g.fes_phi, d.w.fes_phi).l2g
 
 
-def test_partitioned_multigrid_ins_dim_3d_step_matches_global_solve():
-    """3-D INS-DIM (hex Taylor-Hood, one brick with its own diffuse sphere per rank): distributed multigrid-GMRES with
-    open-star patches and per-level phase fields on 2 ranks equals the single-process sparse direct solve."""
+@pytest.mark.parametrize('bricks', [None, 1])
+def test_partitioned_multigrid_ins_dim_3d_step_matches_global_solve(bricks):
+    """3-D INS-DIM (hex Taylor-Hood): distributed multigrid-GMRES with open-star patches and per-level phase fields on
+    2 ranks equals the single-process sparse direct solve — with one brick and its own diffuse sphere per rank
+    (``bricks=None``), and with ONE sphere in [-1,1]^3 whose cells are split between the ranks (``bricks=1``, the
+    layout BASELINE configs[4] describes)."""
     world = 2
     port = _free_port()
     mgr = mp.get_context('spawn').Manager()
     out = mgr.dict()
-    mp.spawn(_mg3d_worker, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_mg3d_worker, args=(world, port, bricks, out), nprocs=world, join=True)
     assert len(out) == world
     assert out[0][1] == out[1][1] and max(out[0][1]) < 80
