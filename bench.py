@@ -335,7 +335,10 @@ def main():
     ap_ms = ap['ms'] / max(1, ap['count'])
     ap_bytes = ap['bytes'] / max(1, ap['count'])
     ap_gbs = ap_bytes / (ap_ms * 1e-3) / 1e9 if ap['count'] else 0.0
-    roofline = {'kernel': 'k_patch_apply (additive-Schwarz smoother, all multigrid levels; launch-weighted mean)',
+    fp32 = os.environ.get('OCMP_PATCH_FP32', '0') == '1'
+    roofline = {'kernel': ('k_patch_apply_f32 (FP32-stored patch inverses, 4 bs^2 bytes per patch' if fp32 else
+                           'k_patch_apply (8 bs^2 bytes per patch') +
+                          '; additive-Schwarz smoother, all multigrid levels; launch-weighted mean)',
                 'bound': 'hbm', 'achieved': ap_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': ap_gbs / peak,
                 'peak_source': peak_src, 'bytes_per_launch': ap_bytes, 'launches': ap['count'],
                 'avg_launch_ms': ap_ms, 'share_of_step': share['asm_apply'],
