@@ -49,10 +49,10 @@ def parse():
                          '(OCMP_MG_REUSE_COARSE=0); default: they are rebuilt only when a Parameter they read (dt, t) '
                          'changes — their operators do not see the Oseen wind — while the finest level (the assembled '
                          'system) is always set up again')
-    ap.add_argument('--precond-storage', default='fp64', choices=['fp64', 'fp32'],
+    ap.add_argument('--precond-storage', default='fp64', choices=['fp64', 'fp32', 'bf16'],
                     help='storage of the multigrid data (patch inverses, level matrices inside the cycle); arithmetic '
-                         'and the Krylov method stay FP64. fp32 = OCMP_PATCH_FP32=1 OCMP_SPMV_FP32=1 (opt-in until it '
-                         'has been measured on a B200)')
+                         'and the Krylov method stay FP64. fp32 = OCMP_PATCH_STORAGE=fp32 OCMP_SPMV_FP32=1; bf16 = '
+                         'bfloat16 patch inverses + FP32 level matrices (opt-in until measured on a B200)')
     ap.add_argument('--dist-poisson', action='store_true', help='also run the distributed Poisson CG leg')
     ap.add_argument('--dist-n', type=int, default=512, help='cells per direction and rank of the distributed leg')
     a = ap.parse_args()
@@ -198,8 +198,9 @@ def main():
     args = parse()
     if args.impl == 'reference':
         return run_reference(args)
-    if args.precond_storage == 'fp32':
-        os.environ['OCMP_PATCH_FP32'] = os.environ['OCMP_SPMV_FP32'] = '1'
+    if args.precond_storage != 'fp64':
+        os.environ['OCMP_PATCH_STORAGE'] = args.precond_storage
+        os.environ['OCMP_SPMV_FP32'] = '1'
     if args.full_mg_setup:
         os.environ['OCMP_MG_REUSE_COARSE'] = '0'
     import numpy as np
@@ -212,7 +213,7 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import opencmp_b200.ngs as ngs
-    from opencmp_b200.backend import CudaBackend, read_profile
+    from opencmp_b200.backend import CudaBackend, patch_storage, read_profile
     from opencmp_b200.workloads import INSTaylorGreen
     be = CudaBackend(local)
     ngs.set_backend(be)
@@ -335,9 +336,10 @@ def main():
     ap_ms = ap['ms'] / max(1, ap['count'])
     ap_bytes = ap['bytes'] / max(1, ap['count'])
     ap_gbs = ap_bytes / (ap_ms * 1e-3) / 1e9 if ap['count'] else 0.0
-    fp32 = os.environ.get('OCMP_PATCH_FP32', '0') == '1'
-    roofline = {'kernel': ('k_patch_apply_f32 (FP32-stored patch inverses, 4 bs^2 bytes per patch' if fp32 else
-                           'k_patch_apply (8 bs^2 bytes per patch') +
+    roofline = {'kernel': {'fp64': 'k_patch_apply (8 bs^2 bytes per patch',
+                           'fp32': 'k_patch_apply_f32 (FP32-stored patch inverses, 4 bs^2 bytes per patch',
+                           'bf16': 'k_patch_apply_bf16 (bfloat16-stored patch inverses, 2 bs^2 bytes per patch'
+                           }[patch_storage()] +
                           '; additive-Schwarz smoother, all multigrid levels; launch-weighted mean)',
                 'bound': 'hbm', 'achieved': ap_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': ap_gbs / peak,
                 'peak_source': peak_src, 'bytes_per_launch': ap_bytes, 'launches': ap['count'],
@@ -356,7 +358,7 @@ def main():
             'rebuilt on every update' if os.environ.get('OCMP_MG_REUSE_COARSE', '1') == '0' else
             'rebuilt when a Parameter they read changes (constant dt: once); finest level on every update'),
             precond_storage={
-            'patch_inverses': 'fp32' if os.environ.get('OCMP_PATCH_FP32', '0') == '1' else 'fp64',
+            'patch_inverses': patch_storage(),
             'level_matrices_in_cycle': 'fp32' if os.environ.get('OCMP_SPMV_FP32', '0') == '1' else 'fp64'}),
         'problem': {'cells': ne, 'dofs': ndof, 'nnz': nnz, 'global_dofs': dins.ndof_global if dins else ndof,
                     'ranks': world, 'picard_per_step': picard / args.steps,

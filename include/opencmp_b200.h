@@ -122,6 +122,13 @@ int ocmp_asm_setup_f32(int npatch, int bs, const int* patch_dofs, const int* row
                        void* stream);
 int ocmp_asm_apply_f32(int npatch, int bs, const int* patch_dofs, const float* inv_blocks, const double* r, double* z,
                        long long n, void* stream);
+/* ... and in bfloat16 (a quarter of the FP64 bytes; bs a multiple of 8). Iteration counts on the CPU restatement:
+ * unchanged in 2-D, +-2 in 3-D (profiles/r1_solver_convergence.md). */
+int ocmp_asm_setup_bf16(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
+                        const double* vals, const double* freemask, unsigned short* inv_blocks, const int* positions,
+                        void* stream);
+int ocmp_asm_apply_bf16(int npatch, int bs, const int* patch_dofs, const unsigned short* inv_blocks, const double* r,
+                        double* z, long long n, void* stream);
 
 /* ---- Krylov: stand in for ngs.solvers.CG / GMRes / PreconditionedRichardson and for mat.Inverse applied to a
  *      residual (reference opencmp/models/base_model.py:886-947) ---------------------------------------------- */
@@ -137,7 +144,7 @@ typedef struct ocmp_system {
     const double* dinv;
     int npatch, bs;
     const int* patch_dofs;
-    const void* inv_blocks;  /* npatch x bs x bs, transposed per patch; double, or float when inv_fp32 is set */
+    const void* inv_blocks;  /* npatch x bs x bs, transposed per patch; double / float / bfloat16, see inv_storage */
     const double* patch_weight; /* optional per-dof weight applied after the additive patch solves (restricted / averaged AS) */
     int nlevels;             /* pre_kind 3: levels[0] coarsest ... levels[nlevels-1] = this system */
     const struct ocmp_mg_level* levels;
@@ -150,7 +157,7 @@ typedef struct ocmp_system {
                                 restriction only see those; NULL = not distributed */
     int halo_fwd;            /* refresh ghost entries after an SpMV / after the coarsest-level solve (0: none) */
     int halo_sum;            /* sum the neighbours' partial patch corrections after the smoother (0: none) */
-    int inv_fp32;            /* 1: inv_blocks holds floats (ocmp_asm_setup_f32); 0: doubles */
+    int inv_storage;         /* type of inv_blocks: 0 double, 1 float (ocmp_asm_setup_f32), 2 bfloat16 (.._bf16) */
     const float* vals32;     /* optional FP32 copy of vals (ocmp_to_f32): used for the operator applications inside
                                 the multigrid cycle only — the Krylov method around it always applies `vals` */
 } ocmp_system;

@@ -49,7 +49,7 @@ class System(C.Structure):
                 ('bs', C.c_int), ('patch_dofs', C.c_void_p), ('inv_blocks', C.c_void_p), ('patch_weight', C.c_void_p),
                 ('nlevels', C.c_int), ('levels', C.c_void_p), ('inv_rowptr', C.c_void_p), ('inv_colidx', C.c_void_p),
                 ('inv_vals', C.c_void_p), ('owned', C.c_void_p), ('halo_fwd', C.c_int), ('halo_sum', C.c_int),
-                ('inv_fp32', C.c_int), ('vals32', C.c_void_p)]
+                ('inv_storage', C.c_int), ('vals32', C.c_void_p)]
 
 
 class MGLevel(C.Structure):
@@ -82,9 +82,9 @@ def load_library() -> C.CDLL:
     lib.ocmp_asm_setup.argtypes = [C.c_int, C.c_int, P, P, P, P, P, P, P, P]
     lib.ocmp_patch_positions.argtypes = [C.c_int, C.c_int, P, P, P, P, P]
     lib.ocmp_asm_apply.argtypes = [C.c_int, C.c_int, P, P, P, P, C.c_longlong, P]
-    lib.ocmp_asm_setup_f32.argtypes = lib.ocmp_asm_setup.argtypes
+    lib.ocmp_asm_setup_f32.argtypes = lib.ocmp_asm_setup_bf16.argtypes = lib.ocmp_asm_setup.argtypes
     lib.ocmp_to_f32.argtypes = [C.c_longlong, P, P, P]
-    lib.ocmp_asm_apply_f32.argtypes = lib.ocmp_asm_apply.argtypes
+    lib.ocmp_asm_apply_f32.argtypes = lib.ocmp_asm_apply_bf16.argtypes = lib.ocmp_asm_apply.argtypes
     lib.ocmp_krylov.argtypes = [C.POINTER(System), C.c_int, P, P, C.c_double, C.c_int, C.c_int, C.c_double, P,
                                 C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_double), P]
     lib.ocmp_krylov_history.argtypes = [C.POINTER(C.c_double), C.c_int]
@@ -119,8 +119,21 @@ def read_profile(lib) -> dict:
 EXPORTED = ['ocmp_mdot', 'ocmp_maxpy', 'ocmp_krylov_history', 'ocmp_comm_unique_id', 'ocmp_comm_init', 'ocmp_halo_plan', 'ocmp_halo_run', 'ocmp_allreduce_sum',
             'ocmp_patch_positions', 'ocmp_profile_bytes', 'ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
             'ocmp_dot', 'ocmp_axpby', 'ocmp_masked_assign', 'ocmp_jacobi_setup', 'ocmp_asm_setup', 'ocmp_asm_apply',
-            'ocmp_asm_setup_f32', 'ocmp_asm_apply_f32', 'ocmp_to_f32',
+            'ocmp_asm_setup_f32', 'ocmp_asm_apply_f32', 'ocmp_asm_setup_bf16', 'ocmp_asm_apply_bf16', 'ocmp_to_f32',
             'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version']
+
+
+# storage type of the smoother's patch inverses (ocmp_system.inv_storage): arithmetic is FP64 in every case
+STORAGE_ID = {'fp64': 0, 'fp32': 1, 'bf16': 2}
+_STORAGE_ALIGN = {'fp64': 2, 'fp32': 4, 'bf16': 8}          # patch stride: every stored column 16-byte aligned
+
+
+def patch_storage() -> str:
+    """OCMP_PATCH_STORAGE = fp64 (default) | fp32 | bf16; OCMP_PATCH_FP32=1 is a synonym of fp32."""
+    kind = os.environ.get('OCMP_PATCH_STORAGE', 'fp32' if os.environ.get('OCMP_PATCH_FP32', '0') == '1' else 'fp64')
+    if kind not in STORAGE_ID:
+        raise ValueError('OCMP_PATCH_STORAGE must be one of {}'.format(sorted(STORAGE_ID)))
+    return kind
 
 
 def _ptr(t) -> Optional[int]:
@@ -542,23 +555,26 @@ class CudaBackend:
             self._invert_patches(pt, pd, mat, fm)
             self.launches += 1
             return _Precond(2, inv=pt['inv'], npatch=pt['npatch'], bs=pt['bs'], pdofs=pt['dofs'], fm=fm,
-                            wgt=pt['wgt'], fp32=pt['fp32'])
+                            wgt=pt['wgt'], storage=pt['storage'])
         raise NotImplementedError('preconditioner type {}'.format(kind))
 
     def _invert_patches(self, pt, pd, mat, fm) -> None:
         """(Re)compute the stored patch inverses of the patch table ``pt`` for the current matrix values. With
-        ``pt['fp32']`` (OCMP_PATCH_FP32=1) they are stored in FP32 — inverted and applied in FP64 arithmetic."""
+        ``pt['storage']`` = fp32 / bf16 (OCMP_PATCH_STORAGE) they are stored in that type — inverted and applied in
+        FP64 arithmetic."""
         t = self.torch
         npatch, bs = pt['npatch'], pt['bs']
         st = self._stream()
         if pt.get('inv') is None:
-            pt['inv'] = t.empty(npatch * bs * bs, dtype=t.float32 if pt['fp32'] else t.float64, device=self.device)
+            dtype = {'fp64': t.float64, 'fp32': t.float32, 'bf16': t.bfloat16}[pt['storage']]
+            pt['inv'] = t.empty(npatch * bs * bs, dtype=dtype, device=self.device)
         if pt.get('pos') is None and bs <= 160:
             npad = 16 * ((bs + 15) // 16)
             pt['pos'] = t.empty(npatch * npad * npad, dtype=t.int32, device=self.device)
             self._ck(self.lib.ocmp_patch_positions(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(),
                                                    pd['colidx'].data_ptr(), pt['pos'].data_ptr(), st))
-        setup = self.lib.ocmp_asm_setup_f32 if pt['fp32'] else self.lib.ocmp_asm_setup
+        setup = {'fp64': self.lib.ocmp_asm_setup, 'fp32': self.lib.ocmp_asm_setup_f32,
+                 'bf16': self.lib.ocmp_asm_setup_bf16}[pt['storage']]
         self._ck(setup(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(),
                        mat.values.data_ptr(), _ptr(fm), pt['inv'].data_ptr(), _ptr(pt.get('pos')), st))
 
@@ -620,18 +636,18 @@ class CudaBackend:
             out = self._patches(fes, 'star' if kind == 'vertex' else 'cell', vmask if kind == 'vertex' else None)
             sd[key] = out
             return out
-        fp32 = os.environ.get('OCMP_PATCH_FP32', '0') == '1'
-        align = 4 if fp32 else 2
-        if dofs.shape[1] % align and (kind != 'cell' or fp32):
+        storage = patch_storage()
+        align = _STORAGE_ALIGN[storage]
+        if dofs.shape[1] % align and (kind != 'cell' or storage != 'fp64'):
             # patch stride padded so that the columns of the stored inverses stay 16-byte aligned, which k_patch_apply
             # needs for its 16-byte loads (double2: even stride, an odd one falls back to 8-byte loads at ~15 % lower
-            # bandwidth; float4 for FP32-stored inverses: multiple of 4, required)
+            # bandwidth; FP32 / bf16 storage: multiple of 4 / 8, required)
             npad = -dofs.shape[1] % align
             dofs = np.concatenate([dofs, -np.ones((dofs.shape[0], npad), dtype=dofs.dtype)], axis=1)
         dofs = np.ascontiguousarray(dofs, dtype=np.int32)
         mult = np.bincount(dofs[dofs >= 0].ravel(), minlength=fes.ndof).astype(np.float64)
         out = dict(npatch=dofs.shape[0], bs=dofs.shape[1], dofs=self._up(dofs),
-                   wgt=self._up(1.0 / np.maximum(mult, 1.0)), inv=None, fp32=fp32)
+                   wgt=self._up(1.0 / np.maximum(mult, 1.0)), inv=None, storage=storage)
         sd[key] = out
         return out
 
@@ -648,7 +664,7 @@ class CudaBackend:
                 s.dinv = pre.dinv.data_ptr()
             elif pre.kind == 3:
                 top = pre.levels[pre.nlevels - 1].sys
-                for name in ('npatch', 'bs', 'patch_dofs', 'inv_blocks', 'patch_weight', 'inv_fp32', 'vals32'):
+                for name in ('npatch', 'bs', 'patch_dofs', 'inv_blocks', 'patch_weight', 'inv_storage', 'vals32'):
                     setattr(s, name, getattr(top, name))
                 s.nlevels = pre.nlevels
                 s.levels = C.addressof(pre.levels)
@@ -656,7 +672,7 @@ class CudaBackend:
                 s.npatch, s.bs = pre.npatch, pre.bs
                 s.patch_dofs, s.inv_blocks = pre.pdofs.data_ptr(), pre.inv.data_ptr()
                 s.patch_weight = _ptr(pre.wgt)
-                s.inv_fp32 = 1 if getattr(pre, 'fp32', False) else 0
+                s.inv_storage = STORAGE_ID[getattr(pre, 'storage', 'fp64')]
         return s
 
     def krylov(self, kind, mat, b, x, pre, freedofs, tol, maxit, initialize, printrates, damp=1.0, restart=None):
@@ -727,7 +743,8 @@ def _cuda_patch_setup(self, mat, pt, fm):
 
 
 def _cuda_patch_apply(self, pt, r, z):
-    apply = self.lib.ocmp_asm_apply_f32 if pt['fp32'] else self.lib.ocmp_asm_apply
+    apply = {'fp64': self.lib.ocmp_asm_apply, 'fp32': self.lib.ocmp_asm_apply_f32,
+             'bf16': self.lib.ocmp_asm_apply_bf16}[pt['storage']]
     self._ck(apply(pt['npatch'], pt['bs'], pt['dofs'].data_ptr(), pt['inv'].data_ptr(), r.data_ptr(), z.data_ptr(),
                    z.numel(), self._stream()))
 

@@ -1,6 +1,7 @@
 // Shared helpers of the opencmp_b200 CUDA sources.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 
 int ocmp_fail(int code, const char* msg);
 int ocmp_check(const char* where);
@@ -9,12 +10,25 @@ int ocmp_patch_invert_registers(int npatch, int bs, const int* pd, const int* rp
                                 const double* fm, double* inv, int* flag_dev, const int* pos, cudaStream_t st);
 int ocmp_patch_apply_cta(int npatch, int bs, const int* pd, const double* inv, const double* r, double* z,
                          cudaStream_t st);
-// FP32-stored inverses (ocmp_system.inv_fp32): same arithmetic in FP64, half the bytes streamed per application
+// FP32-stored inverses (ocmp_system.inv_storage == 1): same arithmetic in FP64, half the bytes streamed per application
 int ocmp_patch_invert_registers_f32(int npatch, int bs, const int* pd, const int* rp, const int* ci,
                                     const double* vals, const double* fm, float* inv, int* flag_dev, const int* pos,
                                     cudaStream_t st);
 int ocmp_patch_apply_cta_f32(int npatch, int bs, const int* pd, const float* inv, const double* r, double* z,
                              cudaStream_t st);
+// bfloat16-stored inverses (ocmp_system.inv_storage == 2): a quarter of the FP64 bytes; bs a multiple of 8
+int ocmp_patch_invert_registers_bf16(int npatch, int bs, const int* pd, const int* rp, const int* ci,
+                                     const double* vals, const double* fm, __nv_bfloat16* inv, int* flag_dev,
+                                     const int* pos, cudaStream_t st);
+int ocmp_patch_apply_cta_bf16(int npatch, int bs, const int* pd, const __nv_bfloat16* inv, const double* r, double* z,
+                              cudaStream_t st);
+// conversions between FP64 arithmetic and the storage type of the preconditioner data
+template <typename T> __device__ __forceinline__ T ocmp_store(double v) { return (T)v; }
+template <> __device__ __forceinline__ __nv_bfloat16 ocmp_store<__nv_bfloat16>(double v) { return __double2bfloat16(v); }
+template <typename T> __device__ __forceinline__ double ocmp_load(const T* p) { return (double)__ldg(p); }
+template <> __device__ __forceinline__ double ocmp_load<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return (double)__bfloat162float(__ldg(p));
+}
 // optional per-category device timing (CUDA events on the launching stream) and launch counting
 enum { PROF_SPMV = 0, PROF_ASM_APPLY, PROF_COEF, PROF_CONTRACT, PROF_LIN, PROF_MDOT, PROF_MAXPY, PROF_VEC,
        PROF_SETUP, PROF_SPMV_MG, PROF_HALO, PROF_NCAT };

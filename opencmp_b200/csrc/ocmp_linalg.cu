@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(256) k_asm_setup(int npatch, int bs, const int
         }
         for (int idx = threadIdx.x; idx < bs * bs; idx += blockDim.x) {
             const int j = idx / bs, i = idx % bs;
-            inv[(long long)p * bs * bs + idx] = (OutT)M[i * bs + j];
+            inv[(long long)p * bs * bs + idx] = ocmp_store<OutT>(M[i * bs + j]);
         }
     }
 }
@@ -430,6 +430,11 @@ static int invert_dispatch(int npatch, int bs, const int* pd, const int* rp, con
 static int invert_dispatch(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
                            const double* fm, float* inv, int* flag, const int* pos, cudaStream_t st) {
     return ocmp_patch_invert_registers_f32(npatch, bs, pd, rp, ci, vals, fm, inv, flag, pos, st);
+}
+
+static int invert_dispatch(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
+                           const double* fm, __nv_bfloat16* inv, int* flag, const int* pos, cudaStream_t st) {
+    return ocmp_patch_invert_registers_bf16(npatch, bs, pd, rp, ci, vals, fm, inv, flag, pos, st);
 }
 
 template <typename OutT>
@@ -471,6 +476,13 @@ extern "C" int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const i
     return asm_setup<double>(npatch, bs, patch_dofs, rowptr, colidx, vals, freemask, inv_blocks, positions, stream);
 }
 
+extern "C" int ocmp_asm_setup_bf16(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
+                                   const double* vals, const double* freemask, unsigned short* inv_blocks,
+                                   const int* positions, void* stream) {
+    return asm_setup<__nv_bfloat16>(npatch, bs, patch_dofs, rowptr, colidx, vals, freemask,
+                                    reinterpret_cast<__nv_bfloat16*>(inv_blocks), positions, stream);
+}
+
 extern "C" int ocmp_asm_setup_f32(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
                                   const double* vals, const double* freemask, float* inv_blocks, const int* positions,
                                   void* stream) {
@@ -497,7 +509,7 @@ __global__ void __launch_bounds__(256) k_asm_apply(int npatch, int bs, const int
         const InT* A = inv + p * bs * bs;
         for (int i = lane; i < bs; i += 32) {
             double s = 0.0;
-            for (int j = 0; j < bs; ++j) s = fma((double)__ldg(A + j * bs + i), rr[j], s);
+            for (int j = 0; j < bs; ++j) s = fma(ocmp_load(A + j * bs + i), rr[j], s);
             const int di = __ldg(d + i);
             if (di >= 0) atomicAdd(z + di, s);
         }
@@ -511,6 +523,11 @@ static int apply_cta(int npatch, int bs, const int* pd, const double* inv, const
 static int apply_cta(int npatch, int bs, const int* pd, const float* inv, const double* r, double* z,
                      cudaStream_t st) {
     return ocmp_patch_apply_cta_f32(npatch, bs, pd, inv, r, z, st);
+}
+
+static int apply_cta(int npatch, int bs, const int* pd, const __nv_bfloat16* inv, const double* r, double* z,
+                     cudaStream_t st) {
+    return ocmp_patch_apply_cta_bf16(npatch, bs, pd, inv, r, z, st);
 }
 
 template <typename InT>
@@ -539,6 +556,12 @@ extern "C" int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const d
     return asm_apply<double>(npatch, bs, patch_dofs, inv_blocks, r, z, n, stream);
 }
 
+extern "C" int ocmp_asm_apply_bf16(int npatch, int bs, const int* patch_dofs, const unsigned short* inv_blocks,
+                                   const double* r, double* z, long long n, void* stream) {
+    return asm_apply<__nv_bfloat16>(npatch, bs, patch_dofs, reinterpret_cast<const __nv_bfloat16*>(inv_blocks), r, z, n,
+                                    stream);
+}
+
 extern "C" int ocmp_asm_apply_f32(int npatch, int bs, const int* patch_dofs, const float* inv_blocks, const double* r,
                                   double* z, long long n, void* stream) {
     return asm_apply<float>(npatch, bs, patch_dofs, inv_blocks, r, z, n, stream);
@@ -565,7 +588,10 @@ struct Ctx {
             ProfScope ps(PROF_VEC, st);
             k_had<<<grid_for(n), 256, 0, st>>>(n, sy->dinv, nullptr, r, z);
         } else if (sy->pre_kind == 2 || sy->pre_kind == 3) {
-            if (sy->inv_fp32)
+            if (sy->inv_storage == 2)
+                ocmp_asm_apply_bf16(sy->npatch, sy->bs, sy->patch_dofs, (const unsigned short*)sy->inv_blocks, r, z, n,
+                                    st);
+            else if (sy->inv_storage == 1)
                 ocmp_asm_apply_f32(sy->npatch, sy->bs, sy->patch_dofs, (const float*)sy->inv_blocks, r, z, n, st);
             else
                 ocmp_asm_apply(sy->npatch, sy->bs, sy->patch_dofs, (const double*)sy->inv_blocks, r, z, n, st);

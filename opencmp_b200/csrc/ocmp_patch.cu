@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256, 1) k_patch_invert(int npatch, int bs, con
 #pragma unroll
             for (int b = 0; b < T; ++b) {
                 const int j = tx + 16 * b;
-                if (i < bs && j < bs) out[(long long)j * bs + i] = (OutT)M[a][b];
+                if (i < bs && j < bs) out[(long long)j * bs + i] = ocmp_store<OutT>(M[a][b]);
             }
         }
     }
@@ -195,6 +195,12 @@ int ocmp_patch_invert_registers_f32(int npatch, int bs, const int* pd, const int
                                     const double* vals, const double* fm, float* inv, int* flag_dev, const int* pos,
                                     cudaStream_t st) {
     return invert_registers<float>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st);
+}
+
+int ocmp_patch_invert_registers_bf16(int npatch, int bs, const int* pd, const int* rp, const int* ci,
+                                     const double* vals, const double* fm, __nv_bfloat16* inv, int* flag_dev,
+                                     const int* pos, cudaStream_t st) {
+    return invert_registers<__nv_bfloat16>(npatch, bs, pd, rp, ci, vals, fm, inv, flag_dev, pos, st);
 }
 
 // ---- application ------------------------------------------------------------------------------------------------
@@ -389,5 +395,107 @@ int ocmp_patch_apply_cta_f32(int npatch, int bs, const int* pd, const float* inv
     const int grid = npatch < cap ? npatch : cap;
     if (bs <= 128) k_patch_apply_f32<1, NW, 4><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
     else k_patch_apply_f32<2, NW, 2><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
+    return 1;
+}
+
+// bfloat16-stored inverses (bs a multiple of 8): every HALF warp streams one column, a lane owns the rows
+// 8*(lane % 16) .. +7 (+ 128*m) and loads them as one 16-byte word; UC columns per half warp in flight. A bf16 is the
+// upper half of an FP32, so the conversion is a shift; products and sums in FP64.
+__device__ __forceinline__ void bf16x2_fma(unsigned w, double rj, double& s0, double& s1) {
+    s0 = fma((double)__uint_as_float(w << 16), rj, s0);
+    s1 = fma((double)__uint_as_float(w & 0xffff0000u), rj, s1);
+}
+
+template <int MR, int NW, int UC>
+__global__ void __launch_bounds__(NW * 32) k_patch_apply_bf16(int npatch, int bs, const int* __restrict__ pdofs,
+                                                              const __nv_bfloat16* __restrict__ inv,
+                                                              const double* __restrict__ r, double* __restrict__ z) {
+    extern __shared__ double sm[];         // r_loc[bs], partial[2 * NW][bs]
+    constexpr int G = 2 * NW;              // column groups of the CTA
+    double* rl = sm;
+    double* part = sm + bs;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15;
+    const int g = 2 * warp + (lane >> 4);
+    for (int p = blockIdx.x; p < npatch; p += gridDim.x) {
+        const int* d = pdofs + (long long)p * bs;
+        __syncthreads();
+        for (int j = threadIdx.x; j < bs; j += NW * 32) {
+            const int dj = __ldg(d + j);
+            rl[j] = dj >= 0 ? __ldg(r + dj) : 0.0;
+        }
+        __syncthreads();
+        const __nv_bfloat16* A = inv + (long long)p * bs * bs;
+        double s[MR][8];
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) s[m][c] = 0.0;
+        int j = g;
+        for (; j + (UC - 1) * G < bs; j += UC * G) {
+            uint4 v[UC][MR];
+            double rj[UC];
+#pragma unroll
+            for (int u = 0; u < UC; ++u) {
+                rj[u] = rl[j + u * G];
+                const uint4* col = reinterpret_cast<const uint4*>(A + (long long)(j + u * G) * bs);
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    const int i8 = l16 + 16 * m;
+                    v[u][m] = (8 * i8 < bs) ? __ldg(col + i8) : make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UC; ++u)
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    bf16x2_fma(v[u][m].x, rj[u], s[m][0], s[m][1]);
+                    bf16x2_fma(v[u][m].y, rj[u], s[m][2], s[m][3]);
+                    bf16x2_fma(v[u][m].z, rj[u], s[m][4], s[m][5]);
+                    bf16x2_fma(v[u][m].w, rj[u], s[m][6], s[m][7]);
+                }
+        }
+        for (; j < bs; j += G) {
+            const double rj = rl[j];
+            const uint4* col = reinterpret_cast<const uint4*>(A + (long long)j * bs);
+#pragma unroll
+            for (int m = 0; m < MR; ++m) {
+                const int i8 = l16 + 16 * m;
+                if (8 * i8 < bs) {
+                    const uint4 v = __ldg(col + i8);
+                    bf16x2_fma(v.x, rj, s[m][0], s[m][1]);
+                    bf16x2_fma(v.y, rj, s[m][2], s[m][3]);
+                    bf16x2_fma(v.z, rj, s[m][4], s[m][5]);
+                    bf16x2_fma(v.w, rj, s[m][6], s[m][7]);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            const int i = 8 * (l16 + 16 * m);
+            if (i < bs) {                      // bs % 8 == 0: all eight rows exist
+#pragma unroll
+                for (int c = 0; c < 8; ++c) part[g * bs + i + c] = s[m][c];
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < bs; i += NW * 32) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < G; ++w) t += part[w * bs + i];
+            const int di = __ldg(d + i);
+            if (di >= 0) atomicAdd(z + di, t);
+        }
+    }
+}
+
+int ocmp_patch_apply_cta_bf16(int npatch, int bs, const int* pd, const __nv_bfloat16* inv, const double* r, double* z,
+                              cudaStream_t st) {
+    if (bs > 256 || (bs & 7)) return 0;
+    constexpr int NW = 4;
+    const size_t smem = sizeof(double) * (2 * NW + 1) * bs;
+    const int cap = ocmp_sm_count() * 16;
+    const int grid = npatch < cap ? npatch : cap;
+    if (bs <= 128) k_patch_apply_bf16<1, NW, 4><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
+    else k_patch_apply_bf16<2, NW, 4><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
     return 1;
 }

@@ -152,7 +152,7 @@ class DistributedMultigrid:
         the whole GMRES + V-cycle then runs inside one C call per solve — halo exchanges (ocmp_halo_run) and the
         all-reduces of the Gram-Schmidt coefficients are issued from there, on the same stream as the kernels."""
         import ctypes as C
-        from .backend import MGLevel, System
+        from .backend import MGLevel, System, STORAGE_ID
         be = self.be
         dist_on = be.comm_init()
         nl = len(self.levels)
@@ -179,7 +179,7 @@ class DistributedMultigrid:
             s.pre_kind = 2
             s.npatch, s.bs = pt['npatch'], pt['bs']
             s.patch_dofs, s.inv_blocks = pt['dofs'].data_ptr(), pt['inv'].data_ptr()
-            s.inv_fp32 = 1 if pt.get('fp32') else 0
+            s.inv_storage = STORAGE_ID[pt.get('storage', 'fp64')]
             if os.environ.get('OCMP_SPMV_FP32', '0') == '1':
                 if self._fresh_coarse or l == nl - 1 or getattr(lv, 'vals32', None) is None:
                     lv.vals32 = be.fp32_copy(lv.mat.values, getattr(lv, 'vals32', None))

@@ -171,9 +171,9 @@ def test_fp32_patch_storage_host_path(dry, monkeypatch):
         pre.Update()
         assert 'ocmp_asm_setup_f32' in be.lib.calls and 'ocmp_asm_setup' not in be.lib.calls
         st = pre.state
-        assert st.inv.dtype == torch.float32 and st.bs % 4 == 0 and st.fp32
+        assert st.inv.dtype == torch.float32 and st.bs % 4 == 0 and st.storage == 'fp32'
         sys_ = be._system(c['a'].mat, None, st)
-        assert sys_.inv_fp32 == 1 and sys_.bs == st.bs
+        assert sys_.inv_storage == 1 and sys_.bs == st.bs
     finally:
         ngs.set_backend(old)
 
@@ -199,7 +199,9 @@ class _FakeStream:
 @pytest.mark.parametrize('argv', [['--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu'],
                                   ['--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu', '--precond-storage', 'fp32',
                                    '--full-mg-setup'],
-                                  ['--workload', 'ins3d_dim', '--N', '4', '--steps', '1', '--warmup', '1', '--no-cpu']])
+                                  ['--workload', 'ins3d_dim', '--N', '4', '--steps', '1', '--warmup', '1', '--no-cpu'],
+                                  ['--workload', 'ins3d_dim', '--N', '4', '--steps', '1', '--warmup', '1', '--no-cpu',
+                                   '--precond-storage', 'bf16']])
 def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
     """bench.py's own arm, start to JSON line, with the CUDA runtime calls stubbed: the line must carry every key of
     the bench contract (values are meaningless here)."""
@@ -215,8 +217,8 @@ def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
     monkeypatch.setattr(torch, 'tensor', lambda data, **kw: real_tensor(data, **{k: v for k, v in kw.items()
                                                                                   if k != 'device'}))
     monkeypatch.setattr(sys, 'argv', ['bench.py'] + argv)
-    for k in ('OCMP_PATCH_FP32', 'OCMP_SPMV_FP32'):          # bench sets them for --precond-storage fp32; restored after
-        monkeypatch.setenv(k, '0')
+    for k, v in (('OCMP_PATCH_STORAGE', 'fp64'), ('OCMP_SPMV_FP32', '0')):   # bench sets them; restored afterwards
+        monkeypatch.setenv(k, v)
     monkeypatch.setenv('OCMP_MG_REUSE_COARSE', '1')
     for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'):
         monkeypatch.delenv(k, raising=False)
@@ -229,8 +231,9 @@ def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
                 'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'e2e', 'gpu_launches', 'clocks'):
         assert key in line, key
     assert line['config']['workload'] and line['dtype'] == 'f64' and line['higher_is_better'] is False
-    want = 'fp32' if 'fp32' in argv else 'fp64'
-    assert line['config']['precond_storage'] == {'patch_inverses': want, 'level_matrices_in_cycle': want}
+    want = 'fp32' if 'fp32' in argv else 'bf16' if 'bf16' in argv else 'fp64'
+    assert line['config']['precond_storage'] == {'patch_inverses': want,
+                                                 'level_matrices_in_cycle': 'fp64' if want == 'fp64' else 'fp32'}
     for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
         assert key in line['roofline'], key
     for key in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'):
@@ -238,14 +241,14 @@ def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
 
 
 @pytest.mark.parametrize('which', ['ins2d', 'ins3d_dim'])
-@pytest.mark.parametrize('fp32', ['0', '1'])
+@pytest.mark.parametrize('fp32', ['0', '1', '2'])
 def test_partitioned_workloads_execute_on_a_null_device(dry, monkeypatch, which, fp32):
     """Set-up and one time step of the element-partitioned workloads (world size 1: no communicator) through the level
     array handed to the C driver (dist_mg._native_levels / _gmres_native)."""
     import opencmp_b200.ngs as ngs
     from opencmp_b200.dist_workload import DistributedINS, DistributedINSDIM3D
-    monkeypatch.setenv('OCMP_PATCH_FP32', fp32)
-    monkeypatch.setenv('OCMP_SPMV_FP32', fp32)
+    monkeypatch.setenv('OCMP_PATCH_STORAGE', ['fp64', 'fp32', 'bf16'][int(fp32)])
+    monkeypatch.setenv('OCMP_SPMV_FP32', '0' if fp32 == '0' else '1')
     be = DryCudaBackend()
     old = ngs._backend
     ngs.set_backend(be)
@@ -254,11 +257,13 @@ def test_partitioned_workloads_execute_on_a_null_device(dry, monkeypatch, which,
         d.step()
         top, arr = d.mg._native
         assert top.pre_kind == 3 and top.nlevels == len(d.mg.levels) >= 2
-        assert top.inv_fp32 == int(fp32) and arr[top.nlevels - 1].sys.inv_fp32 == int(fp32)
-        assert bool(arr[top.nlevels - 1].sys.vals32) == (fp32 == '1') and not arr[0].sys.vals32
+        assert top.inv_storage == int(fp32) and arr[top.nlevels - 1].sys.inv_storage == int(fp32)
+        assert bool(arr[top.nlevels - 1].sys.vals32) == (fp32 != '0') and not arr[0].sys.vals32
         assert 'ocmp_krylov' in be.lib.calls
         assert ('ocmp_asm_setup_f32' in be.lib.calls) == (fp32 == '1')
-        assert ('ocmp_to_f32' in be.lib.calls) == (fp32 == '1')
+        assert ('ocmp_asm_setup_bf16' in be.lib.calls) == (fp32 == '2')
+        assert ('ocmp_to_f32' in be.lib.calls) == (fp32 != '0')
+        assert d.mg.levels[-1].patches['bs'] % [2, 4, 8][int(fp32)] == 0
     finally:
         ngs.set_backend(old)
 
@@ -284,9 +289,9 @@ def test_single_gpu_multigrid_state_on_a_null_device(dry, monkeypatch, fp32):
         assert be.lib.calls.count(setup) == st.updates + (st.nlevels - 2)
         assert st.kind == 3 and st.nlevels >= 2
         top = st.levels[st.nlevels - 1].sys
-        assert top.inv_fp32 == int(fp32) and bool(top.vals32) == (fp32 == '1') and not st.levels[0].sys.vals32
+        assert top.inv_storage == int(fp32) and bool(top.vals32) == (fp32 == '1') and not st.levels[0].sys.vals32
         sys_ = be._system(w.a.mat, st.fm, st)
-        assert sys_.pre_kind == 3 and sys_.inv_fp32 == int(fp32) and bool(sys_.vals32) == (fp32 == '1')
+        assert sys_.pre_kind == 3 and sys_.inv_storage == int(fp32) and bool(sys_.vals32) == (fp32 == '1')
     finally:
         ngs.set_backend(old)
 
@@ -342,7 +347,7 @@ def test_bench_two_ranks_execute_on_a_null_device(argv):
     s.bind(('127.0.0.1', 0))
     port = s.getsockname()[1]
     s.close()
-    out = mp.Manager().dict()
+    out = mp.get_context('spawn').Manager().dict()          # never fork a multi-threaded pytest process
     mp.spawn(_bench_rank, args=(2, port, argv, out), nprocs=2, join=True)
     line = out['line']
     assert out.get('other', '') == ''                       # only rank 0 prints

@@ -185,12 +185,16 @@ def test_cuda_backend_patch_tables_fp32_stride(ngs, monkeypatch):
     cache = {}
     be.space_data = lambda fes: cache.setdefault(id(fes), {})
     p64 = be._patches(f3, 'vertex')
-    assert p64['bs'] == 90 and not p64['fp32']
+    assert p64['bs'] == 90 and p64['storage'] == 'fp64'
     monkeypatch.setenv('OCMP_PATCH_FP32', '1')
     cache.clear()
     p32 = be._patches(f3, 'vertex')
-    assert p32['fp32'] and p32['bs'] == 92 and p32['bs'] % 4 == 0
+    assert p32['storage'] == 'fp32' and p32['bs'] == 92 and p32['bs'] % 4 == 0
     assert (p32['dofs'][:, 90:] == -1).all() and np.array_equal(p32['dofs'][:, :90], p64['dofs'])
+    monkeypatch.setenv('OCMP_PATCH_STORAGE', 'bf16')
+    cache.clear()
+    p16 = be._patches(f3, 'vertex')
+    assert p16['storage'] == 'bf16' and p16['bs'] == 96 and np.array_equal(p16['dofs'][:, :90], p64['dofs'])
 
 
 def test_coarse_levels_are_reused_until_a_parameter_changes(ngs, monkeypatch):

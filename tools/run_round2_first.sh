@@ -12,7 +12,8 @@ tail -15 $O/pytest_gpu.log
 timeout 300 python bench.py --full-mg-setup --no-cpu > $O/bench_full_setup.json 2> $O/bench_full_setup.err
 timeout 300 python bench.py --no-cpu > $O/bench_default.json 2> $O/bench_default.err
 timeout 300 python bench.py --no-cpu --precond-storage fp32 > $O/bench_fp32.json 2> $O/bench_fp32.err
-for f in full_setup default fp32; do
+timeout 300 python bench.py --no-cpu --precond-storage bf16 > $O/bench_bf16.json 2> $O/bench_bf16.err
+for f in full_setup default fp32 bf16; do
   python - <<PY
 import json
 try:
