@@ -263,15 +263,23 @@ class Pattern:
         self.diag = np.ascontiguousarray(maps[-1], dtype=np.int32)
 
 
-def _unique_and_locate(key_lists, queries):
+# above this many keys the sort / search runs in slices of the key range: keeps every single torch call far below
+# 2^31 elements (the 3-D N = 64 pattern has 2.08e9 keys) and bounds the temporary device memory
+_SLICE_KEYS = 1 << 29
+
+
+def _unique_and_locate(key_lists, queries, device=None, slice_keys=None):
     """Sorted unique int64 keys of ``key_lists`` and the position of every query key in them. One-off set-up work:
     done with torch on the GPU when one is visible (sort / searchsorted of 10^8 keys), with NumPy otherwise."""
-    big = sum(k.size for k in key_lists) > (1 << 22)
-    if big:
+    total = sum(k.size for k in key_lists)
+    slice_keys = _SLICE_KEYS if slice_keys is None else slice_keys
+    if total > (1 << 22) or device is not None:
         try:
             import torch
-            if torch.cuda.is_available():
-                dev = torch.device('cuda', torch.cuda.current_device())
+            if device is not None or torch.cuda.is_available():
+                dev = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+                if total > slice_keys:
+                    return _unique_and_locate_sliced(torch, dev, key_lists, queries, -(-total // slice_keys))
                 ukey = torch.unique(torch.cat([torch.from_numpy(k).to(dev) for k in key_lists]))
                 maps = [torch.searchsorted(ukey, torch.from_numpy(np.ascontiguousarray(q)).to(dev)).to(torch.int32)
                         .cpu().numpy() for q in queries]
@@ -280,6 +288,34 @@ def _unique_and_locate(key_lists, queries):
             pass
     ukey = np.unique(np.concatenate(key_lists))
     return ukey, [np.searchsorted(ukey, q) for q in queries]
+
+
+def _unique_and_locate_sliced(torch, dev, key_lists, queries, nslices):
+    """The same in ``nslices`` slices of the key range [lo, hi): the unique keys of a slice are a contiguous run of the
+    global result, so slices are sorted independently and concatenated; a query is located inside its own slice and
+    offset by the number of unique keys before it. Keys stay on the host between slices."""
+    lo = min(int(k.min()) for k in key_lists if k.size)
+    hi = max(int(k.max()) for k in key_lists if k.size) + 1
+    edges = [lo + (hi - lo) * i // nslices for i in range(nslices + 1)]
+    edges[-1] = hi
+    qs = [np.ascontiguousarray(q) for q in queries]
+    maps = [np.empty(q.shape, dtype=np.int32) for q in qs]
+    parts, base = [], 0
+    for a, b in zip(edges[:-1], edges[1:]):
+        sel = [k[(k >= a) & (k < b)] for k in key_lists]
+        sel = [x for x in sel if x.size]
+        if not sel:
+            continue
+        u = torch.unique(torch.cat([torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in sel]))
+        for q, m in zip(qs, maps):
+            idx = np.nonzero((q >= a) & (q < b))[0]
+            if idx.size:
+                loc = torch.searchsorted(u, torch.from_numpy(q[idx]).to(dev)) + base
+                m[idx] = loc.to(torch.int32).cpu().numpy()
+        parts.append(u.cpu().numpy())
+        base += int(u.numel())
+        del u
+    return np.concatenate(parts), maps
 
 
 # NGSolve-style constructors -----------------------------------------------------------------------------------

@@ -200,3 +200,23 @@ def test_gridfunction_set_projects_boundary_data(oracle_backend):
     assert np.abs(full.vec.NumPy()[mask] - g.vec.NumPy()[mask]).max() < 1e-12
     err = ngs.Integrate((full.components[0] - cf) ** 2, m)
     assert err < 1e-24
+
+
+def test_pattern_keys_sorted_in_slices_equal_the_plain_result():
+    """space._unique_and_locate in slices of the key range (used above 2^29 keys, e.g. the 3-D N = 64 pattern with
+    2.08e9 keys) gives the same unique keys and the same positions as the one-shot NumPy / torch paths."""
+    import torch
+    from opencmp_b200.space import _unique_and_locate
+    rng = np.random.default_rng(5)
+    keys = [rng.integers(0, 5000, 20000).astype(np.int64) * 7 + 3, rng.integers(100, 900, 5000).astype(np.int64) * 7 + 3]
+    queries = keys + [np.unique(keys[0])[::3].copy()]
+    ref_u, ref_m = _unique_and_locate(keys, queries)                       # NumPy path (small, no GPU here)
+    for nslices_keys in (4096, 1000, 25000):
+        u, m = _unique_and_locate(keys, queries, device=torch.device('cpu'), slice_keys=nslices_keys)
+        assert np.array_equal(u, ref_u)
+        for a, b in zip(m, ref_m):
+            assert np.array_equal(a, b)
+        for q, a in zip(queries, m):
+            assert np.array_equal(u[a], q)                                  # every query sits at its position
+    one, mone = _unique_and_locate(keys, queries, device=torch.device('cpu'), slice_keys=1 << 40)   # torch, one shot
+    assert np.array_equal(one, ref_u) and all(np.array_equal(a, b) for a, b in zip(mone, ref_m))
