@@ -263,9 +263,10 @@ class Pattern:
         self.diag = np.ascontiguousarray(maps[-1], dtype=np.int32)
 
 
-# above this many keys the sort / search runs in slices of the key range: keeps every single torch call far below
-# 2^31 elements (the 3-D N = 64 pattern has 2.08e9 keys) and bounds the temporary device memory
-_SLICE_KEYS = 1 << 29
+# above this many keys the sort / search runs in slices of the key range: keeps every single torch call well below
+# 2^31 elements (the 3-D N = 64 pattern has 2.08e9 keys) and bounds the temporary device memory. Everything measured
+# in round 1 (up to the 0.88e9 keys of the 3-D N = 48 pattern) stays on the one-shot path.
+_SLICE_KEYS = 1 << 30
 
 
 def _unique_and_locate(key_lists, queries, device=None, slice_keys=None):

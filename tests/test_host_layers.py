@@ -203,7 +203,7 @@ def test_gridfunction_set_projects_boundary_data(oracle_backend):
 
 
 def test_pattern_keys_sorted_in_slices_equal_the_plain_result():
-    """space._unique_and_locate in slices of the key range (used above 2^29 keys, e.g. the 3-D N = 64 pattern with
+    """space._unique_and_locate in slices of the key range (used above 2^30 keys, e.g. the 3-D N = 64 pattern with
     2.08e9 keys) gives the same unique keys and the same positions as the one-shot NumPy / torch paths."""
     import torch
     from opencmp_b200.space import _unique_and_locate
