@@ -56,7 +56,7 @@ def parse():
     ap.add_argument('--dist-poisson', action='store_true', help='also run the distributed Poisson CG leg')
     ap.add_argument('--dist-n', type=int, default=512, help='cells per direction and rank of the distributed leg')
     a = ap.parse_args()
-    d = {'ins2d': (256, 3, 20), 'ins3d_dim': (32, 2, 8)}[a.workload]
+    d = {'ins2d': (256, 3, 28), 'ins3d_dim': (32, 2, 8)}[a.workload]
     a.N = d[0] if a.N is None else a.N
     a.order = d[1] if a.order is None else a.order
     a.cpu_N = d[2] if a.cpu_N is None else a.cpu_N
