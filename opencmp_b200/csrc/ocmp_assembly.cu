@@ -2,8 +2,8 @@
 //
 //   k_coef      evaluates the coefficient bytecode of one integral at every (item, quadrature point):
 //               geometry (x, n, h, measure), field values from DOF vectors, then the register machine -> D slots.
-//   k_contract  forms the local matrices  A = sum_q B^T (D B)  with physical basis tables staged in shared memory,
-//               accumulators in registers, and scatter-adds them through the element -> nnz map (no colouring).
+//   k_contract  forms the local matrices  A = sum_q B^T (D B)  with physical basis tables, Z = D B rows and the
+//               accumulators in shared memory, and scatter-adds them through the element -> nnz map (no colouring).
 //   k_lin       the same for linear forms (local vectors, scatter through the cell dof lists).
 //
 // Stand in for NGSolve's SymbolicBilinearFormIntegrator / SymbolicLinearFormIntegrator element loops that
