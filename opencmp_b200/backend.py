@@ -526,10 +526,22 @@ class CudaBackend:
         self.launches += 1
 
     def _mask(self, fes_or_n, free):
+        """Device copy (1.0 free / 0.0 constrained) of a FreeDofs mask. The callers hand over a fresh host array on
+        every solve (``fes.FreeDofs()``, reference base_model.py:906), so the upload is cached on the packed bits —
+        compared exactly, a handful of entries."""
         if free is None:
             return None
         arr = np.asarray(free.a if hasattr(free, 'a') else free, dtype=bool)
-        return self._up(arr.astype(np.float64))
+        packed = np.packbits(arr).tobytes()
+        cache = self.__dict__.setdefault('_mask_cache', [])
+        for i, (n, bits, dev) in enumerate(cache):
+            if n == arr.size and bits == packed:
+                cache.append(cache.pop(i))                 # most recently used last
+                return dev
+        dev = self._up(arr.astype(np.float64))
+        cache.append((arr.size, packed, dev))
+        del cache[:-8]
+        return dev
 
     def precond_setup(self, mat, kind, free, form=None, state=None, mask=None):
         pd = self.pattern_data(mat.space)

@@ -355,3 +355,20 @@ def test_bench_two_ranks_execute_on_a_null_device(argv):
     if 'sphere' not in argv:                                 # at N = 4 two ghost layers cover the whole single box
         assert line['problem']['global_dofs'] > line['problem']['dofs'] * 1.2
     assert 'element-partitioned' in line['config']['parallelism']
+
+
+def test_free_dof_masks_are_uploaded_once(dry):
+    be = DryCudaBackend()
+    a = np.array([True, False, True, True, False] * 1000)
+    m1 = be._mask(None, a.copy())
+    m2 = be._mask(None, a.copy())                       # a fresh host array with the same bits: no second upload
+    b = a.copy()
+    b[7] = not b[7]
+    m3 = be._mask(None, b)
+    assert m1 is m2 and m3 is not m1
+    assert np.array_equal(m1.numpy(), a.astype(np.float64)) and np.array_equal(m3.numpy(), b.astype(np.float64))
+    for k in range(12):                                 # the cache stays small and keeps the most recent entries
+        c = a.copy()
+        c[k] = not c[k]
+        be._mask(None, c)
+    assert len(be._mask_cache) == 8 and be._mask(None, c) is be._mask_cache[-1][2]
