@@ -49,6 +49,10 @@ def parse():
                          '(OCMP_MG_REUSE_COARSE=0); default: they are rebuilt only when a Parameter they read (dt, t) '
                          'changes — their operators do not see the Oseen wind — while the finest level (the assembled '
                          'system) is always set up again')
+    ap.add_argument('--lag-smoother', action='store_true',
+                    help='OCMP_MG_LAG=1: keep the finest level\'s patch inverses until a solve needs > 1.25 x + 2 '
+                         'iterations of the first solve after the last fresh set-up (opt-in; default: re-invert on '
+                         'every Preconditioner.Update())')
     ap.add_argument('--precond-storage', default='fp64', choices=['fp64', 'fp32', 'bf16'],
                     help='storage of the multigrid data (patch inverses, level matrices inside the cycle); arithmetic '
                          'and the Krylov method stay FP64. fp32 = OCMP_PATCH_STORAGE=fp32 OCMP_SPMV_FP32=1; bf16 = '
@@ -203,6 +207,8 @@ def main():
         os.environ['OCMP_SPMV_FP32'] = '1'
     if args.full_mg_setup:
         os.environ['OCMP_MG_REUSE_COARSE'] = '0'
+    if args.lag_smoother:
+        os.environ['OCMP_MG_LAG'] = '1'
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -357,6 +363,8 @@ def main():
         'config': dict(workload_config(args, 'gpu'), coarse_levels=(
             'rebuilt on every update' if os.environ.get('OCMP_MG_REUSE_COARSE', '1') == '0' else
             'rebuilt when a Parameter they read changes (constant dt: once); finest level on every update'),
+            finest_level_smoother=('lagged: re-inverted when GMRES iterations grow (OCMP_MG_LAG=1)'
+                                   if os.environ.get('OCMP_MG_LAG', '0') == '1' else 're-inverted on every update'),
             precond_storage={
             'patch_inverses': patch_storage(),
             'level_matrices_in_cycle': 'fp32' if os.environ.get('OCMP_SPMV_FP32', '0') == '1' else 'fp64'}),

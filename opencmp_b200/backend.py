@@ -708,6 +708,8 @@ class CudaBackend:
                                       int(restart), float(damp), work.data_ptr(), wl, C.byref(it), C.byref(res),
                                       self._stream()))
         self.last_iters, self.last_resid = it.value, res.value
+        if hasattr(state, 'note_solve'):
+            state.note_solve(it.value)
         if printrates:
             print('{}: {} iterations, residual {:.3e}'.format(kind, it.value, res.value))
 

@@ -23,8 +23,8 @@ from typing import List, Optional
 import numpy as np
 
 from .dist import DofMap, Partition
-from .multigrid import (clone_space, coarse_state_key, coefficient_fields, mesh_levels, prolongation, restrict_field,
-                        reuse_coarse_enabled)
+from .multigrid import (SmootherLag, clone_space, coarse_state_key, coefficient_fields, mesh_levels, prolongation,
+                        restrict_field, reuse_coarse_enabled)
 
 
 def _allreduce(vals, like):
@@ -114,6 +114,7 @@ class DistributedMultigrid:
         self._coarse_key = None
         self._fresh_coarse = True
         self.coarse_setups = 0
+        self.lag = SmootherLag()
 
     # ---- set-up after every assembly ---------------------------------------------------------------------------
     def update(self):
@@ -136,7 +137,8 @@ class DistributedMultigrid:
                 lv.mat = self.bf.mat
             if l == 0:
                 self.inv0 = be.dense_inverse(lv.mat, lv.free)
-            else:
+            elif l < len(self.levels) - 1 or \
+                    self.lag.need_refresh(lv.patches.get('inv') is not None, forced=not reuse):
                 be.patch_setup(lv.mat, lv.patches, lv.free)
         if not reuse:
             self._coarse_key = key
@@ -276,7 +278,13 @@ class DistributedMultigrid:
         """Left-preconditioned restarted GMRES with CGS2 on the free DOFs; x (consistent) holds the initial guess and
         the Dirichlet values. Same recurrence as ocmp_krylov kind 1."""
         if self._native is not None:
-            return self._gmres_native(b, x, tol, maxit, restart)
+            it, res = self._gmres_native(b, x, tol, maxit, restart)
+        else:
+            it, res = self._gmres_python(b, x, tol, maxit, restart)
+        self.lag.note_solve(it)
+        return it, res
+
+    def _gmres_python(self, b, x, tol, maxit, restart):
         be = self.be
         top = len(self.levels) - 1
         lv = self.levels[top]

@@ -151,6 +151,39 @@ def coarse_state_key(programs) -> tuple:
     return tuple(tuple(prog.param_values(integ).tolist()) for prog in programs for integ in prog.integrals)
 
 
+class SmootherLag:
+    """Opt-in (``OCMP_MG_LAG=1``) lagging of the FINEST level's patch inverses: they are a preconditioner, and between
+    Picard iterations / time steps the operator only changes through the Oseen wind, so the inverses of an earlier
+    assembly usually smooth just as well (2-D INS workload on the CPU restatement: 18 / 15 iterations per step with
+    inverses never refreshed over four steps, exactly as with fresh ones). The GMRES iteration counts steer it: a
+    solve that needs more than ``1.25 x + 2`` iterations of the first solve after the last fresh set-up triggers a
+    fresh set-up at the next ``Update()``. Off by default: ``Preconditioner.Update()`` then re-inverts every time, like
+    the library it stands in for."""
+
+    def __init__(self):
+        import os
+        self.enabled = os.environ.get('OCMP_MG_LAG', '0') == '1'
+        self.base = None            # iterations of the first solve after the last fresh set-up
+        self.last = None            # iterations of the most recent solve
+        self._fresh = False
+        self.fresh_setups = 0
+
+    def need_refresh(self, have_inverses: bool, forced: bool = False) -> bool:
+        stale = self.base is not None and self.last is not None and self.last > 1.25 * self.base + 2
+        fresh = forced or not self.enabled or not have_inverses or stale
+        if fresh:
+            self._fresh = True
+            self.base = self.last = None
+            self.fresh_setups += 1
+        return fresh
+
+    def note_solve(self, iterations: int) -> None:
+        if self._fresh:
+            self.base = int(iterations)
+            self._fresh = False
+        self.last = int(iterations)
+
+
 def reuse_coarse_enabled() -> bool:
     import os
     return os.environ.get('OCMP_MG_REUSE_COARSE', '1') != '0'
@@ -214,6 +247,7 @@ class MultigridState:
         self._coarse_key = None
         self.coarse_setups = 0                 # how often the coarse levels were (re)built — diagnostics / tests
         self.updates = 0
+        self.lag = SmootherLag()
 
     def update(self, fine_mat):
         be = self.be
@@ -242,7 +276,10 @@ class MultigridState:
                 sys_.inv_rowptr, sys_.inv_colidx = self.inv_rowptr.data_ptr(), self.inv_colidx.data_ptr()
                 sys_.inv_vals = self.inv_vals.data_ptr()
             else:
-                fresh = not (reuse and l < self.nlevels - 1 and self.smoothers[l] is not None)
+                if l < self.nlevels - 1:
+                    fresh = not (reuse and self.smoothers[l] is not None)
+                else:                       # finest level: always, unless the opt-in lag policy says otherwise
+                    fresh = self.lag.need_refresh(self.smoothers[l] is not None, forced=not reuse)
                 if fresh:
                     self.smoothers[l] = be.precond_setup(mat, 'asm', self.spaces[l].FreeDofs(), mask=self.masks[l])
                 sm = self.smoothers[l]
@@ -259,3 +296,7 @@ class MultigridState:
             lv.work = self.work[l].data_ptr()
             lv.nu, lv.omega = self.nu, self.omega
         return self
+
+    def note_solve(self, iterations: int) -> None:
+        """Called by ``CudaBackend.krylov`` after every solve preconditioned with this state."""
+        self.lag.note_solve(iterations)

@@ -198,7 +198,7 @@ class _FakeStream:
 
 @pytest.mark.parametrize('argv', [['--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu'],
                                   ['--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu', '--precond-storage', 'fp32',
-                                   '--full-mg-setup'],
+                                   '--full-mg-setup', '--lag-smoother'],
                                   ['--workload', 'ins3d_dim', '--N', '4', '--steps', '1', '--warmup', '1', '--no-cpu'],
                                   ['--workload', 'ins3d_dim', '--N', '4', '--steps', '1', '--warmup', '1', '--no-cpu',
                                    '--precond-storage', 'bf16']])
@@ -220,6 +220,7 @@ def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
     for k, v in (('OCMP_PATCH_STORAGE', 'fp64'), ('OCMP_SPMV_FP32', '0')):   # bench sets them; restored afterwards
         monkeypatch.setenv(k, v)
     monkeypatch.setenv('OCMP_MG_REUSE_COARSE', '1')
+    monkeypatch.setenv('OCMP_MG_LAG', '0')
     for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'):
         monkeypatch.delenv(k, raising=False)
     try:
@@ -372,3 +373,23 @@ def test_free_dof_masks_are_uploaded_once(dry):
         c[k] = not c[k]
         be._mask(None, c)
     assert len(be._mask_cache) == 8 and be._mask(None, c) is be._mask_cache[-1][2]
+
+
+def test_lagged_smoother_on_a_null_device(dry, monkeypatch):
+    """OCMP_MG_LAG=1 on one GPU: the krylov call reports its iteration count to the multigrid state, and the finest
+    level is inverted once while the (null) solves keep reporting the same count."""
+    import opencmp_b200.ngs as ngs
+    from opencmp_b200.workloads import INSTaylorGreen
+    monkeypatch.setenv('OCMP_MG_LAG', '1')
+    be = DryCudaBackend()
+    old = ngs._backend
+    ngs.set_backend(be)
+    try:
+        w = INSTaylorGreen(8)
+        w.step()
+        w.step()
+        st = w.pre.state
+        assert st.updates >= 2 and st.lag.enabled and st.lag.fresh_setups == 1 and st.lag.last == 1
+        assert be.lib.calls.count('ocmp_asm_setup') == 1
+    finally:
+        ngs.set_backend(old)

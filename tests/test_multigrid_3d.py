@@ -220,3 +220,50 @@ def test_coarse_levels_are_reused_until_a_parameter_changes(ngs, monkeypatch):
     assert np.abs(u_reuse - u_full).max() <= 1e-13 * np.abs(u_full).max()
     _, its_dt, n_dt = run(True, change_dt=True)
     assert n_dt == 2
+
+
+def test_smoother_lag_policy_unit():
+    """SmootherLag: off -> always fresh; on -> fresh once, again only after a solve needed > 1.25 x + 2 iterations of
+    the first solve after the last fresh set-up, or when forced (coarse levels rebuilt)."""
+    import os
+    from opencmp_b200.multigrid import SmootherLag
+    os.environ.pop('OCMP_MG_LAG', None)
+    off = SmootherLag()
+    assert all(off.need_refresh(True) for _ in range(3)) and off.fresh_setups == 3
+    os.environ['OCMP_MG_LAG'] = '1'
+    try:
+        lag = SmootherLag()
+        assert lag.need_refresh(False)                # nothing stored yet
+        lag.note_solve(18)
+        assert not lag.need_refresh(True)
+        lag.note_solve(15)
+        assert not lag.need_refresh(True)
+        lag.note_solve(24)                            # 24 <= 1.25 * 18 + 2 = 24.5
+        assert not lag.need_refresh(True)
+        lag.note_solve(25)
+        assert lag.need_refresh(True) and lag.fresh_setups == 2
+        lag.note_solve(19)
+        assert not lag.need_refresh(True) and lag.need_refresh(True, forced=True)
+    finally:
+        os.environ.pop('OCMP_MG_LAG', None)
+
+
+def test_lagged_fine_level_smoother_keeps_the_steps(ngs, monkeypatch):
+    """OCMP_MG_LAG=1 on the 2-D INS workload: the finest level's patch inverses are computed once over two time steps,
+    iteration counts and solution stay those of the always-fresh smoother."""
+    from opencmp_b200.dist_workload import DistributedINS
+
+    def run(lag):
+        monkeypatch.setenv('OCMP_MG_LAG', lag)
+        d = DistributedINS(8, 1, 0)
+        its = []
+        for _ in range(2):
+            d.w.linear_iterations = []
+            d.step()
+            its += d.w.linear_iterations
+        return d.w.gfu.vec.NumPy().copy(), its, d.mg.lag.fresh_setups
+    u0, its0, n0 = run('0')
+    u1, its1, n1 = run('1')
+    assert n0 == len(its0) and n1 == 1
+    assert max(abs(a - b) for a, b in zip(its1, its0)) <= 1
+    assert np.abs(u1 - u0).max() < 1e-6 * np.abs(u0).max()          # two GMRES solves to 1e-10, different smoothers

@@ -13,7 +13,8 @@ timeout 300 python bench.py --full-mg-setup --no-cpu > $O/bench_full_setup.json 
 timeout 300 python bench.py --no-cpu > $O/bench_default.json 2> $O/bench_default.err
 timeout 300 python bench.py --no-cpu --precond-storage fp32 > $O/bench_fp32.json 2> $O/bench_fp32.err
 timeout 300 python bench.py --no-cpu --precond-storage bf16 > $O/bench_bf16.json 2> $O/bench_bf16.err
-for f in full_setup default fp32 bf16; do
+timeout 300 python bench.py --no-cpu --precond-storage bf16 --lag-smoother > $O/bench_all.json 2> $O/bench_all.err
+for f in full_setup default fp32 bf16 all; do
   python - <<PY
 import json
 try:
