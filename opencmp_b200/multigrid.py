@@ -285,7 +285,8 @@ class MultigridState:
                 sm = self.smoothers[l]
                 sys_ = be._system(mat, self.masks[l], sm)
                 if self.spmv_fp32:
-                    if fresh or self.vals32[l] is None:
+                    # the finest-level matrix changed with this assembly even when its smoother is lagged
+                    if fresh or l == self.nlevels - 1 or self.vals32[l] is None:
                         self.vals32[l] = be.fp32_copy(mat.values, self.vals32[l])
                     sys_.vals32 = self.vals32[l].data_ptr()
                 P = self.transfers[l - 1]
