@@ -138,3 +138,18 @@ def test_golden_program_plans_respect_kernel_limits():
         finally:
             ngs.set_backend(old)
         assert be.seen, name
+
+
+def test_edge_case_plans_respect_kernel_limits():
+    """The edge cases of tests/test_edge_cases.py (one-cell meshes, order-0 DG, empty regions) through the same probe."""
+    import opencmp_b200.ngs as ngs
+    import test_edge_cases as e
+    for name in e.EDGE_CASES:
+        be = PlanProbe()
+        old = ngs._backend
+        ngs.set_backend(be)
+        try:
+            e.assemble_edge_case(ngs, name)
+        finally:
+            ngs.set_backend(old)
+        assert be.seen and max(be.seen) > 0, name
