@@ -267,3 +267,30 @@ def test_lagged_fine_level_smoother_keeps_the_steps(ngs, monkeypatch):
     assert n0 == len(its0) and n1 == 1
     assert max(abs(a - b) for a, b in zip(its1, its0)) <= 1
     assert np.abs(u1 - u0).max() < 1e-6 * np.abs(u0).max()          # two GMRES solves to 1e-10, different smoothers
+
+
+@pytest.mark.parametrize('storage', ['fp32', 'bf16'])
+def test_reduced_precision_storage_of_patch_inverses_keeps_iteration_counts(ngs, monkeypatch, storage):
+    """The claim behind OCMP_PATCH_STORAGE: patch inverses computed in FP64 and *stored* in FP32 / bfloat16
+    precondition the FP64 GMRES just as well. Emulated on the CPU restatement by rounding the oracle's inverses to the
+    storage type: same iteration counts (bf16: within 2) and the same solution on the 2-D INS workload."""
+    import torch
+    from oracle.backend import OracleBackend
+    from opencmp_b200.dist_workload import DistributedINS
+
+    def run():
+        d = DistributedINS(8, 1, 0)
+        d.w.linear_iterations = []
+        d.step()
+        return d.w.gfu.vec.NumPy().copy(), list(d.w.linear_iterations)
+    u64, its64 = run()
+    plain = OracleBackend.patch_setup
+    dtype = torch.float32 if storage == 'fp32' else torch.bfloat16
+
+    def rounded(self, mat, pt, fm):
+        plain(self, mat, pt, fm)
+        pt['inv'] = [torch.from_numpy(a).to(dtype).to(torch.float64).numpy() for a in pt['inv']]
+    monkeypatch.setattr(OracleBackend, 'patch_setup', rounded)
+    u, its = run()
+    assert len(its) == len(its64) and max(abs(a - b) for a, b in zip(its, its64)) <= (0 if storage == 'fp32' else 2)
+    assert np.abs(u - u64).max() < 1e-6 * np.abs(u64).max()
