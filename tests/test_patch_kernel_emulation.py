@@ -3,7 +3,7 @@
 follows the same column / row / chunk assignment, unrolled main loop, remainder loop and partial-sum layout as the CUDA
 source, phase by phase between the barriers. The result must equal ``z[dofs] += A_p^-1 r[dofs]`` computed directly
 from the (transposed-stored, rounded) inverses. This pins the thread mapping; the arithmetic itself is checked on the
-GPU (tests/test_zz_gpu_late_additions.py)."""
+GPU (tests/test_zzz_gpu_unmeasured_kernels.py)."""
 import numpy as np
 import pytest
 import torch
