@@ -209,3 +209,16 @@ def test_partitioned_multigrid_ins_dim_3d_step_matches_global_solve(bricks):
     mp.spawn(_mg3d_worker, args=(world, port, bricks, out), nprocs=world, join=True)
     assert len(out) == world
     assert out[0][1] == out[1][1] and max(out[0][1]) < 80
+
+
+def test_partitioned_multigrid_with_lagged_smoother(monkeypatch):
+    """The same 2-rank INS step with OCMP_MG_LAG=1: the lag decision is taken from the (global) GMRES iteration count,
+    so both ranks skip the same set-ups; the step still equals the single-process direct solve."""
+    monkeypatch.setenv('OCMP_MG_LAG', '1')
+    world = 2
+    port = _free_port()
+    mgr = mp.get_context('spawn').Manager()
+    out = mgr.dict()
+    mp.spawn(_mg_worker, args=(world, port, 0, out), nprocs=world, join=True)
+    assert len(out) == world
+    assert out[0][1] == out[1][1]
