@@ -547,7 +547,15 @@ solvers = _Solvers()
 
 # ---- reductions --------------------------------------------------------------------------------------------------------
 def Integrate(cf, mesh, VOL_or_BND=None, order: int = 5, definedon=None, **kw):
-    """``ngs.Integrate`` with its default order-5 rule (reference helpers/error.py:66-77)."""
+    """``ngs.Integrate`` with its default order-5 rule (reference helpers/error.py:66-77). The first
+    argument may also be an integrand ``cf * dx(...)`` (reference helpers/error.py:146:
+    ``Integrate((sol - sol.Other())**2 * dx(element_boundary=True), mesh)``)."""
+    from .symbolic import SumOfIntegrals
+    if isinstance(cf, SumOfIntegrals):
+        for c, _ in cf.items:
+            if c.arr.size != 1:
+                raise ValueError('Integrate of an integrand needs a scalar coefficient function')
+        return get_backend().integrate(lower_form(_scalar_space(mesh), cf, 0, intorder=order))
     cf = CoefficientFunction._lift(cf)
     fes = _scalar_space(mesh)
     if cf.arr.size == 1:

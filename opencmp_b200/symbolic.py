@@ -141,6 +141,49 @@ def substitute_fields(c: Coef, mapping: dict, memo: Optional[dict] = None) -> Co
     return out
 
 
+def _map_leaves(c: Coef, fn, memo: dict) -> Coef:
+    """Rebuild the DAG with every leaf replaced by ``fn(leaf)``."""
+    if id(c) in memo:
+        return memo[id(c)]
+    if not c.args:
+        out = fn(c)
+    else:
+        new = tuple(_map_leaves(a, fn, memo) for a in c.args)
+        if all(n is o for n, o in zip(new, c.args)):
+            out = c
+        elif c.op == 'ifpos':
+            out = Coef.ifpos(*new)
+        elif len(new) == 1:
+            out = Coef.unary(c.op, new[0])
+        else:
+            out = Coef.binary(c.op, new[0], new[1])
+    memo[id(c)] = out
+    return out
+
+
+def _seen_from_the_other_cell(c: Coef) -> Coef:
+    """The same expression evaluated from the neighbouring cell of an interior facet: sides of all fields exchanged,
+    outward normal reversed."""
+    def fn(leaf):
+        if leaf.op == 'field':
+            gf, blk, row, side = leaf.val
+            return Coef('field', (), (gf, blk, row, 1 - side))
+        if leaf.op == 'normal':
+            return Coef.unary('neg', leaf)
+        return leaf
+    return _map_leaves(c, fn, {})
+
+
+def _without_neighbour(c: Coef) -> Coef:
+    """On a boundary facet there is no neighbour: ``.Other()`` refers to the cell itself (a jump vanishes)."""
+    def fn(leaf):
+        if leaf.op == 'field' and leaf.val[3] == 1:
+            gf, blk, row, _ = leaf.val
+            return Coef('field', (), (gf, blk, row, 0))
+        return leaf
+    return _map_leaves(c, fn, {})
+
+
 _S0 = S()
 
 
@@ -678,7 +721,19 @@ def lower_form(fes, integrals: SumOfIntegrals, arity: int, intorder: Optional[in
         else:
             kind, rkind, nreg = 'bfacet', 'bnd', len(mesh.bnd_names)
         if m.element_boundary:
-            raise NotImplementedError('dx(element_boundary=True) is not supported')
+            # ``Integrate(f * dx(element_boundary=True), mesh)`` (reference helpers/error.py:146, the facet-jump metric
+            # of examples/INS): the boundary of every cell. An interior facet is visited from both of its cells —
+            # f as written plus f seen from the other cell — a boundary facet once, with no neighbour behind it.
+            # (NGSolve's behaviour of .Other() on boundary facets here is not pinned by any reference test; this choice
+            # makes a continuous field jump-free, as the reference's docstring expects.)
+            if arity != 0 or m.kind != 'vol' or m.definedon is not None:
+                raise NotImplementedError('dx(element_boundary=True) is supported for Integrate over the whole mesh')
+            for k, c in s.t.items():
+                for key, term in ((('ifacet', None, m.bonus), Coef.binary('add', c, _seen_from_the_other_cell(c))),
+                                  (('bfacet', None, m.bonus), _without_neighbour(c))):
+                    g = groups.setdefault(key, {})
+                    g[k] = Coef.binary('add', g[k], term) if k in g else term
+            continue
         region_ids = list(m.definedon.ids) if (m.definedon is not None and rkind is not None) else None
         pw = coef_leaves(list(s.t.values()), 'piecewise')
         if pw and rkind is not None:

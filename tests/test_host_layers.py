@@ -220,3 +220,33 @@ def test_pattern_keys_sorted_in_slices_equal_the_plain_result():
             assert np.array_equal(u[a], q)                                  # every query sits at its position
     one, mone = _unique_and_locate(keys, queries, device=torch.device('cpu'), slice_keys=1 << 40)   # torch, one shot
     assert np.array_equal(one, ref_u) and all(np.array_equal(a, b) for a, b in zip(mone, ref_m))
+
+
+def test_integrate_over_element_boundaries(oracle_backend):
+    """``Integrate(f * dx(element_boundary=True), mesh)`` — the facet-jump metric of the reference
+    (helpers/error.py:131-148, switched on in examples/INS/ref_sol_dir/ref_sol_config): every interior facet is seen
+    from both cells, every boundary facet once; a continuous field has no jumps; the outward normal turns with the
+    cell (divergence theorem cell by cell)."""
+    ngs = oracle_backend
+    from opencmp_b200.mesh import structured_2d
+    m = ngs.Mesh(structured_2d([3, 2]))
+    one = ngs.CoefficientFunction(1.0)
+    skel = ngs.Integrate(one * ngs.dx(skeleton=True), m)
+    assert abs(ngs.Integrate(one * ngs.dx(element_boundary=True), m) - (2 * skel + 4.0)) < 1e-12
+    g = ngs.GridFunction(ngs.H1(m, order=2))
+    g.Set(ngs.x * ngs.y + ngs.sin(ngs.x))
+    assert ngs.Integrate((g - g.Other()) ** 2 * ngs.dx(element_boundary=True), m) < 1e-24
+    L = ngs.L2(m, order=0)
+    q = ngs.GridFunction(L)
+    q.vec.data = ngs.BaseVector(ngs.get_backend().from_numpy(np.arange(L.ndof, dtype=float)))
+    jumps = ngs.Integrate((q - q.Other()) ** 2 * ngs.dx(element_boundary=True), m)
+    assert abs(jumps - 2 * ngs.Integrate((q - q.Other()) ** 2 * ngs.dx(skeleton=True), m)) < 1e-10 and jumps > 1.0
+    w = ngs.GridFunction(ngs.VectorH1(m, order=1))
+    w.Set(ngs.CoefficientFunction((ngs.x, ngs.y)))
+    n = ngs.specialcf.normal(2)
+    assert abs(ngs.Integrate((w * n) * ngs.dx(element_boundary=True), m) - 2.0) < 1e-12
+    u, v = ngs.H1(m, order=1).TnT()
+    with pytest.raises(NotImplementedError):
+        a = ngs.BilinearForm(ngs.H1(m, order=1))
+        a += u * v * ngs.dx(element_boundary=True)
+        a.Assemble()

@@ -72,6 +72,35 @@ def test_reference_poisson_example_h_convergence(ref_tree):
     assert len(rates) == 5 and all(abs(x - 4.0) < 0.1 for x in rates[1:]), r.stdout[-1500:]
 
 
+def test_reference_ins_example_with_all_error_metrics(ref_tree, tmp_path):
+    """examples/INS (BASELINE configs[2]) as shipped — Taylor-Green, HDiv-DG order 3, Oseen, adaptive two step — with its
+    ref_sol_config, which switches on every metric of helpers/error.py incl. ``facet_jumps``
+    (``Integrate(... * dx(element_boundary=True))``, helpers/error.py:146). Only the end time is shortened."""
+    d = tmp_path / 'INS'
+    shutil.copytree(REF + '/examples/INS', d)
+    cfg = (d / 'config').read_text().replace('time_range = 0.0, 0.1', 'time_range = 0.0, 0.02')
+    assert 'time_range = 0.0, 0.02' in cfg
+    (d / 'config').write_text(cfg)
+    script = textwrap.dedent('''
+        import sys
+        sys.path.insert(0, {root!r}); sys.path.insert(0, {tree!r})
+        import conftest
+        from opencmp.run import run
+        run('config')
+    ''').format(root=ROOT, tree=str(ref_tree))
+    r = subprocess.run([sys.executable, '-c', script], cwd=d, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    vals = {}
+    for ln in r.stdout.splitlines():
+        if ':' in ln and any(k in ln for k in ('norm in', 'divergence of', 'jump of')):
+            key, val = ln.rsplit(':', 1)
+            vals[key.strip()] = float(val)
+    assert len(vals) == 9, r.stdout[-1500:]
+    assert vals['l2 norm in u'] < 1e-3 and vals['divergence of u'] < 1e-9          # HDiv: pointwise divergence free
+    assert 0.0 < vals['magnitude of jump of u facets'] < 1e-3                       # tangential jumps only, small
+    assert 1e-3 < vals['magnitude of jump of p facets'] < 1.0                        # L2 pressure is discontinuous
+
+
 def test_reference_vtu_post_processing_through_the_boundary(ref_tree):
     """`save_type = .vtu`: the reference's own post-processing (post_processing/output_conversions.py — a
     multiprocessing.Pool of workers loading every .sol file and calling VTKOutput(...).Do(), then writing the .pvd
