@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(256) k_asm_setup(int npatch, int bs, const int
             else {
                 int lo = __ldg(rowptr + di), hi = __ldg(rowptr + di + 1) - 1;
                 while (lo <= hi) {
-                    const int mid = (lo + hi) >> 1;
+                    const int mid = lo + ((hi - lo) >> 1);     // lo + hi overflows int32 once nnz > 2^30
                     const int c = __ldg(colidx + mid);
                     if (c == dj) { v = vals[mid]; break; }
                     if (c < dj) lo = mid + 1; else hi = mid - 1;

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k_patch_positions(int npatch, int bs, int
             if (di >= 0 && dj >= 0) {
                 int lo = __ldg(rowptr + di), hi = __ldg(rowptr + di + 1) - 1;
                 while (lo <= hi) {
-                    const int mid = (lo + hi) >> 1;
+                    const int mid = lo + ((hi - lo) >> 1);     // lo + hi overflows int32 once nnz > 2^30
                     const int c = __ldg(colidx + mid);
                     if (c == dj) { out = mid; break; }
                     if (c < dj) lo = mid + 1; else hi = mid - 1;

@@ -153,3 +153,26 @@ def test_edge_case_plans_respect_kernel_limits():
         finally:
             ngs.set_backend(old)
         assert be.seen and max(be.seen) > 0, name
+
+
+def test_binary_searches_do_not_overflow_int32():
+    """CSR positions reach 1.42e9 at the 3-D N = 64 workload (> 2^30): a midpoint written as (lo + hi) >> 1 wraps to a
+    negative index there (the illegal address of round 1's N = 64 run, in k_patch_positions). Every bisection in csrc/
+    has to form its midpoint as lo + ((hi - lo) >> 1); the 32-bit arithmetic is replayed here on the offending range."""
+    import glob
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'opencmp_b200', 'csrc')
+    srcs = glob.glob(os.path.join(root, '*.cu')) + glob.glob(os.path.join(root, '*.cuh'))
+    assert srcs
+    nmid = 0
+    for f in srcs:
+        code = '\n'.join(ln.split('//')[0] for ln in open(f).read().splitlines())      # comments stripped
+        assert not re.search(r'\(\s*lo\s*\+\s*hi\s*\)\s*(>>\s*1|/\s*2)', code), f
+        nmid += len(re.findall(r'lo \+ \(\(hi - lo\) >> 1\)', code))
+    assert nmid >= 2
+    lo, hi = np.int32(1_400_000_000), np.int32(1_420_000_000)
+    with np.errstate(over='ignore'):
+        assert (lo + hi) >> np.int32(1) < 0                       # what the old form did
+        mid = lo + ((hi - lo) >> np.int32(1))
+    assert lo <= mid <= hi
