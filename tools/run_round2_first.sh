@@ -30,6 +30,10 @@ done
 timeout 400 python bench.py --workload ins3d_dim --N 48 --steps 2 --warmup 1 --no-cpu > $O/bench3d_48.json 2> $O/bench3d_48.err
 timeout 400 python bench.py --workload ins3d_dim --N 48 --steps 2 --warmup 1 --no-cpu --precond-storage fp32 > $O/bench3d_48_fp32.json 2> $O/bench3d_48_fp32.err
 tail -c 600 $O/bench3d_48.json; echo; tail -c 600 $O/bench3d_48_fp32.json; echo
+# 3b. N = 64 (6.8 M DOFs, nnz 1.42e9): failed in round 1 with an illegal address — int32 midpoint overflow in the
+#     patch-position bisection, fixed since; bounded by its own timeout
+timeout 600 python bench.py --workload ins3d_dim --N 64 --steps 2 --warmup 1 --no-cpu > $O/bench3d_64.json 2> $O/bench3d_64.err
+tail -c 600 $O/bench3d_64.json; echo; tail -3 $O/bench3d_64.err
 # 4. launch list + one full capture of the FP32 smoother kernel (a number printed under ncu is never a bench value)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_fp32.csv \
     python bench.py --N 128 --steps 1 --warmup 1 --no-cpu --precond-storage fp32 > $O/ncu_launches.log 2>&1
