@@ -26,7 +26,7 @@ import numpy as np
 from . import symbolic as sym
 from .symbolic import (CoefficientFunction, Parameter, ProxyFunction, InnerProduct, OuterProduct, Norm, IfPos, Grad,
                        grad, div, sqrt, sin, cos, tan, exp, log, atan, floor, ceil, tanh, erf, x, y, z, specialcf, dx,
-                       ds, Conj, DifferentialSymbol, SumOfIntegrals, CF, lower_form, field_arrays)
+                       ds, Conj, DifferentialSymbol, SumOfIntegrals, CF, lower_form, field_arrays, form_action)
 from .mesh import Mesh as _Mesh, Region, load_mesh
 from . import space as _space
 from .space import FESpace as _FESpace
@@ -426,16 +426,34 @@ class _Form:
 class BilinearForm(_Form):
     arity = 2
 
-    def __init__(self, fes, symmetric=False, check_unused=True, condense=False, **flags):
+    def __init__(self, fes, symmetric=False, check_unused=True, condense=False, nonassemble=False, **flags):
         super().__init__(fes, **flags)
-        self.mat = None
+        self.nonassemble = bool(nonassemble)
+        self._action = None                   # (integrals they were lowered from, GridFunction holding x, program)
+        self.mat = MatrixFreeOperator(self) if self.nonassemble else None
 
     def Assemble(self):
+        if self.nonassemble:                  # NGSolve: nothing is stored; a.mat applies the form
+            return self
         be = get_backend()
         if self.mat is None:
             self.mat = Matrix(self.space)
         be.assemble_matrix(self.program(), self.mat)
         return self
+
+    def Apply(self, x, y):
+        """``y = A x`` without the matrix (NGSolve ``BilinearForm.Apply``): the form is lowered once more with the
+        trial function replaced by a work GridFunction holding ``x`` (``symbolic.form_action``) and assembled as a
+        linear form — quadrature kernels only, no CSR values read. Current Parameter / coefficient-field values are
+        used, like ``Assemble()`` would."""
+        if self._action is None or self._action[0] is not self.integrals:
+            gf = GridFunction(self.space, name='matrix_free_x')
+            prog = lower_form(self.space, form_action(self.space, self.integrals, gf), 1)
+            self._action = (self.integrals, gf, prog)
+        _, gf, prog = self._action
+        be = get_backend()
+        be.copy_into(gf.vec.a, x.a)
+        be.assemble_vector(prog, y.a)
 
 
 class LinearForm(_Form):
@@ -484,6 +502,33 @@ class Matrix:
     def CSR(self):
         be = get_backend()
         return be.to_numpy(self.values), self.pattern.colidx, self.pattern.rowptr
+
+
+class MatrixFreeOperator:
+    """``BilinearForm(fes, nonassemble=True).mat``: applies the form instead of a stored matrix."""
+
+    def __init__(self, bf):
+        self.bf = bf
+        self.space = bf.space
+        self.height = self.width = bf.space.ndof
+
+    def __mul__(self, v):
+        if isinstance(v, BaseVector):
+            out = BaseVector(get_backend().zeros(self.height))
+            self.bf.Apply(v, out)
+            return out
+        return NotImplemented
+
+    def Mult(self, x, y):
+        self.bf.Apply(x, y)
+
+    def CreateColVector(self):
+        return BaseVector(get_backend().zeros(self.height))
+
+    CreateRowVector = CreateColVector
+
+    def Inverse(self, freedofs=None, inverse: str = ''):
+        raise RuntimeError('a nonassemble BilinearForm stores no matrix to factorise')
 
 
 class _Inverse:

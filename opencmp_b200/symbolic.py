@@ -690,6 +690,43 @@ class SumOfIntegrals:
     __rmul__ = __mul__
 
 
+def form_action(fes, integrals: SumOfIntegrals, gf_root) -> SumOfIntegrals:
+    """Matrix-free operator application: the integrals of a *bilinear* form with the trial function replaced by the
+    DOF vector of ``gf_root`` (a GridFunction on ``fes``) — a linear form whose assembled vector is ``A x``. Stands in
+    for NGSolve's ``BilinearForm(fes, nonassemble=True).mat * x`` / ``a.Apply(x, y)``: the trial row (row, side) of
+    every entry becomes the 'field' leaf of the same physical row, so ``k_coef`` evaluates  D_k(x) * trialrow_k(x_h)
+    at the quadrature points and ``k_lin`` contracts with the test rows; no matrix is stored. Neighbour-side trial
+    rows only exist on interior facets (elsewhere ``.Other()`` of a proxy vanishes, as in ``lower_form``)."""
+    ro = list(fes.row_offsets)
+
+    def block_of(row: int) -> int:
+        b = 0
+        while b + 1 < len(ro) and ro[b + 1] <= row:
+            b += 1
+        return b
+
+    items = []
+    for cf, m in integrals.items:
+        if cf.arr.size != 1:
+            raise ValueError('integrand must be scalar, got dims {}'.format(cf.dims))
+        s: S = cf.arr.reshape(())[()]
+        ifacet = m.kind == 'vol' and m.skeleton
+        terms: Dict[Tuple[Key, Key], Coef] = {}
+        for (t, u), c in s.t.items():
+            if t is None or u is None:
+                raise ValueError('bilinear form integrand lacks a trial or test function')
+            if u[1] and not ifacet:
+                continue
+            b = block_of(u[0])
+            c2 = Coef.binary('mul', c, Coef('field', (), (gf_root, b, u[0] - ro[b], u[1])))
+            k = (t, None)
+            terms[k] = Coef.binary('add', terms[k], c2) if k in terms else c2
+        arr = np.empty((), dtype=object)
+        arr[()] = S(terms)
+        items.append((CoefficientFunction(_arr=arr), m))
+    return SumOfIntegrals(items)
+
+
 # ---- lowering ------------------------------------------------------------------------------------------------------
 def lower_form(fes, integrals: SumOfIntegrals, arity: int, intorder: Optional[int] = None,
                drop_fields: bool = False, field_map: Optional[dict] = None) -> FormProgram:

@@ -239,6 +239,7 @@ def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
         assert key in line['roofline'], key
     for key in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'):
         assert key in line['e2e'], key
+    assert 'error' not in line['matrix_free_apply'] and 'ms_per_apply' in line['matrix_free_apply']
 
 
 @pytest.mark.parametrize('which', ['ins2d', 'ins3d_dim'])

@@ -176,3 +176,24 @@ def test_binary_searches_do_not_overflow_int32():
         assert (lo + hi) >> np.int32(1) < 0                       # what the old form did
         mid = lo + ((hi - lo) >> np.int32(1))
     assert lo <= mid <= hi
+
+
+def test_matrix_free_action_plans_respect_kernel_limits():
+    """``BilinearForm.Apply`` turns every trial row (both facet sides) into a field slot of k_coef: the slot count and
+    the register budget of the bytecode stay within MAX_FSLOTS / OCMP_MAX_REGS for every matrix-free case, and k_lin's
+    entry scan sees no contraction plan (arity 1)."""
+    import opencmp_b200.ngs as ngs
+    from test_matrix_free import CASES as MF, matrix_free_vs_csr
+    for name in MF:
+        be = PlanProbe()
+        old = ngs._backend
+        ngs.set_backend(be)
+        try:
+            n0 = None
+            c = MF[name]()
+            c['a'].Assemble()
+            n0 = len(be.seen)
+            matrix_free_vs_csr(c)
+        finally:
+            ngs.set_backend(old)
+        assert len(be.seen) > n0, name
