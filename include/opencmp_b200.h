@@ -160,7 +160,14 @@ typedef struct ocmp_system {
     int inv_storage;         /* type of inv_blocks: 0 double, 1 float (ocmp_asm_setup_f32), 2 bfloat16 (.._bf16) */
     const float* vals32;     /* optional FP32 copy of vals (ocmp_to_f32): used for the operator applications inside
                                 the multigrid cycle only — the Krylov method around it always applies `vals` */
+    const void* apply_fn;    /* optional matrix-free operator (an ocmp_apply_fn, see below): when set, the Krylov method
+                                applies it instead of the CSR product — NGSolve's BilinearForm(nonassemble=True).mat
+                                handed to solvers.CG / GMRes; rowptr / colidx / vals may then be NULL unless the
+                                preconditioner reads them. NULL = stored CSR operator */
+    void* apply_ctx;         /* first argument of apply_fn */
 } ocmp_system;
+/* y = A x on device vectors of length nrows, enqueued on `stream`; returns 0 on success */
+typedef int (*ocmp_apply_fn)(void* ctx, const double* x, double* y, void* stream);
 
 /* One multigrid level: operator + smoother (sys), transfer from the next coarser level, work space.
  * Stands in for ngs.Preconditioner(a, 'multigrid') (reference opencmp/models/base_model.py:365-383). */

@@ -49,7 +49,11 @@ class System(C.Structure):
                 ('bs', C.c_int), ('patch_dofs', C.c_void_p), ('inv_blocks', C.c_void_p), ('patch_weight', C.c_void_p),
                 ('nlevels', C.c_int), ('levels', C.c_void_p), ('inv_rowptr', C.c_void_p), ('inv_colidx', C.c_void_p),
                 ('inv_vals', C.c_void_p), ('owned', C.c_void_p), ('halo_fwd', C.c_int), ('halo_sum', C.c_int),
-                ('inv_storage', C.c_int), ('vals32', C.c_void_p)]
+                ('inv_storage', C.c_int), ('vals32', C.c_void_p), ('apply_fn', C.c_void_p), ('apply_ctx', C.c_void_p)]
+
+
+# ocmp_apply_fn (include/opencmp_b200.h): y = A x of a matrix-free operator, called back by ocmp_krylov
+APPLY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 
 
 class MGLevel(C.Structure):
@@ -664,10 +668,11 @@ class CudaBackend:
         return out
 
     def _system(self, mat, fm, pre) -> System:
-        pd = self.pattern_data(mat.space)
         s = System()
         s.nrows = mat.height
-        s.rowptr, s.colidx, s.vals = pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(), mat.values.data_ptr()
+        if not getattr(mat, 'matrix_free', False):    # a matrix-free operator has no CSR arrays (krylov sets apply_fn)
+            pd = self.pattern_data(mat.space)
+            s.rowptr, s.colidx, s.vals = pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(), mat.values.data_ptr()
         s.freemask = _ptr(fm)
         s.pre_kind = 0
         if pre is not None:
@@ -704,7 +709,36 @@ class CudaBackend:
         wl = self.lib.ocmp_krylov_work_len(mat.height, kid, restart)
         work = self.torch.empty(wl, dtype=self.torch.float64, device=self.device)
         it, res = C.c_int(0), C.c_double(0.0)
-        self._ck(self.lib.ocmp_krylov(C.byref(sys_), kid, b.data_ptr(), x.data_ptr(), float(tol), int(maxit),
+        keep = None
+        if getattr(mat, 'matrix_free', False):
+            # BilinearForm(nonassemble=True).mat as the Krylov operator: ocmp_krylov calls back with device pointers
+            # into its work array / x / b; the form's action runs on them (k_coef + k_lin on the same stream)
+            n, spans, errors = mat.height, (work, x, b), []
+
+            def view(ptr):
+                for tns in spans:
+                    off = ptr - tns.data_ptr()
+                    if 0 <= off and off + 8 * n <= 8 * tns.numel() and off % 8 == 0:
+                        return tns[off // 8: off // 8 + n]
+                raise RuntimeError('matrix-free callback: pointer outside the Krylov vectors')
+
+            def callback(_ctx, xp, yp, _stream):
+                try:
+                    mat.bf.apply_arrays(view(xp), view(yp))
+                    return 0
+                except Exception as exc:                # an exception must not unwind through the C frames
+                    errors.append(exc)
+                    return 1
+            keep = APPLY_FN(callback)
+            sys_.apply_fn = C.cast(keep, C.c_void_p).value
+            rc = self.lib.ocmp_krylov(C.byref(sys_), kid, b.data_ptr(), x.data_ptr(), float(tol), int(maxit),
+                                      int(restart), float(damp), work.data_ptr(), wl, C.byref(it), C.byref(res),
+                                      self._stream())
+            if errors:
+                raise errors[0]
+            self._ck(rc)
+        else:
+            self._ck(self.lib.ocmp_krylov(C.byref(sys_), kid, b.data_ptr(), x.data_ptr(), float(tol), int(maxit),
                                       int(restart), float(damp), work.data_ptr(), wl, C.byref(it), C.byref(res),
                                       self._stream()))
         self.last_iters, self.last_resid = it.value, res.value

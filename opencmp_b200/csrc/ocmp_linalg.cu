@@ -575,10 +575,15 @@ struct Ctx {
     long long n;
     double* dscal;      // device scratch scalars (>= 64)
     double hscal[64];
+    mutable int failed = 0;     // a matrix-free operator callback reported an error
 
     // y = A x; element-partitioned: followed by the ghost refresh, so y is consistent like x
     void A(const double* x, double* y) const {
-        ocmp_spmv(s->nrows, s->rowptr, s->colidx, s->vals, x, y, st);
+        if (s->apply_fn) {      // matrix-free operator: the form's action (quadrature kernels), no CSR values read
+            if (((ocmp_apply_fn)s->apply_fn)(s->apply_ctx, x, y, (void*)st) != 0 && !failed) failed = 1;
+        } else {
+            ocmp_spmv(s->nrows, s->rowptr, s->colidx, s->vals, x, y, st);
+        }
         if (s->halo_fwd) ocmp_halo_run(s->halo_fwd - 1, y, 0, st);
     }
     // one application of the smoother / local preconditioner of system `sy`: z = S r (r masked, result masked)
@@ -835,5 +840,6 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
     cudaStreamSynchronize(c.st);
     if (iters) *iters = it;
     if (resid) *resid = res;
+    if (c.failed) return ocmp_fail(-5, "matrix-free operator callback failed inside ocmp_krylov");
     return ocmp_check("ocmp_krylov");
 }

@@ -446,14 +446,18 @@ class BilinearForm(_Form):
         trial function replaced by a work GridFunction holding ``x`` (``symbolic.form_action``) and assembled as a
         linear form — quadrature kernels only, no CSR values read. Current Parameter / coefficient-field values are
         used, like ``Assemble()`` would."""
+        self.apply_arrays(x.a, y.a)
+
+    def apply_arrays(self, xa, ya):
+        """``Apply`` on backend arrays (what the Krylov drivers hand to a matrix-free operator)."""
         if self._action is None or self._action[0] is not self.integrals:
             gf = GridFunction(self.space, name='matrix_free_x')
             prog = lower_form(self.space, form_action(self.space, self.integrals, gf), 1)
             self._action = (self.integrals, gf, prog)
         _, gf, prog = self._action
         be = get_backend()
-        be.copy_into(gf.vec.a, x.a)
-        be.assemble_vector(prog, y.a)
+        be.copy_into(gf.vec.a, xa)
+        be.assemble_vector(prog, ya)
 
 
 class LinearForm(_Form):
@@ -505,7 +509,10 @@ class Matrix:
 
 
 class MatrixFreeOperator:
-    """``BilinearForm(fes, nonassemble=True).mat``: applies the form instead of a stored matrix."""
+    """``BilinearForm(fes, nonassemble=True).mat``: applies the form instead of a stored matrix. Handed to
+    ``solvers.CG / GMRes / PreconditionedRichardson`` it is the Krylov operator (``ocmp_system.apply_fn``); the
+    preconditioner, if any, is built from an assembled form as usual."""
+    matrix_free = True
 
     def __init__(self, bf):
         self.bf = bf

@@ -90,7 +90,7 @@ class OracleBackend:
         raise NotImplementedError('oracle preconditioner {}'.format(kind))
 
     def krylov(self, kind, mat, b, x, pre, freedofs, tol, maxit, initialize, printrates, damp=1.0, restart=None):
-        A = self._csr(mat)
+        A = _FormAction(mat) if getattr(mat, 'matrix_free', False) else self._csr(mat)
         n = A.shape[0]
         if pre is not None and pre.state is None:
             pre.Update()
@@ -119,6 +119,19 @@ class OracleBackend:
                     break
         else:
             raise ValueError(kind)
+
+
+class _FormAction:
+    """``A @ v`` of a ``BilinearForm(nonassemble=True).mat``: the form's action, assembled as a linear form."""
+
+    def __init__(self, op):
+        self.op = op
+        self.shape = (op.height, op.width)
+
+    def __matmul__(self, v):
+        out = np.zeros(self.shape[0])
+        self.op.bf.apply_arrays(np.ascontiguousarray(v, dtype=np.float64), out)
+        return out
 
 
 def cg(A, b, x, P, tol, maxit, initialize):

@@ -36,6 +36,13 @@ class _NullFn:
         if self.name == 'ocmp_krylov':
             iters, resid = args[10], args[11]
             iters._obj.value, resid._obj.value = 1, 0.0
+            system = args[0]._obj
+            if system.apply_fn:
+                # matrix-free Krylov operator: call back once the way the C driver does — y = A x with x the solution
+                # vector and y the first work vector (device pointers; host addresses here)
+                rc = backend_mod.APPLY_FN(system.apply_fn)(None, args[3], args[8], None)
+                assert rc == 0, 'matrix-free operator callback failed on the null device'
+                self.log.append('apply_fn')
         if self.name == 'ocmp_krylov_work_len':
             return self.real(*args)                      # pure host arithmetic
         if self.name == 'ocmp_last_error':
@@ -394,3 +401,21 @@ def test_lagged_smoother_on_a_null_device(dry, monkeypatch):
         assert be.lib.calls.count('ocmp_asm_setup') == 1
     finally:
         ngs.set_backend(old)
+
+
+def test_matrix_free_krylov_callback_on_a_null_device(dry):
+    """``ocmp_system.apply_fn``: the ctypes callback CudaBackend.krylov installs for a ``nonassemble`` operator resolves
+    the raw pointers the C driver hands it to views of the Krylov vectors and runs the form's action on them."""
+    import opencmp_b200.ngs as ngs
+    from test_matrix_free import krylov_matrix_free_vs_csr
+    be = DryCudaBackend()
+    old = ngs._backend
+    ngs.set_backend(be)
+    try:
+        krylov_matrix_free_vs_csr()
+    finally:
+        ngs.set_backend(old)
+    calls = be.lib.calls
+    assert calls.count('apply_fn') == 2 and calls.count('ocmp_krylov') == 4
+    k = calls.index('apply_fn')
+    assert 'ocmp_contract_vector' in calls[:k] and calls[k + 1:].count('ocmp_krylov') >= 1

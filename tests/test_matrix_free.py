@@ -88,3 +88,38 @@ def test_action_rejects_integrands_without_trial_function(oracle_backend):
     x = bad.mat.CreateColVector()
     with pytest.raises(ValueError):
         bad.mat * x
+
+
+def krylov_matrix_free_vs_csr():
+    """CG and GMRES solutions of a Poisson problem with the stored and with the matrix-free operator (Jacobi from the
+    assembled form): (cg_csr, cg_free, gmres_csr, gmres_free)."""
+    c = cases.poisson(cases.square_mesh(), 2, False)
+    a, L, fes = c['a'], c['L'], c['fes']
+    a.Assemble()
+    L.Assemble()
+    twin = ngs.BilinearForm(fes, nonassemble=True)
+    twin += a.integrals
+    pre = ngs.Preconditioner(a, 'local')
+    pre.Update()
+    free = fes.FreeDofs()
+    be = ngs.get_backend()
+    r = np.array(be.to_numpy(L.vec.a), dtype=np.float64)
+    r[~np.asarray(free, bool)] = 0.0
+    rhs = ngs.BaseVector(be.from_numpy(r))
+    out = []
+    for op in (a.mat, twin.mat):
+        out.append(ngs.solvers.CG(mat=op, rhs=rhs, pre=pre, tol=1e-12, maxsteps=500).NumPy().copy())
+    for op in (a.mat, twin.mat):
+        out.append(ngs.solvers.GMRes(A=op, b=rhs, pre=pre, freedofs=free, tol=1e-12, maxsteps=300).NumPy().copy())
+    return out[0], out[1], out[2], out[3]
+
+
+def test_krylov_on_the_matrix_free_operator(oracle_backend):
+    """``solvers.CG(mat=BilinearForm(nonassemble=True).mat, pre=Preconditioner(assembled form))`` and ``GMRes`` with it:
+    the Krylov operator is the form's action (``ocmp_system.apply_fn`` on the GPU), the preconditioner is built from a
+    stored matrix as usual. Same iterates as with the assembled operator."""
+    u_csr, u_free, g_csr, g_free = krylov_matrix_free_vs_csr()
+    assert np.abs(u_csr).max() > 0
+    assert np.abs(u_free - u_csr).max() <= 1e-10 * np.abs(u_csr).max()
+    assert np.abs(g_free - g_csr).max() <= 1e-10 * np.abs(g_csr).max()
+    assert np.abs(g_csr - u_csr).max() <= 1e-8 * np.abs(u_csr).max()
