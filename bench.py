@@ -297,31 +297,6 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     eu, ep = w.errors()
-    # ---- matrix-free application of the same operator (BilinearForm.Apply: k_coef + k_lin, no CSR values read) next
-    # to the CSR SpMV — outside the step's timed region, its own CUDA events; never allowed to cost the bench line
-    matfree = None
-    try:
-        if world == 1:
-            xv = w.gfu.vec.CreateVector()
-            xv.data = w.gfu.vec
-            yv = w.gfu.vec.CreateVector()
-            for _ in range(2):
-                w.a.Apply(xv, yv)
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            g0.record()
-            for _ in range(5):
-                w.a.Apply(xv, yv)
-            g1.record()
-            torch.cuda.synchronize()
-            ycsr = w.a.mat * xv
-            den = float(ycsr.Norm())
-            matfree = {'ms_per_apply': g0.elapsed_time(g1) / 5,
-                       'rel_diff_vs_csr_spmv': float((yv - ycsr).Norm()) / den if den > 0 else None,
-                       'note': 'BilinearForm.Apply(x, y): trial rows become field slots of k_coef, k_lin contracts with '
-                               'the test rows; FP64-compute bound (quadrature), reads no matrix'}
-    except Exception as exc:                                    # pragma: no cover
-        matfree = {'error': repr(exc)}
     # ---- element-partitioned leg (N > 1): halo-exchange SpMV + all-reduced Jacobi-CG on a distributed Poisson problem
     multi = None
     if world > 1 and args.dist_poisson:
@@ -410,8 +385,6 @@ def main():
     }
     if multi is not None:
         line['multi_gpu'] = multi
-    if matfree is not None:
-        line['matrix_free_apply'] = matfree
     if not args.no_cpu and world == 1:
         try:
             per, cne, cnd, _ = cpu_step_seconds(args.cpu_N, args.order, workload=args.workload)
@@ -421,6 +394,34 @@ def main():
                           '{:.2f} s; scaled linearly by cell count x{:.1f}'.format(args.cpu_N, cne, cnd, per, ne / cne)}
         except Exception as exc:                                    # pragma: no cover
             line['cpu_baseline'] = {'value': None, 'unit': 's', 'cores': 1, 'kind': 'port', 'sample': repr(exc)}
+    # ---- matrix-free application of the same operator (BilinearForm.Apply: k_coef + k_lin, no CSR values read) next
+    # to the CSR SpMV — outside the step's timed region, its own CUDA events. Runs LAST, when every other number is
+    # already on the host: its GPU cases have not run on a B200 yet, and it must never cost the bench line
+    matfree = None
+    try:
+        if world == 1:
+            xv = w.gfu.vec.CreateVector()
+            xv.data = w.gfu.vec
+            yv = w.gfu.vec.CreateVector()
+            for _ in range(2):
+                w.a.Apply(xv, yv)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            g0.record()
+            for _ in range(5):
+                w.a.Apply(xv, yv)
+            g1.record()
+            torch.cuda.synchronize()
+            ycsr = w.a.mat * xv
+            den = float(ycsr.Norm())
+            matfree = {'ms_per_apply': g0.elapsed_time(g1) / 5,
+                       'rel_diff_vs_csr_spmv': float((yv - ycsr).Norm()) / den if den > 0 else None,
+                       'note': 'BilinearForm.Apply(x, y): trial rows become field slots of k_coef, k_lin contracts with '
+                               'the test rows; FP64-compute bound (quadrature), reads no matrix'}
+    except Exception as exc:                                    # pragma: no cover
+        matfree = {'error': repr(exc)}
+    if matfree is not None:
+        line['matrix_free_apply'] = matfree
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
