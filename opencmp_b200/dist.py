@@ -235,14 +235,18 @@ def _layers_of(part: Partition) -> int:
 
 
 class DistributedOperator:
-    """Assembled local matrix + halo exchange = the global operator restricted to this rank's owned rows."""
+    """Assembled local matrix (or the matrix-free action of the local form) + halo exchange = the global operator
+    restricted to this rank's owned rows."""
 
     def __init__(self, be, mat, dofmap: DofMap):
         self.be, self.mat, self.map = be, mat, dofmap
         self.mask = be.from_numpy(dofmap.owned.astype(np.float64))
 
     def mult(self, x, y) -> None:
-        self.be.spmv(self.mat, x, y)
+        if getattr(self.mat, 'matrix_free', False):     # BilinearForm(nonassemble=True).mat of the local mesh: the
+            self.mat.bf.apply_arrays(x, y)              # form's action on owned + ghost cells, owned rows complete
+        else:
+            self.be.spmv(self.mat, x, y)
         self.map.exchange(y)
 
     def dot(self, x, y) -> float:

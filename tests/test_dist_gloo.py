@@ -70,6 +70,12 @@ def _worker(rank, world, port, family, order, dg, out):
         yl = np.zeros(lfes.ndof)
         op.mult(xl, yl)
         assert np.abs(yl - yg[dm.l2g]).max() < 1e-12 * np.abs(yg).max()       # ghosts refreshed too
+        # the same product matrix-free: the action of the local form (BilinearForm(nonassemble=True)) + halo exchange
+        twin = ngs.BilinearForm(lfes, nonassemble=True)
+        twin += la.integrals
+        yf = np.zeros(lfes.ndof)
+        DistributedOperator(be, twin.mat, dm).mult(xl, yf)
+        assert np.abs(yf - yg[dm.l2g]).max() < 1e-12 * np.abs(yg).max()
         # right-hand side: owned entries complete
         assert np.abs(lL.vec.a[dm.owned] - gL.vec.a[dm.l2g[dm.owned]]).max() < 1e-12
         # dot product
