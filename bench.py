@@ -191,7 +191,20 @@ def run_reference(args):
     # weak scaling: one N x N x 2 strip (2-D) / one N^3 brick (3-D) per GPU
     cells_full = (args.N ** 3 if args.workload == 'ins3d_dim' else 2 * args.N * args.N) * \
         (1 if args.workload == 'ins3d_dim' and args.layout == 'sphere' else max(1, args.gpus))
-    procs = max(1, min(args.cpu_procs if args.cpu_procs else (os.cpu_count() or 1), 64))
+    procs = args.cpu_procs
+    if not procs:
+        # one replica per core this process may run on, at most 32, and no more than a quarter of the free memory holds
+        # (a replica of the N = 28 sample peaks at ~0.9 GB)
+        try:
+            procs = len(os.sched_getaffinity(0))
+        except AttributeError:
+            procs = os.cpu_count() or 1
+        try:
+            import psutil
+            procs = min(procs, int(psutil.virtual_memory().available // (4 << 30)))
+        except Exception:
+            pass
+    procs = max(1, min(procs, 32))
     cores, slow = 1, None
     try:
         if procs == 1:
