@@ -21,7 +21,8 @@ try:
     l = json.loads(open('$O/bench_$f.json').read().strip().splitlines()[-1])
     r = l['roofline']
     print('$f', 's/step %.4f' % l['value'], 'e2e %.4f' % l['e2e']['value'], 'its/step', l['problem']['gmres_its_per_step'],
-          'patch_apply %.0f GB/s (%.2f)' % (r['achieved'], r['frac']), 'spmv %.0f' % l['spmv_gbs'], l['kernel_time_share'])
+          'patch_apply %.0f GB/s (%.2f)' % (r['achieved'], r['frac']), 'spmv %.0f' % l['spmv_gbs'], l['kernel_time_share'],
+          'matrix-free apply', l.get('matrix_free_apply'), 'csr spmv ms', l['roofline_spmv']['avg_launch_ms'])
 except Exception as e:
     print('$f', 'FAILED', e)
 PY
