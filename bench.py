@@ -110,26 +110,32 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def _cpu_workload(N, order, workload):
+    """The bench workload on the CPU restatement with the reference's default linear solver (direct,
+    base_model.py:918-922); the oracle backend must be the active one."""
+    from opencmp_b200.workloads import INSTaylorGreen, INSSphereDIM3D
+    if workload != 'ins3d_dim':
+        return INSTaylorGreen(N, order=order, linear_solver='direct', preconditioner=None)
+    w = INSSphereDIM3D(N, order=order, preconditioner=None, nu=1.0)
+
+    def direct():
+        inv = w.a.mat.Inverse(w.fes.FreeDofs())
+        r = w.L.vec.CreateVector()
+        r.data = w.L.vec - w.a.mat * w.gfu.vec
+        w.gfu.vec.data += inv * r
+        w.linear_iterations.append(0)
+    w.linear_solve = direct
+    return w
+
+
 def cpu_step_seconds(N, order, steps=1, workload='ins2d'):
     """Oracle (CPU restatement, NumPy/SciPy; NOT NGSolve) timed on one Picard-iterated time step."""
     import opencmp_b200.ngs as ngs
     from oracle.backend import OracleBackend
-    from opencmp_b200.workloads import INSTaylorGreen, INSSphereDIM3D
     old = ngs._backend
     ngs.set_backend(OracleBackend())
     try:
-        if workload == 'ins3d_dim':
-            w = INSSphereDIM3D(N, order=order, preconditioner=None, nu=1.0)
-
-            def direct():                       # the reference's default linear_solver = direct (base_model.py:918-922)
-                inv = w.a.mat.Inverse(w.fes.FreeDofs())
-                r = w.L.vec.CreateVector()
-                r.data = w.L.vec - w.a.mat * w.gfu.vec
-                w.gfu.vec.data += inv * r
-                w.linear_iterations.append(0)
-            w.linear_solve = direct
-        else:
-            w = INSTaylorGreen(N, order=order, linear_solver='direct', preconditioner=None)
+        w = _cpu_workload(N, order, workload)
         w.step()                          # warm-up (lowering, tabulation caches)
         t0 = time.perf_counter()
         for _ in range(steps):
@@ -147,20 +153,8 @@ def _cpu_replica(job):
         os.environ[k] = '1'                      # one core per replica; set before NumPy / SciPy load their BLAS
     import opencmp_b200.ngs as ngs
     from oracle.backend import OracleBackend
-    from opencmp_b200.workloads import INSTaylorGreen, INSSphereDIM3D
     ngs.set_backend(OracleBackend())
-    if workload == 'ins3d_dim':
-        w = INSSphereDIM3D(N, order=order, preconditioner=None, nu=1.0)
-
-        def direct():
-            inv = w.a.mat.Inverse(w.fes.FreeDofs())
-            r = w.L.vec.CreateVector()
-            r.data = w.L.vec - w.a.mat * w.gfu.vec
-            w.gfu.vec.data += inv * r
-            w.linear_iterations.append(0)
-        w.linear_solve = direct
-    else:
-        w = INSTaylorGreen(N, order=order, linear_solver='direct', preconditioner=None)
+    w = _cpu_workload(N, order, workload)
     w.step()
     out = []
     for _ in range(steps):
