@@ -3,7 +3,7 @@
 replaced by the DOF vector (``symbolic.form_action``) and run it through the linear-form kernels. Checked here on the
 CPU restatement against the assembled CSR matrix times the same vector, over CG, DG (interior facets with ``.Other()``),
 HDiv, Oseen (wind field + ``IfPos`` / ``Norm`` coefficients), phi-weighted DIM and 3-D forms; the GPU cases are in
-``tests/test_zz_gpu_late_additions.py`` and run dry in ``tests/test_gpu_paths_dry.py``."""
+``tests/test_zzzz_gpu_matrix_free.py`` and run dry in ``tests/test_gpu_paths_dry.py``."""
 import numpy as np
 import pytest
 
