@@ -194,6 +194,21 @@ long long ocmp_krylov_work_len(int nrows, int kind, int restart);
  * (reference base_model.py:925-943 passes printrates=self.verbose). */
 int ocmp_krylov_history(double* out_host, int cap);
 
+/* ---- sparse direct solve: stands in for `a.mat.Inverse(freedofs=..., inverse="umfpack"|"pardiso")` applied to a
+ *      residual, the reference's default linear_solver = direct (reference opencmp/models/base_model.py:908-922).
+ * The free-free block is permuted (perm[i] = position of dof i in a bandwidth-reducing order, -1 = constrained; built
+ * once per pattern by the host) and held as a LAPACK-style band array `ab` of ocmp_band_len(n, kl, ku) doubles
+ * (column j: rows j-kl-ku .. j+kl, leading dimension 2 kl + ku + 1). ocmp_band_factor = dgbtrf (partial pivoting,
+ * one persistent cooperative kernel), info_dev[0] = 1-based first zero pivot or 0, info_dev[1] = super-diagonals of U;
+ * ocmp_band_solve = dgbtrs on one right-hand side in place. gather / scatter move between dof order and band order. */
+long long ocmp_band_len(int n, int kl, int ku);
+int ocmp_band_fill(int nrows, const int* rowptr, const int* colidx, const double* vals, const int* perm, int n,
+                   int kl, int ku, double* ab, void* stream);
+int ocmp_band_factor(int n, int kl, int ku, double* ab, int* ipiv, int* info_dev, void* stream);
+int ocmp_band_solve(int n, int kl, int ku, int ubw, const double* ab, const int* ipiv, double* b, void* stream);
+int ocmp_band_gather(int nrows, const int* perm, const double* r, double* b, void* stream);
+int ocmp_band_scatter(int nrows, const int* perm, const double* x, double* out, int accumulate, void* stream);
+
 /* ---- instrumentation: per-category device time from CUDA events recorded around every launch on its own stream.
  * categories: 0 spmv, 1 asm_apply, 2 coefficient eval, 3 matrix contraction, 4 vector contraction, 5 multi-dot,
  * 6 multi-axpy, 7 other vector kernels, 8 preconditioner setup, 9 SpMVs inside the multigrid cycle, 10 halo exchange */

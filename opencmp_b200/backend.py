@@ -97,6 +97,13 @@ def load_library() -> C.CDLL:
     lib.ocmp_halo_plan.argtypes = [C.c_int, P, P, P, P, P, P, P]
     lib.ocmp_halo_run.argtypes = [C.c_int, P, C.c_int, P]
     lib.ocmp_allreduce_sum.argtypes = [P, C.c_int, P]
+    lib.ocmp_band_len.restype = C.c_longlong
+    lib.ocmp_band_len.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.ocmp_band_fill.argtypes = [C.c_int, P, P, P, P, C.c_int, C.c_int, C.c_int, P, P]
+    lib.ocmp_band_factor.argtypes = [C.c_int, C.c_int, C.c_int, P, P, P, P]
+    lib.ocmp_band_solve.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, P]
+    lib.ocmp_band_gather.argtypes = [C.c_int, P, P, P, P]
+    lib.ocmp_band_scatter.argtypes = [C.c_int, P, P, P, C.c_int, P]
     lib.ocmp_profile_enable.argtypes = [C.c_int]
     lib.ocmp_profile_enable.restype = None
     lib.ocmp_profile_reset.restype = None
@@ -124,7 +131,9 @@ EXPORTED = ['ocmp_mdot', 'ocmp_maxpy', 'ocmp_krylov_history', 'ocmp_comm_unique_
             'ocmp_patch_positions', 'ocmp_profile_bytes', 'ocmp_profile_enable', 'ocmp_profile_reset', 'ocmp_profile_read', 'ocmp_launch_count','ocmp_eval_coefficients', 'ocmp_contract_matrix', 'ocmp_contract_vector', 'ocmp_sum', 'ocmp_spmv',
             'ocmp_dot', 'ocmp_axpby', 'ocmp_masked_assign', 'ocmp_jacobi_setup', 'ocmp_asm_setup', 'ocmp_asm_apply',
             'ocmp_asm_setup_f32', 'ocmp_asm_apply_f32', 'ocmp_asm_setup_bf16', 'ocmp_asm_apply_bf16', 'ocmp_to_f32',
-            'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version']
+            'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version',
+            'ocmp_band_len', 'ocmp_band_fill', 'ocmp_band_factor', 'ocmp_band_solve', 'ocmp_band_gather',
+            'ocmp_band_scatter']
 
 
 # storage type of the smoother's patch inverses (ocmp_system.inv_storage): arithmetic is FP64 in every case
@@ -753,20 +762,61 @@ class CudaBackend:
         n = self.lib.ocmp_krylov_history(buf, cap)
         return [buf[i] for i in range(min(n, cap))]
 
-    def solve_free(self, mat, r, out, freedofs):
-        """Stand-in for ``mat.Inverse(freedofs) * r``: GMRES + cell-patch additive Schwarz driven to 1e-13."""
-        free = np.ones(mat.height, bool) if freedofs is None else freedofs
-        state = self.precond_setup(mat, 'asm', free)
+    def factorize(self, mat, freedofs):
+        """``a.mat.Inverse(freedofs)`` (reference base_model.py:908-916): band LU with partial pivoting on the device
+        (direct.BandLU). Systems whose band does not fit the budget get the Krylov stand-in, which checks the TRUE
+        residual and raises when it cannot reach direct-solver quality."""
+        from .direct import BandLU, DirectSolveTooLarge
+        try:
+            return BandLU(self, mat, freedofs)
+        except DirectSolveTooLarge as exc:
+            import warnings
+            warnings.warn('opencmp_b200: {} — using GMRES + additive Schwarz with true-residual refinement '
+                          'instead'.format(exc))
+            return _KrylovInverse(self, mat, freedofs)
 
+    def solve_free(self, mat, r, out, freedofs):
+        """``mat.Inverse(freedofs) * r`` in one call."""
+        self.factorize(mat, freedofs).solve(r, out)
+
+
+class _KrylovInverse:
+    """Stand-in for a factorisation that does not fit: GMRES(100) + vertex-patch additive Schwarz, restarted on the
+    true free-dof residual until it is at round-off level; raises instead of returning an inexact answer."""
+
+    def __init__(self, be, mat, freedofs):
+        self.be, self.mat = be, mat
+        self.free = np.ones(mat.height, bool) if freedofs is None else freedofs
+        self.Update()
+
+    def Update(self):
         class _P:
             pass
-        p = _P()
-        p.state = state
+        self.p = _P()
+        self.p.state = self.be.precond_setup(self.mat, 'asm', self.free)
+
+    def solve(self, r, out, target: float = 1e-13, accept: float = 1e-10):
+        be = self.be
+        fm = self.p.state.fm
         out.zero_()
-        # two passes: the second restarts from the first answer with a fresh residual (iterative refinement), which
-        # brings the result to the round-off level a sparse direct solver with refinement reaches
-        for _ in range(2):
-            self.krylov('gmres', mat, r, out, p, free, 1e-13, 4000, False, False, restart=100)
+        res = be.zeros(self.mat.height)
+        rnorm = float((r * fm).norm()) if fm is not None else float(r.norm())
+        if rnorm == 0.0:
+            return
+        rel, best = 1.0, 1.0
+        for _ in range(8):
+            be.krylov('gmres', self.mat, r, out, self.p, self.free, max(1e-3 * target / rel, 1e-14), 4000, False,
+                      False, restart=100)
+            be.spmv(self.mat, out, res)
+            res.mul_(-1.0).add_(r)
+            rel = float((res * fm).norm() if fm is not None else res.norm()) / rnorm
+            if rel <= target or rel > 0.5 * best:
+                break
+            best = rel
+        if not rel <= accept:
+            raise RuntimeError('opencmp_b200: the Krylov stand-in for mat.Inverse stalled at a true relative residual '
+                               'of {:.2e} (needs {:.0e}); raise OCMP_DIRECT_MAX_GB to factorise instead'
+                               .format(rel, accept))
 
 
 # ---- primitives used by the element-partitioned multigrid driver (dist_mg.py) -----------------------------------

@@ -539,15 +539,28 @@ class MatrixFreeOperator:
 
 
 class _Inverse:
-    """``a.mat.Inverse(freedofs, inverse=...)`` — applied with ``inv * r`` (reference base_model.py:918-922)."""
+    """``a.mat.Inverse(freedofs, inverse=...)`` — factorised at construction like NGSolve's sparse inverse, applied
+    with ``inv * r`` (reference base_model.py:908-922); ``Update()`` re-factorises after a re-assembly."""
 
     def __init__(self, mat, freedofs, kind):
         self.mat, self.freedofs, self.kind = mat, freedofs, kind
+        be = get_backend()
+        self.fact = be.factorize(mat, freedofs) if hasattr(be, 'factorize') else None
+
+    def Update(self):
+        if self.fact is not None:
+            self.fact.Update()
+
+    def Mult(self, r, out):
+        if self.fact is not None:
+            self.fact.solve(r.a, out.a)
+        else:
+            get_backend().solve_free(self.mat, r.a, out.a, self.freedofs)
 
     def __mul__(self, r):
-        out = get_backend().zeros(self.mat.height)
-        get_backend().solve_free(self.mat, r.a, out, self.freedofs)
-        return BaseVector(out)
+        out = BaseVector(get_backend().zeros(self.mat.height))
+        self.Mult(r, out)
+        return out
 
 
 class Preconditioner:

@@ -78,9 +78,9 @@ def _compare_ins(sol, vec):
     assert np.abs(sol[:nu] - vec[:nu]).max() < 1e-9 * np.abs(vec[:nu]).max()
     dp = sol[nu:] - vec[nu:]
     const = dp[0::6]                     # first L2 mode of every cell is the constant
-    assert np.abs(const - const.mean()).max() < 1e-7 * np.abs(vec[nu:]).max()
+    assert np.abs(const - const.mean()).max() < 1e-9 * np.abs(vec[nu:]).max()
     rest = np.delete(dp, np.arange(0, dp.size, 6))
-    assert np.abs(rest).max() < 1e-7 * np.abs(vec[nu:]).max()
+    assert np.abs(rest).max() < 1e-9 * np.abs(vec[nu:]).max()
 
 
 def test_oracle_ins_workload_reproduces_reference_ins_model(oracle_backend):

@@ -1,0 +1,96 @@
+"""GPU: the band LU behind ``a.mat.Inverse(freedofs)`` (csrc/ocmp_direct.cu, opencmp_b200/direct.py) against the
+oracle's sparse LU (SuperLU + two refinement steps) on the same assembled systems — the reference's default
+``linear_solver = direct`` (reference opencmp/models/base_model.py:908-922). Tolerance: 1e-9 relative (north star)."""
+import numpy as np
+import pytest
+
+import cases
+from test_gpu_parity import _with, _rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _direct(build, set_bc=True):
+    def run():
+        c = build()
+        g = c['gfu']
+        if 'exact' in c:
+            g.components[0].Set(c['exact'], definedon=c['mesh'].Boundaries(c['dnames']))
+        elif not c.get('noset'):
+            g.components[0].Set(c['uex'], definedon=c['mesh'].Boundaries(c['walls']))
+        c['a'].Assemble()
+        c['L'].Assemble()
+        return cases.direct_solve(c), c
+    return run
+
+
+@pytest.mark.parametrize('name,build', [
+    ('poisson_p2_n24', lambda: cases.poisson(cases.square_mesh(24), 2, False)),
+    ('poisson_dg_p3', lambda: cases.poisson(cases.square_mesh(8), 3, True)),
+    ('stokes_th_p3', lambda: cases.stokes(cases.channel_mesh(12), 3, False)),
+    ('stokes_hdiv_dg_p3', lambda: cases.stokes(cases.channel_mesh(10), 3, True)),
+    ('ins_hdiv_dg_p3_oseen', lambda: cases.stokes(cases.channel_mesh(8), 3, True,
+                                                   wind=lambda n: cases.random_wind(n), dt_val=0.01, mass=True)),
+    ('stokes_3d_hex_q2q1', lambda: cases.stokes_3d('hex', 2, n=3)),
+])
+def test_band_lu_matches_sparse_lu(name, build):
+    ref, _ = _with('oracle', _direct(build))
+    got, _ = _with('cuda', _direct(build))
+    assert _rel(got, ref) < 1e-9
+
+
+def test_band_lu_is_reused_across_right_hand_sides_and_updates():
+    def run():
+        c = cases.stokes(cases.channel_mesh(8), 2, False, dt_val=0.1, mass=True)
+        ngs = c['ngs']
+        c['gfu'].components[0].Set(c['uex'], definedon=c['mesh'].Boundaries(c['walls']))
+        c['a'].Assemble()
+        c['L'].Assemble()
+        inv = c['a'].mat.Inverse(c['fes'].FreeDofs())
+        out = [np.asarray(c['fes'].FreeDofs(), dtype=bool)]
+        rng = np.random.default_rng(2)
+        for _ in range(2):
+            r = ngs.BaseVector(ngs.get_backend().from_numpy(rng.uniform(-1, 1, c['fes'].ndof)))
+            out.append((inv * r).NumPy().copy())
+        c['params'][0].Set(0.5)                 # a new time step size: re-assemble, re-factorise the same object
+        c['a'].Assemble()
+        inv.Update()
+        out.append((inv * c['L'].vec).NumPy().copy())
+        return out
+    ref = _with('oracle', run)
+    got = _with('cuda', run)
+    for g, r in zip(got[1:], ref[1:]):
+        assert _rel(g, r) < 1e-9
+    assert _rel(ref[3], ref[1]) > 1e-3          # the re-assembled system really is a different one
+    assert np.all(got[1][~got[0]] == 0.0)       # constrained entries of inv * r are exactly zero, like NGSolve's
+
+
+def test_band_lu_raises_on_a_singular_matrix():
+    def run():
+        c = cases.poisson(cases.square_mesh(4), 1, False)
+        c['a'].Assemble()
+        c['a'].mat.values.zero_()
+        try:
+            c['a'].mat.Inverse(c['fes'].FreeDofs())
+        except RuntimeError as exc:
+            assert 'singular' in str(exc)
+        else:
+            assert False, 'a zero matrix must be reported as singular'
+    _with('cuda', run)
+
+
+def test_band_lu_residual_is_at_round_off():
+    """True residual of the free rows after the solve: ||b - A x|| <= 1e-13 ||b|| on a saddle-point system."""
+    def run():
+        c = cases.stokes(cases.channel_mesh(16), 3, True)
+        ngs = c['ngs']
+        c['gfu'].components[0].Set(c['uex'], definedon=c['mesh'].Boundaries(c['walls']))
+        c['a'].Assemble()
+        c['L'].Assemble()
+        cases.direct_solve(c)
+        res = (c['L'].vec - c['a'].mat * c['gfu'].vec).NumPy()
+        free = np.asarray(c['fes'].FreeDofs(), dtype=bool)
+        return np.linalg.norm(res[free]), np.linalg.norm(c['L'].vec.NumPy()[free]), int(free.sum())
+    rn, bn, n = _with('cuda', run)
+    assert n > 10000
+    assert rn <= 1e-13 * bn
