@@ -133,6 +133,7 @@ int ocmp_asm_apply_bf16(int npatch, int bs, const int* patch_dofs, const unsigne
 /* ---- Krylov: stand in for ngs.solvers.CG / GMRes / PreconditionedRichardson and for mat.Inverse applied to a
  *      residual (reference opencmp/models/base_model.py:886-947) ---------------------------------------------- */
 struct ocmp_mg_level;
+struct ocmp_band_lu;
 typedef struct ocmp_system {
     int nrows;
     const int* rowptr;
@@ -140,7 +141,7 @@ typedef struct ocmp_system {
     const double* vals;
     const double* freemask;  /* 1.0 free / 0.0 constrained, NULL = all free */
     int pre_kind;            /* 0 none, 1 Jacobi (dinv), 2 additive Schwarz patches, 3 geometric multigrid V-cycle,
-                                4 explicit inverse stored as CSR (coarsest multigrid level) */
+                                4 explicit inverse stored as CSR (coarsest multigrid level), 5 band LU (direct) */
     const double* dinv;
     int npatch, bs;
     const int* patch_dofs;
@@ -165,7 +166,17 @@ typedef struct ocmp_system {
                                 handed to solvers.CG / GMRes; rowptr / colidx / vals may then be NULL unless the
                                 preconditioner reads them. NULL = stored CSR operator */
     void* apply_ctx;         /* first argument of apply_fn */
+    const struct ocmp_band_lu* direct; /* pre_kind 5: factorised free-free block (ocmp_band_factor) applied as the
+                                preconditioner — ngs.Preconditioner(a, 'direct') */
 } ocmp_system;
+/* A band LU as ocmp_band_fill / ocmp_band_factor leave it, plus the permutation and a work vector of n doubles. */
+typedef struct ocmp_band_lu {
+    int n, kl, ku, ubw;
+    const double* ab;
+    const int* ipiv;
+    const int* perm;         /* nrows of the system: position in band order, -1 = constrained */
+    double* rhs;             /* n doubles of scratch */
+} ocmp_band_lu;
 /* y = A x on device vectors of length nrows, enqueued on `stream`; returns 0 on success */
 typedef int (*ocmp_apply_fn)(void* ctx, const double* x, double* y, void* stream);
 
@@ -184,7 +195,7 @@ typedef struct ocmp_mg_level {
                                 to a distributed one (redundant solves differ by round-off) (0: none) */
 } ocmp_mg_level;
 
-/* kind: 0 CG, 1 GMRES(restart), 2 Richardson. x holds the initial guess (and Dirichlet values) on entry.
+/* kind: 0 CG, 1 GMRES(restart), 2 Richardson, 3 MINRES (symmetric operator, SPD preconditioner). x holds the initial guess (and Dirichlet values) on entry.
  * Stops when the preconditioned residual norm drops below tol * initial. iters / resid are host outputs. */
 int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, double* x, double tol, int maxit, int restart,
                 double damp, double* work, long long work_len, int* iters, double* resid, void* stream);

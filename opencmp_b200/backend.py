@@ -49,7 +49,13 @@ class System(C.Structure):
                 ('bs', C.c_int), ('patch_dofs', C.c_void_p), ('inv_blocks', C.c_void_p), ('patch_weight', C.c_void_p),
                 ('nlevels', C.c_int), ('levels', C.c_void_p), ('inv_rowptr', C.c_void_p), ('inv_colidx', C.c_void_p),
                 ('inv_vals', C.c_void_p), ('owned', C.c_void_p), ('halo_fwd', C.c_int), ('halo_sum', C.c_int),
-                ('inv_storage', C.c_int), ('vals32', C.c_void_p), ('apply_fn', C.c_void_p), ('apply_ctx', C.c_void_p)]
+                ('inv_storage', C.c_int), ('vals32', C.c_void_p), ('apply_fn', C.c_void_p), ('apply_ctx', C.c_void_p),
+                ('direct', C.c_void_p)]
+
+
+class BandHandle(C.Structure):
+    _fields_ = [('n', C.c_int), ('kl', C.c_int), ('ku', C.c_int), ('ubw', C.c_int), ('ab', C.c_void_p),
+                ('ipiv', C.c_void_p), ('perm', C.c_void_p), ('rhs', C.c_void_p)]
 
 
 # ocmp_apply_fn (include/opencmp_b200.h): y = A x of a matrix-free operator, called back by ocmp_krylov
@@ -572,27 +578,43 @@ class CudaBackend:
                                                 dinv.data_ptr(), st))
             self.launches += 1
             return _Precond(1, dinv=dinv, fm=fm)
-        if kind in ('asm', 'asm_cell', 'direct', 'h1amg', 'bddc', 'block'):
+        if kind in ('asm', 'asm_cell', 'block'):
             # overlapping additive Schwarz: vertex-star patches (all dofs of the cells around a vertex) by default,
             # cell patches for kind 'asm_cell'; averaged by the patch multiplicity of every dof
             fes = mat.space
             pt = self._patches(fes, 'cell' if kind == 'asm_cell' else os.environ.get('OCMP_PATCH', 'vertex'))
-            self._invert_patches(pt, pd, mat, fm)
+            # the patch TOPOLOGY is shared per space; the stored inverses belong to this preconditioner state alone
+            # (several preconditioners on one space — adaptive_two_step.py:50-59 — must not overwrite each other)
+            old = getattr(state, 'inv', None) if getattr(state, 'kind', 0) == 2 else None
+            if old is not None and (state.pdofs is not pt['dofs'] or state.storage != pt['storage']):
+                old = None
+            inv = self._invert_patches(pt, pd, mat, fm, old)
             self.launches += 1
-            return _Precond(2, inv=pt['inv'], npatch=pt['npatch'], bs=pt['bs'], pdofs=pt['dofs'], fm=fm,
+            return _Precond(2, inv=inv, npatch=pt['npatch'], bs=pt['bs'], pdofs=pt['dofs'], fm=fm,
                             wgt=pt['wgt'], storage=pt['storage'])
+        if kind == 'direct':
+            # NGSolve's 'direct' preconditioner is a sparse factorisation of the assembled matrix
+            # (reference base_model.py:365-383): the band LU of direct.py, applied as an exact inverse
+            fact = self.factorize(mat, free) if getattr(state, 'kind', 0) != 5 else state.fact
+            if getattr(state, 'kind', 0) == 5:
+                fact.Update()
+            return _Precond(5, fact=fact, fm=fm)
+        if kind in ('h1amg', 'bddc'):
+            raise NotImplementedError(
+                "opencmp_b200: preconditioner type '{}' (reference base_model.py:365-383) is not implemented; "
+                "available: local, direct, multigrid, and the additive-Schwarz types asm / asm_cell".format(kind))
         raise NotImplementedError('preconditioner type {}'.format(kind))
 
-    def _invert_patches(self, pt, pd, mat, fm) -> None:
-        """(Re)compute the stored patch inverses of the patch table ``pt`` for the current matrix values. With
-        ``pt['storage']`` = fp32 / bf16 (OCMP_PATCH_STORAGE) they are stored in that type — inverted and applied in
-        FP64 arithmetic."""
+    def _invert_patches(self, pt, pd, mat, fm, inv=None):
+        """Patch inverses of the patch table ``pt`` for the current matrix values, written into ``inv`` (allocated when
+        None) and returned. With ``pt['storage']`` = fp32 / bf16 (OCMP_PATCH_STORAGE) they are stored in that type —
+        inverted and applied in FP64 arithmetic."""
         t = self.torch
         npatch, bs = pt['npatch'], pt['bs']
         st = self._stream()
-        if pt.get('inv') is None:
+        if inv is None:
             dtype = {'fp64': t.float64, 'fp32': t.float32, 'bf16': t.bfloat16}[pt['storage']]
-            pt['inv'] = t.empty(npatch * bs * bs, dtype=dtype, device=self.device)
+            inv = t.empty(npatch * bs * bs, dtype=dtype, device=self.device)
         if pt.get('pos') is None and bs <= 160:
             npad = 16 * ((bs + 15) // 16)
             pt['pos'] = t.empty(npatch * npad * npad, dtype=t.int32, device=self.device)
@@ -601,7 +623,8 @@ class CudaBackend:
         setup = {'fp64': self.lib.ocmp_asm_setup, 'fp32': self.lib.ocmp_asm_setup_f32,
                  'bf16': self.lib.ocmp_asm_setup_bf16}[pt['storage']]
         self._ck(setup(npatch, bs, pt['dofs'].data_ptr(), pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(),
-                       mat.values.data_ptr(), _ptr(fm), pt['inv'].data_ptr(), _ptr(pt.get('pos')), st))
+                       mat.values.data_ptr(), _ptr(fm), inv.data_ptr(), _ptr(pt.get('pos')), st))
+        return inv
 
     def fp32_copy(self, values, buf=None):
         """FP32 copy of a matrix value array for the operator applications inside the multigrid cycle
@@ -672,7 +695,7 @@ class CudaBackend:
         dofs = np.ascontiguousarray(dofs, dtype=np.int32)
         mult = np.bincount(dofs[dofs >= 0].ravel(), minlength=fes.ndof).astype(np.float64)
         out = dict(npatch=dofs.shape[0], bs=dofs.shape[1], dofs=self._up(dofs),
-                   wgt=self._up(1.0 / np.maximum(mult, 1.0)), inv=None, storage=storage)
+                   wgt=self._up(1.0 / np.maximum(mult, 1.0)), storage=storage)
         sd[key] = out
         return out
 
@@ -688,6 +711,12 @@ class CudaBackend:
             s.pre_kind = pre.kind
             if pre.kind == 1:
                 s.dinv = pre.dinv.data_ptr()
+            elif pre.kind == 5:
+                if not hasattr(pre.fact, 'handle'):
+                    raise NotImplementedError("Preconditioner type 'direct': the system is too large to factorise "
+                                              '(OCMP_DIRECT_MAX_GB)')
+                pre.handle = pre.fact.handle()            # kept alive by the state for the duration of the solve
+                s.direct = C.addressof(pre.handle)
             elif pre.kind == 3:
                 top = pre.levels[pre.nlevels - 1].sys
                 for name in ('npatch', 'bs', 'patch_dofs', 'inv_blocks', 'patch_weight', 'inv_storage', 'vals32'):
@@ -712,7 +741,7 @@ class CudaBackend:
             fm = state.fm
         if initialize:
             x.zero_()
-        kid = {'cg': 0, 'gmres': 1, 'minres': 1, 'richardson': 2}[kind]
+        kid = {'cg': 0, 'gmres': 1, 'minres': 3, 'richardson': 2}[kind]
         restart = min(maxit, 200) if restart is None else restart
         sys_ = self._system(mat, fm, state)
         wl = self.lib.ocmp_krylov_work_len(mat.height, kid, restart)
@@ -833,11 +862,12 @@ def _cuda_csr_mult(self, h, x, y):
 
 
 def _cuda_patch_state(self, fes, vmask):
-    return self._patches(fes, os.environ.get('OCMP_PATCH', 'vertex'), vmask)
+    # the caller owns the returned record and with it the inverse buffer; the topology arrays are shared
+    return dict(self._patches(fes, os.environ.get('OCMP_PATCH', 'vertex'), vmask), inv=None)
 
 
 def _cuda_patch_setup(self, mat, pt, fm):
-    self._invert_patches(pt, self.pattern_data(mat.space), mat, fm)
+    pt['inv'] = self._invert_patches(pt, self.pattern_data(mat.space), mat, fm, pt.get('inv'))
 
 
 def _cuda_patch_apply(self, pt, r, z):

@@ -614,6 +614,12 @@ struct Ctx {
                 ProfScope ps(PROF_VEC, st);
                 k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, z, z);
             }
+        } else if (sy->pre_kind == 5 && sy->direct) {
+            // Preconditioner(a, 'direct'): exact solve with the factorised free-free block (zero on constrained dofs)
+            const ocmp_band_lu* f = sy->direct;
+            ocmp_band_gather(sy->nrows, f->perm, r, f->rhs, st);
+            ocmp_band_solve(f->n, f->kl, f->ku, f->ubw, f->ab, f->ipiv, f->rhs, st);
+            ocmp_band_scatter(sy->nrows, f->perm, f->rhs, z, 0, st);
         } else {
             ProfScope ps(PROF_VEC, st);
             k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, r, z);
@@ -719,6 +725,7 @@ extern "C" long long ocmp_krylov_work_len(int nrows, int kind, int restart) {
     const long long n = nrows;
     if (kind == 0) return 4 * n + 64;
     if (kind == 1) return (long long)(restart + 1) * n + 2 * n + 2 * (restart + 2) + 64;
+    if (kind == 3) return 9 * n + 64;
     return 2 * n + 64;
 }
 
@@ -835,6 +842,60 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
             if (res < tol * r0 || res == 0.0) break;
             c.P(r, z);
             c.axpby(damp, z, 1.0, x);
+        }
+    } else if (kind == 3) {                // preconditioned MINRES (Paige-Saunders; symmetric A, SPD preconditioner)
+        // the Lanczos process in the P-inner product with the two-term Givens update of the solution; stops on the
+        // recurrence value of the P-norm of the residual, relative to the initial one (what NGSolve's MinRes monitors)
+        double* v0 = work;          double* v1 = work + n;     double* v2 = work + 2 * n;
+        double* z1 = work + 3 * n;  double* z2 = work + 4 * n;
+        double* w0 = work + 5 * n;  double* w1 = work + 6 * n; double* w2 = work + 7 * n;
+        double* Az = work + 8 * n;
+        c.dscal = work + 9 * n;
+        cudaMemsetAsync(v0, 0, sizeof(double) * n, c.st);
+        cudaMemsetAsync(w0, 0, sizeof(double) * n, c.st);
+        cudaMemsetAsync(w1, 0, sizeof(double) * n, c.st);
+        c.A(x, v1);
+        k_resid<<<grid_for(n), 256, 0, c.st>>>(n, b, sys->freemask, v1);
+        c.P(v1, z1);
+        double gamma0 = 1.0, gamma1 = sqrt(fabs(c.dot(z1, v1)));
+        double eta = gamma1, s0 = 0.0, s1 = 0.0, c0 = 1.0, c1 = 1.0;
+        const double err0 = gamma1;
+        res = err0;
+        if (gamma1 != 0.0) {
+            for (it = 0; it < maxit;) {
+                c.axpby(0.0, z1, 1.0 / gamma1, z1);                 // z_j normalised
+                c.A(z1, Az);
+                c.mask(Az);
+                const double delta = c.dot(Az, z1);
+                // v_{j+1} = A z_j - (delta / gamma_j) v_j - (gamma_j / gamma_{j-1}) v_{j-1}
+                c.axpby(1.0, Az, 0.0, v2);
+                c.axpby(-delta / gamma1, v1, 1.0, v2);
+                c.axpby(-gamma1 / gamma0, v0, 1.0, v2);
+                c.P(v2, z2);
+                const double gamma2 = sqrt(fabs(c.dot(z2, v2)));
+                const double a0 = c1 * delta - c0 * s1 * gamma1;
+                const double a1 = sqrt(a0 * a0 + gamma2 * gamma2);
+                const double a2 = s1 * delta + c0 * c1 * gamma1;
+                const double a3 = s0 * gamma1;
+                c0 = c1; s0 = s1;
+                c1 = a1 == 0.0 ? 1.0 : a0 / a1;
+                s1 = a1 == 0.0 ? 0.0 : gamma2 / a1;
+                // w_{j+1} = (z_j - a3 w_{j-1} - a2 w_j) / a1
+                c.axpby(1.0, z1, 0.0, w2);
+                c.axpby(-a3, w0, 1.0, w2);
+                c.axpby(-a2, w1, 1.0, w2);
+                if (a1 != 0.0) c.axpby(0.0, w2, 1.0 / a1, w2);
+                c.axpby(c1 * eta, w2, 1.0, x);
+                eta = -s1 * eta;
+                ++it;
+                res = fabs(eta);
+                g_history.push_back(res / err0);
+                if (res < tol * err0 || gamma2 == 0.0) break;
+                double* tv = v0; v0 = v1; v1 = v2; v2 = tv;
+                double* tz = z1; z1 = z2; z2 = tz;
+                double* tw = w0; w0 = w1; w1 = w2; w2 = tw;
+                gamma0 = gamma1; gamma1 = gamma2;
+            }
         }
     } else return ocmp_fail(-1, "unknown krylov kind");
     cudaStreamSynchronize(c.st);

@@ -102,6 +102,15 @@ class BandLU:
                                'column {} of {})'.format(int(info[0]), self.n))
         self.ubw = int(info[1]) if self.n > 1 else 0
 
+    def handle(self):
+        """ocmp_band_lu record for ocmp_system.direct (Preconditioner(a, 'direct') inside ocmp_krylov)."""
+        from .backend import BandHandle
+        h = BandHandle()
+        h.n, h.kl, h.ku, h.ubw = self.n, self.kl, self.ku, self.ubw
+        h.ab, h.ipiv, h.perm, h.rhs = (self.ab.data_ptr(), self.ipiv.data_ptr(), self.perm.data_ptr(),
+                                       self.rhs.data_ptr())
+        return h
+
     def _apply(self, r, out, accumulate: bool):
         be = self.be
         st = be._stream()

@@ -30,11 +30,19 @@ from .mesh import Mesh
 class Partition:
     """Cell partition of a global mesh and the local (owned + ghost) mesh of one rank."""
 
-    def __init__(self, mesh: Mesh, nranks: int, rank: int, layers: Optional[int] = 1):
+    def __init__(self, mesh: Mesh, nranks: int, rank: int, layers: Optional[int] = 1, rank_of_cells=None):
+        """``rank_of_cells(mesh) -> (ne,) ranks`` overrides the default partition into contiguous blocks of the cell
+        order (e.g. ``block_ranks``: compact bricks by cell centroid); it is kept and applied to every level of a
+        refinement hierarchy, so it must give a cell and its children the same rank."""
         self.mesh, self.nranks, self.rank = mesh, nranks, rank
         self._layers = layers
+        self.rank_of_cells = rank_of_cells
         ne = mesh.ne
-        self.cell_rank = (np.arange(ne, dtype=np.int64) * nranks // ne).astype(np.int32)
+        if rank_of_cells is None:
+            self.cell_rank = (np.arange(ne, dtype=np.int64) * nranks // ne).astype(np.int32)
+        else:
+            self.cell_rank = np.asarray(rank_of_cells(mesh), dtype=np.int32)
+            assert self.cell_rank.shape == (ne,) and 0 <= self.cell_rank.min() and self.cell_rank.max() < nranks
         owned = self.cell_rank == rank
         local = owned.copy()
         if layers is None:                            # replicated level: every cell is local
@@ -75,6 +83,37 @@ class Partition:
         loc.global_cells = self.local_cells
         loc.global_vertices = verts
         return loc
+
+
+def block_ranks(blocks, lo, hi):
+    """Partition of the box [lo, hi] into blocks[0] x blocks[1] (x blocks[2]) equal bricks: the rank of a cell is the
+    brick its centroid lies in. Nested under uniform refinement as long as the brick faces are mesh faces of the
+    coarsest partitioned level."""
+    blocks = [int(b) for b in blocks]
+
+    def rank_of_cells(mesh):
+        c = mesh.points[mesh.cells].mean(axis=1)
+        r = np.zeros(mesh.ne, dtype=np.int64)
+        for a in range(mesh.dim):
+            i = np.floor((c[:, a] - lo[a]) / (hi[a] - lo[a]) * blocks[a]).astype(np.int64)
+            r = r * blocks[a] + np.clip(i, 0, blocks[a] - 1)
+        return r
+    return rank_of_cells
+
+
+def brick_grid(world: int):
+    """(bx, by, bz) with bx * by * bz = world, as cubic as powers of two allow: 1 -> (1,1,1), 2 -> (2,1,1),
+    4 -> (2,2,1), 8 -> (2,2,2), 16 -> (4,2,2) ..."""
+    b = [1, 1, 1]
+    a = 0
+    w = world
+    while w > 1:
+        if w % 2:
+            raise ValueError('the brick layout needs a power-of-two number of ranks')
+        b[a % 3] *= 2
+        w //= 2
+        a += 1
+    return tuple(b)
 
 
 class DofMap:

@@ -73,7 +73,8 @@ class DistributedMultigrid:
                 lv.mesh = bf.space.mesh
                 lv.fes = bf.space
             else:
-                lv.part = Partition(gm, world, rank, layers=None if lv.replicated else part_fine._layers)
+                lv.part = Partition(gm, world, rank, layers=None if lv.replicated else part_fine._layers,
+                                    rank_of_cells=part_fine.rank_of_cells)
                 lv.mesh = ngs.Mesh(lv.part.local_mesh())
                 lv.fes = clone_space(bf.space, lv.mesh)
             lv.map = DofMap(lv.part, gfes, lv.fes)

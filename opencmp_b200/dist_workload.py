@@ -155,21 +155,34 @@ class DistributedINSDIM3D:
     coarse level). Per-rank work is fixed as R grows (weak scaling)."""
 
     def __init__(self, N: int, world: int, rank: int, order: int = 2, n0: int = 2, bricks: int = None,
-                 replicate_below: int = 100000, **kw):
+                 replicate_below: int = 100000, layout: str = None, **kw):
+        """layout 'bricks' (default; ``bricks`` = number of [-1,1]^3 bricks in a row along x, one sphere each, N^3
+        cells per brick, contiguous cell blocks per rank) or 'sphere': ONE sphere in [-1,1]^3 (BASELINE configs[4] as
+        written) meshed with (N bx) x (N by) x (N bz) hexes, (bx, by, bz) = dist.brick_grid(world), every rank owning
+        one compact N^3 brick of cells — per-rank work is fixed as the rank count grows and the mesh is refined
+        (weak scaling; the cells have aspect ratio 2 while the rank count is not a cube)."""
         from .mesh import structured_3d
         from .workloads import INSSphereDIM3D
+        from .dist import block_ranks, brick_grid
         from .dist_mg import DistributedMultigrid
         self.world, self.rank = world, rank
         k, n = 0, N
         while n % 2 == 0 and n > n0:
             n //= 2
             k += 1
-        bricks = world if bricks is None else bricks
-        gmesh = structured_3d([n * bricks, n, n], scale=(2.0 * bricks, 2.0, 2.0), offset=(1.0, 1.0, 1.0))
+        if layout == 'sphere':
+            grid = brick_grid(world)
+            gmesh = structured_3d([n * b for b in grid], scale=(2.0, 2.0, 2.0), offset=(1.0, 1.0, 1.0))
+            rank_of_cells = block_ranks(grid, (-1.0,) * 3, (1.0,) * 3)
+            kw.setdefault('periodic', (False, False, False))
+        else:
+            bricks = world if bricks is None else bricks
+            gmesh = structured_3d([n * bricks, n, n], scale=(2.0 * bricks, 2.0, 2.0), offset=(1.0, 1.0, 1.0))
+            rank_of_cells = None
         for _ in range(k):
             gmesh.Refine()
         self.gmesh = gmesh
-        self.part = Partition(gmesh, world, rank, layers=2)
+        self.part = Partition(gmesh, world, rank, layers=2, rank_of_cells=rank_of_cells)
         outer = self
 
         def integrate(cf):
@@ -206,6 +219,12 @@ class DistributedINSDIM3D:
         w = _Local.__new__(_Local)
         self.w = w
         _Local.__init__(w, N, order=order, mesh=self.part.local_mesh(), preconditioner=None, integrate=integrate, **kw)
+        # coefficient fields are projected on the local mesh: on its outer (cut) faces the local average differs from
+        # the global one, so ghost entries take the owner's value like every other consistent vector
+        gH = ngs.H1(ngs.Mesh(gmesh), order=order)
+        hmap = DofMap(self.part, gH, w.fes_phi)
+        for gf in (w.phi, w.mask):
+            hmap.exchange(gf.vec.a)
         self.mg = DistributedMultigrid(ngs.get_backend(), w.a, gmesh, self.part, replicate_below=replicate_below)
         top = self.mg.levels[-1].map
         for gf in (w.gfu, w.gfu_0):

@@ -281,7 +281,8 @@ class MultigridState:
                 else:                       # finest level: always, unless the opt-in lag policy says otherwise
                     fresh = self.lag.need_refresh(self.smoothers[l] is not None, forced=not reuse)
                 if fresh:
-                    self.smoothers[l] = be.precond_setup(mat, 'asm', self.spaces[l].FreeDofs(), mask=self.masks[l])
+                    self.smoothers[l] = be.precond_setup(mat, 'asm', self.spaces[l].FreeDofs(), mask=self.masks[l],
+                                                          state=self.smoothers[l])
                 sm = self.smoothers[l]
                 sys_ = be._system(mat, self.masks[l], sm)
                 if self.spmv_fp32:

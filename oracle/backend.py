@@ -104,10 +104,7 @@ class OracleBackend:
         elif kind == 'minres':
             if initialize:
                 x[:] = 0.0
-            M = spla.LinearOperator((n, n), matvec=P)
-            r0 = b - A @ x
-            dx, _ = spla.minres(A, r0, M=M, rtol=tol, maxiter=maxit)
-            x += dx
+            x[:] = minres(A, b, x, P, proj, tol, maxit)
         elif kind == 'richardson':
             x[:] = 0.0
             r = proj(b - A @ x)
@@ -154,6 +151,51 @@ def cg(A, b, x, P, tol, maxit, initialize):
         s = w + (wdn / wd) * s
         if np.sqrt(abs(wd)) < tol * err0:
             break
+    return u
+
+
+last_history = []
+
+
+def minres(A, b, x, P, proj, tol, maxit):
+    """Preconditioned MINRES (Paige & Saunders 1975; the form of Elman, Silvester & Wathen, Alg. 4.1): Lanczos in the
+    P-inner product, two Givens rotations per step; stops on the recurrence value of the P-norm of the residual relative
+    to the initial one — what ngsolve.solvers.MinRes monitors (reference base_model.py:929-932). Records that ratio per
+    iteration in ``last_history``."""
+    u = x.copy()
+    v0 = np.zeros_like(b)
+    v1 = proj(b - A @ u)
+    z1 = P(v1)
+    w0, w1 = np.zeros_like(b), np.zeros_like(b)
+    gamma0, gamma1 = 1.0, np.sqrt(abs(float(z1 @ v1)))
+    eta, s0, s1, c0, c1 = gamma1, 0.0, 0.0, 1.0, 1.0
+    err0 = gamma1
+    del last_history[:]
+    if gamma1 == 0.0:
+        return u
+    for _ in range(maxit):
+        z1 = z1 / gamma1
+        Az = proj(A @ z1)
+        delta = float(Az @ z1)
+        v2 = Az - (delta / gamma1) * v1 - (gamma1 / gamma0) * v0
+        z2 = P(v2)
+        gamma2 = np.sqrt(abs(float(z2 @ v2)))
+        a0 = c1 * delta - c0 * s1 * gamma1
+        a1 = np.sqrt(a0 * a0 + gamma2 * gamma2)
+        a2 = s1 * delta + c0 * c1 * gamma1
+        a3 = s0 * gamma1
+        c0, s0 = c1, s1
+        c1, s1 = (1.0, 0.0) if a1 == 0.0 else (a0 / a1, gamma2 / a1)
+        w2 = z1 - a3 * w0 - a2 * w1
+        if a1 != 0.0:
+            w2 = w2 / a1
+        u += c1 * eta * w2
+        eta = -s1 * eta
+        last_history.append(abs(eta) / err0)
+        if abs(eta) < tol * err0 or gamma2 == 0.0:
+            break
+        v0, v1, z1, w0, w1 = v1, v2, z2, w1, w2
+        gamma0, gamma1 = gamma1, gamma2
     return u
 
 

@@ -169,7 +169,13 @@ def _mg3d_worker(rank, world, port, bricks, out):
         from opencmp_b200.dist_workload import DistributedINSDIM3D
         from opencmp_b200.workloads import INSSphereDIM3D
         kw = dict(nonlinear_max_iterations=1, linear_tolerance=1e-13, lam=1.0)
-        d = DistributedINSDIM3D(4, world, rank, n0=2, replicate_below=0, bricks=bricks, **kw)
+        if bricks == 'sphere':          # compact bricks of an anisotropically refined [-1,1]^3 (8 x 4 x 4 on 2 ranks)
+            d = DistributedINSDIM3D(4, world, rank, n0=2, replicate_below=0, layout='sphere', **kw)
+            assert d.gmesh.ne == world * 4 ** 3 and np.allclose(d.gmesh.points.max(axis=0), 1.0)
+            assert (d.part.cell_rank == rank).sum() == 4 ** 3
+            kw = dict(kw, periodic=(False, False, False))
+        else:
+            d = DistributedINSDIM3D(4, world, rank, n0=2, replicate_below=0, bricks=bricks, **kw)
         g = INSSphereDIM3D(4, mesh=d.gmesh, preconditioner=None, **kw)
 
         def direct():
@@ -202,12 +208,13 @@ def DofMapOf(d, g):
     return DofMap(d.part, g.fes_phi, d.w.fes_phi).l2g
 
 
-@pytest.mark.parametrize('bricks', [None, 1])
+@pytest.mark.parametrize('bricks', [None, 1, 'sphere'])
 def test_partitioned_multigrid_ins_dim_3d_step_matches_global_solve(bricks):
     """3-D INS-DIM (hex Taylor-Hood): distributed multigrid-GMRES with open-star patches and per-level phase fields on
     2 ranks equals the single-process sparse direct solve — with one brick and its own diffuse sphere per rank
     (``bricks=None``), and with ONE sphere in [-1,1]^3 whose cells are split between the ranks (``bricks=1``, the
-    layout BASELINE configs[4] describes)."""
+    layout BASELINE configs[4] describes; ``'sphere'``: the same with the mesh refined with the rank count and one
+    compact brick of cells per rank, bench.py's weak-scaling layout)."""
     world = 2
     port = _free_port()
     mgr = mp.get_context('spawn').Manager()

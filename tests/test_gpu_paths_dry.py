@@ -148,7 +148,7 @@ def _invoke(fn, params, monkeypatch, ngs_fixture):
 
 @pytest.mark.parametrize('modname', ['test_gpu_parity', 'test_golden_programs', 'test_golden_fixtures',
                                      'test_zz_gpu_late_additions', 'test_zzz_gpu_unmeasured_kernels',
-                                     'test_zzzz_gpu_matrix_free', 'test_gpu_direct'])
+                                     'test_zzzz_gpu_matrix_free', 'test_gpu_direct', 'test_gpu_krylov'])
 def test_gpu_test_bodies_execute_on_a_null_device(dry, monkeypatch, modname):
     import importlib
     import opencmp_b200.ngs as ngs
@@ -175,7 +175,7 @@ def test_fp32_patch_storage_host_path(dry, monkeypatch):
     try:
         c = cases.stokes(cases.channel_mesh(4), 2, True)
         c['a'].Assemble()
-        pre = ngs.Preconditioner(c['a'], 'direct')
+        pre = ngs.Preconditioner(c['a'], 'asm')
         pre.Update()
         assert 'ocmp_asm_setup_f32' in be.lib.calls and 'ocmp_asm_setup' not in be.lib.calls
         st = pre.state
