@@ -112,23 +112,30 @@ int ocmp_asm_setup(int npatch, int bs, const int* patch_dofs, const int* rowptr,
  * pattern; NULL positions in ocmp_asm_setup selects the slower pivoted shared-memory kernel */
 int ocmp_patch_positions(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
                          int* positions, void* stream);
-int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const double* inv_blocks, const double* r, double* z,
-                   long long n, void* stream);
+/* Application z = sum_p scatter(A_p^-1 r[dofs_p]): the stored inverses are streamed once (bulk copies into a shared-
+ * memory ring), the patch products land in the patch-local scratch `ybuf` (npatch x bs doubles) and a per-dof gather
+ * through the incidence list sums them in a fixed order — no atomics, bit-reproducible. inc_ptr (n + 1) / inc_idx:
+ * for every dof the positions p * bs + i of its valid patch entries, ascending (built once per patch table by the
+ * host). The patch stride bs must keep the stored columns 16-byte aligned (even for FP64, % 4 for FP32, % 8 for
+ * bfloat16), bs <= 256. */
+int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const double* inv_blocks, const int* inc_ptr,
+                   const int* inc_idx, double* ybuf, const double* r, double* z, long long n, void* stream);
 /* The same smoother with the patch inverses STORED in FP32 (inverted and applied in FP64 arithmetic): its application
  * is bound by streaming the inverses from HBM, so this halves the bytes of the dominant kernel; as a preconditioner
  * inside FP64 GMRES it leaves iteration counts and solutions unchanged. bs must be a multiple of 4. */
 int ocmp_asm_setup_f32(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
                        const double* vals, const double* freemask, float* inv_blocks, const int* positions,
                        void* stream);
-int ocmp_asm_apply_f32(int npatch, int bs, const int* patch_dofs, const float* inv_blocks, const double* r, double* z,
-                       long long n, void* stream);
+int ocmp_asm_apply_f32(int npatch, int bs, const int* patch_dofs, const float* inv_blocks, const int* inc_ptr,
+                       const int* inc_idx, double* ybuf, const double* r, double* z, long long n, void* stream);
 /* ... and in bfloat16 (a quarter of the FP64 bytes; bs a multiple of 8). Iteration counts on the CPU restatement:
  * unchanged in 2-D, +-2 in 3-D (profiles/r1_solver_convergence.md). */
 int ocmp_asm_setup_bf16(int npatch, int bs, const int* patch_dofs, const int* rowptr, const int* colidx,
                         const double* vals, const double* freemask, unsigned short* inv_blocks, const int* positions,
                         void* stream);
-int ocmp_asm_apply_bf16(int npatch, int bs, const int* patch_dofs, const unsigned short* inv_blocks, const double* r,
-                        double* z, long long n, void* stream);
+int ocmp_asm_apply_bf16(int npatch, int bs, const int* patch_dofs, const unsigned short* inv_blocks,
+                        const int* inc_ptr, const int* inc_idx, double* ybuf, const double* r, double* z, long long n,
+                        void* stream);
 
 /* ---- Krylov: stand in for ngs.solvers.CG / GMRes / PreconditionedRichardson and for mat.Inverse applied to a
  *      residual (reference opencmp/models/base_model.py:886-947) ---------------------------------------------- */
@@ -168,6 +175,9 @@ typedef struct ocmp_system {
     void* apply_ctx;         /* first argument of apply_fn */
     const struct ocmp_band_lu* direct; /* pre_kind 5: factorised free-free block (ocmp_band_factor) applied as the
                                 preconditioner — ngs.Preconditioner(a, 'direct') */
+    const int* patch_inc_ptr;   /* pre_kind 2 / 3: incidence list of the patch table (see ocmp_asm_apply) */
+    const int* patch_inc_idx;
+    double* patch_ybuf;         /* npatch x bs doubles of scratch for the patch products */
 } ocmp_system;
 /* A band LU as ocmp_band_fill / ocmp_band_factor leave it, plus the permutation and a work vector of n doubles. */
 typedef struct ocmp_band_lu {

@@ -50,7 +50,8 @@ class System(C.Structure):
                 ('nlevels', C.c_int), ('levels', C.c_void_p), ('inv_rowptr', C.c_void_p), ('inv_colidx', C.c_void_p),
                 ('inv_vals', C.c_void_p), ('owned', C.c_void_p), ('halo_fwd', C.c_int), ('halo_sum', C.c_int),
                 ('inv_storage', C.c_int), ('vals32', C.c_void_p), ('apply_fn', C.c_void_p), ('apply_ctx', C.c_void_p),
-                ('direct', C.c_void_p)]
+                ('direct', C.c_void_p), ('patch_inc_ptr', C.c_void_p), ('patch_inc_idx', C.c_void_p),
+                ('patch_ybuf', C.c_void_p)]
 
 
 class BandHandle(C.Structure):
@@ -91,7 +92,7 @@ def load_library() -> C.CDLL:
     lib.ocmp_jacobi_setup.argtypes = [C.c_int, P, P, P, P, P]
     lib.ocmp_asm_setup.argtypes = [C.c_int, C.c_int, P, P, P, P, P, P, P, P]
     lib.ocmp_patch_positions.argtypes = [C.c_int, C.c_int, P, P, P, P, P]
-    lib.ocmp_asm_apply.argtypes = [C.c_int, C.c_int, P, P, P, P, C.c_longlong, P]
+    lib.ocmp_asm_apply.argtypes = [C.c_int, C.c_int, P, P, P, P, P, P, P, C.c_longlong, P]
     lib.ocmp_asm_setup_f32.argtypes = lib.ocmp_asm_setup_bf16.argtypes = lib.ocmp_asm_setup.argtypes
     lib.ocmp_to_f32.argtypes = [C.c_longlong, P, P, P]
     lib.ocmp_asm_apply_f32.argtypes = lib.ocmp_asm_apply_bf16.argtypes = lib.ocmp_asm_apply.argtypes
@@ -153,6 +154,19 @@ def patch_storage() -> str:
     if kind not in STORAGE_ID:
         raise ValueError('OCMP_PATCH_STORAGE must be one of {}'.format(sorted(STORAGE_ID)))
     return kind
+
+
+def patch_incidence(dofs: np.ndarray, ndof: int):
+    """Incidence list of a patch table (npatch x bs, -1 padded): for every dof the flat positions p * bs + i of its
+    patch entries in ascending order — the fixed summation order of the deterministic smoother gather
+    (ocmp_asm_apply). Returns (inc_ptr (ndof + 1) int32, inc_idx int32)."""
+    flat = dofs.ravel()
+    pos = np.nonzero(flat >= 0)[0]
+    order = np.argsort(flat[pos], kind='stable')          # stable: positions stay ascending within a dof
+    inc_idx = pos[order].astype(np.int32)
+    counts = np.bincount(flat[pos], minlength=ndof)
+    inc_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    return inc_ptr, inc_idx
 
 
 def _ptr(t) -> Optional[int]:
@@ -591,7 +605,8 @@ class CudaBackend:
             inv = self._invert_patches(pt, pd, mat, fm, old)
             self.launches += 1
             return _Precond(2, inv=inv, npatch=pt['npatch'], bs=pt['bs'], pdofs=pt['dofs'], fm=fm,
-                            wgt=pt['wgt'], storage=pt['storage'])
+                            wgt=pt['wgt'], storage=pt['storage'], inc_ptr=pt['inc_ptr'], inc_idx=pt['inc_idx'],
+                            ybuf=pt['ybuf'])
         if kind == 'direct':
             # NGSolve's 'direct' preconditioner is a sparse factorisation of the assembled matrix
             # (reference base_model.py:365-383): the band LU of direct.py, applied as an exact inverse
@@ -686,16 +701,18 @@ class CudaBackend:
             return out
         storage = patch_storage()
         align = _STORAGE_ALIGN[storage]
-        if dofs.shape[1] % align and (kind != 'cell' or storage != 'fp64'):
-            # patch stride padded so that the columns of the stored inverses stay 16-byte aligned, which k_patch_apply
-            # needs for its 16-byte loads (double2: even stride, an odd one falls back to 8-byte loads at ~15 % lower
-            # bandwidth; FP32 / bf16 storage: multiple of 4 / 8, required)
+        if dofs.shape[1] % align:
+            # patch stride padded so that the columns of the stored inverses stay 16-byte aligned: k_patch_apply_stream
+            # moves whole columns with the bulk-copy engine (FP64: even stride, FP32 / bf16: multiple of 4 / 8)
             npad = -dofs.shape[1] % align
             dofs = np.concatenate([dofs, -np.ones((dofs.shape[0], npad), dtype=dofs.dtype)], axis=1)
         dofs = np.ascontiguousarray(dofs, dtype=np.int32)
         mult = np.bincount(dofs[dofs >= 0].ravel(), minlength=fes.ndof).astype(np.float64)
+        inc_ptr, inc_idx = patch_incidence(dofs, fes.ndof)
         out = dict(npatch=dofs.shape[0], bs=dofs.shape[1], dofs=self._up(dofs),
-                   wgt=self._up(1.0 / np.maximum(mult, 1.0)), storage=storage)
+                   wgt=self._up(1.0 / np.maximum(mult, 1.0)), storage=storage,
+                   inc_ptr=self._up(inc_ptr), inc_idx=self._up(inc_idx),
+                   ybuf=self.zeros(max(1, dofs.size)))
         sd[key] = out
         return out
 
@@ -719,7 +736,8 @@ class CudaBackend:
                 s.direct = C.addressof(pre.handle)
             elif pre.kind == 3:
                 top = pre.levels[pre.nlevels - 1].sys
-                for name in ('npatch', 'bs', 'patch_dofs', 'inv_blocks', 'patch_weight', 'inv_storage', 'vals32'):
+                for name in ('npatch', 'bs', 'patch_dofs', 'inv_blocks', 'patch_weight', 'inv_storage', 'vals32',
+                             'patch_inc_ptr', 'patch_inc_idx', 'patch_ybuf'):
                     setattr(s, name, getattr(top, name))
                 s.nlevels = pre.nlevels
                 s.levels = C.addressof(pre.levels)
@@ -728,6 +746,8 @@ class CudaBackend:
                 s.patch_dofs, s.inv_blocks = pre.pdofs.data_ptr(), pre.inv.data_ptr()
                 s.patch_weight = _ptr(pre.wgt)
                 s.inv_storage = STORAGE_ID[getattr(pre, 'storage', 'fp64')]
+                s.patch_inc_ptr, s.patch_inc_idx = pre.inc_ptr.data_ptr(), pre.inc_idx.data_ptr()
+                s.patch_ybuf = pre.ybuf.data_ptr()
         return s
 
     def krylov(self, kind, mat, b, x, pre, freedofs, tol, maxit, initialize, printrates, damp=1.0, restart=None):
@@ -873,8 +893,9 @@ def _cuda_patch_setup(self, mat, pt, fm):
 def _cuda_patch_apply(self, pt, r, z):
     apply = {'fp64': self.lib.ocmp_asm_apply, 'fp32': self.lib.ocmp_asm_apply_f32,
              'bf16': self.lib.ocmp_asm_apply_bf16}[pt['storage']]
-    self._ck(apply(pt['npatch'], pt['bs'], pt['dofs'].data_ptr(), pt['inv'].data_ptr(), r.data_ptr(), z.data_ptr(),
-                   z.numel(), self._stream()))
+    self._ck(apply(pt['npatch'], pt['bs'], pt['dofs'].data_ptr(), pt['inv'].data_ptr(), pt['inc_ptr'].data_ptr(),
+                   pt['inc_idx'].data_ptr(), pt['ybuf'].data_ptr(), r.data_ptr(), z.data_ptr(), z.numel(),
+                   self._stream()))
 
 
 def _cuda_patch_count(self, pt, n):

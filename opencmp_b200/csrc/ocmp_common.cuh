@@ -8,26 +8,33 @@ int ocmp_check(const char* where);
 int ocmp_sm_count();
 int ocmp_patch_invert_registers(int npatch, int bs, const int* pd, const int* rp, const int* ci, const double* vals,
                                 const double* fm, double* inv, int* flag_dev, const int* pos, cudaStream_t st);
-int ocmp_patch_apply_cta(int npatch, int bs, const int* pd, const double* inv, const double* r, double* z,
-                         cudaStream_t st);
-// FP32-stored inverses (ocmp_system.inv_storage == 1): same arithmetic in FP64, half the bytes streamed per application
+// smoother application: y[p, :] = A_p^-1 r[dofs_p] (bulk-copy streamed, FP64 / FP32 / bfloat16 stored inverses), then
+// the deterministic per-dof gather z (+)= scale * w * m * sum of the patch-local entries
+int ocmp_patch_apply_y(int npatch, int bs, const int* pd, const double* inv, const double* r, double* y,
+                       cudaStream_t st);
+int ocmp_patch_apply_y_f32(int npatch, int bs, const int* pd, const float* inv, const double* r, double* y,
+                           cudaStream_t st);
+int ocmp_patch_apply_y_bf16(int npatch, int bs, const int* pd, const __nv_bfloat16* inv, const double* r, double* y,
+                            cudaStream_t st);
+int ocmp_patch_gather(long long n, const int* inc_ptr, const int* inc_idx, const double* y, const double* w,
+                      const double* m, double scale, double* z, int accumulate, cudaStream_t st);
 int ocmp_patch_invert_registers_f32(int npatch, int bs, const int* pd, const int* rp, const int* ci,
                                     const double* vals, const double* fm, float* inv, int* flag_dev, const int* pos,
                                     cudaStream_t st);
-int ocmp_patch_apply_cta_f32(int npatch, int bs, const int* pd, const float* inv, const double* r, double* z,
-                             cudaStream_t st);
-// bfloat16-stored inverses (ocmp_system.inv_storage == 2): a quarter of the FP64 bytes; bs a multiple of 8
 int ocmp_patch_invert_registers_bf16(int npatch, int bs, const int* pd, const int* rp, const int* ci,
                                      const double* vals, const double* fm, __nv_bfloat16* inv, int* flag_dev,
                                      const int* pos, cudaStream_t st);
-int ocmp_patch_apply_cta_bf16(int npatch, int bs, const int* pd, const __nv_bfloat16* inv, const double* r, double* z,
-                              cudaStream_t st);
 // conversions between FP64 arithmetic and the storage type of the preconditioner data
 template <typename T> __device__ __forceinline__ T ocmp_store(double v) { return (T)v; }
 template <> __device__ __forceinline__ __nv_bfloat16 ocmp_store<__nv_bfloat16>(double v) { return __double2bfloat16(v); }
 template <typename T> __device__ __forceinline__ double ocmp_load(const T* p) { return (double)__ldg(p); }
 template <> __device__ __forceinline__ double ocmp_load<__nv_bfloat16>(const __nv_bfloat16* p) {
     return (double)__bfloat162float(__ldg(p));
+}
+// the same from shared memory (no read-only path)
+template <typename T> __device__ __forceinline__ double ocmp_smem_load(const T* p) { return (double)*p; }
+template <> __device__ __forceinline__ double ocmp_smem_load<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return (double)__bfloat162float(*p);
 }
 // optional per-category device timing (CUDA events on the launching stream) and launch counting
 enum { PROF_SPMV = 0, PROF_ASM_APPLY, PROF_COEF, PROF_CONTRACT, PROF_LIN, PROF_MDOT, PROF_MAXPY, PROF_VEC,

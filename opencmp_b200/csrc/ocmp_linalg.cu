@@ -100,40 +100,35 @@ extern "C" long long ocmp_launch_count(void) { return g_launches; }
 extern "C" const char* ocmp_last_error(void) { return g_err; }
 extern "C" int ocmp_version(void) { return 100; }
 
-// ---- SpMV: CSR, LPR lanes cooperate on one row -----------------------------------------------------------------
-template <int LPR>
+// ---- SpMV: CSR, LPR lanes cooperate on one row; the epilogue is fused into the row store ---------------------------
+//   EP_PLAIN  y = A x                     EP_RESID  y = m .* m2 .* (b - A x)   (residual, restriction input)
+//   EP_MASK   y = m .* (A x)              EP_ADD    y += m .* (A x)            (prolongation + correction)
+// VT = double | float: the matrix values may be an FP32 copy (operator applications INSIDE the multigrid cycle when
+// ocmp_system.vals32 is set — 8 instead of 12 bytes per non-zero); products and sums are FP64.
+enum { EP_PLAIN = 0, EP_RESID = 1, EP_MASK = 2, EP_ADD = 3 };
+template <int LPR, typename VT, int EP>
 __global__ void __launch_bounds__(256) k_spmv(int nrows, const int* __restrict__ rowptr, const int* __restrict__ col,
-                                              const double* __restrict__ val, const double* __restrict__ x,
-                                              double* __restrict__ y) {
+                                              const VT* __restrict__ val, const double* __restrict__ x,
+                                              double* __restrict__ y, const double* __restrict__ b,
+                                              const double* __restrict__ m, const double* __restrict__ m2) {
     const int lane = threadIdx.x % LPR;
     const long long row0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
     const long long stride = (long long)gridDim.x * blockDim.x / LPR;
     for (long long row = row0; row < nrows; row += stride) {
-        const int a = __ldg(rowptr + row), b = __ldg(rowptr + row + 1);
+        const int a = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
         double s = 0.0;
-        for (int k = a + lane; k < b; k += LPR) s = fma(__ldg(val + k), __ldg(x + __ldg(col + k)), s);
+        for (int k = a + lane; k < e; k += LPR) s = fma((double)__ldg(val + k), __ldg(x + __ldg(col + k)), s);
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LPR);
-        if (lane == 0) y[row] = s;
-    }
-}
-
-// the same with the matrix values stored in FP32 (products and sums in FP64): used for the operator applications
-// INSIDE the multigrid cycle when ocmp_system.vals32 is set — 8 instead of 12 bytes per non-zero
-template <int LPR>
-__global__ void __launch_bounds__(256) k_spmv_f32(int nrows, const int* __restrict__ rowptr,
-                                                  const int* __restrict__ col, const float* __restrict__ val,
-                                                  const double* __restrict__ x, double* __restrict__ y) {
-    const int lane = threadIdx.x % LPR;
-    const long long row0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-    const long long stride = (long long)gridDim.x * blockDim.x / LPR;
-    for (long long row = row0; row < nrows; row += stride) {
-        const int a = __ldg(rowptr + row), b = __ldg(rowptr + row + 1);
-        double s = 0.0;
-        for (int k = a + lane; k < b; k += LPR) s = fma((double)__ldg(val + k), __ldg(x + __ldg(col + k)), s);
-#pragma unroll
-        for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LPR);
-        if (lane == 0) y[row] = s;
+        if (lane == 0) {
+            if (EP == EP_PLAIN) y[row] = s;
+            else {
+                double v = (EP == EP_RESID) ? __ldg(b + row) - s : s;
+                if (m) v *= __ldg(m + row);
+                if (EP == EP_RESID && m2) v *= __ldg(m2 + row);
+                y[row] = (EP == EP_ADD) ? y[row] + v : v;
+            }
+        }
     }
 }
 
@@ -142,34 +137,36 @@ __global__ void __launch_bounds__(256) k_to_f32(long long n, const double* __res
         dst[i] = (float)src[i];
 }
 
-static int spmv_cat(int cat, int nrows, const int* rowptr, const int* colidx, const double* vals, const double* x,
-                    double* y, cudaStream_t st);
-extern "C" int ocmp_spmv(int nrows, const int* rowptr, const int* colidx, const double* vals, const double* x,
-                         double* y, void* stream) {
-    return spmv_cat(PROF_SPMV, nrows, rowptr, colidx, vals, x, y, (cudaStream_t)stream);
-}
-static int spmv_cat(int cat, int nrows, const int* rowptr, const int* colidx, const double* vals, const double* x,
-                    double* y, cudaStream_t st) {
+// one launch: category `cat`, values from `vals32` when given, else `vals`
+static int spmv_ep(int cat, int ep, int nrows, const int* rowptr, const int* colidx, const double* vals,
+                   const float* vals32, const double* x, double* y, const double* b, const double* m,
+                   const double* m2, cudaStream_t st) {
     if (nrows <= 0) return 0;
     const int threads = 256;
     const long long want = ((long long)nrows * 16 + threads - 1) / threads;
     const long long cap = (long long)ocmp_sm_count() * 64;
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     ProfScope ps(cat, st);
-    k_spmv<16><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, vals, x, y);
+#define SPMV_GO(VT, V, EP) k_spmv<16, VT, EP><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, V, x, y, b, m, m2)
+    if (vals32) {
+        if (ep == EP_PLAIN) SPMV_GO(float, vals32, EP_PLAIN);
+        else if (ep == EP_RESID) SPMV_GO(float, vals32, EP_RESID);
+        else if (ep == EP_MASK) SPMV_GO(float, vals32, EP_MASK);
+        else SPMV_GO(float, vals32, EP_ADD);
+    } else {
+        if (ep == EP_PLAIN) SPMV_GO(double, vals, EP_PLAIN);
+        else if (ep == EP_RESID) SPMV_GO(double, vals, EP_RESID);
+        else if (ep == EP_MASK) SPMV_GO(double, vals, EP_MASK);
+        else SPMV_GO(double, vals, EP_ADD);
+    }
+#undef SPMV_GO
     return ocmp_check("ocmp_spmv");
 }
 
-static int spmv_cat_f32(int cat, int nrows, const int* rowptr, const int* colidx, const float* vals, const double* x,
-                        double* y, cudaStream_t st) {
-    if (nrows <= 0) return 0;
-    const int threads = 256;
-    const long long want = ((long long)nrows * 16 + threads - 1) / threads;
-    const long long cap = (long long)ocmp_sm_count() * 64;
-    const unsigned blocks = (unsigned)(want < cap ? want : cap);
-    ProfScope ps(cat, st);
-    k_spmv_f32<16><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, vals, x, y);
-    return ocmp_check("ocmp_spmv_f32");
+extern "C" int ocmp_spmv(int nrows, const int* rowptr, const int* colidx, const double* vals, const double* x,
+                         double* y, void* stream) {
+    return spmv_ep(PROF_SPMV, EP_PLAIN, nrows, rowptr, colidx, vals, nullptr, x, y, nullptr, nullptr, nullptr,
+                   (cudaStream_t)stream);
 }
 
 extern "C" int ocmp_to_f32(long long n, const double* src, float* dst, void* stream) {
@@ -205,15 +202,16 @@ __global__ void __launch_bounds__(256) k_masked_assign(long long n, double* __re
         if (mask[i] > 0.0) dst[i] = src[i] * inv[i];
 }
 
-// z = m .* (a .* r)   (a, m optional)
+// z (+)= scale * a .* m .* r   (a, m optional)
 __global__ void __launch_bounds__(256) k_had(long long n, const double* __restrict__ a, const double* __restrict__ m,
-                                             const double* __restrict__ r, double* __restrict__ z) {
+                                             const double* __restrict__ r, double* __restrict__ z, double scale,
+                                             int accumulate) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
-        double v = r[i];
+        double v = r[i] * scale;
         if (a) v *= a[i];
         if (m) v *= m[i];
-        z[i] = v;
+        z[i] = accumulate ? z[i] + v : v;
     }
 }
 
@@ -228,20 +226,22 @@ __global__ void __launch_bounds__(256) k_resid(long long n, const double* __rest
     }
 }
 
-// out[j] += <V_j, w>, j < k <= 8 ; V_j = V + j*ld
+// out[j] += <V_j, w>, j < k <= K ; V_j = V + j*ld ; and, when `extra` is given, out[k] += <extra, w> (the squared
+// norm of w rides along with the second Gram-Schmidt pass)
 template <int K>
 __global__ void __launch_bounds__(256) k_mdot(long long n, const double* __restrict__ V, long long ld, int k,
                                               const double* __restrict__ w, double* __restrict__ out,
-                                              const double* __restrict__ m = nullptr) {
-    double s[K];
+                                              const double* __restrict__ m, const double* __restrict__ extra) {
+    double s[K + 1];
 #pragma unroll
-    for (int j = 0; j < K; ++j) s[j] = 0.0;
+    for (int j = 0; j <= K; ++j) s[j] = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
         const double wi = m ? w[i] * m[i] : w[i];
 #pragma unroll
         for (int j = 0; j < K; ++j)
             if (j < k) s[j] = fma(V[j * ld + i], wi, s[j]);
+        if (extra) s[K] = fma(extra[i], wi, s[K]);
     }
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -250,19 +250,47 @@ __global__ void __launch_bounds__(256) k_mdot(long long n, const double* __restr
             if (threadIdx.x == 0) atomicAdd(out + j, t);
         }
     }
+    if (extra) {
+        const double t = block_reduce_sum(s[K]);
+        if (threadIdx.x == 0) atomicAdd(out + k, t);
+    }
 }
 
-// w += sum_j c[j] V_j  (c on device)
+// w += sign * sum_j c[j] V_j  (c on device)
 __global__ void __launch_bounds__(256) k_maxpy(long long n, const double* __restrict__ V, long long ld, int k,
-                                               const double* __restrict__ c, double* __restrict__ w) {
+                                               const double* __restrict__ c, double* __restrict__ w, double sign) {
     extern __shared__ double sc[];
-    for (int j = threadIdx.x; j < k; j += blockDim.x) sc[j] = c[j];
+    for (int j = threadIdx.x; j < k; j += blockDim.x) sc[j] = sign * c[j];
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
         double s = w[i];
         for (int j = 0; j < k; ++j) s = fma(sc[j], V[j * ld + i], s);
         w[i] = s;
+    }
+}
+
+// Second Gram-Schmidt correction and normalisation in one pass: out = (w - sum_j c[j] V_j) / hn with
+// hn^2 = c[k] - sum_j c[j]^2  (c[k] = <w, w> before the correction; V orthonormal). out = 0 when hn^2 <= 0.
+__global__ void __launch_bounds__(256) k_gs_finish(long long n, const double* __restrict__ V, long long ld, int k,
+                                                   const double* __restrict__ c, const double* __restrict__ w,
+                                                   double* __restrict__ out) {
+    extern __shared__ double sc[];
+    __shared__ double s_inv;
+    for (int j = threadIdx.x; j <= k; j += blockDim.x) sc[j] = c[j];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double h2 = sc[k];
+        for (int j = 0; j < k; ++j) h2 -= sc[j] * sc[j];
+        s_inv = h2 > 0.0 ? 1.0 / sqrt(h2) : 0.0;
+    }
+    __syncthreads();
+    const double inv = s_inv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double s = w[i];
+        for (int j = 0; j < k; ++j) s = fma(-sc[j], V[j * ld + i], s);
+        out[i] = s * inv;
     }
 }
 
@@ -295,7 +323,7 @@ extern "C" int ocmp_mdot(long long n, const double* V, long long ld, int k, cons
     ocmp_prof_begin(PROF_MDOT, st);
     for (int j0 = 0; j0 < k && n > 0; j0 += 8) {
         const int kk = (k - j0) < 8 ? (k - j0) : 8;
-        k_mdot<8><<<grid_for(n), 256, 0, st>>>(n, V + (long long)j0 * ld, ld, kk, w, out + j0);
+        k_mdot<8><<<grid_for(n), 256, 0, st>>>(n, V + (long long)j0 * ld, ld, kk, w, out + j0, nullptr, nullptr);
     }
     ocmp_prof_end(PROF_MDOT, st);
     return ocmp_check("ocmp_mdot");
@@ -305,7 +333,7 @@ extern "C" int ocmp_maxpy(long long n, const double* V, long long ld, int k, con
     cudaStream_t st = (cudaStream_t)stream;
     if (k <= 0 || n <= 0) return 0;
     ProfScope ps(PROF_MAXPY, st);
-    k_maxpy<<<grid_for(n), 256, sizeof(double) * k, st>>>(n, V, ld, k, coef, w);
+    k_maxpy<<<grid_for(n), 256, sizeof(double) * k, st>>>(n, V, ld, k, coef, w, 1.0);
     return ocmp_check("ocmp_maxpy");
 }
 extern "C" int ocmp_masked_assign(long long n, double* dst, const double* src, const double* inv, const double* mask,
@@ -490,195 +518,183 @@ extern "C" int ocmp_asm_setup_f32(int npatch, int bs, const int* patch_dofs, con
 }
 
 
-// one warp per patch: z[dofs] += A_p^-1 r[dofs]
-template <typename InT>
-__global__ void __launch_bounds__(256) k_asm_apply(int npatch, int bs, const int* __restrict__ pdofs,
-                                                   const InT* __restrict__ inv, const double* __restrict__ r,
-                                                   double* __restrict__ z) {
-    extern __shared__ double sr[];         // [warps][bs]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    double* rr = sr + warp * bs;
-    for (long long p = (long long)blockIdx.x * wpb + warp; p < npatch; p += (long long)gridDim.x * wpb) {
-        const int* d = pdofs + p * bs;
-        __syncwarp();
-        for (int j = lane; j < bs; j += 32) {
-            const int dj = __ldg(d + j);
-            rr[j] = dj >= 0 ? __ldg(r + dj) : 0.0;
-        }
-        __syncwarp();
-        const InT* A = inv + p * bs * bs;
-        for (int i = lane; i < bs; i += 32) {
-            double s = 0.0;
-            for (int j = 0; j < bs; ++j) s = fma(ocmp_load(A + j * bs + i), rr[j], s);
-            const int di = __ldg(d + i);
-            if (di >= 0) atomicAdd(z + di, s);
-        }
-    }
-}
-
-static int apply_cta(int npatch, int bs, const int* pd, const double* inv, const double* r, double* z,
-                     cudaStream_t st) {
-    return ocmp_patch_apply_cta(npatch, bs, pd, inv, r, z, st);
-}
-static int apply_cta(int npatch, int bs, const int* pd, const float* inv, const double* r, double* z,
-                     cudaStream_t st) {
-    return ocmp_patch_apply_cta_f32(npatch, bs, pd, inv, r, z, st);
-}
-
-static int apply_cta(int npatch, int bs, const int* pd, const __nv_bfloat16* inv, const double* r, double* z,
-                     cudaStream_t st) {
-    return ocmp_patch_apply_cta_bf16(npatch, bs, pd, inv, r, z, st);
-}
-
-template <typename InT>
-static int asm_apply(int npatch, int bs, const int* patch_dofs, const InT* inv_blocks, const double* r, double* z,
-                     long long n, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(z, 0, sizeof(double) * n, st);
+// z = sum over the patches of A_p^-1 r[dofs_p] scattered back: the streamed patch products into the patch-local
+// buffer `ybuf` (npatch x bs doubles), then the per-dof gather through the incidence list (inc_ptr: n + 1, inc_idx:
+// positions p * bs + i of every valid patch entry of the dof, ascending). Two launches, no atomics, deterministic.
+static int patch_products(int npatch, int bs, const int* patch_dofs, const void* inv, int storage, const double* r,
+                          double* ybuf, long long n, cudaStream_t st) {
     if (npatch <= 0) return 0;
-    ocmp_prof_bytes(PROF_ASM_APPLY, (double)sizeof(InT) * npatch * bs * bs + 16.0 * n);
-    if (bs >= 48) {
-        ProfScope ps(PROF_ASM_APPLY, st);
-        if (apply_cta(npatch, bs, patch_dofs, inv_blocks, r, z, st)) return ocmp_check("ocmp_asm_apply");
-    }
-    const int wpb = 8;
-    const size_t smem = sizeof(double) * wpb * bs;
-    long long blocks = (npatch + wpb - 1) / wpb;
-    const long long cap = (long long)ocmp_sm_count() * 8;
-    if (blocks > cap) blocks = cap;
+    const double elem = storage == 0 ? 8.0 : storage == 1 ? 4.0 : 2.0;
+    ocmp_prof_bytes(PROF_ASM_APPLY, elem * npatch * bs * bs + 16.0 * n);
     ProfScope ps(PROF_ASM_APPLY, st);
-    k_asm_apply<InT><<<(unsigned)blocks, wpb * 32, smem, st>>>(npatch, bs, patch_dofs, inv_blocks, r, z);
-    return ocmp_check("ocmp_asm_apply");
+    int rc;
+    if (storage == 2) rc = ocmp_patch_apply_y_bf16(npatch, bs, patch_dofs, (const __nv_bfloat16*)inv, r, ybuf, st);
+    else if (storage == 1) rc = ocmp_patch_apply_y_f32(npatch, bs, patch_dofs, (const float*)inv, r, ybuf, st);
+    else rc = ocmp_patch_apply_y(npatch, bs, patch_dofs, (const double*)inv, r, ybuf, st);
+    return rc ? rc : ocmp_check("ocmp_asm_apply");
+}
+static int patch_gather(long long n, const int* inc_ptr, const int* inc_idx, const double* ybuf, const double* w,
+                        const double* m, double scale, double* z, int accumulate, cudaStream_t st) {
+    ProfScope ps(PROF_VEC, st);
+    ocmp_patch_gather(n, inc_ptr, inc_idx, ybuf, w, m, scale, z, accumulate, st);
+    return ocmp_check("ocmp_asm_apply (gather)");
 }
 
-extern "C" int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const double* inv_blocks, const double* r,
-                              double* z, long long n, void* stream) {
-    return asm_apply<double>(npatch, bs, patch_dofs, inv_blocks, r, z, n, stream);
+static int asm_apply(int npatch, int bs, const int* patch_dofs, const void* inv, int storage, const int* inc_ptr,
+                     const int* inc_idx, double* ybuf, const double* r, double* z, long long n, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (npatch <= 0) { cudaMemsetAsync(z, 0, sizeof(double) * n, st); return 0; }
+    if (int rc = patch_products(npatch, bs, patch_dofs, inv, storage, r, ybuf, n, st)) return rc;
+    return patch_gather(n, inc_ptr, inc_idx, ybuf, nullptr, nullptr, 1.0, z, 0, st);
 }
 
+extern "C" int ocmp_asm_apply(int npatch, int bs, const int* patch_dofs, const double* inv_blocks, const int* inc_ptr,
+                              const int* inc_idx, double* ybuf, const double* r, double* z, long long n,
+                              void* stream) {
+    return asm_apply(npatch, bs, patch_dofs, inv_blocks, 0, inc_ptr, inc_idx, ybuf, r, z, n, stream);
+}
+extern "C" int ocmp_asm_apply_f32(int npatch, int bs, const int* patch_dofs, const float* inv_blocks,
+                                  const int* inc_ptr, const int* inc_idx, double* ybuf, const double* r, double* z,
+                                  long long n, void* stream) {
+    return asm_apply(npatch, bs, patch_dofs, inv_blocks, 1, inc_ptr, inc_idx, ybuf, r, z, n, stream);
+}
 extern "C" int ocmp_asm_apply_bf16(int npatch, int bs, const int* patch_dofs, const unsigned short* inv_blocks,
-                                   const double* r, double* z, long long n, void* stream) {
-    return asm_apply<__nv_bfloat16>(npatch, bs, patch_dofs, reinterpret_cast<const __nv_bfloat16*>(inv_blocks), r, z, n,
-                                    stream);
-}
-
-extern "C" int ocmp_asm_apply_f32(int npatch, int bs, const int* patch_dofs, const float* inv_blocks, const double* r,
-                                  double* z, long long n, void* stream) {
-    return asm_apply<float>(npatch, bs, patch_dofs, inv_blocks, r, z, n, stream);
+                                   const int* inc_ptr, const int* inc_idx, double* ybuf, const double* r, double* z,
+                                   long long n, void* stream) {
+    return asm_apply(npatch, bs, patch_dofs, inv_blocks, 2, inc_ptr, inc_idx, ybuf, r, z, n, stream);
 }
 
 // ---- Krylov drivers ---------------------------------------------------------------------------------------------
 namespace {
+// pinned host staging for the Gram-Schmidt coefficients (asynchronous device -> host copies)
+double* pinned_scalars(size_t count) {
+    static double* buf = nullptr;
+    static size_t cap = 0;
+    if (count > cap) {
+        if (buf) cudaFreeHost(buf);
+        cap = count < 1024 ? 1024 : 2 * count;
+        if (cudaMallocHost(&buf, sizeof(double) * cap) != cudaSuccess) { buf = nullptr; cap = 0; }
+    }
+    return buf;
+}
+
 struct Ctx {
     const ocmp_system* s;
     cudaStream_t st;
     long long n;
-    double* dscal;      // device scratch scalars (>= 64)
+    double* dscal;      // device scratch scalars
     double hscal[64];
     mutable int failed = 0;     // a matrix-free operator callback reported an error
 
-    // y = A x; element-partitioned: followed by the ghost refresh, so y is consistent like x
-    void A(const double* x, double* y) const {
+    static void had(cudaStream_t st, long long n, const double* a, const double* m, const double* r, double* z,
+                    double scale, int accumulate) {
+        ProfScope ps(PROF_VEC, st);
+        if (n > 0) k_had<<<grid_for(n), 256, 0, st>>>(n, a, m, r, z, scale, accumulate);
+    }
+    // y = m .* (A x) of the Krylov operator (mask optional); element-partitioned: followed by the ghost refresh, so
+    // y is consistent like x
+    void A(const double* x, double* y, bool masked) const {
         if (s->apply_fn) {      // matrix-free operator: the form's action (quadrature kernels), no CSR values read
             if (((ocmp_apply_fn)s->apply_fn)(s->apply_ctx, x, y, (void*)st) != 0 && !failed) failed = 1;
+            if (masked && s->freemask) had(st, n, nullptr, s->freemask, y, y, 1.0, 0);
         } else {
-            ocmp_spmv(s->nrows, s->rowptr, s->colidx, s->vals, x, y, st);
+            spmv_ep(PROF_SPMV, masked && s->freemask ? EP_MASK : EP_PLAIN, s->nrows, s->rowptr, s->colidx, s->vals,
+                    nullptr, x, y, nullptr, s->freemask, nullptr, st);
         }
         if (s->halo_fwd) ocmp_halo_run(s->halo_fwd - 1, y, 0, st);
     }
-    // one application of the smoother / local preconditioner of system `sy`: z = S r (r masked, result masked)
-    static void smooth(const ocmp_system* sy, cudaStream_t st, const double* r, double* z) {
+    // r = m .* (b - A x) of the Krylov operator
+    void residual(const double* b, const double* x, double* r) const {
+        if (s->apply_fn) {
+            A(x, r, false);
+            ProfScope ps(PROF_VEC, st);
+            k_resid<<<grid_for(n), 256, 0, st>>>(n, b, s->freemask, r);
+        } else {
+            spmv_ep(PROF_SPMV, EP_RESID, s->nrows, s->rowptr, s->colidx, s->vals, nullptr, x, r, b, s->freemask,
+                    nullptr, st);
+            if (s->halo_fwd) ocmp_halo_run(s->halo_fwd - 1, r, 0, st);
+        }
+    }
+    // One application of the smoother / local preconditioner of system `sy`: z (+)= scale * S r (r masked, result
+    // masked). `tmp` (n doubles) is only needed for accumulate on an element-partitioned patch smoother.
+    static void smooth(const ocmp_system* sy, cudaStream_t st, const double* r, double* z, double scale,
+                       int accumulate, double* tmp) {
         const long long n = sy->nrows;
         if (sy->pre_kind == 1) {
-            ProfScope ps(PROF_VEC, st);
-            k_had<<<grid_for(n), 256, 0, st>>>(n, sy->dinv, nullptr, r, z);
+            had(st, n, sy->dinv, nullptr, r, z, scale, accumulate);
         } else if (sy->pre_kind == 2 || sy->pre_kind == 3) {
-            if (sy->inv_storage == 2)
-                ocmp_asm_apply_bf16(sy->npatch, sy->bs, sy->patch_dofs, (const unsigned short*)sy->inv_blocks, r, z, n,
-                                    st);
-            else if (sy->inv_storage == 1)
-                ocmp_asm_apply_f32(sy->npatch, sy->bs, sy->patch_dofs, (const float*)sy->inv_blocks, r, z, n, st);
-            else
-                ocmp_asm_apply(sy->npatch, sy->bs, sy->patch_dofs, (const double*)sy->inv_blocks, r, z, n, st);
-            // a rank applies the patches of the vertices it owns; DOFs shared with a neighbour get the sum
-            if (sy->halo_sum) ocmp_halo_run(sy->halo_sum - 1, z, 1, st);
-            if (sy->freemask || sy->patch_weight) {
-                ProfScope ps(PROF_VEC, st);
-                k_had<<<grid_for(n), 256, 0, st>>>(n, sy->patch_weight, sy->freemask, z, z);
+            patch_products(sy->npatch, sy->bs, sy->patch_dofs, sy->inv_blocks, sy->inv_storage, r, sy->patch_ybuf, n,
+                           st);
+            if (sy->halo_sum && accumulate) {
+                // a rank applies the patches of the vertices it owns; DOFs shared with a neighbour get the sum
+                patch_gather(n, sy->patch_inc_ptr, sy->patch_inc_idx, sy->patch_ybuf, sy->patch_weight, sy->freemask,
+                             scale, tmp, 0, st);
+                ocmp_halo_run(sy->halo_sum - 1, tmp, 1, st);
+                ocmp_axpby(n, 1.0, tmp, 1.0, z, st);
+            } else {
+                patch_gather(n, sy->patch_inc_ptr, sy->patch_inc_idx, sy->patch_ybuf, sy->patch_weight, sy->freemask,
+                             scale, z, accumulate, st);
+                if (sy->halo_sum) ocmp_halo_run(sy->halo_sum - 1, z, 1, st);
             }
         } else if (sy->pre_kind == 4) {
-            spmv_cat(PROF_SPMV_MG, sy->nrows, sy->inv_rowptr, sy->inv_colidx, sy->inv_vals, r, z, st);
-            // replicated coarsest level: every rank solved with its own (round-off different) copy; owners' values win
+            // explicit inverse of the coarsest level, stored as a (dense) CSR matrix
+            spmv_ep(PROF_SPMV_MG, accumulate ? EP_ADD : EP_MASK, sy->nrows, sy->inv_rowptr, sy->inv_colidx,
+                    sy->inv_vals, nullptr, r, z, nullptr, sy->freemask, nullptr, st);
+            // replicated coarsest level: every rank solved with its own copy; the owners' values win
             if (sy->halo_fwd) ocmp_halo_run(sy->halo_fwd - 1, z, 0, st);
-            if (sy->freemask) {
-                ProfScope ps(PROF_VEC, st);
-                k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, z, z);
-            }
         } else if (sy->pre_kind == 5 && sy->direct) {
             // Preconditioner(a, 'direct'): exact solve with the factorised free-free block (zero on constrained dofs)
             const ocmp_band_lu* f = sy->direct;
             ocmp_band_gather(sy->nrows, f->perm, r, f->rhs, st);
             ocmp_band_solve(f->n, f->kl, f->ku, f->ubw, f->ab, f->ipiv, f->rhs, st);
-            ocmp_band_scatter(sy->nrows, f->perm, f->rhs, z, 0, st);
+            ocmp_band_scatter(sy->nrows, f->perm, f->rhs, z, accumulate, st);
         } else {
-            ProfScope ps(PROF_VEC, st);
-            k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, r, z);
+            had(st, n, nullptr, sy->freemask, r, z, scale, accumulate);
         }
     }
-    // operator application inside the cycle: FP32-stored copy of the level matrix when the host provided one
-    static void level_spmv(const ocmp_system* sy, const double* x, double* y, cudaStream_t st) {
-        if (sy->vals32) spmv_cat_f32(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals32, x, y, st);
-        else spmv_cat(PROF_SPMV_MG, sy->nrows, sy->rowptr, sy->colidx, sy->vals, x, y, st);
+    // r = m .* m2 .* (b - A x) on a multigrid level: FP32-stored copy of the level matrix when the host provided one
+    static void level_residual(const ocmp_system* sy, const double* b, const double* x, double* r, const double* m2,
+                               bool refresh, cudaStream_t st) {
+        spmv_ep(PROF_SPMV_MG, EP_RESID, sy->nrows, sy->rowptr, sy->colidx, sy->vals, sy->vals32, x, r, b, sy->freemask,
+                m2, st);
+        if (refresh && sy->halo_fwd) ocmp_halo_run(sy->halo_fwd - 1, r, 0, st);
     }
-    // V-cycle on level l: x = MG(b); b is masked on entry, x is masked on exit
+    // V-cycle on level l: x = MG(b); b is masked on entry, x is masked on exit. Launches per level and cycle with
+    // nu = 1: smoother 2 + residual 1 + restriction 1 + prolongation 1 + residual 1 + smoother 2.
     static void vcycle(const ocmp_mg_level* L, int l, cudaStream_t st, const double* b, double* x) {
         const ocmp_mg_level& lv = L[l];
         const ocmp_system* sy = &lv.sys;
         const long long n = sy->nrows;
-        if (l == 0) { smooth(sy, st, b, x); return; }
+        if (l == 0) { smooth(sy, st, b, x, 1.0, 0, nullptr); return; }
         double* r = lv.work + 2 * n;
         double* t = lv.work + 3 * n;
-        smooth(sy, st, b, x);
-        ocmp_axpby(n, 0.0, x, lv.omega, x, st);
+        smooth(sy, st, b, x, lv.omega, 0, t);                 // x = omega S b   (zero initial guess)
         for (int s = 1; s < lv.nu; ++s) {
-            level_spmv(sy, x, r, st);
-            if (sy->halo_fwd) ocmp_halo_run(sy->halo_fwd - 1, r, 0, st);
-            k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
-            smooth(sy, st, r, t);
-            ocmp_axpby(n, lv.omega, t, 1.0, x, st);
+            level_residual(sy, b, x, r, nullptr, true, st);
+            smooth(sy, st, r, x, lv.omega, 1, t);
         }
-        // residual to restrict: only the owned entries are used, so no ghost refresh after this SpMV
-        level_spmv(sy, x, r, st);
-        k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
-        if (sy->owned) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->owned, r, r);
+        // residual to restrict: only the owned entries are used, so no ghost refresh after this product
+        level_residual(sy, b, x, r, sy->owned, false, st);
         const ocmp_mg_level& lc = L[l - 1];
         const long long nc = lc.sys.nrows;
         double* xc = lc.work;
         double* bc = lc.work + nc;
-        spmv_cat(PROF_SPMV_MG, (int)nc, lv.r_rowptr, lv.r_colidx, lv.r_vals, r, bc, st);
+        spmv_ep(PROF_SPMV_MG, EP_MASK, (int)nc, lv.r_rowptr, lv.r_colidx, lv.r_vals, nullptr, r, bc, nullptr,
+                lc.sys.freemask, nullptr, st);
         if (lv.restrict_sum) ocmp_halo_run(lv.restrict_sum - 1, bc, 1, st);
-        if (lc.sys.freemask) k_had<<<grid_for(nc), 256, 0, st>>>(nc, nullptr, lc.sys.freemask, bc, bc);
         vcycle(L, l - 1, st, bc, xc);
         if (lv.handover) ocmp_halo_run(lv.handover - 1, xc, 0, st);
-        spmv_cat(PROF_SPMV_MG, sy->nrows, lv.p_rowptr, lv.p_colidx, lv.p_vals, xc, t, st);
-        if (sy->freemask) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, sy->freemask, t, t);
-        ocmp_axpby(n, 1.0, t, 1.0, x, st);
+        spmv_ep(PROF_SPMV_MG, EP_ADD, sy->nrows, lv.p_rowptr, lv.p_colidx, lv.p_vals, nullptr, xc, x, nullptr,
+                sy->freemask, nullptr, st);                  // x += m .* (P xc)
         for (int s = 0; s < lv.nu; ++s) {
-            level_spmv(sy, x, r, st);
-            if (sy->halo_fwd) ocmp_halo_run(sy->halo_fwd - 1, r, 0, st);
-            k_resid<<<grid_for(n), 256, 0, st>>>(n, b, sy->freemask, r);
-            smooth(sy, st, r, t);
-            ocmp_axpby(n, lv.omega, t, 1.0, x, st);
+            level_residual(sy, b, x, r, nullptr, true, st);
+            smooth(sy, st, r, x, lv.omega, 1, t);
         }
     }
     // z = P (already masked r); result masked
     void P(const double* r, double* z) const {
         if (s->pre_kind == 3 && s->nlevels > 1) vcycle(s->levels, s->nlevels - 1, st, r, z);
-        else smooth(s, st, r, z);
-    }
-    void mask(double* v) const {
-        ProfScope ps(PROF_VEC, st);
-        if (s->freemask) k_had<<<grid_for(n), 256, 0, st>>>(n, nullptr, s->freemask, v, v);
+        else smooth(s, st, r, z, 1.0, 0, nullptr);
     }
     // <x, y> over the owned entries, summed over the ranks (one FP64 all-reduce) when element-partitioned
     double dot(const double* x, const double* y) {
@@ -693,22 +709,27 @@ struct Ctx {
         return hscal[0];
     }
     void axpby(double a, const double* x, double b, double* y) const { ocmp_axpby(n, a, x, b, y, st); }
-    void mdot(const double* V, int k, const double* w, double* hout) {
+    // dout[j] = <V_j, w>, j < k, and dout[k] = <extra, w> when extra is given; all-reduced; stays on the device
+    void mdot_dev(const double* V, int k, const double* w, const double* extra, double* dout) {
+        const int tot = k + (extra ? 1 : 0);
+        cudaMemsetAsync(dout, 0, sizeof(double) * tot, st);
         ocmp_prof_begin(PROF_MDOT, st);
-        cudaMemsetAsync(dscal, 0, sizeof(double) * k, st);
-        for (int j0 = 0; j0 < k; j0 += 8) {
+        for (int j0 = 0; j0 < k || (j0 == 0 && extra); j0 += 8) {
             const int kk = (k - j0) < 8 ? (k - j0) : 8;
-            k_mdot<8><<<grid_for(n), 256, 0, st>>>(n, V + (long long)j0 * n, n, kk, w, dscal + j0, s->owned);
+            const bool last = j0 + 8 >= k;
+            k_mdot<8><<<grid_for(n), 256, 0, st>>>(n, V + (long long)j0 * n, n, kk, w, dout + j0, s->owned,
+                                                   last ? extra : nullptr);
         }
         ocmp_prof_end(PROF_MDOT, st);
-        if (s->owned) ocmp_allreduce_sum(dscal, k, st);
-        cudaMemcpyAsync(hout, dscal, sizeof(double) * k, cudaMemcpyDeviceToHost, st);
-        cudaStreamSynchronize(st);
+        if (s->owned) ocmp_allreduce_sum(dout, tot, st);
+    }
+    void maxpy_dev(const double* V, int k, const double* dc, double sign, double* w) {
+        ProfScope ps(PROF_MAXPY, st);
+        k_maxpy<<<grid_for(n), 256, sizeof(double) * k, st>>>(n, V, n, k, dc, w, sign);
     }
     void maxpy(const double* V, int k, const double* hc, double* w) {
         cudaMemcpyAsync(dscal, hc, sizeof(double) * k, cudaMemcpyHostToDevice, st);
-        ProfScope ps(PROF_MAXPY, st);
-        k_maxpy<<<grid_for(n), 256, sizeof(double) * k, st>>>(n, V, n, k, dscal, w);
+        maxpy_dev(V, k, dscal, 1.0, w);
     }
 };
 }  // namespace
@@ -724,7 +745,7 @@ extern "C" int ocmp_krylov_history(double* out, int cap) {
 extern "C" long long ocmp_krylov_work_len(int nrows, int kind, int restart) {
     const long long n = nrows;
     if (kind == 0) return 4 * n + 64;
-    if (kind == 1) return (long long)(restart + 1) * n + 2 * n + 2 * (restart + 2) + 64;
+    if (kind == 1) return (long long)(restart + 2) * n + 2 * n + 2 * (restart + 2) + 128;
     if (kind == 3) return 9 * n + 64;
     return 2 * n + 64;
 }
@@ -742,8 +763,7 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
     if (kind == 0) {                       // preconditioned CG on the free dofs
         double *r = work, *z = work + n, *p = work + 2 * n, *Ap = work + 3 * n;
         c.dscal = work + 4 * n;
-        c.A(x, r);
-        k_resid<<<grid_for(n), 256, 0, c.st>>>(n, b, sys->freemask, r);
+        c.residual(b, x, r);
         c.P(r, z);
         c.axpby(1.0, z, 0.0, p);
         double rz = c.dot(r, z);
@@ -751,8 +771,7 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
         res = err0;
         if (rz != 0.0) {
             for (it = 0; it < maxit;) {
-                c.A(p, Ap);
-                c.mask(Ap);
+                c.A(p, Ap, true);
                 const double pAp = c.dot(p, Ap);
                 const double alpha = rz / pAp;
                 c.axpby(alpha, p, 1.0, x);
@@ -768,17 +787,27 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
             }
         }
     } else if (kind == 1) {                // left-preconditioned restarted GMRES, CGS2 orthogonalisation
+        // Per iteration: operator + preconditioner, two batched Gram-Schmidt passes whose coefficients stay on the
+        // device (the corrections read them there), the squared norm of the new vector riding along with the second
+        // pass (||w - V h2||^2 = ||w||^2 - ||h2||^2), correction + normalisation fused — ONE host synchronisation and,
+        // element-partitioned, TWO all-reduces per iteration. The Hessenberg / Givens recurrences run on the host
+        // from the coefficients copied back asynchronously into pinned memory.
         const int m = restart;
         double* V = work;
         double* w = work + (long long)(m + 1) * n;
         double* t = w + n;
-        c.dscal = t + n;
-        std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), h(m + 2), h2(m + 2), yv(m);
+        c.dscal = t + n;                                      // [0, 64): dot(); then two coefficient arrays of m + 2
+        double* d1 = c.dscal + 64;
+        double* d2 = d1 + (m + 2);
+        double* pin = pinned_scalars(2 * (size_t)(m + 2));
+        if (!pin) return ocmp_fail(-6, "ocmp_krylov: cannot allocate pinned host memory");
+        double* h1 = pin;
+        double* h2 = pin + (m + 2);
+        std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), yv(m);
         double beta0 = -1.0;
         bool done = false;
         while (!done && it < maxit) {
-            c.A(x, t);
-            k_resid<<<grid_for(n), 256, 0, c.st>>>(n, b, sys->freemask, t);
+            c.residual(b, x, t);
             c.P(t, V);
             double beta = sqrt(c.dot(V, V));
             if (beta0 < 0.0) beta0 = beta;
@@ -789,17 +818,29 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
             g[0] = beta;
             int k = 0;
             for (; k < m && it < maxit; ++k) {
-                c.A(V + (long long)k * n, t);
-                c.mask(t);
+                double* vn = V + (long long)(k + 1) * n;
+                c.A(V + (long long)k * n, t, true);
                 c.P(t, w);
-                c.mdot(V, k + 1, w, h.data());
-                for (int j = 0; j <= k; ++j) h2[j] = -h[j];
-                c.maxpy(V, k + 1, h2.data(), w);
-                c.mdot(V, k + 1, w, h2.data());          // second Gram-Schmidt pass
-                for (int j = 0; j <= k; ++j) { h[j] += h2[j]; h2[j] = -h2[j]; }
-                c.maxpy(V, k + 1, h2.data(), w);
-                const double hn = sqrt(c.dot(w, w));
-                for (int j = 0; j <= k; ++j) H[(size_t)j * m + k] = h[j];
+                c.mdot_dev(V, k + 1, w, nullptr, d1);
+                cudaMemcpyAsync(h1, d1, sizeof(double) * (k + 1), cudaMemcpyDeviceToHost, c.st);
+                c.maxpy_dev(V, k + 1, d1, -1.0, w);
+                c.mdot_dev(V, k + 1, w, w, d2);              // second pass; d2[k + 1] = <w, w>
+                cudaMemcpyAsync(h2, d2, sizeof(double) * (k + 2), cudaMemcpyDeviceToHost, c.st);
+                {
+                    ProfScope ps(PROF_MAXPY, c.st);
+                    k_gs_finish<<<grid_for(n), 256, sizeof(double) * (k + 2), c.st>>>(n, V, n, k + 1, d2, w, vn);
+                }
+                cudaStreamSynchronize(c.st);
+                double ww = h2[k + 1], hh = ww;
+                for (int j = 0; j <= k; ++j) hh -= h2[j] * h2[j];
+                double hn = hh > 0.0 ? sqrt(hh) : 0.0;
+                if (hn > 0.0 && hh < 1e-4 * ww) {
+                    // the second pass removed a large part of w (cancellation in ww - |h2|^2): measure the stored
+                    // vector instead and renormalise it
+                    const double nv = sqrt(c.dot(vn, vn));
+                    if (nv > 0.0) { c.axpby(0.0, vn, 1.0 / nv, vn); hn *= nv; } else hn = 0.0;
+                }
+                for (int j = 0; j <= k; ++j) H[(size_t)j * m + k] = h1[j] + h2[j];
                 H[(size_t)(k + 1) * m + k] = hn;
                 for (int i = 0; i < k; ++i) {
                     const double a = H[(size_t)i * m + k], bb = H[(size_t)(i + 1) * m + k];
@@ -817,16 +858,12 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
                 ++it;
                 res = fabs(g[k + 1]);
                 g_history.push_back(res / beta0);
-                if (hn > 0.0) {
-                    double* vn = V + (long long)(k + 1) * n;
-                    c.axpby(1.0 / hn, w, 0.0, vn);
-                }
                 if (res < tol * beta0 || hn == 0.0) { done = true; ++k; break; }
             }
             for (int i = k - 1; i >= 0; --i) {
-                double s = g[i];
-                for (int j = i + 1; j < k; ++j) s -= H[(size_t)i * m + j] * yv[j];
-                yv[i] = s / H[(size_t)i * m + i];
+                double sacc = g[i];
+                for (int j = i + 1; j < k; ++j) sacc -= H[(size_t)i * m + j] * yv[j];
+                yv[i] = sacc / H[(size_t)i * m + i];
             }
             c.maxpy(V, k, yv.data(), x);
         }
@@ -835,8 +872,7 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
         c.dscal = work + 2 * n;
         double r0 = -1.0;
         for (it = 0; it < maxit; ++it) {
-            c.A(x, r);
-            k_resid<<<grid_for(n), 256, 0, c.st>>>(n, b, sys->freemask, r);
+            c.residual(b, x, r);
             res = sqrt(c.dot(r, r));
             if (r0 < 0.0) r0 = res;
             if (res < tol * r0 || res == 0.0) break;
@@ -854,8 +890,7 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
         cudaMemsetAsync(v0, 0, sizeof(double) * n, c.st);
         cudaMemsetAsync(w0, 0, sizeof(double) * n, c.st);
         cudaMemsetAsync(w1, 0, sizeof(double) * n, c.st);
-        c.A(x, v1);
-        k_resid<<<grid_for(n), 256, 0, c.st>>>(n, b, sys->freemask, v1);
+        c.residual(b, x, v1);
         c.P(v1, z1);
         double gamma0 = 1.0, gamma1 = sqrt(fabs(c.dot(z1, v1)));
         double eta = gamma1, s0 = 0.0, s1 = 0.0, c0 = 1.0, c1 = 1.0;
@@ -864,8 +899,7 @@ extern "C" int ocmp_krylov(const ocmp_system* sys, int kind, const double* b, do
         if (gamma1 != 0.0) {
             for (it = 0; it < maxit;) {
                 c.axpby(0.0, z1, 1.0 / gamma1, z1);                 // z_j normalised
-                c.A(z1, Az);
-                c.mask(Az);
+                c.A(z1, Az, true);
                 const double delta = c.dot(Az, z1);
                 // v_{j+1} = A z_j - (delta / gamma_j) v_j - (gamma_j / gamma_{j-1}) v_{j-1}
                 c.axpby(1.0, Az, 0.0, v2);

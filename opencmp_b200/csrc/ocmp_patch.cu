@@ -204,298 +204,190 @@ int ocmp_patch_invert_registers_bf16(int npatch, int bs, const int* pd, const in
 }
 
 // ---- application ------------------------------------------------------------------------------------------------
-// One CTA per patch. Columns of the (transposed-stored) inverse are dealt round-robin to the 8 warps; within a column
-// every lane owns the row pairs (2*lane, 2*lane+1) + 64*m and streams them with 16-byte loads, two columns per
-// iteration, so a warp keeps up to 2*MR independent 512-byte requests in flight.
-template <int MR, int NW>
-__global__ void __launch_bounds__(NW * 32) k_patch_apply(int npatch, int bs, const int* __restrict__ pdofs,
-                                                     const double* __restrict__ inv, const double* __restrict__ r,
-                                                     double* __restrict__ z) {
-    extern __shared__ double sm[];         // r_loc[bs], partial[NW][bs]
-    double* rl = sm;
-    double* part = sm + bs;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool even = (bs & 1) == 0;
-    for (int p = blockIdx.x; p < npatch; p += gridDim.x) {
-        const int* d = pdofs + (long long)p * bs;
-        __syncthreads();
-        for (int j = threadIdx.x; j < bs; j += NW * 32) {
-            const int dj = __ldg(d + j);
-            rl[j] = dj >= 0 ? __ldg(r + dj) : 0.0;
+// y[p, :] = A_p^-1 r[dofs_p] for every patch — the smoother streams its stored inverses once per application, so the
+// kernel is a pure HBM stream and is built like one: persistent CTAs, each walking its patches as ONE sequence of
+// chunks (a chunk = CC whole columns of the transposed-stored inverse = one contiguous byte range), copied into a
+// ring of NSTAGE shared-memory buffers by the bulk-copy engine (cp.async.bulk + mbarrier transaction counts, issued
+// by one thread), so the bytes in flight per SM are set by the ring, not by registers or occupancy. Thread i owns
+// row i of the current patch and accumulates over the columns of the chunk from shared memory (FP64 FMA; the stored
+// type may be FP64 / FP32 / bfloat16). The right-hand side of the NEXT patch is gathered into a register while the
+// current one streams. Results go to the patch-local output y (coalesced stores, no atomics); k_patch_gather then
+// sums, for every dof, the entries of its patches in a fixed order — the smoother is deterministic.
+namespace {
+constexpr int NSTAGE = 4;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+}  // namespace
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_patch_apply_stream(int npatch, int bs, int cc, int nchunk, int stage_bytes,
+                                                            const int* __restrict__ pdofs, const T* __restrict__ inv,
+                                                            const double* __restrict__ r, double* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smraw);            // NSTAGE barriers
+    double* rl = reinterpret_cast<double*>(smraw + 128);                                // bs doubles
+    const int rl_bytes = ((bs * 8 + 127) / 128) * 128;
+    unsigned char* stages = smraw + 128 + rl_bytes;
+    const int tid = threadIdx.x;
+    if ((int)blockIdx.x >= npatch) return;
+    const int mine = (npatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long total = (long long)mine * nchunk;
+    const long long colbytes = (long long)bs * sizeof(T);
+    const long long patch_elems = (long long)bs * bs;
+
+    auto issue = [&](long long g) {          // thread 0: start the copy of chunk g of this CTA's sequence
+        const long long k = g / nchunk;
+        const int c = (int)(g - k * nchunk);
+        const long long p = blockIdx.x + k * gridDim.x;
+        const int cols = (c == nchunk - 1) ? bs - c * cc : cc;
+        const unsigned bytes = (unsigned)(cols * colbytes);
+        const int s = (int)(g % NSTAGE);
+        const unsigned bar = smem_u32(bars + s);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(stages + (size_t)s * stage_bytes), inv + p * patch_elems + (long long)c * cc * bs, bytes, bar);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(smem_u32(bars + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (long long g = 0; g < NSTAGE && g < total; ++g) issue(g);
+    long long p = blockIdx.x;
+    if (tid < bs) {
+        const int d = __ldg(pdofs + p * bs + tid);
+        rl[tid] = d >= 0 ? __ldg(r + d) : 0.0;
+    }
+    __syncthreads();
+    double acc = 0.0, rnext = 0.0;
+    int c = 0;
+    for (long long g = 0; g < total; ++g) {
+        const int s = (int)(g % NSTAGE);
+        if (c == 0 && tid < bs && p + gridDim.x < npatch) {
+            // right-hand side of the next patch: two dependent loads whose latency the chunks of this patch hide
+            const int d = __ldg(pdofs + (p + gridDim.x) * bs + tid);
+            rnext = d >= 0 ? __ldg(r + d) : 0.0;
         }
-        __syncthreads();
-        const double* A = inv + (long long)p * bs * bs;
-        double s0[MR], s1[MR];
-#pragma unroll
-        for (int m = 0; m < MR; ++m) { s0[m] = 0.0; s1[m] = 0.0; }
-        if (even) {
-            int j = warp;
-            for (; j + NW < bs; j += 2 * NW) {
-                const double ra = rl[j], rb = rl[j + NW];
-                const double2* ca = reinterpret_cast<const double2*>(A + (long long)j * bs);
-                const double2* cb = reinterpret_cast<const double2*>(A + (long long)(j + NW) * bs);
-                double2 va[MR], vb[MR];
-#pragma unroll
-                for (int m = 0; m < MR; ++m) {
-                    const int i2 = lane + 32 * m;
-                    const bool ok = 2 * i2 < bs;
-                    va[m] = ok ? __ldg(ca + i2) : make_double2(0.0, 0.0);
-                    vb[m] = ok ? __ldg(cb + i2) : make_double2(0.0, 0.0);
-                }
-#pragma unroll
-                for (int m = 0; m < MR; ++m) {
-                    s0[m] = fma(va[m].x, ra, s0[m]); s1[m] = fma(va[m].y, ra, s1[m]);
-                    s0[m] = fma(vb[m].x, rb, s0[m]); s1[m] = fma(vb[m].y, rb, s1[m]);
-                }
+        mbar_wait(smem_u32(bars + s), (unsigned)((g / NSTAGE) & 1));
+        const int cols = (c == nchunk - 1) ? bs - c * cc : cc;
+        if (tid < bs) {
+            const T* A = reinterpret_cast<const T*>(stages + (size_t)s * stage_bytes) + tid;
+            const double* rr = rl + c * cc;
+            int j = 0;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (; j + 3 < cols; j += 4) {
+                a0 = fma(ocmp_smem_load(A + (size_t)j * bs), rr[j], a0);
+                a1 = fma(ocmp_smem_load(A + (size_t)(j + 1) * bs), rr[j + 1], a1);
+                a2 = fma(ocmp_smem_load(A + (size_t)(j + 2) * bs), rr[j + 2], a2);
+                a3 = fma(ocmp_smem_load(A + (size_t)(j + 3) * bs), rr[j + 3], a3);
             }
-            for (; j < bs; j += NW) {
-                const double ra = rl[j];
-                const double2* ca = reinterpret_cast<const double2*>(A + (long long)j * bs);
-#pragma unroll
-                for (int m = 0; m < MR; ++m) {
-                    const int i2 = lane + 32 * m;
-                    if (2 * i2 < bs) {
-                        const double2 v = __ldg(ca + i2);
-                        s0[m] = fma(v.x, ra, s0[m]); s1[m] = fma(v.y, ra, s1[m]);
-                    }
-                }
-            }
-        } else {
-            for (int j = warp; j < bs; j += NW) {
-                const double ra = rl[j];
-                const double* ca = A + (long long)j * bs;
-#pragma unroll
-                for (int m = 0; m < MR; ++m) {
-                    const int i = 2 * (lane + 32 * m);
-                    if (i < bs) s0[m] = fma(__ldg(ca + i), ra, s0[m]);
-                    if (i + 1 < bs) s1[m] = fma(__ldg(ca + i + 1), ra, s1[m]);
-                }
-            }
+            for (; j < cols; ++j) a0 = fma(ocmp_smem_load(A + (size_t)j * bs), rr[j], a0);
+            acc += (a0 + a1) + (a2 + a3);
         }
-#pragma unroll
-        for (int m = 0; m < MR; ++m) {
-            const int i = 2 * (lane + 32 * m);
-            if (i < bs) part[warp * bs + i] = s0[m];
-            if (i + 1 < bs) part[warp * bs + i + 1] = s1[m];
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < bs; i += NW * 32) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) t += part[w * bs + i];
-            const int di = __ldg(d + i);
-            if (di >= 0) atomicAdd(z + di, t);
+        __syncthreads();                      // stage s (and, on the last chunk, rl) may be overwritten now
+        if (tid == 0 && g + NSTAGE < total) issue(g + NSTAGE);
+        if (++c == nchunk) {
+            if (tid < bs) {
+                y[p * bs + tid] = acc;
+                rl[tid] = rnext;
+            }
+            acc = 0.0;
+            c = 0;
+            p += gridDim.x;
+            __syncthreads();
         }
     }
 }
 
-int ocmp_patch_apply_cta(int npatch, int bs, const int* pd, const double* inv, const double* r, double* z,
-                         cudaStream_t st) {
-    if (bs > 256) return 0;
-    constexpr int NW = 4;
-    const size_t smem = sizeof(double) * (NW + 1) * bs;
-    const int cap = ocmp_sm_count() * 16;
-    const int grid = npatch < cap ? npatch : cap;
-    if (bs <= 64) k_patch_apply<1, NW><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
-    else if (bs <= 128) k_patch_apply<2, NW><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
-    else if (bs <= 192) k_patch_apply<3, NW><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
-    else k_patch_apply<4, NW><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
-    return 1;
-}
-
-// FP32-stored inverses (bs a multiple of 4 so that every column starts 16-byte aligned): the same column-per-warp
-// scheme, every lane owns the rows 4*lane .. 4*lane+3 (+ 128*m) and streams them with 16-byte loads, UC columns per
-// iteration in flight; products and sums in FP64.
-template <int MR, int NW, int UC>
-__global__ void __launch_bounds__(NW * 32) k_patch_apply_f32(int npatch, int bs, const int* __restrict__ pdofs,
-                                                             const float* __restrict__ inv,
-                                                             const double* __restrict__ r, double* __restrict__ z) {
-    extern __shared__ double sm[];         // r_loc[bs], partial[NW][bs]
-    double* rl = sm;
-    double* part = sm + bs;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int p = blockIdx.x; p < npatch; p += gridDim.x) {
-        const int* d = pdofs + (long long)p * bs;
-        __syncthreads();
-        for (int j = threadIdx.x; j < bs; j += NW * 32) {
-            const int dj = __ldg(d + j);
-            rl[j] = dj >= 0 ? __ldg(r + dj) : 0.0;
-        }
-        __syncthreads();
-        const float* A = inv + (long long)p * bs * bs;
-        double s[MR][4];
-#pragma unroll
-        for (int m = 0; m < MR; ++m)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) s[m][c] = 0.0;
-        int j = warp;
-        for (; j + (UC - 1) * NW < bs; j += UC * NW) {
-            float4 v[UC][MR];
-            double rj[UC];
-#pragma unroll
-            for (int u = 0; u < UC; ++u) {
-                rj[u] = rl[j + u * NW];
-                const float4* col = reinterpret_cast<const float4*>(A + (long long)(j + u * NW) * bs);
-#pragma unroll
-                for (int m = 0; m < MR; ++m) {
-                    const int i4 = lane + 32 * m;
-                    v[u][m] = (4 * i4 < bs) ? __ldg(col + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UC; ++u)
-#pragma unroll
-                for (int m = 0; m < MR; ++m) {
-                    s[m][0] = fma((double)v[u][m].x, rj[u], s[m][0]);
-                    s[m][1] = fma((double)v[u][m].y, rj[u], s[m][1]);
-                    s[m][2] = fma((double)v[u][m].z, rj[u], s[m][2]);
-                    s[m][3] = fma((double)v[u][m].w, rj[u], s[m][3]);
-                }
-        }
-        for (; j < bs; j += NW) {
-            const double rj = rl[j];
-            const float4* col = reinterpret_cast<const float4*>(A + (long long)j * bs);
-#pragma unroll
-            for (int m = 0; m < MR; ++m) {
-                const int i4 = lane + 32 * m;
-                if (4 * i4 < bs) {
-                    const float4 v = __ldg(col + i4);
-                    s[m][0] = fma((double)v.x, rj, s[m][0]);
-                    s[m][1] = fma((double)v.y, rj, s[m][1]);
-                    s[m][2] = fma((double)v.z, rj, s[m][2]);
-                    s[m][3] = fma((double)v.w, rj, s[m][3]);
-                }
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < MR; ++m) {
-            const int i = 4 * (lane + 32 * m);
-            if (i < bs) {                      // bs % 4 == 0: all four rows exist
-#pragma unroll
-                for (int c = 0; c < 4; ++c) part[warp * bs + i + c] = s[m][c];
-            }
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < bs; i += NW * 32) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) t += part[w * bs + i];
-            const int di = __ldg(d + i);
-            if (di >= 0) atomicAdd(z + di, t);
-        }
+// z[d] (+)= scale * w[d] * m[d] * sum over the (patch, slot) entries of dof d, in the fixed order of the incidence list
+__global__ void __launch_bounds__(256) k_patch_gather(long long n, const int* __restrict__ inc_ptr,
+                                                      const int* __restrict__ inc_idx, const double* __restrict__ y,
+                                                      const double* __restrict__ w, const double* __restrict__ m,
+                                                      double scale, double* __restrict__ z, int accumulate) {
+    for (long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x; d < n; d += (long long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        const int a = __ldg(inc_ptr + d), b = __ldg(inc_ptr + d + 1);
+        for (int k = a; k < b; ++k) s += __ldg(y + __ldg(inc_idx + k));
+        if (w) s *= __ldg(w + d);
+        if (m) s *= __ldg(m + d);
+        s *= scale;
+        z[d] = accumulate ? z[d] + s : s;
     }
 }
 
-int ocmp_patch_apply_cta_f32(int npatch, int bs, const int* pd, const float* inv, const double* r, double* z,
-                             cudaStream_t st) {
-    if (bs > 256 || (bs & 3)) return 0;
-    constexpr int NW = 4;
-    const size_t smem = sizeof(double) * (NW + 1) * bs;
-    const int cap = ocmp_sm_count() * 16;
-    const int grid = npatch < cap ? npatch : cap;
-    if (bs <= 128) k_patch_apply_f32<1, NW, 4><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
-    else k_patch_apply_f32<2, NW, 2><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
-    return 1;
-}
-
-// bfloat16-stored inverses (bs a multiple of 8): every HALF warp streams one column, a lane owns the rows
-// 8*(lane % 16) .. +7 (+ 128*m) and loads them as one 16-byte word; UC columns per half warp in flight. A bf16 is the
-// upper half of an FP32, so the conversion is a shift; products and sums in FP64.
-__device__ __forceinline__ void bf16x2_fma(unsigned w, double rj, double& s0, double& s1) {
-    s0 = fma((double)__uint_as_float(w << 16), rj, s0);
-    s1 = fma((double)__uint_as_float(w & 0xffff0000u), rj, s1);
-}
-
-template <int MR, int NW, int UC>
-__global__ void __launch_bounds__(NW * 32) k_patch_apply_bf16(int npatch, int bs, const int* __restrict__ pdofs,
-                                                              const __nv_bfloat16* __restrict__ inv,
-                                                              const double* __restrict__ r, double* __restrict__ z) {
-    extern __shared__ double sm[];         // r_loc[bs], partial[2 * NW][bs]
-    constexpr int G = 2 * NW;              // column groups of the CTA
-    double* rl = sm;
-    double* part = sm + bs;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15;
-    const int g = 2 * warp + (lane >> 4);
-    for (int p = blockIdx.x; p < npatch; p += gridDim.x) {
-        const int* d = pdofs + (long long)p * bs;
-        __syncthreads();
-        for (int j = threadIdx.x; j < bs; j += NW * 32) {
-            const int dj = __ldg(d + j);
-            rl[j] = dj >= 0 ? __ldg(r + dj) : 0.0;
-        }
-        __syncthreads();
-        const __nv_bfloat16* A = inv + (long long)p * bs * bs;
-        double s[MR][8];
-#pragma unroll
-        for (int m = 0; m < MR; ++m)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) s[m][c] = 0.0;
-        int j = g;
-        for (; j + (UC - 1) * G < bs; j += UC * G) {
-            uint4 v[UC][MR];
-            double rj[UC];
-#pragma unroll
-            for (int u = 0; u < UC; ++u) {
-                rj[u] = rl[j + u * G];
-                const uint4* col = reinterpret_cast<const uint4*>(A + (long long)(j + u * G) * bs);
-#pragma unroll
-                for (int m = 0; m < MR; ++m) {
-                    const int i8 = l16 + 16 * m;
-                    v[u][m] = (8 * i8 < bs) ? __ldg(col + i8) : make_uint4(0u, 0u, 0u, 0u);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UC; ++u)
-#pragma unroll
-                for (int m = 0; m < MR; ++m) {
-                    bf16x2_fma(v[u][m].x, rj[u], s[m][0], s[m][1]);
-                    bf16x2_fma(v[u][m].y, rj[u], s[m][2], s[m][3]);
-                    bf16x2_fma(v[u][m].z, rj[u], s[m][4], s[m][5]);
-                    bf16x2_fma(v[u][m].w, rj[u], s[m][6], s[m][7]);
-                }
-        }
-        for (; j < bs; j += G) {
-            const double rj = rl[j];
-            const uint4* col = reinterpret_cast<const uint4*>(A + (long long)j * bs);
-#pragma unroll
-            for (int m = 0; m < MR; ++m) {
-                const int i8 = l16 + 16 * m;
-                if (8 * i8 < bs) {
-                    const uint4 v = __ldg(col + i8);
-                    bf16x2_fma(v.x, rj, s[m][0], s[m][1]);
-                    bf16x2_fma(v.y, rj, s[m][2], s[m][3]);
-                    bf16x2_fma(v.z, rj, s[m][4], s[m][5]);
-                    bf16x2_fma(v.w, rj, s[m][6], s[m][7]);
-                }
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < MR; ++m) {
-            const int i = 8 * (l16 + 16 * m);
-            if (i < bs) {                      // bs % 8 == 0: all eight rows exist
-#pragma unroll
-                for (int c = 0; c < 8; ++c) part[g * bs + i + c] = s[m][c];
-            }
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < bs; i += NW * 32) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < G; ++w) t += part[w * bs + i];
-            const int di = __ldg(d + i);
-            if (di >= 0) atomicAdd(z + di, t);
-        }
-    }
-}
-
-int ocmp_patch_apply_cta_bf16(int npatch, int bs, const int* pd, const __nv_bfloat16* inv, const double* r, double* z,
+template <typename T>
+static int patch_apply_stream(int npatch, int bs, const int* pd, const T* inv, const double* r, double* y,
                               cudaStream_t st) {
-    if (bs > 256 || (bs & 7)) return 0;
-    constexpr int NW = 4;
-    const size_t smem = sizeof(double) * (2 * NW + 1) * bs;
-    const int cap = ocmp_sm_count() * 16;
+    if (npatch <= 0) return 0;
+    if (bs > 256) return ocmp_fail(-20, "patch apply: more than 256 dofs per patch");
+    if ((bs * sizeof(T)) % 16) return ocmp_fail(-21, "patch apply: the patch stride must keep columns 16-byte aligned");
+    const long long colbytes = (long long)bs * sizeof(T);
+    // chunk: whole columns, about 8 KB; at most 64 chunks per patch
+    int cc = (int)(8192 / colbytes);
+    if (cc < 1) cc = 1;
+    if (cc > bs) cc = bs;
+    const int nchunk = (bs + cc - 1) / cc;
+    const int stage_bytes = (int)(((cc * colbytes) + 127) / 128 * 128);
+    const int rl_bytes = ((bs * 8 + 127) / 128) * 128;
+    const size_t smem = 128 + rl_bytes + (size_t)NSTAGE * stage_bytes;
+    static size_t configured[3] = {0, 0, 0};
+    const int slot = sizeof(T) == 8 ? 0 : sizeof(T) == 4 ? 1 : 2;
+    if (smem > 48 * 1024 && smem > configured[slot]) {
+        cudaFuncSetAttribute(k_patch_apply_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[slot] = smem;
+    }
+    const int threads = ((bs + 31) / 32) * 32;
+    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    if (per_sm > 6) per_sm = 6;
+    if (per_sm < 1) per_sm = 1;
+    const int cap = ocmp_sm_count() * per_sm;
     const int grid = npatch < cap ? npatch : cap;
-    if (bs <= 128) k_patch_apply_bf16<1, NW, 4><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
-    else k_patch_apply_bf16<2, NW, 4><<<grid, NW * 32, smem, st>>>(npatch, bs, pd, inv, r, z);
-    return 1;
+    k_patch_apply_stream<T><<<grid, threads, smem, st>>>(npatch, bs, cc, nchunk, stage_bytes, pd, inv, r, y);
+    return 0;
+}
+
+int ocmp_patch_apply_y(int npatch, int bs, const int* pd, const double* inv, const double* r, double* y,
+                       cudaStream_t st) {
+    return patch_apply_stream<double>(npatch, bs, pd, inv, r, y, st);
+}
+int ocmp_patch_apply_y_f32(int npatch, int bs, const int* pd, const float* inv, const double* r, double* y,
+                           cudaStream_t st) {
+    return patch_apply_stream<float>(npatch, bs, pd, inv, r, y, st);
+}
+int ocmp_patch_apply_y_bf16(int npatch, int bs, const int* pd, const __nv_bfloat16* inv, const double* r, double* y,
+                            cudaStream_t st) {
+    return patch_apply_stream<__nv_bfloat16>(npatch, bs, pd, inv, r, y, st);
+}
+int ocmp_patch_gather(long long n, const int* inc_ptr, const int* inc_idx, const double* y, const double* w,
+                      const double* m, double scale, double* z, int accumulate, cudaStream_t st) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)ocmp_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_patch_gather<<<(unsigned)blocks, 256, 0, st>>>(n, inc_ptr, inc_idx, y, w, m, scale, z, accumulate);
+    return 0;
 }

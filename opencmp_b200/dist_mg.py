@@ -183,6 +183,8 @@ class DistributedMultigrid:
             s.npatch, s.bs = pt['npatch'], pt['bs']
             s.patch_dofs, s.inv_blocks = pt['dofs'].data_ptr(), pt['inv'].data_ptr()
             s.inv_storage = STORAGE_ID[pt.get('storage', 'fp64')]
+            s.patch_inc_ptr, s.patch_inc_idx = pt['inc_ptr'].data_ptr(), pt['inc_idx'].data_ptr()
+            s.patch_ybuf = pt['ybuf'].data_ptr()
             if os.environ.get('OCMP_SPMV_FP32', '0') == '1':
                 if self._fresh_coarse or l == nl - 1 or getattr(lv, 'vals32', None) is None:
                     lv.vals32 = be.fp32_copy(lv.mat.values, getattr(lv, 'vals32', None))

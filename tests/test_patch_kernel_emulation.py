@@ -1,146 +1,158 @@
-"""Thread-by-thread emulation (NumPy) of the index logic of the reduced-precision smoother kernels
-``k_patch_apply_f32`` and ``k_patch_apply_bf16`` (csrc/ocmp_patch.cu), written while no GPU was available: every lane
-follows the same column / row / chunk assignment, unrolled main loop, remainder loop and partial-sum layout as the CUDA
-source, phase by phase between the barriers. The result must equal ``z[dofs] += A_p^-1 r[dofs]`` computed directly
-from the (transposed-stored, rounded) inverses. This pins the thread mapping; the arithmetic itself is checked on the
-GPU (tests/test_zzz_gpu_unmeasured_kernels.py)."""
+"""Index-level emulation (NumPy) of the smoother application (csrc/ocmp_patch.cu): ``k_patch_apply_stream`` — persistent
+CTAs walking their patches as one sequence of column chunks through a ring of NSTAGE shared-memory stages, thread i
+owning row i — followed by ``k_patch_gather`` over the incidence list built by ``backend.patch_incidence``. Same chunk
+geometry (host-side sizing of ``patch_apply_stream``), same chunk -> (patch, first column, byte offset) arithmetic, same
+stage / parity schedule. The result must equal ``z[dofs] += A_p^-1 r[dofs]`` computed directly from the
+(transposed-stored, rounded) inverses; the arithmetic itself is checked on the GPU."""
 import numpy as np
 import pytest
 import torch
+
+from opencmp_b200.backend import patch_incidence, _STORAGE_ALIGN
+
+NSTAGE = 4
+ELEM = {'fp64': 8, 'fp32': 4, 'bf16': 2}
 
 
 def _round(a, storage):
     t = torch.from_numpy(np.ascontiguousarray(a))
     if storage == 'fp32':
         return t.to(torch.float32).to(torch.float64).numpy()
-    return t.to(torch.bfloat16).to(torch.float64).numpy()
+    if storage == 'bf16':
+        return t.to(torch.bfloat16).to(torch.float64).numpy()
+    return a
 
 
-def emulate_f32(npatch, bs, pdofs, inv, r, n, MR, NW, UC, grid):
-    """k_patch_apply_f32<MR, NW, UC>: lane owns rows 4*lane .. +3 (+ 128 m), one column per warp and iteration slot."""
-    z = np.zeros(n)
-    for block in range(grid):
-        for p in range(block, npatch, grid):
-            d = pdofs[p]
-            rl = np.array([r[dj] if dj >= 0 else 0.0 for dj in d])
-            A = inv[p]                                            # flat: A[j * bs + i]
-            part = np.zeros((NW, bs))
-            for warp in range(NW):
-                for lane in range(32):
-                    s = np.zeros((MR, 4))
-                    j = warp
-                    while j + (UC - 1) * NW < bs:
-                        for u in range(UC):
-                            col = (j + u * NW) * bs
-                            for m in range(MR):
-                                i4 = lane + 32 * m
-                                if 4 * i4 < bs:
-                                    s[m] += A[col + 4 * i4: col + 4 * i4 + 4] * rl[j + u * NW]
-                        j += UC * NW
-                    while j < bs:
-                        for m in range(MR):
-                            i4 = lane + 32 * m
-                            if 4 * i4 < bs:
-                                s[m] += A[j * bs + 4 * i4: j * bs + 4 * i4 + 4] * rl[j]
-                        j += NW
-                    for m in range(MR):
-                        i = 4 * (lane + 32 * m)
-                        if i < bs:
-                            part[warp, i:i + 4] = s[m]
-            for i in range(bs):
-                if d[i] >= 0:
-                    z[d[i]] += part[:, i].sum()
-    return z
+def chunk_geometry(bs, storage):
+    """Host-side sizing in patch_apply_stream."""
+    colbytes = bs * ELEM[storage]
+    assert colbytes % 16 == 0, 'columns must stay 16-byte aligned for the bulk copies'
+    cc = max(1, min(bs, 8192 // colbytes))
+    nchunk = (bs + cc - 1) // cc
+    stage_bytes = (cc * colbytes + 127) // 128 * 128
+    return cc, nchunk, stage_bytes
 
 
-def emulate_bf16(npatch, bs, pdofs, inv, r, n, MR, NW, UC, grid):
-    """k_patch_apply_bf16<MR, NW, UC>: a half warp per column group, lane owns rows 8*(lane % 16) .. +7 (+ 128 m)."""
-    G = 2 * NW
-    z = np.zeros(n)
-    for block in range(grid):
-        for p in range(block, npatch, grid):
-            d = pdofs[p]
-            rl = np.array([r[dj] if dj >= 0 else 0.0 for dj in d])
-            A = inv[p]
-            part = np.zeros((G, bs))
-            for warp in range(NW):
-                for lane in range(32):
-                    l16, g = lane & 15, 2 * warp + (lane >> 4)
-                    s = np.zeros((MR, 8))
-                    j = g
-                    while j + (UC - 1) * G < bs:
-                        for u in range(UC):
-                            col = (j + u * G) * bs
-                            for m in range(MR):
-                                i8 = l16 + 16 * m
-                                if 8 * i8 < bs:
-                                    s[m] += A[col + 8 * i8: col + 8 * i8 + 8] * rl[j + u * G]
-                        j += UC * G
-                    while j < bs:
-                        for m in range(MR):
-                            i8 = l16 + 16 * m
-                            if 8 * i8 < bs:
-                                s[m] += A[j * bs + 8 * i8: j * bs + 8 * i8 + 8] * rl[j]
-                        j += G
-                    for m in range(MR):
-                        i = 8 * (l16 + 16 * m)
-                        if i < bs:
-                            part[g, i:i + 8] = s[m]
-            for i in range(bs):
-                if d[i] >= 0:
-                    z[d[i]] += part[:, i].sum()
-    return z
+def emulate_stream(npatch, bs, pdofs, inv_flat, r, storage, grid):
+    """inv_flat: one flat array of npatch * bs * bs stored entries (A_p[j * bs + i] = (A_p^-1)_{ij})."""
+    cc, nchunk, stage_bytes = chunk_geometry(bs, storage)
+    es = ELEM[storage]
+    y = np.full(npatch * bs, np.nan)
+    for block in range(min(grid, npatch)):
+        mine = (npatch - block + grid - 1) // grid
+        total = mine * nchunk
+        stages = [None] * NSTAGE
+        filled = [0] * NSTAGE                      # how often each stage's barrier completed a phase
+        waited = [0] * NSTAGE
+
+        def issue(g):
+            k, c = divmod(g, nchunk)
+            p = block + k * grid
+            cols = bs - c * cc if c == nchunk - 1 else cc
+            nbytes = cols * bs * es
+            assert nbytes % 16 == 0 and nbytes <= stage_bytes
+            src = p * bs * bs + c * cc * bs                        # element offset of the chunk
+            assert (src * es) % 16 == 0
+            s = g % NSTAGE
+            stages[s] = inv_flat[src: src + cols * bs].copy()
+            filled[s] += 1
+        for g in range(min(NSTAGE, total)):
+            issue(g)
+        p = block
+        rl = np.array([r[d] if d >= 0 else 0.0 for d in pdofs[p]])
+        acc = np.zeros(bs)
+        c = 0
+        for g in range(total):
+            s = g % NSTAGE
+            rnext = None
+            if c == 0 and p + grid < npatch:
+                rnext_vals = np.array([r[d] if d >= 0 else 0.0 for d in pdofs[p + grid]])
+            parity = (g // NSTAGE) & 1
+            assert filled[s] == g // NSTAGE + 1 and (filled[s] - 1) & 1 == parity      # the phase being waited on
+            waited[s] += 1
+            cols = bs - c * cc if c == nchunk - 1 else cc
+            A = stages[s]
+            for tid in range(bs):
+                acc[tid] += sum(A[j * bs + tid] * rl[c * cc + j] for j in range(cols))
+            if g + NSTAGE < total:
+                issue(g + NSTAGE)
+            c += 1
+            if c == nchunk:
+                y[p * bs: (p + 1) * bs] = acc
+                if p + grid < npatch:
+                    rl = rnext_vals
+                acc = np.zeros(bs)
+                c = 0
+                p += grid
+    return y
 
 
-def _case(bs, nreal, npatch=3, n=400, seed=0):
-    rng = np.random.default_rng(seed)
-    pdofs = -np.ones((npatch, bs), dtype=np.int64)
-    for p in range(npatch):
-        pdofs[p, :nreal] = np.sort(rng.choice(n, nreal, replace=False))
-    inv = rng.uniform(-1, 1, (npatch, bs * bs))
-    r = rng.uniform(-1, 1, n)
-    return pdofs, inv, r, n
+def emulate_gather(n, inc_ptr, inc_idx, y, w, m, scale, z, accumulate):
+    out = z.copy()
+    for d in range(n):
+        s = 0.0
+        for k in range(inc_ptr[d], inc_ptr[d + 1]):
+            s += y[inc_idx[k]]
+        s *= w[d] * m[d] * scale
+        out[d] = out[d] + s if accumulate else s
+    return out
 
 
 def _direct(pdofs, inv, r, n, bs):
     z = np.zeros(n)
-    for p in range(pdofs.shape[0]):
-        d = pdofs[p]
-        ok = d >= 0
-        rl = np.where(ok, r[np.maximum(d, 0)], 0.0)
-        At = inv[p].reshape(bs, bs)                               # At[j, i] = (A^-1)_{ij}
-        zl = At.T @ rl
-        np.add.at(z, d[ok], zl[ok])
+    for p, d in enumerate(pdofs):
+        rl = np.array([r[dj] if dj >= 0 else 0.0 for dj in d])
+        A = inv[p].reshape(bs, bs)                    # A[j, i]
+        for i, di in enumerate(d):
+            if di >= 0:
+                z[di] += A[:, i] @ rl
     return z
 
 
-# (bs, real dofs, MR) as launched by ocmp_patch_apply_cta_f32 / _bf16: MR = 1 up to 128 rows, 2 above
-@pytest.mark.parametrize('bs,nreal', [(92, 89), (132, 132), (48, 41), (128, 128), (256, 250)])
-def test_f32_kernel_thread_mapping(bs, nreal):
-    pdofs, inv, r, n = _case(bs, nreal)
-    inv = _round(inv, 'fp32')
-    MR, UC = (1, 4) if bs <= 128 else (2, 2)
-    got = emulate_f32(pdofs.shape[0], bs, pdofs, inv, r, n, MR, 4, UC, grid=2)
+def _case(npatch, nvalid, storage, seed, n=211):
+    rng = np.random.default_rng(seed)
+    align = _STORAGE_ALIGN[storage]
+    bs = nvalid + (-nvalid % align)
+    pdofs = -np.ones((npatch, bs), dtype=np.int32)
+    inv = np.zeros((npatch, bs * bs))
+    for p in range(npatch):
+        k = nvalid - (p % 3)                          # ragged: some patches carry extra padding
+        pdofs[p, :k] = np.sort(rng.choice(n, k, replace=False))
+        M = rng.standard_normal((bs, bs))
+        M[k:, :] = 0.0
+        M[:, k:] = 0.0
+        M[np.arange(k, bs), np.arange(k, bs)] = 1.0   # identity rows / columns on the padding, like the set-up kernel
+        inv[p] = _round(M.ravel(), storage)
+    r = rng.standard_normal(n)
+    return bs, pdofs, inv, r, n
+
+
+@pytest.mark.parametrize('storage,nvalid,npatch,grid', [
+    ('fp64', 13, 7, 3), ('fp64', 132, 5, 2), ('fp32', 90, 6, 4), ('fp32', 132, 3, 5), ('bf16', 89, 5, 2),
+    ('fp64', 7, 9, 2)])
+def test_stream_apply_and_gather_match_direct_patch_products(storage, nvalid, npatch, grid):
+    bs, pdofs, inv, r, n = _case(npatch, nvalid, storage, seed=nvalid + npatch)
+    y = emulate_stream(npatch, bs, pdofs, inv.ravel(), r, storage, grid)
+    assert not np.isnan(y).any()                      # every patch-local entry was written exactly once
+    inc_ptr, inc_idx = patch_incidence(pdofs, n)
+    assert inc_ptr[-1] == (pdofs >= 0).sum()
+    for d in range(n):                                # ascending positions = fixed summation order
+        seg = inc_idx[inc_ptr[d]: inc_ptr[d + 1]]
+        assert (np.diff(seg) > 0).all() and (pdofs.ravel()[seg] == d).all()
+    w = np.random.default_rng(1).uniform(0.2, 1.0, n)
+    m = (np.random.default_rng(2).uniform(size=n) > 0.2).astype(float)
     ref = _direct(pdofs, inv, r, n, bs)
-    assert np.abs(got - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+    z0 = np.random.default_rng(3).standard_normal(n)
+    got = emulate_gather(n, inc_ptr, inc_idx, y, w, m, 0.7, z0, False)
+    assert np.abs(got - 0.7 * w * m * ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+    got = emulate_gather(n, inc_ptr, inc_idx, y, w, m, 0.7, z0, True)
+    assert np.abs(got - (z0 + 0.7 * w * m * ref)).max() < 1e-12 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize('bs,nreal', [(96, 89), (136, 132), (48, 41), (128, 128), (256, 250)])
-def test_bf16_kernel_thread_mapping(bs, nreal):
-    pdofs, inv, r, n = _case(bs, nreal, seed=1)
-    inv = _round(inv, 'bf16')
-    MR = 1 if bs <= 128 else 2
-    got = emulate_bf16(pdofs.shape[0], bs, pdofs, inv, r, n, MR, 4, 4, grid=2)
-    ref = _direct(pdofs, inv, r, n, bs)
-    assert np.abs(got - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
-
-
-def test_bf16_word_unpacking_convention():
-    """bf16x2_fma takes element 2k of a 16-byte load from the LOW half of word k and element 2k+1 from the HIGH half
-    (little endian), and widens a bf16 by a 16-bit shift."""
-    vals = torch.tensor([1.5, -2.25, 3.0e-8, 1.0e10], dtype=torch.float64).to(torch.bfloat16)
-    words = vals.view(torch.int16).numpy().view(np.uint16).astype(np.uint32)
-    w0 = words[0] | (words[1] << 16)                              # as the 32-bit load sees two consecutive elements
-    lo = np.array([w0 << 16], dtype=np.uint32).view(np.float32)[0]
-    hi = np.array([w0 & 0xffff0000], dtype=np.uint32).view(np.float32)[0]
-    assert lo == float(vals[0]) and hi == float(vals[1])
+def test_chunk_geometry_fits_the_shared_memory_budget():
+    for storage, align in _STORAGE_ALIGN.items():
+        for bs in range(align, 257, align):
+            cc, nchunk, stage_bytes = chunk_geometry(bs, storage)
+            assert 1 <= cc <= bs and (nchunk - 1) * cc < bs <= nchunk * cc
+            smem = 128 + (bs * 8 + 127) // 128 * 128 + NSTAGE * stage_bytes
+            assert smem <= 64 * 1024, (storage, bs, smem)

@@ -30,7 +30,7 @@ st = g.pre.state
 r = xg * st.masks[-1]
 zg = torch.zeros_like(r)
 sm = st.smoothers[-1]
-be.lib.ocmp_asm_apply(sm.npatch, sm.bs, sm.pdofs.data_ptr(), sm.inv.data_ptr(), r.data_ptr(), zg.data_ptr(), zg.numel(), be._stream())
+be.lib.ocmp_asm_apply(sm.npatch, sm.bs, sm.pdofs.data_ptr(), sm.inv.data_ptr(), sm.inc_ptr.data_ptr(), sm.inc_idx.data_ptr(), sm.ybuf.data_ptr(), r.data_ptr(), zg.data_ptr(), zg.numel(), be._stream())
 zg = zg * sm.wgt * st.masks[-1]
 zl = d.mg.smooth(len(d.mg.levels) - 1, r[l2g].clone())
 print(rank, 'smooth', rel(zl, zg[l2g]), flush=True)
