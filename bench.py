@@ -1,17 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — one JSON line for the OpenCMP hot path on B200.
+"""bench.py — one JSON line for the OpenCMP hot path (assemble + solve per time step) on B200.
 
-Workload (BASELINE.json metric "INS s/timestep, assembly Mnnz/s, SpMV GB/s"; configs[2] scaled to SURVEY 8(d)'s
-throughput size): one time step of the 2-D incompressible Navier-Stokes Taylor-Green problem on a structured
-N x N x 2 triangle mesh of [0,pi]^2, HDiv-DG order 3 / L2 order 2, Oseen linearisation, implicit Euler — Dirichlet
-projection, full re-assembly of matrix and right-hand side, additive-Schwarz setup, GMRES solve and the two L2-norm
-integrals per Picard iteration, exactly the sequence of opencmp/solvers/base_solver.py:521-587 and
-opencmp/models/ins.py:323-355 (see opencmp_b200/workloads.py).
+Headline workload (BASELINE.json metric "INS s/timestep ... at 1/2/4/8 B200", configs[4]): one time step of the 3-D
+incompressible Navier-Stokes problem with a diffuse-interface sphere (reference opencmp/models/ins_dim.py), Taylor-Hood
+Q2/Q1 on structured hexes of [-1,1]^3, Oseen linearisation + implicit Euler — per Picard iteration: Dirichlet
+projection, full re-assembly of matrix and right-hand side, multigrid set-up, GMRES solve and the two L2-norm integrals,
+the sequence of opencmp/solvers/base_solver.py:521-587 and opencmp/models/ins.py:323-355 (opencmp_b200/workloads.py).
+N GPUs: ONE sphere, the mesh refined with the rank count, every rank
+owning one compact brick of cells: 48^3, 64^3, 80^3, 96^3 isotropic hexes on 1, 2, 4, 8 GPUs (110.6 k, 131 k, 128 k,
+110.6 k cells per GPU; 2.86 M DOFs on one GPU, 22.6 M on 8 — weak scaling, per-GPU load within +19 % of N = 1).
 
-`value` = seconds per time step with all inputs resident in HBM; `e2e` = the same step with the previous solution
-and wind uploaded from pinned host memory and the new solution read back inside the timed region.
-`--impl reference` times the CPU restatement (oracle/, NumPy/SciPy + sparse LU, the reference's own default
-`linear_solver = direct`) on a bounded sample of the same workload.
+At N = 1 the line also carries `ins2d`: the 2-D INS Taylor-Green step (configs[2] scaled to SURVEY 8(d)'s throughput
+size, HDiv-DG order 3 on 256 x 256 x 2 triangles, 2.6 M DOFs) — the workload the SpMV / smoother / assembly rooflines of
+round 1 were quoted on.
+
+`value`  = seconds per time step, inputs resident in HBM, timed with CUDA events around a loop WITHOUT per-launch
+           profiling; the per-kernel shares and rooflines come from a second, profiled loop of the same steps.
+`e2e`    = the same step with the previous solution and wind uploaded from pinned host memory and the new solution
+           read back inside the timed region.
+`--impl reference` times the CPU restatement (oracle/: NumPy assembly + SciPy SuperLU, the reference's default
+`linear_solver = direct`) on a sample of the same workload small enough to finish, reports that MEASURED time as
+`value` with the sample's own size in `config`, runs the GPU path on the same sample in the same invocation
+(`gpu_same_config`, `measured_ratio`) and keeps the linear extrapolation to the full size as a labelled extra.
 """
 import argparse
 import json
@@ -24,49 +34,54 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+DEFAULTS = {'ins3d_dim': dict(N=48, order=2), 'ins2d': dict(N=256, order=3)}
 
-def parse():
+
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='ins2d', choices=['ins2d', 'ins3d_dim'],
-                    help='ins2d: 2-D INS Taylor-Green, HDiv-DG order 3 (BASELINE configs[2] scaled up, the default); '
-                         'ins3d_dim: 3-D INS with a diffuse-interface sphere, Taylor-Hood Q2/Q1 hexes (configs[4])')
-    ap.add_argument('--N', type=int, default=None, help='cells per direction of the structured mesh '
-                                                        '(default 256 for ins2d, 32 for ins3d_dim)')
+    ap.add_argument('--workload', default='ins3d_dim', choices=['ins3d_dim', 'ins2d'],
+                    help='ins3d_dim: 3-D INS with a diffuse-interface sphere, Taylor-Hood Q2/Q1 hexes (BASELINE '
+                         'configs[4], the default and the scaling workload); ins2d: 2-D INS Taylor-Green, HDiv-DG '
+                         'order 3 (configs[2] scaled up; also reported as the `ins2d` object of the default line)')
+    ap.add_argument('--N', type=int, default=None, help='cells per direction (and per GPU) of the structured mesh '
+                                                        '(default 48 for ins3d_dim, 256 for ins2d)')
     ap.add_argument('--order', type=int, default=None)
     ap.add_argument('--cpu-N', type=int, default=None, help='mesh size of the bounded CPU sample')
-    ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--cpu-procs', type=int, default=0, help='replicas of the CPU sample the reference arm runs '
-                                                             'concurrently (default: one per host core)')
-    ap.add_argument('--layout', default='bricks', choices=['bricks', 'sphere'],
-                    help='ins3d_dim on several GPUs. bricks: one N^3 brick with its own sphere per GPU, lined up along x '
-                         '(weak scaling, the default); sphere: ONE sphere in [-1,1]^3 meshed with N^3 hexes in total, '
-                         'cells split between the GPUs (BASELINE configs[4] as written; use N = 96 on 8 GPUs for the '
-                         'per-GPU size of N = 48 on one)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the in-line cpu_baseline leg')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the ins2d object of the default line')
+    ap.add_argument('--profile-steps', type=int, default=2, help='steps of the second, per-launch profiled loop')
+    ap.add_argument('--layout', default='sphere', choices=['sphere', 'bricks'],
+                    help='ins3d_dim on several GPUs. sphere (default): ONE sphere in [-1,1]^3, mesh refined with the '
+                         'rank count, one compact N^3 brick of cells per rank; bricks: one [-1,1]^3 brick with its own '
+                         'sphere per GPU, lined up along x')
     ap.add_argument('--full-mg-setup', action='store_true',
                     help='re-assemble and re-invert the coarse multigrid levels on every Preconditioner.Update() '
-                         '(OCMP_MG_REUSE_COARSE=0); default: they are rebuilt only when a Parameter they read (dt, t) '
-                         'changes — their operators do not see the Oseen wind — while the finest level (the assembled '
-                         'system) is always set up again')
+                         '(OCMP_MG_REUSE_COARSE=0); default: only when a Parameter they read changes')
     ap.add_argument('--lag-smoother', action='store_true',
-                    help='OCMP_MG_LAG=1: keep the finest level\'s patch inverses until a solve needs > 1.25 x + 2 '
-                         'iterations of the first solve after the last fresh set-up (opt-in; default: re-invert on '
-                         'every Preconditioner.Update())')
-    ap.add_argument('--precond-storage', default='fp64', choices=['fp64', 'fp32', 'bf16'],
+                    help='OCMP_MG_LAG=1: keep the finest level\'s patch inverses while GMRES iteration counts hold')
+    ap.add_argument('--precond-storage', default='fp32', choices=['fp64', 'fp32', 'bf16'],
                     help='storage of the multigrid data (patch inverses, level matrices inside the cycle); arithmetic '
-                         'and the Krylov method stay FP64. fp32 = OCMP_PATCH_STORAGE=fp32 OCMP_SPMV_FP32=1; bf16 = '
-                         'bfloat16 patch inverses + FP32 level matrices (opt-in until measured on a B200)')
-    ap.add_argument('--dist-poisson', action='store_true', help='also run the distributed Poisson CG leg')
-    ap.add_argument('--dist-n', type=int, default=512, help='cells per direction and rank of the distributed leg')
-    a = ap.parse_args()
-    d = {'ins2d': (256, 3, 28), 'ins3d_dim': (32, 2, 8)}[a.workload]
-    a.N = d[0] if a.N is None else a.N
-    a.order = d[1] if a.order is None else a.order
-    a.cpu_N = d[2] if a.cpu_N is None else a.cpu_N
+                         'and the Krylov method around the cycle stay FP64. Default fp32: same GMRES iteration counts '
+                         'as fp64 on both workloads (measured, profiles/r2_bench_results.md)')
+    a = ap.parse_args(argv)
+    d = DEFAULTS[a.workload]
+    a.N = d['N'] if a.N is None else a.N
+    a.order = d['order'] if a.order is None else a.order
     return a
+
+
+def cpu_sample_size(workload, steps, cpu_N=None):
+    """Mesh size of the CPU sample: about 10-15 s (3-D N = 8) / 10 s (2-D N = 28) of oracle work per step when few
+    steps are asked for, a smaller one when the driver asks for many, so that the whole run ends within minutes."""
+    if cpu_N:
+        return cpu_N
+    if workload == 'ins3d_dim':
+        return 8 if steps <= 6 else 6
+    return 28 if steps <= 10 else 20
 
 
 class ClockSampler:
@@ -110,13 +125,14 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+# ---- CPU restatement (oracle) ---------------------------------------------------------------------------------------
 def _cpu_workload(N, order, workload):
     """The bench workload on the CPU restatement with the reference's default linear solver (direct,
     base_model.py:918-922); the oracle backend must be the active one."""
     from opencmp_b200.workloads import INSTaylorGreen, INSSphereDIM3D
     if workload != 'ins3d_dim':
         return INSTaylorGreen(N, order=order, linear_solver='direct', preconditioner=None)
-    w = INSSphereDIM3D(N, order=order, preconditioner=None, nu=1.0)
+    w = INSSphereDIM3D(N, order=order, preconditioner=None, nu=1.0, periodic=(False, False, False))
 
     def direct():
         inv = w.a.mat.Inverse(w.fes.FreeDofs())
@@ -128,153 +144,253 @@ def _cpu_workload(N, order, workload):
     return w
 
 
-def cpu_step_seconds(N, order, steps=1, workload='ins2d'):
-    """Oracle (CPU restatement, NumPy/SciPy; NOT NGSolve) timed on one Picard-iterated time step."""
+def cpu_step_seconds(N, order, steps=1, workload='ins2d', budget_s=None):
+    """Oracle (CPU restatement, NumPy/SciPy; NOT NGSolve) timed on Picard-iterated time steps: one untimed warm-up
+    step (lowering, tabulation caches), then up to ``steps`` timed ones (fewer when ``budget_s`` runs out). Returns
+    (mean seconds per step, steps timed, cells, DOFs, nnz)."""
     import opencmp_b200.ngs as ngs
     from oracle.backend import OracleBackend
     old = ngs._backend
     ngs.set_backend(OracleBackend())
     try:
         w = _cpu_workload(N, order, workload)
-        w.step()                          # warm-up (lowering, tabulation caches)
-        t0 = time.perf_counter()
+        w.step()
+        times = []
+        t_all = time.perf_counter()
         for _ in range(steps):
+            t0 = time.perf_counter()
             w.step()
-        dt = (time.perf_counter() - t0) / steps
-        return dt, w.mesh.ne, w.ndof, w.nnz
+            times.append(time.perf_counter() - t0)
+            if budget_s is not None and time.perf_counter() - t_all + times[-1] > budget_s:
+                break
+        return sum(times) / len(times), len(times), w.mesh.ne, w.ndof, w.nnz
     finally:
         ngs.set_backend(old)
 
 
-def _cpu_replica(job):
-    """One worker of the reference arm: its own copy of the CPU sample, warm-up step, then ``steps`` timed steps."""
-    N, order, workload, steps = job
-    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
-        os.environ[k] = '1'                      # one core per replica; set before NumPy / SciPy load their BLAS
-    import opencmp_b200.ngs as ngs
-    from oracle.backend import OracleBackend
-    ngs.set_backend(OracleBackend())
-    w = _cpu_workload(N, order, workload)
-    w.step()
-    out = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        w.step()
-        out.append(time.perf_counter() - t0)
-    return out, w.mesh.ne, w.ndof, w.nnz
-
-
-def cpu_replicas(N, order, workload, steps, procs):
-    """The CPU restatement is a single-threaded NumPy / SciPy program (SuperLU does not thread). To put every host core
-    to work, like a TaskManager-threaded NGSolve run would, ``procs`` independent replicas of the sample run at the same
-    time, one per core, and share the memory system: aggregate throughput = procs steps per slowest replica's step —
-    the figure a perfectly scaling threaded assembly + solve would reach, i.e. an upper bound in the reference's favour.
-    Returns (effective seconds per step of the sample, slowest replica's seconds per step, cells, DOFs, nnz)."""
-    import multiprocessing as mp
-    with mp.get_context('spawn').Pool(procs) as pool:
-        res = pool.map(_cpu_replica, [(N, order, workload, steps)] * procs)
-    per_step = [max(r[0][i] for r in res) for i in range(steps)]      # all replicas run step i concurrently
-    slow = sum(per_step) / len(per_step)
-    return slow / procs, slow, res[0][1], res[0][2], res[0][3]
-
-
-def run_reference(args):
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
-        return
-    # weak scaling: one N x N x 2 strip (2-D) / one N^3 brick (3-D) per GPU
-    cells_full = (args.N ** 3 if args.workload == 'ins3d_dim' else 2 * args.N * args.N) * \
-        (1 if args.workload == 'ins3d_dim' and args.layout == 'sphere' else max(1, args.gpus))
-    procs = args.cpu_procs
-    if not procs:
-        # one replica per core this process may run on, at most 32, and no more than a quarter of the free memory holds
-        # (a replica of the N = 28 sample peaks at ~0.9 GB)
-        try:
-            procs = len(os.sched_getaffinity(0))
-        except AttributeError:
-            procs = os.cpu_count() or 1
-        try:
-            import psutil
-            procs = min(procs, int(psutil.virtual_memory().available // (4 << 30)))
-        except Exception:
-            pass
-    procs = max(1, min(procs, 32))
-    cores, slow = 1, None
-    try:
-        if procs == 1:
-            raise RuntimeError('one core')
-        per, slow, ne, ndof, nnz = cpu_replicas(args.cpu_N, args.order, args.workload, args.steps, procs)
-        cores = procs
-    except Exception:                            # e.g. no second core / process pool unavailable: the scalar run
-        times = []
-        ne = ndof = nnz = 0
-        for _ in range(max(1, args.warmup // 3)):
-            cpu_step_seconds(args.cpu_N, args.order, workload=args.workload)
-        for _ in range(args.steps):
-            dt, ne, ndof, nnz = cpu_step_seconds(args.cpu_N, args.order, workload=args.workload)
-            times.append(dt)
-        per = sum(times) / len(times)
-    scaled = per * cells_full / ne
-    sample = ('one time step (2 Picard iterations: assemble + SciPy SuperLU) at N={} ({} cells, {} DOFs), '
-              'scaled linearly by cell count x{:.1f} to {} strip(s) of N={}'.format(args.cpu_N, ne, ndof, cells_full / ne,
-                                                                              max(1, args.gpus), args.N))
-    if cores > 1:
-        sample += ('; {0} single-threaded replicas of the sample ran concurrently, one per host core (slowest replica '
-                   '{1:.2f} s per step), value = that / {0}: the throughput of a perfectly scaling threaded run, an '
-                   'upper bound in the CPU path\'s favour'.format(cores, slow))
-    line = {'impl': 'reference', 'metric': 'INS s/timestep', 'value': scaled, 'unit': 's', 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': scaled * 1e3, 'higher_is_better': False,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args, 'cpu'),
-            'cpu_baseline': {'value': scaled, 'unit': 's', 'cores': cores, 'kind': 'port', 'sample': sample,
-                             'sample_value_s': per},
-            'e2e': {'value': scaled, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
-
-
-def workload_config(args, where):
+def workload_config(args, where, N=None, gpus=None):
+    N = args.N if N is None else N
+    gpus = args.gpus if gpus is None else gpus
     if args.workload == 'ins3d_dim':
-        return {'workload': 'INS-DIM 3D (BASELINE configs[4]): structured {0}^3 hexes on [-1,1]^3, Taylor-Hood Q{1}/Q{2}, '
-                            'diffuse-interface sphere R=0.5 (erf profile, lambda = 0.25, phi clamped to [1e-10,1]), rotating '
-                            'wall as DIM Dirichlet data, Oseen + implicit Euler, dt=1e-2, nu=1 '
-                            '(reference models/ins_dim.py forms)'.format(args.N, args.order, args.order - 1),
-                'N': args.N, 'order': args.order,
+        if gpus <= 1:
+            par = 'single'
+        elif args.layout == 'sphere':
+            from opencmp_b200.dist import brick_grid
+            from opencmp_b200.dist_workload import sphere_total_cells
+            g, nt = brick_grid(gpus), sphere_total_cells(N, gpus)
+            par = ('element-partitioned: ONE sphere in [-1,1]^3 meshed with {0}^3 isotropic hexes (N, 4N/3, 5N/3, 2N per '
+                   'direction on 1, 2, 4, 8 GPUs), split into {1} x {2} x {3} compact bricks of {4} cells, one per GPU '
+                   '({5:.2f} x the single-GPU cell count), two ghost layers, halo exchange + all-reduce over NCCL issued '
+                   'by the C ABI Krylov driver, distributed multigrid-GMRES'
+                   .format(nt, g[0], g[1], g[2], nt ** 3 // gpus, nt ** 3 / gpus / N ** 3))
+        else:
+            par = ('element-partitioned: one {0}^3 brick with its own sphere per GPU (domain [-1,{1}] x [-1,1]^2), two '
+                   'ghost layers, halo exchange + all-reduce over NCCL issued by the C ABI Krylov driver, distributed '
+                   'multigrid-GMRES'.format(N, 2 * gpus - 1))
+        return {'workload': 'INS-DIM 3D (BASELINE configs[4]): structured hexes on [-1,1]^3 ({0}^3 on one GPU), Taylor-Hood '
+                            'Q{1}/Q{2}, diffuse-interface sphere R=0.5 (erf profile, lambda = 0.25, phi clamped to '
+                            '[1e-10,1]), rotating wall as DIM Dirichlet data, Oseen + implicit Euler, dt=1e-2, nu=1 '
+                            '(reference models/ins_dim.py forms)'.format(N, args.order, args.order - 1),
+                'N': N, 'order': args.order,
                 'linear_solver': 'GMRES(200) + geometric multigrid V(1,1) on the hex hierarchy, open-star vertex-patch '
                                  'additive Schwarz smoother (damping 0.7), coarse-level phase field, tol 1e-12'
-                if where == 'gpu' else 'direct (SuperLU)', 'nonlinear_max_iterations': 3,
+                if where == 'gpu' else 'direct (SciPy SuperLU), the reference\'s default linear_solver',
+                'nonlinear_max_iterations': 3,
                 'l2': 'inputs larger than L2 (CSR matrix and patch inverses are GBs); no explicit flush',
-                'parallelism': ('single' if args.gpus <= 1 else
-                                'element-partitioned: ONE sphere in [-1,1]^3, the {0}^3 hexes split into {1} contiguous '
-                                'blocks of the refinement-tree cell order, two ghost layers, halo exchange + all-reduce '
-                                'over NCCL issued by the C ABI Krylov driver, distributed multigrid-GMRES'
-                                .format(args.N, args.gpus) if args.layout == 'sphere' else
-                                'element-partitioned: one {0}^3 brick with its own sphere per GPU (domain [-1,{1}] x '
-                                '[-1,1]^2), two ghost layers, halo exchange + all-reduce over NCCL issued by the C ABI '
-                                'Krylov driver, distributed multigrid-GMRES'.format(args.N, 2 * args.gpus - 1))}
-    return {'workload': 'INS Taylor-Green 2D, structured {0}x{0}x2 triangles on [0,pi]^2, HDiv-DG order {1} / L2 order {2}, '
-                        'Oseen + implicit Euler, dt=1e-3, nu=1 (examples/INS scaled up)'.format(args.N, args.order,
-                                                                                               args.order - 1),
-            'N': args.N, 'order': args.order, 'linear_solver': 'GMRES(100) + geometric multigrid V(1,1), vertex-patch additive Schwarz smoother (damping 0.7), tol 1e-10'
-            if where == 'gpu' else 'direct (SuperLU)', 'nonlinear_max_iterations': 3,
-            'l2': 'inputs larger than L2 (CSR matrix 3.3 GB, patch inverses 9 GB at N=256); no explicit flush',
+                'parallelism': par}
+    return {'workload': 'INS Taylor-Green 2D, structured {0}x{0}x2 triangles on [0,pi]^2, HDiv-DG order {1} / L2 order '
+                        '{2}, Oseen + implicit Euler, dt=1e-3, nu=1 (examples/INS scaled up)'
+                        .format(N, args.order, args.order - 1),
+            'N': N, 'order': args.order,
+            'linear_solver': 'GMRES(100) + geometric multigrid V(1,1), vertex-patch additive Schwarz smoother (damping '
+                             '0.7), tol 1e-10' if where == 'gpu' else
+                             'direct (SciPy SuperLU), the reference\'s default linear_solver',
+            'nonlinear_max_iterations': 3,
+            'l2': 'inputs larger than L2 (CSR matrix and patch inverses are GBs at N=256); no explicit flush',
             'parallelism': ('element-partitioned: one {0}x{0}x2 strip per GPU (domain [0,pi] x [0,{1} pi]), two ghost '
                             'layers, halo exchange + all-reduce over NCCL issued by the C ABI Krylov driver, distributed '
-                            'multigrid-GMRES'
-                            .format(args.N, args.gpus)) if args.gpus > 1 else 'single'}
+                            'multigrid-GMRES'.format(N, gpus)) if gpus > 1 else 'single'}
 
 
-def main():
-    args = parse()
-    if args.impl == 'reference':
-        return run_reference(args)
-    if args.precond_storage != 'fp64':
-        os.environ['OCMP_PATCH_STORAGE'] = args.precond_storage
-        os.environ['OCMP_SPMV_FP32'] = '1'
+# ---- GPU side ---------------------------------------------------------------------------------------------------------
+def set_storage_env(args):
+    os.environ['OCMP_PATCH_STORAGE'] = args.precond_storage
+    os.environ['OCMP_SPMV_FP32'] = '0' if args.precond_storage == 'fp64' else '1'
     if args.full_mg_setup:
         os.environ['OCMP_MG_REUSE_COARSE'] = '0'
     if args.lag_smoother:
         os.environ['OCMP_MG_LAG'] = '1'
-    import numpy as np
+
+
+def make_gpu_workload(workload, N, order, world=1, rank=0, layout='sphere'):
+    """(workload object, distributed wrapper or None)"""
+    if world > 1 and workload == 'ins3d_dim':
+        from opencmp_b200.dist_workload import DistributedINSDIM3D
+        d = DistributedINSDIM3D(N, world, rank, order=order, layout='sphere' if layout == 'sphere' else None)
+        return d.w, d
+    if world > 1:
+        from opencmp_b200.dist_workload import DistributedINS
+        d = DistributedINS(N, world, rank, order=order)
+        return d.w, d
+    if workload == 'ins3d_dim':
+        from opencmp_b200.workloads import INSSphereDIM3D
+        return INSSphereDIM3D(N, order=order, nu=1.0, linear_tolerance=1e-12, periodic=(False, False, False)), None
+    from opencmp_b200.workloads import INSTaylorGreen
+    return INSTaylorGreen(N, order=order), None
+
+
+class GpuTimer:
+    """The three timed loops of one workload: clean (value), e2e (host buffers), profiled (shares / rooflines)."""
+
+    def __init__(self, torch, lib, w, barrier):
+        self.torch, self.lib, self.w, self.barrier = torch, lib, w, barrier
+
+    def clean(self, steps):
+        torch, w = self.torch, self.w
+        self.lib.ocmp_profile_enable(0)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = self.lib.ocmp_launch_count()
+        e0.record()
+        picard = its = 0
+        for _ in range(steps):
+            w.linear_iterations = []
+            w.step()
+            picard += w.picard_iterations
+            its += sum(w.linear_iterations)
+        e1.record()
+        self.barrier()
+        return dict(ms=e0.elapsed_time(e1), picard=picard, its=its, launches=int(self.lib.ocmp_launch_count() - l0))
+
+    def e2e(self, steps):
+        torch, w = self.torch, self.w
+        ndof = w.ndof
+        h_prev = torch.empty(ndof, dtype=torch.float64).pin_memory()
+        h_wind = torch.empty(w.V.ndof, dtype=torch.float64).pin_memory()
+        h_out = torch.empty(ndof, dtype=torch.float64).pin_memory()
+        h_prev.copy_(w.gfu.vec.a)
+        h_wind.copy_(w.W.vec.a)
+        self.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(steps):
+            w.gfu_0.vec.a.copy_(h_prev, non_blocking=True)
+            w.gfu.vec.a.copy_(h_prev, non_blocking=True)
+            w.W.vec.a.copy_(h_wind, non_blocking=True)
+            w.step()
+            h_out.copy_(w.gfu.vec.a, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            h_prev.copy_(h_out)
+            h_wind.copy_(h_out[:w.V.ndof])
+        f1.record()
+        self.barrier()
+        return dict(ms=f0.elapsed_time(f1), h2d=int(8 * (2 * ndof + w.V.ndof)), d2h=int(8 * ndof))
+
+    def profiled(self, steps):
+        from opencmp_b200.backend import read_profile
+        torch, w, lib = self.torch, self.w, self.lib
+        lib.ocmp_profile_reset()
+        lib.ocmp_profile_enable(1)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        picard = 0
+        for _ in range(steps):
+            w.step()
+            picard += w.picard_iterations
+        e1.record()
+        self.barrier()
+        prof = read_profile(lib)
+        lib.ocmp_profile_enable(0)
+        return dict(ms=e0.elapsed_time(e1), picard=picard, prof=prof)
+
+
+def fp64_peak_tflops(torch, n=8192, reps=6):
+    """cuBLAS DGEMM n^3 through torch.matmul (a library GEMM used as the FP64 yardstick only — BASELINE.md section 2
+    asks for this calibration before an assembly roofline is quoted): best of ``reps`` and the mean of ~1 s back to back."""
+    a = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    b = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = max(3, int(1000.0 / best))
+    e0.record()
+    for _ in range(k):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    torch.cuda.synchronize()
+    fl = 2.0 * n ** 3
+    return {'burst': fl / best / 1e9, 'sustained': fl * k / e0.elapsed_time(e1) / 1e9,
+            'how': 'torch.matmul float64 {0}^3 (cuBLAS DGEMM), best of {1} / mean of {2} back to back'.format(n, reps, k)}
+
+
+def rooflines(be, w, prof, ms_prof, picard, peak, peak_src, storage, fp64_peak):
+    """Roofline objects from one profiled loop. Algorithmic bytes: the fine-level CSR SpMV moves nnz (8 + 4) + nrows
+    (4 + 8) + ncols 8 bytes; the smoother application bs^2 x (8 | 4 | 2) bytes per patch + 16 per dof
+    (counted per launch inside the library); assembly: flops of the B^T D B contraction from the launch plans."""
+    nnz, ndof = w.nnz, w.ndof
+    share = {k: round(v['ms'] / ms_prof, 4) for k, v in prof.items()}
+    sp = prof['spmv']
+    spmv_bytes = nnz * 12 + ndof * 12 + ndof * 8
+    spmv_ms = sp['ms'] / max(1, sp['count'])
+    spmv_gbs = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if sp['count'] else 0.0
+    ap = prof['asm_apply']
+    ap_ms = ap['ms'] / max(1, ap['count'])
+    ap_bytes = ap['bytes'] / max(1, ap['count'])
+    ap_gbs = ap_bytes / (ap_ms * 1e-3) / 1e9 if ap['count'] else 0.0
+    kname = {'fp64': 'k_patch_apply_stream<double> (8 bs^2 bytes per patch',
+             'fp32': 'k_patch_apply_stream<float> (FP32-stored patch inverses, 4 bs^2 bytes per patch',
+             'bf16': 'k_patch_apply_stream<bf16> (bfloat16-stored patch inverses, 2 bs^2 bytes per patch'}[storage]
+    r_patch = {'kernel': kname + '; additive-Schwarz smoother, all multigrid levels: total bytes / total time)',
+               'bound': 'hbm', 'achieved': ap_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': ap_gbs / peak,
+               'peak_source': peak_src, 'bytes_per_launch': ap_bytes, 'launches': ap['count'], 'avg_launch_ms': ap_ms,
+               'share_of_step': share['asm_apply'], 'traffic': None,
+               'traffic_note': 'dram bytes per launch of the ncu --set full capture: profiles/r2_ncu_kernels.md'}
+    r_spmv = {'kernel': 'k_spmv<16, double> fine level (CSR FP64 values + int32 columns; Krylov operator)',
+              'bound': 'hbm', 'achieved': spmv_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs / peak,
+              'frac_of_8000_nominal': spmv_gbs / 8000.0, 'peak_source': peak_src, 'bytes_per_launch': spmv_bytes,
+              'launches': sp['count'], 'avg_launch_ms': spmv_ms, 'share_of_step': share['spmv'], 'traffic': None}
+    asm_ms = prof['coef']['ms'] + prof['contract_matrix']['ms'] + prof['contract_vector']['ms']
+    n_asm = max(1, picard)
+    asm_mnnz = nnz / (asm_ms / n_asm * 1e-3) / 1e6 if asm_ms > 0 else 0.0
+    flops = be.matrix_flops(w.a.program())
+    cm_ms = prof['contract_matrix']['ms'] / n_asm
+    tfl = flops / (cm_ms * 1e-3) / 1e12 if cm_ms > 0 else 0.0
+    r_asm = {'kernel': 'k_contract (B^T D B local matrices + scatter), fine-level matrix assembly', 'bound': 'fp64',
+             'achieved': tfl, 'peak': fp64_peak['burst'] if fp64_peak else None, 'unit': 'TFLOP/s',
+             'frac': (tfl / fp64_peak['burst']) if fp64_peak else None,
+             'peak_source': fp64_peak['how'] if fp64_peak else 'not calibrated in this run',
+             'flops_per_assembly': flops, 'ms_per_assembly': cm_ms, 'assembly_mnnz_per_s': asm_mnnz,
+             'share_of_step': round(share['contract_matrix'] + share['coef'] + share['contract_vector'], 4),
+             'note': 'ms_per_assembly also holds the re-discretised coarse multigrid levels when they are rebuilt'}
+    return share, r_patch, r_spmv, r_asm, asm_mnnz, spmv_gbs
+
+
+def measure_workload(args, torch, be, w, dins, steps, warmup, profile_steps, barrier, peaks, fp64_peak, sampler_rank):
+    lib = be.lib
+    for _ in range(warmup):
+        w.step()
+    gt = GpuTimer(torch, lib, w, barrier)
+    sampler = ClockSampler(sampler_rank) if sampler_rank is not None else None
+    clean = gt.clean(steps)
+    clocks = sampler.stop() if sampler is not None else None
+    e2e = gt.e2e(steps)
+    prof = gt.profiled(profile_steps) if profile_steps > 0 else None
+    eu, ep = w.errors()
+    return dict(clean=clean, e2e=e2e, prof=prof, clocks=clocks, errs=(eu, ep))
+
+
+def run_b200(args):
+    set_storage_env(args)
     import torch
     import torch.distributed as dist
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -284,109 +400,15 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import opencmp_b200.ngs as ngs
-    from opencmp_b200.backend import CudaBackend, patch_storage, read_profile
-    from opencmp_b200.workloads import INSTaylorGreen
+    from opencmp_b200.backend import CudaBackend, patch_storage
     be = CudaBackend(local)
     ngs.set_backend(be)
-    lib = be.lib
-    t_setup = time.perf_counter()
-    if world > 1 and args.workload == 'ins3d_dim':
-        # element-partitioned 3-D INS-DIM step: rank r owns the brick [-1 + 2r, 1 + 2r] x [-1,1]^2 at N^3 hexes
-        from opencmp_b200.dist_workload import DistributedINSDIM3D
-        dins = DistributedINSDIM3D(args.N, world, rank, order=args.order,
-                                   bricks=1 if args.layout == 'sphere' else None)
-        w = dins.w
-    elif world > 1:
-        # element-partitioned INS step: rank r owns the strip [0,pi] x [r pi, (r+1) pi] at N x N x 2 triangles
-        from opencmp_b200.dist_workload import DistributedINS
-        dins = DistributedINS(args.N, world, rank, order=args.order)
-        w = dins.w
-    elif args.workload == 'ins3d_dim':
-        from opencmp_b200.workloads import INSSphereDIM3D
-        dins = None
-        w = INSSphereDIM3D(args.N, order=args.order, nu=1.0, linear_tolerance=1e-12)
-    else:
-        dins = None
-        w = INSTaylorGreen(args.N, order=args.order)
-    torch.cuda.synchronize()
-    t_setup = time.perf_counter() - t_setup
-    ndof, nnz, ne = w.ndof, w.nnz, w.mesh.ne
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        w.step()
-    # ---- timed region: K steps, device-resident ------------------------------------------------------------
-    lib.ocmp_profile_reset()
-    lib.ocmp_profile_enable(1)
-    sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = lib.ocmp_launch_count()
-    e0.record()
-    picard = lin_its = 0
-    for _ in range(args.steps):
-        w.linear_iterations = []
-        w.step()
-        picard += w.picard_iterations
-        lin_its += sum(w.linear_iterations)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler is not None else None
-    launches = int(lib.ocmp_launch_count() - l0)
-    prof = read_profile(lib)
-    lib.ocmp_profile_enable(0)
-    # ---- e2e: host buffers in, solution out, copies inside the timed region -------------------------------------
-    h_prev = torch.empty(ndof, dtype=torch.float64).pin_memory()
-    h_wind = torch.empty(w.V.ndof, dtype=torch.float64).pin_memory()
-    h_out = torch.empty(ndof, dtype=torch.float64).pin_memory()
-    h_prev.copy_(w.gfu.vec.a)
-    h_wind.copy_(w.W.vec.a)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        w.gfu_0.vec.a.copy_(h_prev, non_blocking=True)
-        w.gfu.vec.a.copy_(h_prev, non_blocking=True)
-        w.W.vec.a.copy_(h_wind, non_blocking=True)
-        w.step()
-        h_out.copy_(w.gfu.vec.a, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        h_prev.copy_(h_out)
-        h_wind.copy_(h_out[:w.V.ndof])
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
-    eu, ep = w.errors()
-    # ---- element-partitioned leg (N > 1): halo-exchange SpMV + all-reduced Jacobi-CG on a distributed Poisson problem
-    multi = None
-    if world > 1 and args.dist_poisson:
-        from opencmp_b200.dist_workload import DistributedPoisson
-        dp = DistributedPoisson(args.dist_n, 2, world, rank)
-        sp_ms = dp.time_spmv()
-        its, res, sec_cg, _ = dp.solve(maxit=100)
-        tt = torch.tensor([sp_ms, sec_cg / max(1, its) * 1e3], dtype=torch.float64, device='cuda')
-        bb = torch.tensor([float(dp.spmv_bytes_owned())], dtype=torch.float64, device='cuda')
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(bb)
-        multi = {'workload': 'Poisson H1 order 2, structured {0}x{1}x2 triangles, one cell block per rank, one ghost '
-                             'layer'.format(args.dist_n, args.dist_n * world),
-                 'global_dofs': dp.nglobal, 'spmv_ms_max_over_ranks': float(tt[0]),
-                 'spmv_gbs_aggregate': float(bb[0]) / float(tt[0]) / 1e6, 'cg_ms_per_iteration': float(tt[1]),
-                 'collectives': 'halo exchange: batched isend/irecv (NCCL); dot products: all_reduce'}
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    sec = ms / 1e3 / args.steps
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -394,102 +416,169 @@ def main():
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
-    sp = prof['spmv']
-    spmv_bytes = nnz * 12 + ndof * 12 + ndof * 8
-    spmv_ms = sp['ms'] / max(1, sp['count'])
-    spmv_gbs = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if sp['count'] else 0.0
-    asm_ms = prof['coef']['ms'] + prof['contract_matrix']['ms'] + prof['contract_vector']['ms']
-    n_asm = max(1, picard)
-    asm_mnnz = nnz / (asm_ms / n_asm * 1e-3) / 1e6 if asm_ms > 0 else 0.0
-    share = {k: round(v['ms'] / ms, 4) for k, v in prof.items()}
-    # dominant kernel of the step: the smoother application k_patch_apply (HBM bound: streams the patch inverses)
-    ap = prof['asm_apply']
-    ap_ms = ap['ms'] / max(1, ap['count'])
-    ap_bytes = ap['bytes'] / max(1, ap['count'])
-    ap_gbs = ap_bytes / (ap_ms * 1e-3) / 1e9 if ap['count'] else 0.0
-    roofline = {'kernel': {'fp64': 'k_patch_apply (8 bs^2 bytes per patch',
-                           'fp32': 'k_patch_apply_f32 (FP32-stored patch inverses, 4 bs^2 bytes per patch',
-                           'bf16': 'k_patch_apply_bf16 (bfloat16-stored patch inverses, 2 bs^2 bytes per patch'
-                           }[patch_storage()] +
-                          '; additive-Schwarz smoother, all multigrid levels; launch-weighted mean)',
-                'bound': 'hbm', 'achieved': ap_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': ap_gbs / peak,
-                'peak_source': peak_src, 'bytes_per_launch': ap_bytes, 'launches': ap['count'],
-                'avg_launch_ms': ap_ms, 'share_of_step': share['asm_apply'],
-                # ncu --set full of the fine-level launch at N=128 (16 641 patches, 2.330 GB algorithmic): dram read
-                # 2.368 GB + write 0.018 GB (profiles/r1_ncu_kernels.md) — 1.024 x the algorithmic bytes, scaled here
-                'traffic': 1.024 * ap_bytes if args.workload == 'ins2d' and args.precond_storage == 'fp64' else None,
-                'traffic_note': 'per launch, from the measured dram/algorithmic ratio 1.024 of the ncu --set full capture '
-                                'at N=128 (dram read 2.368 GB + write 0.018 GB vs 2.330 GB algorithmic, '
-                                'profiles/r1_ncu_kernels.md)'}
+    fp64_peak = fp64_peak_tflops(torch) if rank == 0 else None
+
+    t_setup = time.perf_counter()
+    w, dins = make_gpu_workload(args.workload, args.N, args.order, world, rank, args.layout)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    ndof, nnz, ne = w.ndof, w.nnz, w.mesh.ne
+    m = measure_workload(args, torch, be, w, dins, args.steps, args.warmup, args.profile_steps, barrier, peaks,
+                         fp64_peak, local if rank == 0 else None)
+    t = torch.tensor([m['clean']['ms'], m['e2e']['ms']], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    storage = patch_storage()
+    pr = m['prof']
+    share, r_patch, r_spmv, r_asm, asm_mnnz, spmv_gbs = rooflines(be, w, pr['prof'], pr['ms'], pr['picard'], peak,
+                                                                  peak_src, storage, fp64_peak)
+    # the dominant kernel of the step leads the line
+    by_share = sorted(((share['asm_apply'], r_patch), (share['spmv'], r_spmv)), key=lambda x: -x[0])
+    sec = ms / 1e3 / args.steps
     line = {
         'metric': 'INS s/timestep', 'value': sec, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': False, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': dict(workload_config(args, 'gpu'), coarse_levels=(
+        'config': dict(workload_config(args, 'gpu', gpus=world), coarse_levels=(
             'rebuilt on every update' if os.environ.get('OCMP_MG_REUSE_COARSE', '1') == '0' else
             'rebuilt when a Parameter they read changes (constant dt: once); finest level on every update'),
             finest_level_smoother=('lagged: re-inverted when GMRES iterations grow (OCMP_MG_LAG=1)'
                                    if os.environ.get('OCMP_MG_LAG', '0') == '1' else 're-inverted on every update'),
-            precond_storage={
-            'patch_inverses': patch_storage(),
-            'level_matrices_in_cycle': 'fp32' if os.environ.get('OCMP_SPMV_FP32', '0') == '1' else 'fp64'}),
+            precond_storage={'patch_inverses': storage,
+                             'level_matrices_in_cycle': 'fp32' if os.environ.get('OCMP_SPMV_FP32', '0') == '1'
+                             else 'fp64'}),
         'problem': {'cells': ne, 'dofs': ndof, 'nnz': nnz, 'global_dofs': dins.ndof_global if dins else ndof,
-                    'ranks': world, 'picard_per_step': picard / args.steps,
-                    'gmres_its_per_step': lin_its / args.steps, 'l2_err_u': eu, 'l2_err_p': ep,
-                    'setup_s': t_setup},
+                    'ranks': world, 'owned_cells_per_gpu': (dins.gmesh.ne // world) if dins else ne,
+                    'picard_per_step': m['clean']['picard'] / args.steps,
+                    'gmres_its_per_step': m['clean']['its'] / args.steps, 'l2_err_u': m['errs'][0],
+                    'l2_err_p': m['errs'][1], 'setup_s': t_setup},
+        'timing': 'value: CUDA events around {0} steps with per-launch profiling OFF; kernel shares and rooflines: a '
+                  'second loop of {1} steps with an event pair around every launch'.format(args.steps,
+                                                                                          args.profile_steps),
         'assembly_mnnz_per_s': asm_mnnz, 'spmv_gbs': spmv_gbs,
-        'roofline': roofline,
-        'roofline_spmv': {'kernel': 'k_spmv<16> fine level (CSR FP64 values + int32 columns)', 'bound': 'hbm',
-                          'achieved': spmv_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs / peak,
-                          'frac_of_8000_nominal': spmv_gbs / 8000.0, 'bytes_per_launch': spmv_bytes,
-                          'launches': sp['count'], 'avg_launch_ms': spmv_ms},
-        'kernel_time_share': share,
-        'e2e': {'value': ms_e2e / 1e3 / args.steps, 'unit': 's', 'h2d_bytes_per_step': int(8 * (2 * ndof + w.V.ndof)),
-                'd2h_bytes_per_step': int(8 * ndof)},
-        'gpu_launches': launches, 'clocks': clocks,
+        'roofline': by_share[0][1], 'roofline_patch_apply': r_patch, 'roofline_spmv': r_spmv,
+        'roofline_assembly': r_asm, 'fp64_peak_tflops': fp64_peak,
+        'kernel_time_share': share, 'profiled_ms_per_step': pr['ms'] / max(1, args.profile_steps),
+        'e2e': {'value': ms_e2e / 1e3 / args.steps, 'unit': 's', 'h2d_bytes_per_step': m['e2e']['h2d'],
+                'd2h_bytes_per_step': m['e2e']['d2h']},
+        'gpu_launches': m['clean']['launches'], 'clocks': m['clocks'],
     }
-    if multi is not None:
-        line['multi_gpu'] = multi
-    if not args.no_cpu and world == 1:
+    if world == 1:
+        # ---- the GPU path on the CPU sample's size (what --impl reference measures on the host) -----------------------
+        cN = cpu_sample_size(args.workload, args.steps, args.cpu_N)
         try:
-            per, cne, cnd, _ = cpu_step_seconds(args.cpu_N, args.order, workload=args.workload)
-            line['cpu_baseline'] = {
-                'value': per * ne / cne, 'unit': 's', 'cores': 1, 'kind': 'port',
-                'sample': 'CPU restatement (NumPy/SciPy, not NGSolve): one time step at N={} ({} cells, {} DOFs) took '
-                          '{:.2f} s; scaled linearly by cell count x{:.1f}'.format(args.cpu_N, cne, cnd, per, ne / cne)}
-        except Exception as exc:                                    # pragma: no cover
-            line['cpu_baseline'] = {'value': None, 'unit': 's', 'cores': 1, 'kind': 'port', 'sample': repr(exc)}
-    # ---- matrix-free application of the same operator (BilinearForm.Apply: k_coef + k_lin, no CSR values read) next
-    # to the CSR SpMV — outside the step's timed region, its own CUDA events. Runs LAST, when every other number is
-    # already on the host: its GPU cases have not run on a B200 yet, and it must never cost the bench line
-    matfree = None
-    try:
-        if world == 1:
-            xv = w.gfu.vec.CreateVector()
-            xv.data = w.gfu.vec
-            yv = w.gfu.vec.CreateVector()
+            ws, _ = make_gpu_workload(args.workload, cN, args.order)
             for _ in range(2):
-                w.a.Apply(xv, yv)
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            g0.record()
-            for _ in range(5):
-                w.a.Apply(xv, yv)
-            g1.record()
-            torch.cuda.synchronize()
-            ycsr = w.a.mat * xv
-            den = float(ycsr.Norm())
-            matfree = {'ms_per_apply': g0.elapsed_time(g1) / 5,
-                       'rel_diff_vs_csr_spmv': float((yv - ycsr).Norm()) / den if den > 0 else None,
-                       'note': 'BilinearForm.Apply(x, y): trial rows become field slots of k_coef, k_lin contracts with '
-                               'the test rows; FP64-compute bound (quadrature), reads no matrix'}
-    except Exception as exc:                                    # pragma: no cover
-        matfree = {'error': repr(exc)}
-    if matfree is not None:
-        line['matrix_free_apply'] = matfree
+                ws.step()
+            small = GpuTimer(torch, be.lib, ws, barrier).clean(3)
+            line['same_size_as_cpu_sample'] = {'N': cN, 'dofs': ws.ndof, 'value': small['ms'] / 3e3, 'unit': 's',
+                                               'gmres_its_per_step': small['its'] / 3}
+            del ws
+        except Exception as exc:                                    # pragma: no cover
+            line['same_size_as_cpu_sample'] = {'N': cN, 'error': repr(exc)}
+        if not args.no_cpu:
+            try:
+                per, nst, cne, cnd, _ = cpu_step_seconds(cN, args.order, steps=2, workload=args.workload, budget_s=30.0)
+                line['cpu_baseline'] = {
+                    'value': per * ne / cne, 'unit': 's', 'cores': 1, 'kind': 'port',
+                    'sample': 'CPU restatement (NumPy/SciPy, not NGSolve): {} time step(s) at N={} ({} cells, {} DOFs) took '
+                              '{:.2f} s each (measured); value = that scaled linearly by cell count x{:.1f} (an '
+                              'extrapolation)'.format(nst, cN, cne, cnd, per, ne / cne),
+                    'sample_value_s': per, 'sample_N': cN}
+                ss = line.get('same_size_as_cpu_sample', {})
+                if 'value' in ss:
+                    line['cpu_baseline']['measured_ratio_at_sample_size'] = per / ss['value']
+            except Exception as exc:                                # pragma: no cover
+                line['cpu_baseline'] = {'value': None, 'unit': 's', 'cores': 1, 'kind': 'port', 'sample': repr(exc)}
+        # ---- secondary workload of the default line: 2-D INS at the round-1 throughput size -------------------------
+        if args.workload == 'ins3d_dim' and not args.no_secondary:
+            try:
+                del w
+                torch.cuda.empty_cache()
+                a2 = parse(['--workload', 'ins2d'])
+                w2, _ = make_gpu_workload('ins2d', a2.N, a2.order)
+                m2 = measure_workload(a2, torch, be, w2, None, 3, 2, 2, barrier, peaks, fp64_peak, None)
+                p2 = m2['prof']
+                sh2, rp2, rs2, ra2, mn2, sg2 = rooflines(be, w2, p2['prof'], p2['ms'], p2['picard'], peak, peak_src,
+                                                         storage, fp64_peak)
+                line['ins2d'] = {'config': workload_config(a2, 'gpu', gpus=1), 'value': m2['clean']['ms'] / 3e3,
+                                 'unit': 's', 'steps': 3, 'warmup': 2,
+                                 'e2e': {'value': m2['e2e']['ms'] / 3e3, 'unit': 's',
+                                         'h2d_bytes_per_step': m2['e2e']['h2d'], 'd2h_bytes_per_step': m2['e2e']['d2h']},
+                                 'problem': {'cells': w2.mesh.ne, 'dofs': w2.ndof, 'nnz': w2.nnz,
+                                             'gmres_its_per_step': m2['clean']['its'] / 3,
+                                             'picard_per_step': m2['clean']['picard'] / 3,
+                                             'l2_err_u': m2['errs'][0], 'l2_err_p': m2['errs'][1]},
+                                 'gpu_launches': m2['clean']['launches'], 'assembly_mnnz_per_s': mn2, 'spmv_gbs': sg2,
+                                 'roofline_patch_apply': rp2, 'roofline_spmv': rs2, 'roofline_assembly': ra2,
+                                 'kernel_time_share': sh2}
+            except Exception as exc:                                # pragma: no cover
+                line['ins2d'] = {'error': repr(exc)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---- reference arm -----------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cN = cpu_sample_size(args.workload, args.steps, args.cpu_N)
+    # ---- the CPU path, measured: K steps of the sample (fewer only if ~4 minutes would not hold them) -----------------
+    for _ in range(max(0, args.warmup // 3 - 1)):
+        cpu_step_seconds(cN, args.order, steps=1, workload=args.workload)
+    per, nst, ne, ndof, nnz = cpu_step_seconds(cN, args.order, steps=args.steps, workload=args.workload, budget_s=240.0)
+    full_cells = (args.N ** 3 if args.workload == 'ins3d_dim' else 2 * args.N * args.N) * max(1, args.gpus)
+    sample = ('{} time step(s) (Picard-iterated: assemble with NumPy, solve with SciPy SuperLU) of the same workload at '
+              'N={} ({} cells, {} DOFs, {} non-zeros), measured on this host, one process'.format(nst, cN, ne, ndof, nnz))
+    ref_args = argparse.Namespace(**vars(args))
+    line = {'impl': 'reference', 'metric': 'INS s/timestep', 'value': per, 'unit': 's', 'n_gpus': args.gpus,
+            'steps': nst, 'warmup': 1, 'ms_per_step': per * 1e3, 'higher_is_better': False, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': dict(workload_config(ref_args, 'cpu', N=cN, gpus=1),
+                           sample_of='the b200 arm\'s N={} per GPU on {} GPU(s); the CPU path cannot hold that size '
+                                     '(sparse LU of {} cells)'.format(args.N, max(1, args.gpus), full_cells)),
+            'cpu_baseline': {'value': per, 'unit': 's', 'cores': 1, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': per, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'scaled_to_full_config': {'value': per * full_cells / ne, 'unit': 's',
+                                      'note': 'EXTRAPOLATION, not a measurement: the sample time scaled linearly by '
+                                              'cell count x{:.1f} (sparse LU grows faster than linearly, so this '
+                                              'flatters the CPU path)'.format(full_cells / ne)}}
+    # ---- the GPU path on the SAME sample, same invocation: a measured same-config ratio -------------------------------
+    try:
+        import torch
+        if torch.cuda.is_available():
+            set_storage_env(args)
+            import opencmp_b200.ngs as ngs
+            from opencmp_b200.backend import CudaBackend
+            torch.cuda.set_device(0)
+            be = CudaBackend(0)
+            ngs.set_backend(be)
+            ws, _ = make_gpu_workload(args.workload, cN, args.order)
+            for _ in range(2):
+                ws.step()
+            g = GpuTimer(torch, be.lib, ws, torch.cuda.synchronize).clean(3)
+            line['gpu_same_config'] = {'value': g['ms'] / 3e3, 'unit': 's', 'N': cN, 'dofs': ws.ndof,
+                                       'linear_solver': workload_config(ref_args, 'gpu', N=cN, gpus=1)['linear_solver'],
+                                       'gmres_its_per_step': g['its'] / 3}
+            line['measured_ratio'] = per / (g['ms'] / 3e3)
+            ngs.set_backend(None)
+    except Exception as exc:                                        # pragma: no cover
+        line['gpu_same_config'] = {'error': repr(exc)}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_b200(args)
 
 
 if __name__ == '__main__':

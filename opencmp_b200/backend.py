@@ -500,6 +500,10 @@ class CudaBackend:
                 break
         xp.eb = eb_pick
         plan['contract'] = xp
+        # FP64 flops of one item in k_contract (2 per multiply-add): Z = D B rows, then A += B^T Z over the active pairs
+        z_fma = sum(k1 - k0 for k0, k1, _, _ in zdesc)
+        a_fma = sum(blocks[bt].nloc * blocks[bu].nloc * len(lst) for (st, bt, su, bu), lst in pairs.items())
+        plan['flops_per_item'] = 2.0 * nq * (z_fma + a_fma)
         return plan
 
     def _plans(self, program: FormProgram) -> list:
@@ -541,6 +545,10 @@ class CudaBackend:
     def assemble_matrix(self, program, mat):
         mat.values.zero_()
         self._run(program, mat.values, 'matrix')
+
+    def matrix_flops(self, program) -> float:
+        """FP64 flops of one assembly of ``program`` in the contraction kernel (for the assembly roofline)."""
+        return float(sum(p['nitems'] * p.get('flops_per_item', 0.0) for p in self._plans(program)))
 
     def assemble_vector(self, program, out):
         out.zero_()

@@ -148,6 +148,19 @@ class DistributedINS:
         return self.mg.levels[-1].map.nglobal
 
 
+def sphere_total_cells(N: int, world: int) -> int:
+    """Cells per direction of the one-sphere box on ``world`` ranks: the even number closest to N world^(1/3) whose
+    coarsening ends on a small coarsest mesh — N, 4N/3, 5N/3, 2N for 1, 2, 4, 8 ranks (48, 64, 80, 96 at N = 48)."""
+    factor = {1: (1, 1), 2: (4, 3), 4: (5, 3), 8: (2, 1)}.get(world)
+    if factor is None:
+        raise ValueError("layout 'sphere' is defined for 1, 2, 4 or 8 ranks")
+    ntot = N * factor[0] // factor[1]
+    if (N * factor[0]) % factor[1] or ntot % 2:
+        raise ValueError("layout 'sphere' on {} ranks needs N divisible by {} with an even total ({})".format(
+            world, 2 * factor[1], ntot))
+    return ntot
+
+
 class DistributedINSDIM3D:
     """The 3-D INS-DIM time step of workloads.INSSphereDIM3D, element-partitioned: R ranks, rank r owns the brick
     [-1 + 2r, 1 + 2r] x [-1,1]^2 (n0^3 coarse hexes refined k times) with its own diffuse-interface sphere; geometric
@@ -158,24 +171,33 @@ class DistributedINSDIM3D:
                  replicate_below: int = 100000, layout: str = None, **kw):
         """layout 'bricks' (default; ``bricks`` = number of [-1,1]^3 bricks in a row along x, one sphere each, N^3
         cells per brick, contiguous cell blocks per rank) or 'sphere': ONE sphere in [-1,1]^3 (BASELINE configs[4] as
-        written) meshed with (N bx) x (N by) x (N bz) hexes, (bx, by, bz) = dist.brick_grid(world), every rank owning
-        one compact N^3 brick of cells — per-rank work is fixed as the rank count grows and the mesh is refined
-        (weak scaling; the cells have aspect ratio 2 while the rank count is not a cube)."""
+        written), the box meshed with Ntot^3 hexes, Ntot = sphere_total_cells(N, world) growing with the rank count
+        (N, 4N/3, 5N/3, 2N on 1, 2, 4, 8 ranks), split into dist.brick_grid(world) compact bricks of cells, one per
+        rank. Isotropic cells throughout: refining only the split directions (cells of aspect ratio 2) kept the cell
+        count per rank exactly constant but GMRES no longer converged (48 x 24 x 24 on one B200: 400 iterations
+        without reaching 1e-12 against 45 on 24^3; profiles/r2_bench_results.md), so the per-rank load varies
+        instead: N^3, 1.19 N^3, 1.16 N^3, N^3 cells on 1, 2, 4, 8 ranks."""
         from .mesh import structured_3d
         from .workloads import INSSphereDIM3D
         from .dist import block_ranks, brick_grid
         from .dist_mg import DistributedMultigrid
         self.world, self.rank = world, rank
-        k, n = 0, N
-        while n % 2 == 0 and n > n0:
-            n //= 2
-            k += 1
         if layout == 'sphere':
             grid = brick_grid(world)
-            gmesh = structured_3d([n * b for b in grid], scale=(2.0, 2.0, 2.0), offset=(1.0, 1.0, 1.0))
+            ntot = sphere_total_cells(N, world)
+            k, n = 0, ntot
+            while n % 2 == 0 and n > n0:
+                n //= 2
+                k += 1
+            gmesh = structured_3d([n, n, n], scale=(2.0, 2.0, 2.0), offset=(1.0, 1.0, 1.0))
             rank_of_cells = block_ranks(grid, (-1.0,) * 3, (1.0,) * 3)
             kw.setdefault('periodic', (False, False, False))
+            N = ntot
         else:
+            k, n = 0, N
+            while n % 2 == 0 and n > n0:
+                n //= 2
+                k += 1
             bricks = world if bricks is None else bricks
             gmesh = structured_3d([n * bricks, n, n], scale=(2.0 * bricks, 2.0, 2.0), offset=(1.0, 1.0, 1.0))
             rank_of_cells = None

@@ -169,14 +169,14 @@ def _mg3d_worker(rank, world, port, bricks, out):
         from opencmp_b200.dist_workload import DistributedINSDIM3D
         from opencmp_b200.workloads import INSSphereDIM3D
         kw = dict(nonlinear_max_iterations=1, linear_tolerance=1e-13, lam=1.0)
-        if bricks == 'sphere':          # compact bricks of an anisotropically refined [-1,1]^3 (8 x 4 x 4 on 2 ranks)
-            d = DistributedINSDIM3D(4, world, rank, n0=2, replicate_below=0, layout='sphere', **kw)
-            assert d.gmesh.ne == world * 4 ** 3 and np.allclose(d.gmesh.points.max(axis=0), 1.0)
-            assert (d.part.cell_rank == rank).sum() == 4 ** 3
+        if bricks == 'sphere':          # ONE sphere, [-1,1]^3 meshed with 8^3 hexes on 2 ranks, one compact brick each
+            d = DistributedINSDIM3D(6, world, rank, n0=2, replicate_below=0, layout='sphere', **kw)
+            assert d.gmesh.ne == 8 ** 3 and np.allclose(d.gmesh.points.max(axis=0), 1.0)
+            assert (d.part.cell_rank == rank).sum() == 8 ** 3 // 2
             kw = dict(kw, periodic=(False, False, False))
         else:
             d = DistributedINSDIM3D(4, world, rank, n0=2, replicate_below=0, bricks=bricks, **kw)
-        g = INSSphereDIM3D(4, mesh=d.gmesh, preconditioner=None, **kw)
+        g = INSSphereDIM3D(d.gmesh.ne, mesh=d.gmesh, preconditioner=None, **kw)
 
         def direct():
             inv = g.a.mat.Inverse(g.fes.FreeDofs())

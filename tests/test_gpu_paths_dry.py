@@ -204,12 +204,13 @@ class _FakeStream:
         pass
 
 
-@pytest.mark.parametrize('argv', [['--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu'],
-                                  ['--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu', '--precond-storage', 'fp32',
-                                   '--full-mg-setup', '--lag-smoother'],
-                                  ['--workload', 'ins3d_dim', '--N', '4', '--steps', '1', '--warmup', '1', '--no-cpu'],
-                                  ['--workload', 'ins3d_dim', '--N', '4', '--steps', '1', '--warmup', '1', '--no-cpu',
-                                   '--precond-storage', 'bf16']])
+@pytest.mark.parametrize('argv', [['--workload', 'ins2d', '--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu'],
+                                  ['--workload', 'ins2d', '--N', '8', '--steps', '1', '--warmup', '1', '--no-cpu',
+                                   '--precond-storage', 'fp64', '--full-mg-setup', '--lag-smoother'],
+                                  ['--N', '4', '--steps', '1', '--warmup', '1', '--no-cpu', '--no-secondary',
+                                   '--cpu-N', '4'],
+                                  ['--N', '4', '--steps', '1', '--warmup', '1', '--no-cpu', '--no-secondary',
+                                   '--cpu-N', '4', '--precond-storage', 'bf16']])
 def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
     """bench.py's own arm, start to JSON line, with the CUDA runtime calls stubbed: the line must carry every key of
     the bench contract (values are meaningless here)."""
@@ -219,11 +220,13 @@ def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
     real_tensor = torch.tensor
     monkeypatch.setattr(torch.cuda, 'set_device', lambda *a: None)
     monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a: None)
+    monkeypatch.setattr(torch.cuda, 'empty_cache', lambda *a: None)
     monkeypatch.setattr(torch.cuda, 'Event', _FakeEvent)
     monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a: _FakeStream())
     monkeypatch.setattr(torch.Tensor, 'pin_memory', lambda self: self)
     monkeypatch.setattr(torch, 'tensor', lambda data, **kw: real_tensor(data, **{k: v for k, v in kw.items()
                                                                                   if k != 'device'}))
+    monkeypatch.setattr(bench, 'fp64_peak_tflops', lambda t: {'burst': 40.0, 'sustained': 39.0, 'how': 'stub'})
     monkeypatch.setattr(sys, 'argv', ['bench.py'] + argv)
     for k, v in (('OCMP_PATCH_STORAGE', 'fp64'), ('OCMP_SPMV_FP32', '0')):   # bench sets them; restored afterwards
         monkeypatch.setenv(k, v)
@@ -237,17 +240,56 @@ def test_bench_main_executes_on_a_null_device(dry, monkeypatch, capsys, argv):
         pytest.skip('all-zero fields: a norm of the workload vanished before the JSON line (numerics, not host logic)')
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
-                'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'e2e', 'gpu_launches', 'clocks'):
+                'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'e2e', 'gpu_launches', 'clocks',
+                'roofline_patch_apply', 'roofline_spmv', 'roofline_assembly', 'fp64_peak_tflops',
+                'same_size_as_cpu_sample'):
         assert key in line, key
     assert line['config']['workload'] and line['dtype'] == 'f64' and line['higher_is_better'] is False
-    want = 'fp32' if 'fp32' in argv else 'bf16' if 'bf16' in argv else 'fp64'
+    want = 'fp64' if 'fp64' in argv else 'bf16' if 'bf16' in argv else 'fp32'
     assert line['config']['precond_storage'] == {'patch_inverses': want,
                                                  'level_matrices_in_cycle': 'fp64' if want == 'fp64' else 'fp32'}
     for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
         assert key in line['roofline'], key
+    assert line['roofline_assembly']['flops_per_assembly'] > 0 and line['roofline_assembly']['bound'] == 'fp64'
     for key in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'):
         assert key in line['e2e'], key
-    assert 'error' not in line['matrix_free_apply'] and 'ms_per_apply' in line['matrix_free_apply']
+    assert 'error' not in line['same_size_as_cpu_sample'], line['same_size_as_cpu_sample']
+
+
+def test_bench_default_line_carries_the_2d_workload(dry, monkeypatch, capsys):
+    """The default (3-D) line on one GPU also reports the 2-D INS step as the object ``ins2d``."""
+    import json
+    import sys
+    import bench
+    real_tensor = torch.tensor
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda *a: None)
+    monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a: None)
+    monkeypatch.setattr(torch.cuda, 'empty_cache', lambda *a: None)
+    monkeypatch.setattr(torch.cuda, 'Event', _FakeEvent)
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a: _FakeStream())
+    monkeypatch.setattr(torch.Tensor, 'pin_memory', lambda self: self)
+    monkeypatch.setattr(torch, 'tensor', lambda data, **kw: real_tensor(data, **{k: v for k, v in kw.items()
+                                                                                  if k != 'device'}))
+    monkeypatch.setattr(bench, 'fp64_peak_tflops', lambda t: {'burst': 40.0, 'sustained': 39.0, 'how': 'stub'})
+    monkeypatch.setitem(bench.DEFAULTS, 'ins2d', dict(N=8, order=3))
+    monkeypatch.setattr(sys, 'argv', ['bench.py', '--N', '4', '--steps', '1', '--warmup', '1', '--no-cpu', '--cpu-N', '4'])
+    for k, v in (('OCMP_PATCH_STORAGE', 'fp64'), ('OCMP_SPMV_FP32', '0'), ('OCMP_MG_REUSE_COARSE', '1'),
+                 ('OCMP_MG_LAG', '0')):
+        monkeypatch.setenv(k, v)
+    for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'):
+        monkeypatch.delenv(k, raising=False)
+    try:
+        bench.main()
+    except ZeroDivisionError:
+        pytest.skip('all-zero fields: a norm of the workload vanished before the JSON line')
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert 'INS-DIM 3D' in line['config']['workload']
+    two = line['ins2d']
+    assert 'error' not in two, two
+    for key in ('config', 'value', 'e2e', 'problem', 'roofline_patch_apply', 'roofline_spmv', 'roofline_assembly',
+                'kernel_time_share', 'gpu_launches'):
+        assert key in two, key
+    assert 'Taylor-Green 2D' in two['config']['workload']
 
 
 @pytest.mark.parametrize('which', ['ins2d', 'ins3d_dim'])
@@ -328,6 +370,7 @@ def _bench_rank(rank, world, port, argv, out):
     real_tensor, real_init = torch.tensor, dist.init_process_group
     torch.cuda.set_device = lambda *a: None
     torch.cuda.synchronize = lambda *a: None
+    torch.cuda.empty_cache = lambda *a: None
     torch.cuda.Event = _FakeEvent
     torch.cuda.current_stream = lambda *a: _FakeStream()
     torch.Tensor.pin_memory = lambda self: self
@@ -335,6 +378,7 @@ def _bench_rank(rank, world, port, argv, out):
     dist.init_process_group = lambda backend=None, **kw: real_init('gloo', rank=rank, world_size=world)
     sys.argv = ['bench.py'] + argv
     import bench
+    bench.fp64_peak_tflops = lambda t: {'burst': 40.0, 'sustained': 39.0, 'how': 'stub'}
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         bench.main()
@@ -344,10 +388,9 @@ def _bench_rank(rank, world, port, argv, out):
         out['other'] = buf.getvalue().strip()
 
 
-@pytest.mark.parametrize('argv', [['--gpus', '2', '--N', '8', '--steps', '1', '--warmup', '1'],
-                                  ['--gpus', '2', '--workload', 'ins3d_dim', '--N', '4', '--steps', '1', '--warmup', '1'],
-                                  ['--gpus', '2', '--workload', 'ins3d_dim', '--N', '4', '--steps', '1', '--warmup', '1',
-                                   '--layout', 'sphere']])
+@pytest.mark.parametrize('argv', [['--gpus', '2', '--workload', 'ins2d', '--N', '8', '--steps', '1', '--warmup', '1'],
+                                  ['--gpus', '2', '--N', '4', '--steps', '1', '--warmup', '1', '--layout', 'bricks'],
+                                  ['--gpus', '2', '--N', '6', '--steps', '1', '--warmup', '1']])
 def test_bench_two_ranks_execute_on_a_null_device(argv):
     """The multi-GPU arm of bench.py (element-partitioned workload, communicator set-up through the C ABI, halo plans,
     level array of the distributed C driver, max-over-ranks timing, rank 0 prints) with two gloo ranks."""
@@ -362,8 +405,7 @@ def test_bench_two_ranks_execute_on_a_null_device(argv):
     line = out['line']
     assert out.get('other', '') == ''                       # only rank 0 prints
     assert line['n_gpus'] == 2 and line['scaling'] == 'weak' and line['problem']['ranks'] == 2
-    if 'sphere' not in argv:                                 # at N = 4 two ghost layers cover the whole single box
-        assert line['problem']['global_dofs'] > line['problem']['dofs'] * 1.2
+    assert line['problem']['global_dofs'] > line['problem']['dofs'] * 1.2
     assert 'element-partitioned' in line['config']['parallelism']
 
 
