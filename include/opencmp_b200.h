@@ -178,6 +178,10 @@ typedef struct ocmp_system {
     const int* patch_inc_ptr;   /* pre_kind 2 / 3: incidence list of the patch table (see ocmp_asm_apply) */
     const int* patch_inc_idx;
     double* patch_ybuf;         /* npatch x bs doubles of scratch for the patch products */
+    const int* spmv_rows;       /* element-partitioned: the rows this rank owns (ascending). Operator applications and
+                                   residuals only compute those — the ghost rows of a local matrix are incomplete and
+                                   their entries are overwritten by the halo exchange that follows. NULL = all rows */
+    int n_spmv_rows;
 } ocmp_system;
 /* A band LU as ocmp_band_fill / ocmp_band_factor leave it, plus the permutation and a work vector of n doubles. */
 typedef struct ocmp_band_lu {

@@ -51,7 +51,7 @@ class System(C.Structure):
                 ('inv_vals', C.c_void_p), ('owned', C.c_void_p), ('halo_fwd', C.c_int), ('halo_sum', C.c_int),
                 ('inv_storage', C.c_int), ('vals32', C.c_void_p), ('apply_fn', C.c_void_p), ('apply_ctx', C.c_void_p),
                 ('direct', C.c_void_p), ('patch_inc_ptr', C.c_void_p), ('patch_inc_idx', C.c_void_p),
-                ('patch_ybuf', C.c_void_p)]
+                ('patch_ybuf', C.c_void_p), ('spmv_rows', C.c_void_p), ('n_spmv_rows', C.c_int)]
 
 
 class BandHandle(C.Structure):

@@ -110,11 +110,13 @@ template <int LPR, typename VT, int EP>
 __global__ void __launch_bounds__(256) k_spmv(int nrows, const int* __restrict__ rowptr, const int* __restrict__ col,
                                               const VT* __restrict__ val, const double* __restrict__ x,
                                               double* __restrict__ y, const double* __restrict__ b,
-                                              const double* __restrict__ m, const double* __restrict__ m2) {
+                                              const double* __restrict__ m, const double* __restrict__ m2,
+                                              const int* __restrict__ rows) {
     const int lane = threadIdx.x % LPR;
     const long long row0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
     const long long stride = (long long)gridDim.x * blockDim.x / LPR;
-    for (long long row = row0; row < nrows; row += stride) {
+    for (long long rr = row0; rr < nrows; rr += stride) {
+        const long long row = rows ? __ldg(rows + rr) : rr;      // `nrows` counts the listed rows when a list is given
         const int a = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
         double s = 0.0;
         for (int k = a + lane; k < e; k += LPR) s = fma((double)__ldg(val + k), __ldg(x + __ldg(col + k)), s);
@@ -140,14 +142,15 @@ __global__ void __launch_bounds__(256) k_to_f32(long long n, const double* __res
 // one launch: category `cat`, values from `vals32` when given, else `vals`
 static int spmv_ep(int cat, int ep, int nrows, const int* rowptr, const int* colidx, const double* vals,
                    const float* vals32, const double* x, double* y, const double* b, const double* m,
-                   const double* m2, cudaStream_t st) {
+                   const double* m2, cudaStream_t st, const int* rows = nullptr) {
     if (nrows <= 0) return 0;
     const int threads = 256;
     const long long want = ((long long)nrows * 16 + threads - 1) / threads;
     const long long cap = (long long)ocmp_sm_count() * 64;
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     ProfScope ps(cat, st);
-#define SPMV_GO(VT, V, EP) k_spmv<16, VT, EP><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, V, x, y, b, m, m2)
+#define SPMV_GO(VT, V, EP) \
+    k_spmv<16, VT, EP><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, V, x, y, b, m, m2, rows)
     if (vals32) {
         if (ep == EP_PLAIN) SPMV_GO(float, vals32, EP_PLAIN);
         else if (ep == EP_RESID) SPMV_GO(float, vals32, EP_RESID);
@@ -586,6 +589,9 @@ struct Ctx {
     double hscal[64];
     mutable int failed = 0;     // a matrix-free operator callback reported an error
 
+    // the rows an operator application has to compute: a rank's own rows when the halo exchange supplies the others
+    static const int* row_list(const ocmp_system* sy) { return (sy->halo_fwd && sy->spmv_rows) ? sy->spmv_rows : nullptr; }
+    static int active_rows(const ocmp_system* sy) { return row_list(sy) ? sy->n_spmv_rows : sy->nrows; }
     static void had(cudaStream_t st, long long n, const double* a, const double* m, const double* r, double* z,
                     double scale, int accumulate) {
         ProfScope ps(PROF_VEC, st);
@@ -598,8 +604,8 @@ struct Ctx {
             if (((ocmp_apply_fn)s->apply_fn)(s->apply_ctx, x, y, (void*)st) != 0 && !failed) failed = 1;
             if (masked && s->freemask) had(st, n, nullptr, s->freemask, y, y, 1.0, 0);
         } else {
-            spmv_ep(PROF_SPMV, masked && s->freemask ? EP_MASK : EP_PLAIN, s->nrows, s->rowptr, s->colidx, s->vals,
-                    nullptr, x, y, nullptr, s->freemask, nullptr, st);
+            spmv_ep(PROF_SPMV, masked && s->freemask ? EP_MASK : EP_PLAIN, active_rows(s), s->rowptr, s->colidx,
+                    s->vals, nullptr, x, y, nullptr, s->freemask, nullptr, st, row_list(s));
         }
         if (s->halo_fwd) ocmp_halo_run(s->halo_fwd - 1, y, 0, st);
     }
@@ -610,8 +616,8 @@ struct Ctx {
             ProfScope ps(PROF_VEC, st);
             k_resid<<<grid_for(n), 256, 0, st>>>(n, b, s->freemask, r);
         } else {
-            spmv_ep(PROF_SPMV, EP_RESID, s->nrows, s->rowptr, s->colidx, s->vals, nullptr, x, r, b, s->freemask,
-                    nullptr, st);
+            spmv_ep(PROF_SPMV, EP_RESID, active_rows(s), s->rowptr, s->colidx, s->vals, nullptr, x, r, b, s->freemask,
+                    nullptr, st, row_list(s));
             if (s->halo_fwd) ocmp_halo_run(s->halo_fwd - 1, r, 0, st);
         }
     }
@@ -655,8 +661,8 @@ struct Ctx {
     // r = m .* m2 .* (b - A x) on a multigrid level: FP32-stored copy of the level matrix when the host provided one
     static void level_residual(const ocmp_system* sy, const double* b, const double* x, double* r, const double* m2,
                                bool refresh, cudaStream_t st) {
-        spmv_ep(PROF_SPMV_MG, EP_RESID, sy->nrows, sy->rowptr, sy->colidx, sy->vals, sy->vals32, x, r, b, sy->freemask,
-                m2, st);
+        spmv_ep(PROF_SPMV_MG, EP_RESID, active_rows(sy), sy->rowptr, sy->colidx, sy->vals, sy->vals32, x, r, b,
+                sy->freemask, m2, st, row_list(sy));
         if (refresh && sy->halo_fwd) ocmp_halo_run(sy->halo_fwd - 1, r, 0, st);
     }
     // V-cycle on level l: x = MG(b); b is masked on entry, x is masked on exit. Launches per level and cycle with

@@ -97,7 +97,15 @@ class DistributedMultigrid:
                 assert (prev.part.local_cells[parent] == parent_global).all(), 'parent of a local cell is not local'
                 P = prolongation(prev.fes, lv.fes, parent)
                 lv.P = be.csr_handle(P)
-                lv.R = be.csr_handle(P.T.tocsr())
+                # restriction = transpose of the prolongation restricted to the fine entries this rank OWNS: every
+                # fine entry is then counted by exactly one rank (the partial sums are added up by restrict_sum), and
+                # the product never reads the ghost entries of the residual — which the owned-row products leave stale
+                R = P.T.tocsr()
+                if not lv.replicated:
+                    import scipy.sparse as sp
+                    R = (R @ sp.diags(lv.map.owned.astype(np.float64))).tocsr()
+                    R.eliminate_zeros()
+                lv.R = be.csr_handle(R)
             self.levels.append(lv)
         # coefficient fields (DIM phase field, masks) get a stand-in on every coarse level, finest to coarsest
         cur = {id(gf): gf for gf in cfields}
@@ -168,6 +176,10 @@ class DistributedMultigrid:
             s.freemask = lv.free.data_ptr()
             distributed = dist_on and not lv.replicated
             s.owned = lv.owned.data_ptr() if distributed else None
+            if distributed:
+                if not hasattr(lv, 'own_rows'):
+                    lv.own_rows = be._up(np.nonzero(lv.map.owned)[0].astype(np.int32))
+                s.spmv_rows, s.n_spmv_rows = lv.own_rows.data_ptr(), int(lv.own_rows.numel())
             if not hasattr(lv, 'work'):
                 lv.work = be.zeros(4 * lv.n)
             arr[l].work = lv.work.data_ptr()
