@@ -258,14 +258,17 @@ class GpuTimer:
         l0 = self.lib.ocmp_launch_count()
         e0.record()
         picard = its = 0
+        per_step = []
         for _ in range(steps):
             w.linear_iterations = []
             w.step()
             picard += w.picard_iterations
             its += sum(w.linear_iterations)
+            per_step.append(list(w.linear_iterations))
         e1.record()
         self.barrier()
-        return dict(ms=e0.elapsed_time(e1), picard=picard, its=its, launches=int(self.lib.ocmp_launch_count() - l0))
+        return dict(ms=e0.elapsed_time(e1), picard=picard, its=its, launches=int(self.lib.ocmp_launch_count() - l0),
+                    its_per_solve=per_step)
 
     def e2e(self, steps):
         torch, w = self.torch, self.w
@@ -278,7 +281,9 @@ class GpuTimer:
         self.barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
+        per_step = []
         for _ in range(steps):
+            w.linear_iterations = []
             w.gfu_0.vec.a.copy_(h_prev, non_blocking=True)
             w.gfu.vec.a.copy_(h_prev, non_blocking=True)
             w.W.vec.a.copy_(h_wind, non_blocking=True)
@@ -287,9 +292,11 @@ class GpuTimer:
             torch.cuda.current_stream().synchronize()
             h_prev.copy_(h_out)
             h_wind.copy_(h_out[:w.V.ndof])
+            per_step.append(list(w.linear_iterations))
         f1.record()
         self.barrier()
-        return dict(ms=f0.elapsed_time(f1), h2d=int(8 * (2 * ndof + w.V.ndof)), d2h=int(8 * ndof))
+        return dict(ms=f0.elapsed_time(f1), h2d=int(8 * (2 * ndof + w.V.ndof)), d2h=int(8 * ndof),
+                    its_per_solve=per_step)
 
     def profiled(self, steps):
         from opencmp_b200.backend import read_profile
@@ -460,7 +467,9 @@ def run_b200(args):
         'problem': {'cells': ne, 'dofs': ndof, 'nnz': nnz, 'global_dofs': dins.ndof_global if dins else ndof,
                     'ranks': world, 'owned_cells_per_gpu': (dins.gmesh.ne // world) if dins else ne,
                     'picard_per_step': m['clean']['picard'] / args.steps,
-                    'gmres_its_per_step': m['clean']['its'] / args.steps, 'l2_err_u': m['errs'][0],
+                    'gmres_its_per_step': m['clean']['its'] / args.steps,
+                    'gmres_its_per_solve': m['clean']['its_per_solve'],
+                    'gmres_its_per_solve_e2e': m['e2e']['its_per_solve'], 'l2_err_u': m['errs'][0],
                     'l2_err_p': m['errs'][1], 'setup_s': t_setup},
         'timing': 'value: CUDA events around {0} steps with per-launch profiling OFF; kernel shares and rooflines: a '
                   'second loop of {1} steps with an event pair around every launch'.format(args.steps,

@@ -49,13 +49,15 @@ typedef struct {
     int dim, kind, nq, nside;
     int nblk;                /* blocks per side */
     int nloc;                /* local dofs per side */
-    int sbsz;                /* doubles of one side's physical table at one quadrature point */
+    int sbsz;                /* doubles of one side's physical table at one quadrature point (rows padded to x4) */
     int zsz;                 /* doubles of the Z rows of one item (every segment padded to a multiple of 4) */
     int nact;                /* active (structurally non-zero) local entries per item */
     int nslots;              /* D slots (== coef plan nout) */
-    int eb;                  /* items per CTA */
-    int asz;                 /* doubles of one item's accumulators (pair widths padded to a multiple of 4) */
-    int nzd, nent, npairs, nseg;
+    int eb;                  /* items per 256-thread CTA */
+    int ntiles;              /* 4 x 4 accumulator tiles covering the active block pairs of one item */
+    int maxt;                /* tiles per thread: 1 | 2 | 4, ntiles <= maxt * 256 / eb */
+    int nzd, nent, nseg;
+    int qb;                  /* quadrature points staged in shared memory per barrier round */
     const int* items;
     const double* geo;
     const int* facet_cells;
@@ -63,12 +65,13 @@ typedef struct {
     const int* blk;          /* (nblk, 6): kind, nloc, nrows, tab_off, loc_off, sb_off — vector assembly */
     const double* tab;       /* reference tables of the form's blocks at this rule */
     const int* zdesc;        /* (nzd, 4): entry k0, k1, sB base (side*sbsz + sb_off + j), z index */
-    const int* ent;          /* matrices (nent, 2): slot, trial row * row stride; vectors: slot, side-block << 8 | row */
-    const int* dofdesc;      /* (nside*nloc, 4): kind | nrows << 8, nloc of the block, tab_off + il, sb_off + il */
-    const int* pairs;        /* (npairs, 8): acc offset, ni, nj/4 (padded), sB base of the test block, seg start,
-                                seg count, magic = floor(2^32 / (nj/4)) + 1, 0 */
-    const int* amap;         /* (nact, 2): test side << 30 | trial side << 29 | (i * nloc + j), accumulator index */
-    const int* seg;          /* (nseg, 2): test row * ni, z offset of the segment */
+    const int* ent;          /* matrices (nent, 2): slot, trial row * padded row stride; vectors: slot, side-block << 8 | row */
+    const int* dofdesc;      /* (nside*nloc, 4): kind | nrows << 8 | padded nloc << 16, nloc of the block, tab_off + il,
+                                sb_off + il */
+    const int* tiles;        /* (ntiles, 8): sB offset of the test rows (side*sbsz + sb_off + i0), j0, first segment,
+                                segments, test side | trial side << 1, row i0 and column j0 of the local matrix (within
+                                one side), valid rows | valid columns << 8 */
+    const int* seg;          /* (nseg, 2): test row * padded ni, z offset of the segment */
     const int* cell2nnz;     /* (ncells, nloc*nloc) */
     const int* facet2nnz;    /* (n interior facets, 2, nloc*nloc) indexed by item */
     const int* cell_dofs;    /* (ncells, nloc) — vector assembly */

@@ -35,11 +35,11 @@ class CoefPlan(C.Structure):
 class ContractPlan(C.Structure):
     _fields_ = [('dim', C.c_int), ('kind', C.c_int), ('nq', C.c_int), ('nside', C.c_int), ('nblk', C.c_int),
                 ('nloc', C.c_int), ('sbsz', C.c_int), ('zsz', C.c_int), ('nact', C.c_int), ('nslots', C.c_int),
-                ('eb', C.c_int), ('asz', C.c_int), ('nzd', C.c_int), ('nent', C.c_int), ('npairs', C.c_int),
-                ('nseg', C.c_int),
+                ('eb', C.c_int), ('ntiles', C.c_int), ('maxt', C.c_int), ('nzd', C.c_int), ('nent', C.c_int),
+                ('nseg', C.c_int), ('qb', C.c_int),
                 ('items', C.c_void_p), ('geo', C.c_void_p), ('facet_cells', C.c_void_p), ('facet_local', C.c_void_p),
                 ('blk', C.c_void_p), ('tab', C.c_void_p), ('zdesc', C.c_void_p), ('ent', C.c_void_p),
-                ('dofdesc', C.c_void_p), ('pairs', C.c_void_p), ('amap', C.c_void_p), ('seg', C.c_void_p),
+                ('dofdesc', C.c_void_p), ('tiles', C.c_void_p), ('seg', C.c_void_p),
                 ('cell2nnz', C.c_void_p), ('facet2nnz', C.c_void_p), ('cell_dofs', C.c_void_p)]
 
 
@@ -167,6 +167,70 @@ def patch_incidence(dofs: np.ndarray, ndof: int):
     counts = np.bincount(flat[pos], minlength=ndof)
     inc_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
     return inc_ptr, inc_idx
+
+
+def contract_smem_bytes(xp, eb: int, gs: int) -> int:
+    """Mirror of contract_smem() in csrc/ocmp_assembly.cu."""
+    dbl = eb * xp.qb * (xp.zsz + xp.nside * xp.sbsz + xp.nslots) + eb * xp.nside * gs
+    dbl += dbl % 2
+    ints = 4 * eb + 4 * xp.nside * xp.nloc + 4 * xp.nzd + 2 * xp.nent + 2 * xp.nseg
+    return 8 * dbl + 4 * ints + 16
+
+
+def contract_tables(entries, decode, nloc, kind, nrows, tab_off, sb_off, sbsz, loc_off, nside):
+    """Descriptor tables of k_contract for one bilinear integral. ``entries``: (test row, trial row, D slot) of the
+    lowered integrand; ``decode(row) -> (side, block, physical row of the block)``. Per item and quadrature point the
+    kernel forms Z_g[j] = sum_k D[slot_k] B_trial[row_k][j] for every group g = (test side/block/row, trial side/block)
+    and then updates 4 x 4 register tiles A[i0:i0+4, j0:j0+4] += B_test[row_g][i] Z_g[j] over the groups ("segments")
+    of the tile's block pair. Shared-memory rows are padded to multiples of 4 so that tile edges are 16-byte loads."""
+    pad4 = lambda v: (v + 3) // 4 * 4
+    nblk = len(nloc)
+    segs: Dict[tuple, list] = {}
+    for tr, ur, slot in entries:
+        st, bt, rt = decode(tr)
+        su, bu, ru = decode(ur)
+        segs.setdefault((st, bt, rt, su, bu), []).append((slot, ru))
+    # per (side, local dof): how to build its physical table column
+    dofdesc = []
+    for s_ in range(nside):
+        for b in range(nblk):
+            for il in range(nloc[b]):
+                dofdesc.append([kind[b] | (nrows[b] << 8) | (pad4(nloc[b]) << 16), nloc[b], tab_off[b] + il,
+                                sb_off[b] + il])
+    # Z rows: one (padded) segment per (test row, trial side-block)
+    zdesc, ent, seg_z = [], [], {}
+    zoff = z_fma = 0
+    for key in sorted(segs):
+        st, bt, rt, su, bu = key
+        k0 = len(ent)
+        nl = nloc[bu]
+        ent += [[slot, ru * pad4(nl)] for slot, ru in segs[key]]
+        k1 = len(ent)
+        seg_z[key] = zoff
+        for j in range(nl):
+            zdesc.append([k0, k1, su * sbsz + sb_off[bu] + j, zoff + j])
+        z_fma += (k1 - k0) * nl
+        zoff += pad4(nl)
+    # active block pairs -> segments and 4 x 4 tiles
+    pairs: Dict[tuple, list] = {}
+    for key in sorted(segs):
+        st, bt, rt, su, bu = key
+        pairs.setdefault((st, bt, su, bu), []).append((rt, seg_z[key]))
+    seg_arr, tiles = [], []
+    nact = a_fma = 0
+    for (st, bt, su, bu), lst in sorted(pairs.items()):
+        ni, nj = nloc[bt], nloc[bu]
+        s0 = len(seg_arr)
+        seg_arr += [[rt * pad4(ni), z] for rt, z in lst]
+        for i0 in range(0, ni, 4):
+            for j0 in range(0, nj, 4):
+                tiles.append([st * sbsz + sb_off[bt] + i0, j0, s0, len(lst), st | (su << 1), loc_off[bt] + i0,
+                              loc_off[bu] + j0, min(4, ni - i0) | (min(4, nj - j0) << 8)])
+        nact += ni * nj
+        a_fma += ni * nj * len(lst)
+    i32 = lambda a, w: np.asarray(a, dtype=np.int32).reshape(-1, w)
+    return dict(zdesc=i32(zdesc, 4), ent=i32(ent, 2), seg=i32(seg_arr, 2), dofdesc=i32(dofdesc, 4),
+                tiles=i32(tiles, 8), zsz=zoff, nact=nact, z_fma=z_fma, a_fma=a_fma)
 
 
 def _ptr(t) -> Optional[int]:
@@ -396,6 +460,7 @@ class CudaBackend:
         blocks = fes.blocks
         nblk = len(blocks)
         tkind = 'cell' if integ.kind == 'cell' else 'facet'
+        pad4 = lambda v: (v + 3) // 4 * 4
         blk_tab, tabs = [], []
         toff = sboff = 0
         sb_off = []
@@ -405,7 +470,7 @@ class CudaBackend:
             sb_off.append(sboff)
             tabs.append(tab)
             toff += tab.size
-            sboff += b.basis.nrows * b.nloc
+            sboff += b.basis.nrows * pad4(b.nloc)       # shared-memory rows padded: 16-byte loads of 4 x 4 tile edges
         sbsz = sboff
         nrows_tot = fes.nrows
         ro = fes.row_offsets
@@ -436,74 +501,34 @@ class CudaBackend:
             return plan
         pd = self.pattern_data(fes)
         xp.cell2nnz, xp.facet2nnz = pd['cell2nnz'].data_ptr(), pd['facet2nnz'].data_ptr()
-        segs: Dict[tuple, list] = {}
-        for tr, ur, slot in integ.entries:
-            st, bt, rt = decode(tr)
-            su, bu, ru = decode(ur)
-            segs.setdefault((st, bt, rt, su, bu), []).append((slot, ru))
-        pad4 = lambda v: (v + 3) // 4 * 4
-        # per (side, local dof): how to build its physical table column
-        dofdesc = []
-        for s_ in range(nside):
-            for bidx, b in enumerate(blocks):
-                for il in range(b.nloc):
-                    dofdesc.append([(0 if b.kind == 'scalar' else 1) | (b.basis.nrows << 8), b.nloc,
-                                    blk_tab[bidx][3] + il, sb_off[bidx] + il])
-        # Z rows: one (padded) segment per (test row, trial side-block)
-        zdesc, ent, seg_z = [], [], {}
-        zoff = 0
-        for key in sorted(segs):
-            st, bt, rt, su, bu = key
-            k0 = len(ent)
-            nl = blocks[bu].nloc
-            ent += [[slot, ru * nl] for slot, ru in segs[key]]
-            k1 = len(ent)
-            seg_z[key] = zoff
-            for j in range(nl):
-                zdesc.append([k0, k1, su * sbsz + sb_off[bu] + j, zoff + j])
-            zoff += pad4(nl)
-        # active block pairs
-        pairs: Dict[tuple, list] = {}
-        for key in sorted(segs):
-            st, bt, rt, su, bu = key
-            pairs.setdefault((st, bt, su, bu), []).append((rt, seg_z[key]))
-        pair_arr, seg_arr, amap = [], [], []
-        aoff = 0
-        for (st, bt, su, bu), lst in sorted(pairs.items()):
-            ni, nj = blocks[bt].nloc, blocks[bu].nloc
-            njp = pad4(nj)
-            s0 = len(seg_arr)
-            seg_arr += [[rt * ni, z] for rt, z in lst]
-            nj4 = njp // 4
-            magic = ((1 << 32) // nj4 + 1) & 0xffffffff if nj4 > 1 else 0
-            pair_arr.append([aoff, ni, nj4, st * sbsz + sb_off[bt], s0, len(lst), magic, 0])
-            lot, lou = fes.loc_offsets[bt], fes.loc_offsets[bu]
-            for i in range(ni):
-                for j in range(nj):
-                    amap.append([(st << 30) | (su << 29) | ((lot + i) * fes.nloc + lou + j), aoff + i * njp + j])
-            aoff += ni * njp
-        xp.zsz, xp.nact, xp.asz = zoff, len(amap), aoff
-        xp.nzd, xp.nent, xp.npairs, xp.nseg = len(zdesc), len(ent), len(pair_arr), len(seg_arr)
-        xp.zdesc = up(np.array(zdesc), np.int32).data_ptr()
-        xp.ent = up(np.array(ent), np.int32).data_ptr()
-        xp.seg = up(np.array(seg_arr), np.int32).data_ptr()
-        xp.dofdesc = up(np.array(dofdesc), np.int32).data_ptr()
-        xp.pairs = up(np.array(pair_arr, dtype=np.int64).astype(np.uint32).view(np.int32), np.int32).data_ptr()
-        xp.amap = up(np.array(amap, dtype=np.int64).astype(np.int32), np.int32).data_ptr()
+        tb = contract_tables(integ.entries, decode, [b.nloc for b in blocks],
+                             [0 if b.kind == 'scalar' else 1 for b in blocks], [b.basis.nrows for b in blocks],
+                             [t[3] for t in blk_tab], sb_off, sbsz, list(fes.loc_offsets), nside)
+        xp.zsz, xp.nact, xp.ntiles = tb['zsz'], tb['nact'], len(tb['tiles'])
+        xp.nzd, xp.nent, xp.nseg = len(tb['zdesc']), len(tb['ent']), len(tb['seg'])
+        xp.zdesc = up(tb['zdesc'], np.int32).data_ptr()
+        xp.ent = up(tb['ent'], np.int32).data_ptr()
+        xp.seg = up(tb['seg'], np.int32).data_ptr()
+        xp.dofdesc = up(tb['dofdesc'], np.int32).data_ptr()
+        xp.tiles = up(tb['tiles'], np.int32).data_ptr()
         gs = dim + 2 * dim * dim + 1
-        nints = 4 * nside * fes.nloc + 4 * len(zdesc) + 2 * len(ent) + 8 * len(pair_arr) + 2 * len(seg_arr)
-        eb_pick = 1
-        for eb in (8, 4, 2, 1):
-            smem = 8 * eb * (aoff + nside * sbsz + zoff + prog.nout + nside * gs) + 4 * (nints + 4 * eb) + 16
-            if smem <= 100 * 1024:
+        xp.qb = min(4, nq)                              # quadrature points staged per barrier round
+        # items per 256-thread CTA: as many as leave every thread at most one 4 x 4 tile (16 FP64 accumulators in
+        # registers); items with more than 256 tiles take 2 or 4 tiles per thread
+        eb_pick, maxt = 1, 1
+        for eb in (16, 8, 4, 2, 1):
+            if xp.ntiles <= 256 // eb and contract_smem_bytes(xp, eb, gs) <= 96 * 1024:
                 eb_pick = eb
                 break
-        xp.eb = eb_pick
+        else:
+            maxt = 2 if xp.ntiles <= 512 else 4
+            if xp.ntiles > 1024:
+                raise ValueError('a local matrix of {} 4 x 4 tiles does not fit k_contract (limit 1024)'
+                                 .format(xp.ntiles))
+        xp.eb, xp.maxt = eb_pick, maxt
         plan['contract'] = xp
-        # FP64 flops of one item in k_contract (2 per multiply-add): Z = D B rows, then A += B^T Z over the active pairs
-        z_fma = sum(k1 - k0 for k0, k1, _, _ in zdesc)
-        a_fma = sum(blocks[bt].nloc * blocks[bu].nloc * len(lst) for (st, bt, su, bu), lst in pairs.items())
-        plan['flops_per_item'] = 2.0 * nq * (z_fma + a_fma)
+        plan['tables'] = tb
+        plan['flops_per_item'] = 2.0 * nq * (tb['z_fma'] + tb['a_fma'])
         return plan
 
     def _plans(self, program: FormProgram) -> list:

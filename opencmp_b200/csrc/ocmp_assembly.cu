@@ -232,31 +232,32 @@ __device__ __forceinline__ void dof_phys_rows(int kind, int nloc, int nrows, con
     phys_rows<DIM>(kind, R, g + DIM, g + DIM + DIM * DIM, g[GS - 1], PH);
 }
 
-// Contraction kernel. One CTA handles EB items; per quadrature point the physical tables (sB), the D values (sD) and
-// the rows Z_g = sum_k D_k B[trial row_k] (sZ) are staged in shared memory, then every *active block pair* (test block,
-// trial block) is updated as a small GEMM  A_p[i][j] += sum_g B[row_g][i] * Z_g[j]  with the accumulators in shared
-// memory and each thread owning 1 x 4 strips (one B load and two 16-byte Z loads per 4 FMAs). Pair widths are padded
-// to a multiple of 4 (Z padding stays zero). All descriptor tables are copied to shared memory once per CTA.
-template <int DIM>
-__global__ void __launch_bounds__(256) k_contract(const __grid_constant__ ocmp_contract_plan P, int item0, int nitems,
+// Contraction kernel: local matrices A = sum_q B^T (D B) in REGISTERS. One 256-thread CTA handles EB items, 256 / EB
+// threads per item; every thread owns up to MAXT 4 x 4 tiles of the item's active block pairs (16 FP64 accumulators
+// each) for the whole quadrature loop. Per quadrature point the physical basis tables (sB), the D values (sD) and the
+// rows Z_g = sum_k D_k B[trial row_k] (sZ) are staged in shared memory; a tile update reads, per segment g of its
+// pair, 4 B values and 4 Z values as four 16-byte loads (rows padded to multiples of 4; neighbouring lanes share
+// tile rows / columns, so the loads are mostly broadcasts) for 16 FMAs. Structurally empty block pairs are neither
+// computed nor scattered. The finished tiles are scatter-added through the element -> nnz map (no colouring).
+template <int DIM, int MAXT>
+__global__ void __launch_bounds__(256, (MAXT == 1 ? (DIM == 2 ? 3 : 2) : 1)) k_contract(const __grid_constant__ ocmp_contract_plan P, int item0, int nitems,
                                                   const double* __restrict__ dbuf, double* __restrict__ values) {
     constexpr int GS = GeoT<DIM>::GS;
     extern __shared__ double smem[];
     const int EB = P.eb, TPE = 256 / EB;
     const int nside = P.nside;
-    double* sA = smem;                                   // [EB][asz]
-    double* sZ = sA + EB * P.asz;                        // [EB][zsz]   (padded; sA and sZ stay 32-byte aligned)
-    double* sB = sZ + EB * P.zsz;                        // [EB][nside][sbsz]
-    double* sD = sB + EB * nside * P.sbsz;               // [EB][nslots]
-    double* sG = sD + EB * P.nslots;                     // [EB][nside][GS]
-    // [EB][4]: cell0, cell1, lf0, lf1 — rounded up to 16 bytes (an odd number of doubles precedes it for some EB = 1
-    // plans; the descriptor tables behind it are read with int4 loads; contract_smem() reserves the slack)
+    const int QB = P.qb;                                 // quadrature points staged per barrier round
+    double* sZ = smem;                                   // [EB][QB][zsz]         (zsz % 4 == 0: 32-byte aligned rows)
+    double* sB = sZ + EB * QB * P.zsz;                   // [EB][QB][nside][sbsz] (sbsz % 4 == 0)
+    double* sD = sB + EB * QB * nside * P.sbsz;          // [EB][QB][nslots]
+    double* sG = sD + EB * QB * P.nslots;                // [EB][nside][GS]
+    // [EB][4]: cell0, cell1, lf0, lf1 — rounded up to 16 bytes (the descriptor tables behind it are read with int4
+    // loads; contract_smem() reserves the slack)
     int* sI = reinterpret_cast<int*>((reinterpret_cast<size_t>(sG + EB * nside * GS) + 15) & ~(size_t)15);
-    int* tDof = sI + 4 * EB;                             // [nside*nloc][4]: kind | nr << 8, nl, tab offset, sB offset(+il)
+    int* tDof = sI + 4 * EB;                             // [nside*nloc][4]: kind | nr << 8 | padded nl << 16, nl, tab offset, sB offset(+il)
     int* tZ = tDof + 4 * nside * P.nloc;                 // [nzd][4]: entry k0, k1, sB base (incl. j), z index
-    int* tEnt = tZ + 4 * P.nzd;                          // [nent][2]: slot, row offset (row * stride)
-    int* tPair = tEnt + 2 * P.nent;                      // [npairs][8]
-    int* tSeg = tPair + 8 * P.npairs;                    // [nseg][2]: row offset (row * ni), z offset
+    int* tEnt = tZ + 4 * P.nzd;                          // [nent][2]: slot, row offset (row * padded stride)
+    int* tSeg = tEnt + 2 * P.nent;                       // [nseg][2]: test row offset (row * padded ni), z offset
     const int tid = threadIdx.x;
     const int e_own = tid / TPE, lane = tid % TPE;
     const long long dstride = (long long)nitems * P.nq;
@@ -266,9 +267,24 @@ __global__ void __launch_bounds__(256) k_contract(const __grid_constant__ ocmp_c
     for (int i = tid; i < 4 * nside * P.nloc; i += 256) tDof[i] = __ldg(P.dofdesc + i);
     for (int i = tid; i < 4 * P.nzd; i += 256) tZ[i] = __ldg(P.zdesc + i);
     for (int i = tid; i < 2 * P.nent; i += 256) tEnt[i] = __ldg(P.ent + i);
-    for (int i = tid; i < 8 * P.npairs; i += 256) tPair[i] = __ldg(P.pairs + i);
     for (int i = tid; i < 2 * P.nseg; i += 256) tSeg[i] = __ldg(P.seg + i);
-    for (int i = tid; i < EB * P.zsz; i += 256) sZ[i] = 0.0;
+    for (int i = tid; i < EB * QB * P.zsz; i += 256) sZ[i] = 0.0;
+    for (int i = tid; i < EB * QB * nside * P.sbsz; i += 256) sB[i] = 0.0;  // the row padding stays zero
+
+    // my tiles: (sB offset of the tile's test rows, j0, first segment, segments, sides, row / column of the local
+    // matrix, valid rows | valid columns << 8)
+    int tB[MAXT], tJ[MAXT], tS0[MAXT], tNS[MAXT], tSide[MAXT], tRow[MAXT], tCol[MAXT], tRem[MAXT];
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) {
+        const int tile = lane + t * TPE;
+        tNS[t] = 0; tB[t] = 0; tJ[t] = 0; tS0[t] = 0; tSide[t] = 0; tRow[t] = 0; tCol[t] = 0; tRem[t] = 0;
+        if (tile < P.ntiles) {
+            const int4 a = __ldg(reinterpret_cast<const int4*>(P.tiles) + 2 * tile);
+            const int4 b = __ldg(reinterpret_cast<const int4*>(P.tiles) + 2 * tile + 1);
+            tB[t] = a.x; tJ[t] = a.y; tS0[t] = a.z; tNS[t] = a.w;
+            tSide[t] = b.x; tRow[t] = b.y; tCol[t] = b.z; tRem[t] = b.w;
+        }
+    }
 
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         __syncthreads();
@@ -285,7 +301,6 @@ __global__ void __launch_bounds__(256) k_contract(const __grid_constant__ ocmp_c
             }
             sI[4 * tid] = c0; sI[4 * tid + 1] = c1; sI[4 * tid + 2] = l0; sI[4 * tid + 3] = l1;
         }
-        for (int i = tid; i < EB * P.asz; i += 256) sA[i] = 0.0;
         __syncthreads();
         for (int idx = tid; idx < EB * nside * GS; idx += 256) {
             const int e = idx / (nside * GS), rem = idx % (nside * GS), s = rem / GS, k = rem % GS;
@@ -293,24 +308,39 @@ __global__ void __launch_bounds__(256) k_contract(const __grid_constant__ ocmp_c
             sG[idx] = (c >= 0) ? __ldg(P.geo + (long long)c * GS + k) : (k == GS - 1 ? 1.0 : 0.0);
         }
         const int it_own = grp * EB + e_own;
+        double acc[MAXT][16];
+#pragma unroll
+        for (int t = 0; t < MAXT; ++t)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[t][k] = 0.0;
 
-        for (int q = 0; q < P.nq; ++q) {
+        // Quadrature loop in rounds of QB points: the staging phases (tables, D, Z rows) have far fewer independent
+        // work items per point than the CTA has threads, so QB points are staged together between two barriers.
+        double* bE = sB + e_own * QB * nside * P.sbsz;
+        double* dE = sD + e_own * QB * P.nslots;
+        double* zE = sZ + e_own * QB * P.zsz;
+        const int ncol = nside * P.nloc;
+        for (int q0 = 0; q0 < P.nq; q0 += QB) {
+            const int nqq = min(QB, P.nq - q0);
             __syncthreads();
-            // D values of this quadrature point
-            for (int k = lane; k < P.nslots; k += TPE)
-                sD[e_own * P.nslots + k] = (it_own < nitems)
-                    ? __ldg(dbuf + (long long)k * dstride + (long long)it_own * P.nq + q) : 0.0;
-            // physical basis tables of my item: one (side, dof) column per thread
-            for (int sd = lane; sd < nside * P.nloc; sd += TPE) {
+            // D values of these quadrature points
+            for (int k = lane; k < nqq * P.nslots; k += TPE) {
+                const int qq = k / P.nslots, sl = k - qq * P.nslots;
+                dE[k] = (it_own < nitems)
+                    ? __ldg(dbuf + (long long)sl * dstride + (long long)it_own * P.nq + q0 + qq) : 0.0;
+            }
+            // physical basis tables of my item: one (point, side, dof) column per thread
+            for (int w = lane; w < nqq * ncol; w += TPE) {
+                const int qq = w / ncol, sd = w - qq * ncol;
                 const int4 dd = *reinterpret_cast<const int4*>(tDof + 4 * sd);
                 const int s = sd >= P.nloc ? 1 : 0;
-                const int kind = dd.x & 0xff, nr = dd.x >> 8, nl = dd.y;
+                const int kind = dd.x & 0xff, nr = (dd.x >> 8) & 0xff, nlp = dd.x >> 16, nl = dd.y;
                 const int c = sI[4 * e_own + s];
-                double* out = sB + (e_own * nside + s) * P.sbsz + dd.w;
+                double* out = bE + (qq * nside + s) * P.sbsz + dd.w;
                 if (c < 0) {
-                    for (int r = 0; r < nr; ++r) out[r * nl] = 0.0;
+                    for (int r = 0; r < nr; ++r) out[r * nlp] = 0.0;
                 } else {
-                    const int lfq = (P.kind == 0 ? 0 : sI[4 * e_own + 2 + s] * P.nq) + q;
+                    const int lfq = (P.kind == 0 ? 0 : sI[4 * e_own + 2 + s] * P.nq) + q0 + qq;
                     const double* tq = P.tab + dd.z + (long long)lfq * nr * nl;      // dd.z includes the local dof
                     const double* g = sG + (e_own * nside + s) * GS;
                     if (kind == 0) {
@@ -319,73 +349,71 @@ __global__ void __launch_bounds__(256) k_contract(const __grid_constant__ ocmp_c
                         for (int r = 0; r < 1 + DIM; ++r) R[r] = __ldg(tq + r * nl);
                         phys_rows<DIM>(0, R, g + DIM, g + DIM + DIM * DIM, g[GS - 1], PH);
 #pragma unroll
-                        for (int r = 0; r < 1 + DIM; ++r) out[r * nl] = PH[r];
+                        for (int r = 0; r < 1 + DIM; ++r) out[r * nlp] = PH[r];
                     } else {
                         double R[DIM + DIM * DIM], PH[MAX_ROWS];
 #pragma unroll
                         for (int r = 0; r < DIM + DIM * DIM; ++r) R[r] = __ldg(tq + r * nl);
                         phys_rows<DIM>(1, R, g + DIM, g + DIM + DIM * DIM, g[GS - 1], PH);
 #pragma unroll
-                        for (int r = 0; r < DIM + DIM * DIM; ++r) out[r * nl] = PH[r];
+                        for (int r = 0; r < DIM + DIM * DIM; ++r) out[r * nlp] = PH[r];
                     }
                 }
             }
             __syncthreads();
-            // Z rows
-            {
-                const double* bE = sB + e_own * nside * P.sbsz;
-                const double* dE = sD + e_own * P.nslots;
-                double* zE = sZ + e_own * P.zsz;
-                for (int z = lane; z < P.nzd; z += TPE) {
-                    const int4 zd = *reinterpret_cast<const int4*>(tZ + 4 * z);
-                    double s = 0.0;
-                    for (int k = zd.x; k < zd.y; ++k) s = fma(dE[tEnt[2 * k]], bE[zd.z + tEnt[2 * k + 1]], s);
-                    zE[zd.w] = s;
+            // Z rows of these points
+            for (int w = lane; w < nqq * P.nzd; w += TPE) {
+                const int qq = w / P.nzd, z = w - qq * P.nzd;
+                const int4 zd = *reinterpret_cast<const int4*>(tZ + 4 * z);
+                const double* bq = bE + qq * nside * P.sbsz + zd.z;
+                const double* dq = dE + qq * P.nslots;
+                double sacc = 0.0;
+                for (int k = zd.x; k < zd.y; ++k) {
+                    const int2 en = *reinterpret_cast<const int2*>(tEnt + 2 * k);
+                    sacc = fma(dq[en.x], bq[en.y], sacc);
                 }
+                zE[qq * P.zsz + zd.w] = sacc;
             }
             __syncthreads();
-            // pair-wise update of the accumulators, 1 x 4 strips
-            {
-                const double* bE = sB + e_own * nside * P.sbsz;
-                const double* zE = sZ + e_own * P.zsz;
-                double* aE = sA + e_own * P.asz;
-                for (int p = 0; p < P.npairs; ++p) {
-                    const int* pd = tPair + 8 * p;
-                    const int aoff = pd[0], ni = pd[1], nj4 = pd[2], bbase = pd[3], s0 = pd[4], ns = pd[5];
-                    const unsigned magic = (unsigned)pd[6];
-                    const int nstrips = ni * nj4;
-                    for (int k = lane; k < nstrips; k += TPE) {
-                        const int i = nj4 == 1 ? k : (int)__umulhi((unsigned)k, magic);
-                        const int j4 = k - i * nj4;
-                        double* ap = aE + aoff + (i * nj4 + j4) * 4;
-                        double2 a0 = *reinterpret_cast<double2*>(ap), a1 = *reinterpret_cast<double2*>(ap + 2);
-                        const double* bp = bE + bbase + i;
-                        const double* zp = zE + 4 * j4;
-                        for (int s = s0; s < s0 + ns; ++s) {
-                            const double b = bp[tSeg[2 * s]];
-                            const double2 z0 = *reinterpret_cast<const double2*>(zp + tSeg[2 * s + 1]);
-                            const double2 z1 = *reinterpret_cast<const double2*>(zp + tSeg[2 * s + 1] + 2);
-                            a0.x = fma(b, z0.x, a0.x); a0.y = fma(b, z0.y, a0.y);
-                            a1.x = fma(b, z1.x, a1.x); a1.y = fma(b, z1.y, a1.y);
-                        }
-                        *reinterpret_cast<double2*>(ap) = a0;
-                        *reinterpret_cast<double2*>(ap + 2) = a1;
+            // tile updates: A[i0 + a][j0 + b] += B[row_g][i0 + a] * Z_g[j0 + b] over the segments g of the tile's pair
+#pragma unroll
+            for (int t = 0; t < MAXT; ++t) {
+                const int s1 = tS0[t] + tNS[t];
+                for (int qq = 0; qq < nqq; ++qq) {
+                    const double* bp = bE + qq * nside * P.sbsz + tB[t];
+                    const double* zp = zE + qq * P.zsz + tJ[t];
+                    for (int sg = tS0[t]; sg < s1; ++sg) {
+                        const int2 so = *reinterpret_cast<const int2*>(tSeg + 2 * sg);
+                        const double2 b01 = *reinterpret_cast<const double2*>(bp + so.x);
+                        const double2 b23 = *reinterpret_cast<const double2*>(bp + so.x + 2);
+                        const double2 z01 = *reinterpret_cast<const double2*>(zp + so.y);
+                        const double2 z23 = *reinterpret_cast<const double2*>(zp + so.y + 2);
+                        const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+                        const double zv[4] = {z01.x, z01.y, z23.x, z23.y};
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) acc[t][4 * a + b] = fma(bv[a], zv[b], acc[t][4 * a + b]);
                     }
                 }
             }
         }
-        __syncthreads();
         // ---- scatter-add through the element -> nnz map ------------------------------------------------------
         if (it_own < nitems) {
             const int c0 = sI[4 * e_own], c1 = sI[4 * e_own + 1];
-            const double* aE = sA + e_own * P.asz;
-            for (int ai = lane; ai < P.nact; ai += TPE) {
-                const int2 m = __ldg(reinterpret_cast<const int2*>(P.amap) + ai);
-                const int st = (m.x >> 30) & 1, su = (m.x >> 29) & 1, ij = m.x & 0x1fffffff;
-                int pos;
-                if (st == su) pos = __ldg(P.cell2nnz + (long long)(st ? c1 : c0) * n2 + ij);
-                else pos = __ldg(P.facet2nnz + ((long long)(item0 + it_own) * 2 + st) * n2 + ij);
-                atomicAdd(values + pos, aE[m.y]);
+#pragma unroll
+            for (int t = 0; t < MAXT; ++t) {
+                if (tNS[t] == 0) continue;
+                const int st = tSide[t] & 1, su = (tSide[t] >> 1) & 1;
+                const int ni = tRem[t] & 0xff, nj = tRem[t] >> 8;
+                const int* map = (st == su) ? P.cell2nnz + (long long)(st ? c1 : c0) * n2
+                                            : P.facet2nnz + ((long long)(item0 + it_own) * 2 + st) * n2;
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (a < ni && b < nj)
+                            atomicAdd(values + __ldg(map + (tRow[t] + a) * P.nloc + tCol[t] + b), acc[t][4 * a + b]);
             }
         }
     }
@@ -463,32 +491,41 @@ extern "C" int ocmp_eval_coefficients(const ocmp_coef_plan* plan, int item0, int
 
 static size_t contract_smem(const ocmp_contract_plan* p) {
     const int gs = p->dim + 2 * p->dim * p->dim + 1;
-    const size_t dbl = (size_t)p->eb * p->asz + (size_t)p->eb * p->nside * p->sbsz + (size_t)p->eb * p->zsz +
-                       (size_t)p->eb * p->nslots + (size_t)p->eb * p->nside * gs;
+    size_t dbl = (size_t)p->eb * p->qb * ((size_t)p->nside * p->sbsz + p->zsz + p->nslots) +
+                 (size_t)p->eb * p->nside * gs;
+    dbl += dbl & 1;
     const size_t ints = 4 * (size_t)p->eb + 4 * (size_t)p->nside * p->nloc + 4 * (size_t)p->nzd + 2 * (size_t)p->nent +
-                        8 * (size_t)p->npairs + 2 * (size_t)p->nseg;
+                        2 * (size_t)p->nseg;
     return sizeof(double) * dbl + sizeof(int) * ints + 16;
 }
 
-template <int DIM>
+template <int DIM, int MAXT>
 static int launch_contract(const ocmp_contract_plan* plan, int item0, int nitems, const double* dbuf, double* values,
                            cudaStream_t st) {
     const size_t smem = contract_smem(plan);
     if (smem > 220 * 1024) return ocmp_fail(-3, "contraction plan needs more than 220 KB of shared memory");
     static size_t configured = 0;
     if (smem > configured) {
-        cudaFuncSetAttribute(k_contract<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_contract<DIM, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     const int ngroups = (nitems + plan->eb - 1) / plan->eb;
     int sms = ocmp_sm_count();
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contract<DIM>, 256, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contract<DIM, MAXT>, 256, smem);
     if (per_sm < 1) per_sm = 1;
     const int grid = ngroups < sms * per_sm ? ngroups : sms * per_sm;
     ProfScope ps(PROF_CONTRACT, st);
-    k_contract<DIM><<<grid, 256, smem, st>>>(*plan, item0, nitems, dbuf, values);
+    k_contract<DIM, MAXT><<<grid, 256, smem, st>>>(*plan, item0, nitems, dbuf, values);
     return ocmp_check("ocmp_contract_matrix");
+}
+
+template <int DIM>
+static int launch_contract_t(const ocmp_contract_plan* plan, int item0, int nitems, const double* dbuf,
+                             double* values, cudaStream_t st) {
+    if (plan->maxt <= 1) return launch_contract<DIM, 1>(plan, item0, nitems, dbuf, values, st);
+    if (plan->maxt == 2) return launch_contract<DIM, 2>(plan, item0, nitems, dbuf, values, st);
+    return launch_contract<DIM, 4>(plan, item0, nitems, dbuf, values, st);
 }
 
 extern "C" int ocmp_contract_matrix(const ocmp_contract_plan* plan, int item0, int nitems, const double* dbuf,
@@ -497,8 +534,11 @@ extern "C" int ocmp_contract_matrix(const ocmp_contract_plan* plan, int item0, i
     cudaStream_t st = (cudaStream_t)stream;
     const int eb = plan->eb;
     if (eb < 1 || eb > 16 || (eb & (eb - 1))) return ocmp_fail(-1, "eb must be a power of two <= 16");
-    if (plan->dim == 2) return launch_contract<2>(plan, item0, nitems, dbuf, values, st);
-    if (plan->dim == 3) return launch_contract<3>(plan, item0, nitems, dbuf, values, st);
+    if (plan->qb < 1) return ocmp_fail(-1, "contraction plan: qb must be >= 1");
+    if (plan->ntiles > plan->maxt * (256 / eb) || plan->maxt > 4)
+        return ocmp_fail(-1, "contraction plan: more tiles than the threads of an item can hold");
+    if (plan->dim == 2) return launch_contract_t<2>(plan, item0, nitems, dbuf, values, st);
+    if (plan->dim == 3) return launch_contract_t<3>(plan, item0, nitems, dbuf, values, st);
     return ocmp_fail(-1, "dim must be 2 or 3");
 }
 

@@ -1,8 +1,7 @@
 """Host-side check of the launch plans the CUDA backend builds (no GPU needed): for every GPU parity case the plan
 builder runs with host tensors standing in for device buffers, and the compile-time limits and alignment assumptions
 of the kernels in csrc/ocmp_assembly.cu are checked on the resulting structs — shared-memory budget of k_contract,
-MAX_ROWS / MAX_FSLOTS / OCMP_MAX_REGS, the bit packing of the scatter map, 16-byte alignment of the descriptor
-tables read with int4 loads. The numbers are computed by the oracle backend; only the plan construction of
+MAX_ROWS / MAX_FSLOTS / OCMP_MAX_REGS, tile coverage and the 16-byte alignment of every tile edge. The numbers are computed by the oracle backend; only the plan construction of
 ``CudaBackend`` runs (it is pure host logic)."""
 import weakref
 
@@ -50,15 +49,8 @@ class PlanProbe(OracleBackend):
         return super().integrate(program)
 
 
-def contract_smem(xp, dim):
-    """Mirror of contract_smem() in csrc/ocmp_assembly.cu."""
-    gs = dim + 2 * dim * dim + 1
-    dbl = xp.eb * (xp.asz + xp.nside * xp.sbsz + xp.zsz + xp.nslots + xp.nside * gs)
-    ints = 4 * xp.eb + 4 * xp.nside * xp.nloc + 4 * xp.nzd + 2 * xp.nent + 8 * xp.npairs + 2 * xp.nseg
-    return 8 * dbl + 4 * ints + 16, dbl
-
-
 def check_plan(program, integ, plan):
+    from opencmp_b200.backend import contract_smem_bytes
     cp = plan['coef']
     assert cp.nfslots <= MAX_FSLOTS
     assert cp.nreg <= MAX_REGS
@@ -70,16 +62,25 @@ def check_plan(program, integ, plan):
         return 0
     fes = program.fes
     for b in fes.blocks:
-        assert b.basis.nrows <= MAX_ROWS and b.basis.nrows < 256          # row index packed in 8 bits
+        assert b.basis.nrows <= MAX_ROWS and b.basis.nrows < 256          # row count packed in 8 bits
+        assert b.nloc + 3 < (1 << 15)                                     # padded block size packed above bit 16
     if program.arity == 1:
         return 0
-    smem, dbl = contract_smem(xp, cp.dim)
+    gs = cp.dim + 2 * cp.dim * cp.dim + 1
+    smem = contract_smem_bytes(xp, xp.eb, gs)
     assert smem <= 220 * 1024, 'k_contract needs {} bytes of shared memory'.format(smem)
-    assert xp.eb in (1, 2, 4, 8, 16)
-    assert xp.asz % 4 == 0 and xp.zsz % 4 == 0                              # sA / sZ strips read as double2 pairs
-    # sI (and the int4-read descriptor tables behind it) start after `dbl` doubles of the 16-byte aligned base
-    assert dbl % 2 == 0, 'descriptor tables of k_contract would be 8- but not 16-byte aligned'
-    assert fes.nloc * fes.nloc < (1 << 29)                                   # amap packs i * nloc + j in 29 bits
+    assert xp.eb in (1, 2, 4, 8, 16) and xp.maxt in (1, 2, 4)
+    assert xp.ntiles <= xp.maxt * (256 // xp.eb)                             # every tile has a thread
+    assert xp.sbsz % 4 == 0 and xp.zsz % 4 == 0                              # tile edges are read as double2 pairs
+    tb = plan['tables']
+    t = tb['tiles']
+    assert (t[:, 0] % 4 == 0).all() and (t[:, 1] % 4 == 0).all()             # 16-byte aligned B and Z offsets
+    assert (tb['seg'] % 4 == 0).all()
+    assert (t[:, 3] > 0).all() and (t[:, 2] + t[:, 3] <= len(tb['seg'])).all()
+    rem_i, rem_j = t[:, 7] & 0xff, t[:, 7] >> 8
+    assert ((rem_i >= 1) & (rem_i <= 4) & (rem_j >= 1) & (rem_j <= 4)).all()
+    assert (t[:, 5] + rem_i <= fes.nloc).all() and (t[:, 6] + rem_j <= fes.nloc).all()
+    assert int((rem_i * rem_j).sum()) == xp.nact                             # the tiles cover the active entries once
     return smem
 
 
