@@ -90,6 +90,13 @@ int ocmp_sum(const double* x, long long n, double* out_accumulate, void* stream)
  *      (reference opencmp/models/base_model.py:918-922) ------------------------------------------------------- */
 int ocmp_spmv(int nrows, const int* rowptr, const int* colidx, const double* vals, const double* x, double* y,
               void* stream);
+/* Column-index compression for vector-valued spaces whose components are numbered one after the other, `shift` apart
+ * (VectorH1: u_x, u_y[, u_z]): ocmp_spmv_runs marks every row whose columns start with nc runs of equal length L
+ * holding the same scalar columns shifted by 0, shift, (2 shift) — runlen[row] = L, else 0. Products over such rows
+ * read only the first run's indices (4 index bytes per nc values). ocmp_spmv_compressed = ocmp_spmv with the marks. */
+int ocmp_spmv_runs(int nrows, const int* rowptr, const int* colidx, int shift, int nc, int* runlen, void* stream);
+int ocmp_spmv_compressed(int nrows, const int* rowptr, const int* colidx, const double* vals, const int* runlen,
+                         int shift, int nc, const double* x, double* y, void* stream);
 int ocmp_dot(long long n, const double* x, const double* y, double* out, void* stream);
 int ocmp_axpby(long long n, double a, const double* x, double b, double* y, void* stream);   /* y = a x + b y */
 int ocmp_masked_assign(long long n, double* dst, const double* src, const double* inv, const double* mask,
@@ -185,6 +192,8 @@ typedef struct ocmp_system {
                                    residuals only compute those — the ghost rows of a local matrix are incomplete and
                                    their entries are overwritten by the halo exchange that follows. NULL = all rows */
     int n_spmv_rows;
+    const int* run_len;         /* optional marks of ocmp_spmv_runs for the CSR pattern of this system (NULL = none) */
+    int run_shift, run_nc;
 } ocmp_system;
 /* A band LU as ocmp_band_fill / ocmp_band_factor leave it, plus the permutation and a work vector of n doubles. */
 typedef struct ocmp_band_lu {

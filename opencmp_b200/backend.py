@@ -51,7 +51,8 @@ class System(C.Structure):
                 ('inv_vals', C.c_void_p), ('owned', C.c_void_p), ('halo_fwd', C.c_int), ('halo_sum', C.c_int),
                 ('inv_storage', C.c_int), ('vals32', C.c_void_p), ('apply_fn', C.c_void_p), ('apply_ctx', C.c_void_p),
                 ('direct', C.c_void_p), ('patch_inc_ptr', C.c_void_p), ('patch_inc_idx', C.c_void_p),
-                ('patch_ybuf', C.c_void_p), ('spmv_rows', C.c_void_p), ('n_spmv_rows', C.c_int)]
+                ('patch_ybuf', C.c_void_p), ('spmv_rows', C.c_void_p), ('n_spmv_rows', C.c_int),
+                ('run_len', C.c_void_p), ('run_shift', C.c_int), ('run_nc', C.c_int)]
 
 
 class BandHandle(C.Structure):
@@ -84,6 +85,8 @@ def load_library() -> C.CDLL:
     lib.ocmp_contract_vector.argtypes = [C.POINTER(ContractPlan), C.c_int, C.c_int, P, P, P]
     lib.ocmp_sum.argtypes = [P, C.c_longlong, P, P]
     lib.ocmp_spmv.argtypes = [C.c_int, P, P, P, P, P, P]
+    lib.ocmp_spmv_runs.argtypes = [C.c_int, P, P, C.c_int, C.c_int, P, P]
+    lib.ocmp_spmv_compressed.argtypes = [C.c_int, P, P, P, P, C.c_int, C.c_int, P, P, P]
     lib.ocmp_dot.argtypes = [C.c_longlong, P, P, P, P]
     lib.ocmp_axpby.argtypes = [C.c_longlong, C.c_double, P, C.c_double, P, P]
     lib.ocmp_masked_assign.argtypes = [C.c_longlong, P, P, P, P, P]
@@ -140,7 +143,7 @@ EXPORTED = ['ocmp_mdot', 'ocmp_maxpy', 'ocmp_krylov_history', 'ocmp_comm_unique_
             'ocmp_asm_setup_f32', 'ocmp_asm_apply_f32', 'ocmp_asm_setup_bf16', 'ocmp_asm_apply_bf16', 'ocmp_to_f32',
             'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version',
             'ocmp_band_len', 'ocmp_band_fill', 'ocmp_band_factor', 'ocmp_band_solve', 'ocmp_band_gather',
-            'ocmp_band_scatter']
+            'ocmp_band_scatter', 'ocmp_spmv_runs', 'ocmp_spmv_compressed']
 
 
 # storage type of the smoother's patch inverses (ocmp_system.inv_storage): arithmetic is FP64 in every case
@@ -231,6 +234,23 @@ def contract_tables(entries, decode, nloc, kind, nrows, tab_off, sb_off, sbsz, l
     i32 = lambda a, w: np.asarray(a, dtype=np.int32).reshape(-1, w)
     return dict(zdesc=i32(zdesc, 4), ent=i32(ent, 2), seg=i32(seg_arr, 2), dofdesc=i32(dofdesc, 4),
                 tiles=i32(tiles, 8), zsz=zoff, nact=nact, z_fma=z_fma, a_fma=a_fma)
+
+
+def component_runs(fes):
+    """(shift, nc) when the space starts with nc = 2 or 3 scalar blocks of equal size numbered one after the other
+    (the components of a VectorH1 block): the CSR rows then hold nc shifted copies of the same scalar columns and the
+    SpMV kernels read only the first copy's indices (ocmp_spmv_runs verifies it row by row). None otherwise."""
+    blocks, offs = fes.blocks, list(fes.block_offsets)
+    if len(blocks) < 2 or blocks[0].kind != 'scalar' or offs[0] != 0:
+        return None
+    size = blocks[0].ndof
+    nc = 1
+    while nc < min(3, len(blocks)) and blocks[nc].kind == 'scalar' and blocks[nc].ndof == size and \
+            blocks[nc].nloc == blocks[0].nloc and offs[nc] == nc * size:
+        nc += 1
+    if nc < 2 or size <= 0:
+        return None
+    return int(size), int(nc)
 
 
 def _ptr(t) -> Optional[int]:
@@ -381,7 +401,14 @@ class CudaBackend:
             pat = fes.pattern()
             d.update(rowptr=self._up(pat.rowptr.astype(np.int32)), colidx=self._up(pat.colidx),
                      cell2nnz=self._up(pat.cell2nnz), facet2nnz=self._up(pat.facet2nnz), diag=self._up(pat.diag),
-                     nnz=pat.nnz)
+                     nnz=pat.nnz, runs=None)
+            comp = component_runs(fes)
+            if comp is not None and os.environ.get('OCMP_SPMV_RUNS', '1') != '0':
+                shift, nc = comp
+                runlen = self.torch.zeros(fes.ndof, dtype=self.torch.int32, device=self.device)
+                self._ck(self.lib.ocmp_spmv_runs(fes.ndof, d['rowptr'].data_ptr(), d['colidx'].data_ptr(), shift, nc,
+                                                 runlen.data_ptr(), self._stream()))
+                d['runs'] = (runlen, shift, nc)
         return d
 
     # ---- plan construction -------------------------------------------------------------------------------------
@@ -755,6 +782,8 @@ class CudaBackend:
         if not getattr(mat, 'matrix_free', False):    # a matrix-free operator has no CSR arrays (krylov sets apply_fn)
             pd = self.pattern_data(mat.space)
             s.rowptr, s.colidx, s.vals = pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(), mat.values.data_ptr()
+            if pd.get('runs') is not None:
+                s.run_len, s.run_shift, s.run_nc = pd['runs'][0].data_ptr(), pd['runs'][1], pd['runs'][2]
         s.freemask = _ptr(fm)
         s.pre_kind = 0
         if pre is not None:

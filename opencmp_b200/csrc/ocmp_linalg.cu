@@ -106,19 +106,51 @@ extern "C" int ocmp_version(void) { return 100; }
 // VT = double | float: the matrix values may be an FP32 copy (operator applications INSIDE the multigrid cycle when
 // ocmp_system.vals32 is set — 8 instead of 12 bytes per non-zero); products and sums are FP64.
 enum { EP_PLAIN = 0, EP_RESID = 1, EP_MASK = 2, EP_ADD = 3 };
+// Column-index compression for vector-valued spaces ("component runs"): the components of a VectorH1 block are
+// numbered one after the other (u_x dofs, then u_y, then u_z, each `shift` apart), and the pattern keeps every
+// component pair, so a row's columns start with nc runs of equal length L holding the same scalar columns shifted by
+// 0, shift, 2 shift. Such rows (runlen[row] = L > 0, verified once by k_spmv_runs) read only the FIRST run's indices:
+// 4 index bytes per nc values instead of 4 per value. The rest of the row (pressure columns) is read as usual.
+struct SpmvRuns {
+    const int* runlen;       // per row: L, or 0 for a plain row; NULL = no compression
+    int shift, nc;
+};
+
 template <int LPR, typename VT, int EP>
 __global__ void __launch_bounds__(256) k_spmv(int nrows, const int* __restrict__ rowptr, const int* __restrict__ col,
                                               const VT* __restrict__ val, const double* __restrict__ x,
                                               double* __restrict__ y, const double* __restrict__ b,
                                               const double* __restrict__ m, const double* __restrict__ m2,
-                                              const int* __restrict__ rows) {
+                                              const int* __restrict__ rows, SpmvRuns runs) {
     const int lane = threadIdx.x % LPR;
     const long long row0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
     const long long stride = (long long)gridDim.x * blockDim.x / LPR;
     for (long long rr = row0; rr < nrows; rr += stride) {
         const long long row = rows ? __ldg(rows + rr) : rr;      // `nrows` counts the listed rows when a list is given
-        const int a = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+        int a = __ldg(rowptr + row);
+        const int e = __ldg(rowptr + row + 1);
         double s = 0.0;
+        const int L = runs.runlen ? __ldg(runs.runlen + row) : 0;
+        if (L > 0) {
+            const VT* v0 = val + a;
+            const VT* v1 = v0 + L;
+            const VT* v2 = v1 + L;
+            if (runs.nc == 3) {
+                for (int k = lane; k < L; k += LPR) {
+                    const double* xp = x + __ldg(col + a + k);
+                    s = fma((double)__ldg(v0 + k), __ldg(xp), s);
+                    s = fma((double)__ldg(v1 + k), __ldg(xp + runs.shift), s);
+                    s = fma((double)__ldg(v2 + k), __ldg(xp + 2 * (long long)runs.shift), s);
+                }
+            } else {
+                for (int k = lane; k < L; k += LPR) {
+                    const double* xp = x + __ldg(col + a + k);
+                    s = fma((double)__ldg(v0 + k), __ldg(xp), s);
+                    s = fma((double)__ldg(v1 + k), __ldg(xp + runs.shift), s);
+                }
+            }
+            a += runs.nc * L;
+        }
         for (int k = a + lane; k < e; k += LPR) s = fma((double)__ldg(val + k), __ldg(x + __ldg(col + k)), s);
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LPR);
@@ -134,6 +166,22 @@ __global__ void __launch_bounds__(256) k_spmv(int nrows, const int* __restrict__
     }
 }
 
+// runlen[row] = L if the row starts with nc runs of length L whose columns are those of the first run shifted by
+// k * shift (k < nc) and the first run lies in [0, shift); else 0
+__global__ void __launch_bounds__(256) k_spmv_runs(int nrows, const int* __restrict__ rowptr,
+                                                   const int* __restrict__ col, int shift, int nc,
+                                                   int* __restrict__ runlen) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const int a = rowptr[row], e = rowptr[row + 1];
+    int L = 0;
+    while (a + L < e && col[a + L] < shift) ++L;
+    bool ok = L > 0 && a + (long long)nc * L <= e;
+    for (int k = 0; ok && k < L; ++k)
+        for (int c = 1; c < nc; ++c) ok = ok && col[a + c * L + k] == col[a + k] + c * shift;
+    runlen[row] = ok ? L : 0;
+}
+
 __global__ void __launch_bounds__(256) k_to_f32(long long n, const double* __restrict__ src, float* __restrict__ dst) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dst[i] = (float)src[i];
@@ -142,7 +190,8 @@ __global__ void __launch_bounds__(256) k_to_f32(long long n, const double* __res
 // one launch: category `cat`, values from `vals32` when given, else `vals`
 static int spmv_ep(int cat, int ep, int nrows, const int* rowptr, const int* colidx, const double* vals,
                    const float* vals32, const double* x, double* y, const double* b, const double* m,
-                   const double* m2, cudaStream_t st, const int* rows = nullptr) {
+                   const double* m2, cudaStream_t st, const int* rows = nullptr,
+                   SpmvRuns runs = SpmvRuns{nullptr, 0, 0}) {
     if (nrows <= 0) return 0;
     const int threads = 256;
     const long long want = ((long long)nrows * 16 + threads - 1) / threads;
@@ -150,7 +199,7 @@ static int spmv_ep(int cat, int ep, int nrows, const int* rowptr, const int* col
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     ProfScope ps(cat, st);
 #define SPMV_GO(VT, V, EP) \
-    k_spmv<16, VT, EP><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, V, x, y, b, m, m2, rows)
+    k_spmv<16, VT, EP><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, V, x, y, b, m, m2, rows, runs)
     if (vals32) {
         if (ep == EP_PLAIN) SPMV_GO(float, vals32, EP_PLAIN);
         else if (ep == EP_RESID) SPMV_GO(float, vals32, EP_RESID);
@@ -170,6 +219,18 @@ extern "C" int ocmp_spmv(int nrows, const int* rowptr, const int* colidx, const 
                          double* y, void* stream) {
     return spmv_ep(PROF_SPMV, EP_PLAIN, nrows, rowptr, colidx, vals, nullptr, x, y, nullptr, nullptr, nullptr,
                    (cudaStream_t)stream);
+}
+extern "C" int ocmp_spmv_runs(int nrows, const int* rowptr, const int* colidx, int shift, int nc, int* runlen,
+                              void* stream) {
+    if (nrows <= 0) return 0;
+    if (nc < 2 || nc > 3 || shift <= 0) return ocmp_fail(-1, "ocmp_spmv_runs: nc must be 2 or 3, shift > 0");
+    k_spmv_runs<<<(nrows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nrows, rowptr, colidx, shift, nc, runlen);
+    return ocmp_check("ocmp_spmv_runs");
+}
+extern "C" int ocmp_spmv_compressed(int nrows, const int* rowptr, const int* colidx, const double* vals,
+                                    const int* runlen, int shift, int nc, const double* x, double* y, void* stream) {
+    return spmv_ep(PROF_SPMV, EP_PLAIN, nrows, rowptr, colidx, vals, nullptr, x, y, nullptr, nullptr, nullptr,
+                   (cudaStream_t)stream, nullptr, SpmvRuns{runlen, shift, nc});
 }
 
 extern "C" int ocmp_to_f32(long long n, const double* src, float* dst, void* stream) {
@@ -592,6 +653,7 @@ struct Ctx {
     // the rows an operator application has to compute: a rank's own rows when the halo exchange supplies the others
     static const int* row_list(const ocmp_system* sy) { return (sy->halo_fwd && sy->spmv_rows) ? sy->spmv_rows : nullptr; }
     static int active_rows(const ocmp_system* sy) { return row_list(sy) ? sy->n_spmv_rows : sy->nrows; }
+    static SpmvRuns runs_of(const ocmp_system* sy) { return SpmvRuns{sy->run_len, sy->run_shift, sy->run_nc}; }
     static void had(cudaStream_t st, long long n, const double* a, const double* m, const double* r, double* z,
                     double scale, int accumulate) {
         ProfScope ps(PROF_VEC, st);
@@ -605,7 +667,7 @@ struct Ctx {
             if (masked && s->freemask) had(st, n, nullptr, s->freemask, y, y, 1.0, 0);
         } else {
             spmv_ep(PROF_SPMV, masked && s->freemask ? EP_MASK : EP_PLAIN, active_rows(s), s->rowptr, s->colidx,
-                    s->vals, nullptr, x, y, nullptr, s->freemask, nullptr, st, row_list(s));
+                    s->vals, nullptr, x, y, nullptr, s->freemask, nullptr, st, row_list(s), runs_of(s));
         }
         if (s->halo_fwd) ocmp_halo_run(s->halo_fwd - 1, y, 0, st);
     }
@@ -617,7 +679,7 @@ struct Ctx {
             k_resid<<<grid_for(n), 256, 0, st>>>(n, b, s->freemask, r);
         } else {
             spmv_ep(PROF_SPMV, EP_RESID, active_rows(s), s->rowptr, s->colidx, s->vals, nullptr, x, r, b, s->freemask,
-                    nullptr, st, row_list(s));
+                    nullptr, st, row_list(s), runs_of(s));
             if (s->halo_fwd) ocmp_halo_run(s->halo_fwd - 1, r, 0, st);
         }
     }
@@ -662,7 +724,7 @@ struct Ctx {
     static void level_residual(const ocmp_system* sy, const double* b, const double* x, double* r, const double* m2,
                                bool refresh, cudaStream_t st) {
         spmv_ep(PROF_SPMV_MG, EP_RESID, active_rows(sy), sy->rowptr, sy->colidx, sy->vals, sy->vals32, x, r, b,
-                sy->freemask, m2, st, row_list(sy));
+                sy->freemask, m2, st, row_list(sy), runs_of(sy));
         if (refresh && sy->halo_fwd) ocmp_halo_run(sy->halo_fwd - 1, r, 0, st);
     }
     // V-cycle on level l: x = MG(b); b is masked on entry, x is masked on exit. Launches per level and cycle with

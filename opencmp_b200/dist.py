@@ -146,7 +146,7 @@ class DofMap:
             idx = ghosts[self.owner_local[ghosts] == s]
             self.recv[int(s)] = idx[np.argsort(l2g[idx])]
         for s in _candidate_peers(part):
-            other = Partition(part.mesh, R, s, layers=_layers_of(part))
+            other = Partition(part.mesh, R, s, layers=_layers_of(part), rank_of_cells=part.rank_of_cells)
             theirs = np.unique(gcd[other.local_cells].ravel())
             mine = theirs[owner[theirs] == me]          # ascending global id = their recv order
             if mine.size:

@@ -235,3 +235,56 @@ def test_partitioned_multigrid_with_lagged_smoother(monkeypatch):
     mp.spawn(_mg_worker, args=(world, port, 0, out), nprocs=world, join=True)
     assert len(out) == world
     assert out[0][1] == out[1][1]
+
+
+def _block_exchange_worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import opencmp_b200.ngs as ngs
+        from oracle.backend import OracleBackend
+        ngs.set_backend(OracleBackend())
+        from opencmp_b200.dist import Partition, DofMap, block_ranks, brick_grid
+        from opencmp_b200.mesh import structured_3d
+        gmesh = structured_3d([6, 6, 4], scale=(2.0,) * 3, offset=(1.0,) * 3)
+        grid = brick_grid(world)
+        part = Partition(gmesh, world, rank, layers=2, rank_of_cells=block_ranks(grid, (-1.0,) * 3, (1.0,) * 3))
+        assert (part.cell_rank == rank).sum() == gmesh.ne // world        # compact bricks of equal size
+        gfes = ngs.FESpace([ngs.VectorH1(ngs.Mesh(gmesh), order=2), ngs.H1(ngs.Mesh(gmesh), order=1)])
+        lmesh = ngs.Mesh(part.local_mesh())
+        lfes = ngs.FESpace([ngs.VectorH1(lmesh, order=2), ngs.H1(lmesh, order=1)])
+        m = DofMap(part, gfes, lfes)
+        # ghost refresh: owners hold a function of the global dof number, ghosts start as garbage
+        x = np.where(m.owned, np.sin(0.1 * m.l2g) + m.l2g, -1e30)
+        m.exchange(x)
+        assert np.array_equal(x, np.sin(0.1 * m.l2g) + m.l2g)
+        # partial sums: every rank contributes 1 on each of its local entries; the total is the number of ranks that
+        # hold the dof, which must agree on all of them
+        y = np.ones(m.nlocal)
+        m.exchange_sum(y)
+        cnt = np.zeros(m.nglobal)
+        cnt[m.l2g] = 1.0
+        tot = torch.from_numpy(cnt)
+        dist.all_reduce(tot)
+        assert np.array_equal(y, tot.numpy()[m.l2g])
+        # ownership is a partition of the global dofs
+        own = np.zeros(m.nglobal)
+        own[m.l2g[m.owned]] = 1.0
+        t2 = torch.from_numpy(own)
+        dist.all_reduce(t2)
+        assert np.array_equal(t2.numpy(), np.ones(m.nglobal))
+        out[rank] = int(len(m.send))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_plans_of_a_brick_partition_on_four_ranks():
+    """2 x 2 x 1 compact bricks (bench.py's layout on 4 GPUs): the halo plans are built from the peers' partitions, which
+    must use the same cell -> rank rule — the default contiguous blocks only coincide with the bricks on 2 ranks."""
+    world = 4
+    port = _free_port()
+    mgr = mp.get_context('spawn').Manager()
+    out = mgr.dict()
+    mp.spawn(_block_exchange_worker, args=(world, port, out), nprocs=world, join=True)
+    assert len(out) == world and all(v == 3 for v in out.values())       # every brick touches the three others

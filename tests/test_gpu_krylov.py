@@ -88,3 +88,35 @@ def test_unimplemented_preconditioner_types_raise():
             else:
                 assert False, kind + ' must not be silently replaced by another preconditioner'
     _with('cuda', run)
+
+
+@pytest.mark.parametrize('name', ['stokes_3d_hex_q2q1', 'stokes_th_p2_oseen', 'ins_dim_3d_hex_q2q1'])
+def test_component_run_spmv_equals_plain_csr_product(name):
+    """The column-index compression of vector-valued spaces (ocmp_spmv_runs / ocmp_spmv_compressed): every row of a
+    Taylor-Hood pattern is recognised, and the product equals the plain CSR product (and the oracle's) to round-off."""
+    from test_gpu_parity import CASES
+
+    def run():
+        c = CASES[name]()
+        ngs = c['ngs']
+        c['a'].Assemble()
+        be = ngs.get_backend()
+        x = np.random.default_rng(4).uniform(-1, 1, c['fes'].ndof)
+        xv = ngs.BaseVector(be.from_numpy(x))
+        y_plain = (c['a'].mat * xv).NumPy().copy()
+        out = [y_plain]
+        if be.name == 'cuda':
+            pd = be.pattern_data(c['fes'])
+            assert pd['runs'] is not None
+            runlen, shift, nc = pd['runs']
+            assert int((runlen > 0).sum()) == c['fes'].ndof          # all rows carry the component runs
+            y = be.zeros(c['fes'].ndof)
+            be._ck(be.lib.ocmp_spmv_compressed(c['fes'].ndof, pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(),
+                                               c['a'].mat.values.data_ptr(), runlen.data_ptr(), shift, nc,
+                                               xv.a.data_ptr(), y.data_ptr(), be._stream()))
+            out.append(be.to_numpy(y))
+        return out
+    ref = _with('oracle', run)
+    got = _with('cuda', run)
+    assert _rel(got[0], ref[0]) < 1e-12
+    assert _rel(got[1], got[0]) < 1e-13
