@@ -75,6 +75,9 @@ typedef struct {
     const int* cell2nnz;     /* (ncells, nloc*nloc) */
     const int* facet2nnz;    /* (n interior facets, 2, nloc*nloc) indexed by item */
     const int* cell_dofs;    /* (ncells, nloc) — vector assembly */
+    double* abuf;            /* deterministic assembly (NULL = atomicAdd scatter): matrices — nitems x ntiles x 16
+                                doubles, the finished 4 x 4 tiles of every item; vectors — nitems x nside x nloc local
+                                vector entries. ocmp_gather_add then adds them into the CSR values / the vector */
 } ocmp_contract_plan;
 
 /* ---- assembly: stands in for BilinearForm.Assemble / LinearForm.Assemble (reference
@@ -85,6 +88,12 @@ int ocmp_contract_matrix(const ocmp_contract_plan* plan, int item0, int nitems, 
 int ocmp_contract_vector(const ocmp_contract_plan* plan, int item0, int nitems, const double* dbuf,
                          double* vec, void* stream);
 int ocmp_sum(const double* x, long long n, double* out_accumulate, void* stream);
+/* Second phase of the deterministic assembly: dst[seg_tgt[s]] += sum_k src[order[k]], k in [seg_ptr[s], seg_ptr[s+1]).
+ * The lists are built once per plan and chunk by the host (stable sort of the element -> nnz map): every target has
+ * one writer and a fixed summation order, so two assemblies of the same form are bit-identical — on one GPU and
+ * between the ranks of an element-partitioned run. */
+int ocmp_gather_add(int nseg, const int* seg_ptr, const int* seg_tgt, const int* order, const double* src,
+                    double* dst, void* stream);
 
 /* ---- sparse / dense vector kernels: stand in for `a.mat * x`, BaseVector arithmetic and InnerProduct
  *      (reference opencmp/models/base_model.py:918-922) ------------------------------------------------------- */
@@ -94,9 +103,14 @@ int ocmp_spmv(int nrows, const int* rowptr, const int* colidx, const double* val
  * (VectorH1: u_x, u_y[, u_z]): ocmp_spmv_runs marks every row whose columns start with nc runs of equal length L
  * holding the same scalar columns shifted by 0, shift, (2 shift) — runlen[row] = L, else 0. Products over such rows
  * read only the first run's indices (4 index bytes per nc values). ocmp_spmv_compressed = ocmp_spmv with the marks. */
-int ocmp_spmv_runs(int nrows, const int* rowptr, const int* colidx, int shift, int nc, int* runlen, void* stream);
+int ocmp_spmv_runs(int nrows, const int* rowptr, const int* colidx, int shift, int nc, int* runlen,
+                   int* grouped_bad_dev, void* stream);
+/* grouped_bad_dev (optional, one int): left 0 when, in addition, the nc component rows of every node (row, row +
+ * shift, ...; row < shift) have identical column lists. Then `grouped` products let one lane group compute the nc
+ * rows of a node together: x values and indices are fetched once per nc x nc matrix values, which divides the L2
+ * gather traffic of a scattered CG numbering by nc. */
 int ocmp_spmv_compressed(int nrows, const int* rowptr, const int* colidx, const double* vals, const int* runlen,
-                         int shift, int nc, const double* x, double* y, void* stream);
+                         int shift, int nc, int grouped, const double* x, double* y, void* stream);
 int ocmp_dot(long long n, const double* x, const double* y, double* out, void* stream);
 int ocmp_axpby(long long n, double a, const double* x, double b, double* y, void* stream);   /* y = a x + b y */
 int ocmp_masked_assign(long long n, double* dst, const double* src, const double* inv, const double* mask,
@@ -194,6 +208,9 @@ typedef struct ocmp_system {
     int n_spmv_rows;
     const int* run_len;         /* optional marks of ocmp_spmv_runs for the CSR pattern of this system (NULL = none) */
     int run_shift, run_nc;
+    int run_grouped;            /* 0, or run_shift when the grouped product is valid for the full row range */
+    int n_spmv_groups;          /* with spmv_rows: 0, or the number of listed rows below run_shift when the list holds,
+                                   in this order, those rows, their nc - 1 shifted copies, then the other rows */
 } ocmp_system;
 /* A band LU as ocmp_band_fill / ocmp_band_factor leave it, plus the permutation and a work vector of n doubles. */
 typedef struct ocmp_band_lu {

@@ -40,7 +40,7 @@ class ContractPlan(C.Structure):
                 ('items', C.c_void_p), ('geo', C.c_void_p), ('facet_cells', C.c_void_p), ('facet_local', C.c_void_p),
                 ('blk', C.c_void_p), ('tab', C.c_void_p), ('zdesc', C.c_void_p), ('ent', C.c_void_p),
                 ('dofdesc', C.c_void_p), ('tiles', C.c_void_p), ('seg', C.c_void_p),
-                ('cell2nnz', C.c_void_p), ('facet2nnz', C.c_void_p), ('cell_dofs', C.c_void_p)]
+                ('cell2nnz', C.c_void_p), ('facet2nnz', C.c_void_p), ('cell_dofs', C.c_void_p), ('abuf', C.c_void_p)]
 
 
 class System(C.Structure):
@@ -52,7 +52,8 @@ class System(C.Structure):
                 ('inv_storage', C.c_int), ('vals32', C.c_void_p), ('apply_fn', C.c_void_p), ('apply_ctx', C.c_void_p),
                 ('direct', C.c_void_p), ('patch_inc_ptr', C.c_void_p), ('patch_inc_idx', C.c_void_p),
                 ('patch_ybuf', C.c_void_p), ('spmv_rows', C.c_void_p), ('n_spmv_rows', C.c_int),
-                ('run_len', C.c_void_p), ('run_shift', C.c_int), ('run_nc', C.c_int)]
+                ('run_len', C.c_void_p), ('run_shift', C.c_int), ('run_nc', C.c_int), ('run_grouped', C.c_int),
+                ('n_spmv_groups', C.c_int)]
 
 
 class BandHandle(C.Structure):
@@ -84,9 +85,10 @@ def load_library() -> C.CDLL:
     lib.ocmp_contract_matrix.argtypes = [C.POINTER(ContractPlan), C.c_int, C.c_int, P, P, P]
     lib.ocmp_contract_vector.argtypes = [C.POINTER(ContractPlan), C.c_int, C.c_int, P, P, P]
     lib.ocmp_sum.argtypes = [P, C.c_longlong, P, P]
+    lib.ocmp_gather_add.argtypes = [C.c_int, P, P, P, P, P, P]
     lib.ocmp_spmv.argtypes = [C.c_int, P, P, P, P, P, P]
-    lib.ocmp_spmv_runs.argtypes = [C.c_int, P, P, C.c_int, C.c_int, P, P]
-    lib.ocmp_spmv_compressed.argtypes = [C.c_int, P, P, P, P, C.c_int, C.c_int, P, P, P]
+    lib.ocmp_spmv_runs.argtypes = [C.c_int, P, P, C.c_int, C.c_int, P, P, P]
+    lib.ocmp_spmv_compressed.argtypes = [C.c_int, P, P, P, P, C.c_int, C.c_int, C.c_int, P, P, P]
     lib.ocmp_dot.argtypes = [C.c_longlong, P, P, P, P]
     lib.ocmp_axpby.argtypes = [C.c_longlong, C.c_double, P, C.c_double, P, P]
     lib.ocmp_masked_assign.argtypes = [C.c_longlong, P, P, P, P, P]
@@ -143,12 +145,18 @@ EXPORTED = ['ocmp_mdot', 'ocmp_maxpy', 'ocmp_krylov_history', 'ocmp_comm_unique_
             'ocmp_asm_setup_f32', 'ocmp_asm_apply_f32', 'ocmp_asm_setup_bf16', 'ocmp_asm_apply_bf16', 'ocmp_to_f32',
             'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version',
             'ocmp_band_len', 'ocmp_band_fill', 'ocmp_band_factor', 'ocmp_band_solve', 'ocmp_band_gather',
-            'ocmp_band_scatter', 'ocmp_spmv_runs', 'ocmp_spmv_compressed']
+            'ocmp_band_scatter', 'ocmp_spmv_runs', 'ocmp_spmv_compressed', 'ocmp_gather_add']
 
 
 # storage type of the smoother's patch inverses (ocmp_system.inv_storage): arithmetic is FP64 in every case
 STORAGE_ID = {'fp64': 0, 'fp32': 1, 'bf16': 2}
 _STORAGE_ALIGN = {'fp64': 2, 'fp32': 4, 'bf16': 8}          # patch stride: every stored column 16-byte aligned
+
+
+def deterministic_assembly() -> bool:
+    """OCMP_DETERMINISTIC=0 selects the atomicAdd scatter; default: two-phase assembly (item-local tiles + ordered gather),
+    bit-reproducible between runs and between the ranks of an element-partitioned run."""
+    return os.environ.get('OCMP_DETERMINISTIC', '1') != '0'
 
 
 def patch_storage() -> str:
@@ -277,6 +285,7 @@ class CudaBackend:
         self._space_cache: Dict[int, dict] = {}
         self._plan_cache = weakref.WeakKeyDictionary()     # plans die with their FormProgram (Integrate builds one per call)
         self._dbuf = None
+        self._abuf = None
         self._scal = torch.zeros(64, dtype=torch.float64, device=self.device)
         self.launches = 0
         self.last_iters = 0
@@ -406,9 +415,11 @@ class CudaBackend:
             if comp is not None and os.environ.get('OCMP_SPMV_RUNS', '1') != '0':
                 shift, nc = comp
                 runlen = self.torch.zeros(fes.ndof, dtype=self.torch.int32, device=self.device)
+                bad = self.torch.zeros(1, dtype=self.torch.int32, device=self.device)
                 self._ck(self.lib.ocmp_spmv_runs(fes.ndof, d['rowptr'].data_ptr(), d['colidx'].data_ptr(), shift, nc,
-                                                 runlen.data_ptr(), self._stream()))
-                d['runs'] = (runlen, shift, nc)
+                                                 runlen.data_ptr(), bad.data_ptr(), self._stream()))
+                grouped = int(bad.item()) == 0 and os.environ.get('OCMP_SPMV_GROUPED', '1') != '0'
+                d['runs'] = (runlen, shift, nc, grouped)
         return d
 
     # ---- plan construction -------------------------------------------------------------------------------------
@@ -579,19 +590,97 @@ class CudaBackend:
             need = chunk * nq * nout
             if self._dbuf is None or self._dbuf.numel() < need:
                 self._dbuf = torch.empty(need, dtype=torch.float64, device=self.device)
+            det = mode in ('matrix', 'vector') and deterministic_assembly()
             for i0 in range(0, nitems, chunk):
                 n = min(chunk, nitems - i0)
                 self._ck(self.lib.ocmp_eval_coefficients(C.byref(cp), i0, n, self._dbuf.data_ptr(), st))
                 self.launches += 1
-                if mode == 'matrix':
-                    self._ck(self.lib.ocmp_contract_matrix(C.byref(plan['contract']), i0, n, self._dbuf.data_ptr(),
-                                                           out.data_ptr(), st))
-                elif mode == 'vector':
-                    self._ck(self.lib.ocmp_contract_vector(C.byref(plan['contract']), i0, n, self._dbuf.data_ptr(),
-                                                           out.data_ptr(), st))
-                else:
+                if mode == 'sum':
                     self._ck(self.lib.ocmp_sum(self._dbuf.data_ptr(), n * nq * nout, out.data_ptr(), st))
-                self.launches += 1
+                    self.launches += 1
+                    continue
+                xp = plan['contract']
+                fn = self.lib.ocmp_contract_matrix if mode == 'matrix' else self.lib.ocmp_contract_vector
+                if not det:
+                    xp.abuf = None
+                    self._ck(fn(C.byref(xp), i0, n, self._dbuf.data_ptr(), out.data_ptr(), st))
+                    self.launches += 1
+                    continue
+                # deterministic: local tiles / vectors into the item-local buffer, then the ordered gather
+                per_item = xp.ntiles * 16 if mode == 'matrix' else xp.nside * xp.nloc
+                need_a = n * per_item
+                if self._abuf is None or self._abuf.numel() < need_a:
+                    self._abuf = torch.empty(max(need_a, 1 << 20), dtype=torch.float64, device=self.device)
+                if mode == 'vector':
+                    self._abuf[:need_a].zero_()               # k_lin skips sides without a cell / untested blocks
+                lists = plan.setdefault('gather_' + mode, {})
+                if i0 not in lists:
+                    lists[i0] = self._gather_lists(program, integ, plan, i0, n, mode)
+                seg_ptr, seg_tgt, order = lists[i0]
+                xp.abuf = self._abuf.data_ptr()
+                self._ck(fn(C.byref(xp), i0, n, self._dbuf.data_ptr(), out.data_ptr(), st))
+                self._ck(self.lib.ocmp_gather_add(seg_tgt.numel(), seg_ptr.data_ptr(), seg_tgt.data_ptr(),
+                                                  order.data_ptr(), self._abuf.data_ptr(), out.data_ptr(), st))
+                xp.abuf = None
+                self.launches += 2
+
+    def _gather_lists(self, program, integ, plan, i0: int, n: int, mode: str):
+        """Contributor lists of one chunk of one integral for ocmp_gather_add: the flat index of every local tile entry
+        (matrices) / local vector entry in the item-local buffer, stably sorted by its target (CSR position / dof).
+        Returns (seg_ptr, seg_tgt, order) as int32 device tensors. Built once; a pure function of the mesh, the space
+        and the plan tables — identical on every rank that holds the same cells."""
+        t = self.torch
+        fes = program.fes
+        mesh = fes.mesh
+        md = self.mesh_data(mesh)
+        dev = self.device
+        xp = plan['contract']
+        ids = t.arange(i0, i0 + n, device=dev, dtype=t.int64)             # item index (facet2nnz is indexed by it)
+        gid = ids if integ.items is None else self._up(np.asarray(integ.items[i0:i0 + n], dtype=np.int64))
+        if integ.kind == 'cell':
+            cells = t.stack([gid, gid], dim=1)
+        else:
+            cells = md['facet_cells'][gid].to(t.int64)                    # (n, 2), -1 where there is no second cell
+        nloc = fes.nloc
+        if mode == 'vector':
+            cd = self.space_data(fes)['cell_dofs'].to(t.int64)            # (ncells, nloc)
+            nside = xp.nside
+            c = cells[:, :nside]                                          # (n, nside)
+            tgt = cd[c.clamp(min=0)]                                      # (n, nside, nloc)
+            tgt = t.where(c[:, :, None] >= 0, tgt, t.full_like(tgt, -1)).reshape(-1)
+        else:
+            pd = self.pattern_data(fes)
+            n2 = nloc * nloc
+            tiles = plan['tables']['tiles'].astype(np.int64)
+            a = np.arange(4)
+            ii = tiles[:, 5][:, None, None] + a[None, :, None]            # (ntiles, 4, 4) local row
+            jj = tiles[:, 6][:, None, None] + a[None, None, :]
+            ok = (a[None, :, None] < (tiles[:, 7] & 0xff)[:, None, None]) & \
+                 (a[None, None, :] < (tiles[:, 7] >> 8)[:, None, None])
+            ij = self._up((ii * nloc + jj).reshape(-1))                   # (ntiles * 16)
+            okd = self._up(ok.reshape(-1))
+            st_ = self._up(np.repeat(tiles[:, 4] & 1, 16))
+            su_ = self._up(np.repeat((tiles[:, 4] >> 1) & 1, 16))
+            c_st = t.where(st_[None, :] == 0, cells[:, 0:1], cells[:, 1:2])           # (n, ntiles*16)
+            same = (st_ == su_)[None, :]
+            idx_same = c_st.clamp(min=0) * n2 + ij[None, :]
+            idx_cross = (ids[:, None] * 2 + st_[None, :]) * n2 + ij[None, :]
+            c2n = pd['cell2nnz'].reshape(-1)
+            f2n = pd['facet2nnz'].reshape(-1)
+            if f2n.numel() == 0:
+                f2n = c2n
+            tgt = t.where(same, c2n[idx_same.clamp(max=c2n.numel() - 1)].to(t.int64),
+                          f2n[idx_cross.clamp(max=f2n.numel() - 1)].to(t.int64))
+            tgt = t.where(okd[None, :] & (c_st >= 0), tgt, t.full_like(tgt, -1)).reshape(-1)
+        order = t.sort(tgt, stable=True).indices
+        ninv = int((tgt < 0).sum().item())
+        order = order[ninv:]
+        sorted_tgt = tgt[order]
+        seg_tgt, counts = t.unique_consecutive(sorted_tgt, return_counts=True)
+        seg_ptr = t.zeros(seg_tgt.numel() + 1, dtype=t.int64, device=dev)
+        if seg_tgt.numel():
+            seg_ptr[1:] = t.cumsum(counts, 0)
+        return seg_ptr.to(t.int32), seg_tgt.to(t.int32), order.to(t.int32)
 
     # ---- assembly ----------------------------------------------------------------------------------------------
     def assemble_matrix(self, program, mat):
@@ -784,6 +873,7 @@ class CudaBackend:
             s.rowptr, s.colidx, s.vals = pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(), mat.values.data_ptr()
             if pd.get('runs') is not None:
                 s.run_len, s.run_shift, s.run_nc = pd['runs'][0].data_ptr(), pd['runs'][1], pd['runs'][2]
+                s.run_grouped = pd['runs'][1] if pd['runs'][3] else 0
         s.freemask = _ptr(fm)
         s.pre_kind = 0
         if pre is not None:

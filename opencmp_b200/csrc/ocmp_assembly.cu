@@ -398,6 +398,21 @@ __global__ void __launch_bounds__(256, (MAXT == 1 ? (DIM == 2 ? 3 : 2) : 1)) k_c
                 }
             }
         }
+        // ---- deterministic path: the finished tiles go to the item-local buffer (16 doubles per tile, coalesced);
+        //      ocmp_gather_add then sums, for every non-zero, its contributions in a fixed order
+        if (P.abuf) {
+            if (it_own < nitems) {
+#pragma unroll
+                for (int t = 0; t < MAXT; ++t) {
+                    const int tile = lane + t * TPE;
+                    if (tile >= P.ntiles) continue;
+                    double2* dst = reinterpret_cast<double2*>(P.abuf + ((long long)it_own * P.ntiles + tile) * 16);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) dst[k] = make_double2(acc[t][2 * k], acc[t][2 * k + 1]);
+                }
+            }
+            continue;
+        }
         // ---- scatter-add through the element -> nnz map ------------------------------------------------------
         if (it_own < nitems) {
             const int c0 = sI[4 * e_own], c1 = sI[4 * e_own + 1];
@@ -462,7 +477,21 @@ __global__ void __launch_bounds__(128) k_lin(const __grid_constant__ ocmp_contra
             acc = fma(__ldg(dbuf + (long long)P.ent[2 * k] * dstride + (long long)it * P.nq + q), val, acc);
         }
     }
-    atomicAdd(vec + __ldg(P.cell_dofs + (long long)c * P.nloc + i), acc);
+    if (P.abuf) P.abuf[gid] = acc;             // deterministic path: local vectors, summed by ocmp_gather_add
+    else atomicAdd(vec + __ldg(P.cell_dofs + (long long)c * P.nloc + i), acc);
+}
+
+// dst[seg_tgt[s]] += sum of src[order[k]], k in [seg_ptr[s], seg_ptr[s + 1]): every target has exactly one thread and
+// a fixed summation order, so the result does not depend on the scheduling (unlike atomicAdd scatter)
+__global__ void __launch_bounds__(256) k_gather_add(int nseg, const int* __restrict__ seg_ptr,
+                                                    const int* __restrict__ seg_tgt, const int* __restrict__ order,
+                                                    const double* __restrict__ src, double* __restrict__ dst) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const int a = __ldg(seg_ptr + s), e = __ldg(seg_ptr + s + 1);
+    double v = 0.0;
+    for (int k = a; k < e; ++k) v += __ldg(src + __ldg(order + k));
+    dst[__ldg(seg_tgt + s)] += v;
 }
 
 __global__ void __launch_bounds__(256) k_sum(const double* __restrict__ x, long long n, double* __restrict__ out) {
@@ -553,6 +582,15 @@ extern "C" int ocmp_contract_vector(const ocmp_contract_plan* plan, int item0, i
     else if (plan->dim == 3) k_lin<3><<<blocks, 128, 0, st>>>(*plan, item0, nitems, dbuf, vec);
     else return ocmp_fail(-1, "dim must be 2 or 3");
     return ocmp_check("ocmp_contract_vector");
+}
+
+extern "C" int ocmp_gather_add(int nseg, const int* seg_ptr, const int* seg_tgt, const int* order, const double* src,
+                               double* dst, void* stream) {
+    if (nseg <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps(PROF_CONTRACT, st);
+    k_gather_add<<<(nseg + 255) / 256, 256, 0, st>>>(nseg, seg_ptr, seg_tgt, order, src, dst);
+    return ocmp_check("ocmp_gather_add");
 }
 
 extern "C" int ocmp_sum(const double* x, long long n, double* out, void* stream) {

@@ -114,6 +114,8 @@ enum { EP_PLAIN = 0, EP_RESID = 1, EP_MASK = 2, EP_ADD = 3 };
 struct SpmvRuns {
     const int* runlen;       // per row: L, or 0 for a plain row; NULL = no compression
     int shift, nc;
+    int grouped;             // > 0: the nc component rows of every node have identical column lists (k_spmv_vec);
+                             // with a row list: the number of listed rows below `shift`
 };
 
 template <int LPR, typename VT, int EP>
@@ -166,6 +168,114 @@ __global__ void __launch_bounds__(256) k_spmv(int nrows, const int* __restrict__
     }
 }
 
+// The nc component rows of a node (row, row + shift, ...) have the SAME column list, so one lane group computes all of
+// them: the x values and the column indices are fetched once per nc x nc values — the gather traffic through L2
+// (one 32-byte sector per 8-byte x value for a scattered CG numbering) drops by nc, which is what bounds the plain
+// CSR product on the 3-D Taylor-Hood matrices (210 non-zeros per row). Groups [0, ngroups) are nodes, the remaining
+// `nsingle` rows (pressure) are handled like in k_spmv.
+template <int LPR, typename VT, int EP, int NC>
+__global__ void __launch_bounds__(256) k_spmv_vec(int ngroups, int nsingle, const int* __restrict__ rowptr,
+                                                  const int* __restrict__ col, const VT* __restrict__ val,
+                                                  const double* __restrict__ x, double* __restrict__ y,
+                                                  const double* __restrict__ b, const double* __restrict__ m,
+                                                  const double* __restrict__ m2, const int* __restrict__ rows,
+                                                  SpmvRuns runs) {
+    const int lane = threadIdx.x % LPR;
+    const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    const long long stride = (long long)gridDim.x * blockDim.x / LPR;
+    const long long shift = runs.shift;
+    for (long long g = g0; g < (long long)ngroups + nsingle; g += stride) {
+        if (g < ngroups) {
+            const long long row0 = rows ? __ldg(rows + g) : g;
+            const int a0 = __ldg(rowptr + row0), len = __ldg(rowptr + row0 + 1) - a0;
+            const int L = __ldg(runs.runlen + row0);
+            const VT* v[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) v[c] = val + __ldg(rowptr + row0 + c * shift);
+            double s[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) s[c] = 0.0;
+            for (int k = lane; k < L; k += LPR) {
+                const double* xp = x + __ldg(col + a0 + k);
+                double xv[NC];
+#pragma unroll
+                for (int c2 = 0; c2 < NC; ++c2) xv[c2] = __ldg(xp + c2 * shift);
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int c2 = 0; c2 < NC; ++c2) s[c] = fma((double)__ldg(v[c] + c2 * L + k), xv[c2], s[c]);
+            }
+            for (int k = NC * L + lane; k < len; k += LPR) {
+                const double xv = __ldg(x + __ldg(col + a0 + k));
+#pragma unroll
+                for (int c = 0; c < NC; ++c) s[c] = fma((double)__ldg(v[c] + k), xv, s[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) s[c] += __shfl_down_sync(0xffffffffu, s[c], o, LPR);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const long long row = row0 + c * shift;
+                    if (EP == EP_PLAIN) y[row] = s[c];
+                    else {
+                        double vv = (EP == EP_RESID) ? __ldg(b + row) - s[c] : s[c];
+                        if (m) vv *= __ldg(m + row);
+                        if (EP == EP_RESID && m2) vv *= __ldg(m2 + row);
+                        y[row] = (EP == EP_ADD) ? y[row] + vv : vv;
+                    }
+                }
+            }
+        } else {
+            const long long si = g - ngroups;
+            const long long row = rows ? __ldg(rows + (long long)NC * ngroups + si) : NC * shift + si;
+            int a = __ldg(rowptr + row);
+            const int e = __ldg(rowptr + row + 1);
+            double s = 0.0;
+            const int L = __ldg(runs.runlen + row);
+            if (L > 0) {
+                for (int k = lane; k < L; k += LPR) {
+                    const double* xp = x + __ldg(col + a + k);
+#pragma unroll
+                    for (int c2 = 0; c2 < NC; ++c2) s = fma((double)__ldg(val + a + c2 * L + k), __ldg(xp + c2 * shift), s);
+                }
+                a += NC * L;
+            }
+            for (int k = a + lane; k < e; k += LPR) s = fma((double)__ldg(val + k), __ldg(x + __ldg(col + k)), s);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LPR);
+            if (lane == 0) {
+                if (EP == EP_PLAIN) y[row] = s;
+                else {
+                    double vv = (EP == EP_RESID) ? __ldg(b + row) - s : s;
+                    if (m) vv *= __ldg(m + row);
+                    if (EP == EP_RESID && m2) vv *= __ldg(m2 + row);
+                    y[row] = (EP == EP_ADD) ? y[row] + vv : vv;
+                }
+            }
+        }
+    }
+}
+
+// group check of k_spmv_vec: rows row + c * shift (row < shift, c < nc) have the length, run length and columns of
+// row; *bad is raised otherwise
+__global__ void __launch_bounds__(256) k_spmv_groups(int shift, int nc, const int* __restrict__ rowptr,
+                                                     const int* __restrict__ col, const int* __restrict__ runlen,
+                                                     int* __restrict__ bad) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= shift) return;
+    const int a = rowptr[row], len = rowptr[row + 1] - a;
+    bool ok = runlen[row] > 0;
+    for (int c = 1; ok && c < nc; ++c) {
+        const int r2 = row + c * shift, a2 = rowptr[r2];
+        ok = ok && rowptr[r2 + 1] - a2 == len && runlen[r2] == runlen[row];
+        for (int k = 0; ok && k < len; ++k) ok = ok && col[a2 + k] == col[a + k];
+    }
+    if (!ok) *bad = 1;
+}
+
 // runlen[row] = L if the row starts with nc runs of length L whose columns are those of the first run shifted by
 // k * shift (k < nc) and the first run lies in [0, shift); else 0
 __global__ void __launch_bounds__(256) k_spmv_runs(int nrows, const int* __restrict__ rowptr,
@@ -191,13 +301,33 @@ __global__ void __launch_bounds__(256) k_to_f32(long long n, const double* __res
 static int spmv_ep(int cat, int ep, int nrows, const int* rowptr, const int* colidx, const double* vals,
                    const float* vals32, const double* x, double* y, const double* b, const double* m,
                    const double* m2, cudaStream_t st, const int* rows = nullptr,
-                   SpmvRuns runs = SpmvRuns{nullptr, 0, 0}) {
+                   SpmvRuns runs = SpmvRuns{nullptr, 0, 0, 0}) {
     if (nrows <= 0) return 0;
     const int threads = 256;
     const long long want = ((long long)nrows * 16 + threads - 1) / threads;
     const long long cap = (long long)ocmp_sm_count() * 64;
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     ProfScope ps(cat, st);
+    if (runs.runlen && runs.grouped > 0) {
+        // node-grouped product: listed rows (or all rows) = nc * ngroups component rows followed by single rows
+        const int ngroups = runs.grouped, nsingle = nrows - runs.nc * ngroups;
+        const long long wantg = ((long long)(ngroups + nsingle) * 16 + threads - 1) / threads;
+        const unsigned bg = (unsigned)(wantg < cap ? wantg : cap);
+#define SPMV_VEC(VT, V, EP, NC) \
+    k_spmv_vec<16, VT, EP, NC><<<bg, threads, 0, st>>>(ngroups, nsingle, rowptr, colidx, V, x, y, b, m, m2, rows, runs)
+#define SPMV_VEC_EP(VT, V, NC)                                           \
+    do {                                                                 \
+        if (ep == EP_PLAIN) SPMV_VEC(VT, V, EP_PLAIN, NC);               \
+        else if (ep == EP_RESID) SPMV_VEC(VT, V, EP_RESID, NC);          \
+        else if (ep == EP_MASK) SPMV_VEC(VT, V, EP_MASK, NC);            \
+        else SPMV_VEC(VT, V, EP_ADD, NC);                                \
+    } while (0)
+        if (vals32) { if (runs.nc == 3) SPMV_VEC_EP(float, vals32, 3); else SPMV_VEC_EP(float, vals32, 2); }
+        else { if (runs.nc == 3) SPMV_VEC_EP(double, vals, 3); else SPMV_VEC_EP(double, vals, 2); }
+#undef SPMV_VEC_EP
+#undef SPMV_VEC
+        return ocmp_check("ocmp_spmv (grouped)");
+    }
 #define SPMV_GO(VT, V, EP) \
     k_spmv<16, VT, EP><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, V, x, y, b, m, m2, rows, runs)
     if (vals32) {
@@ -221,16 +351,23 @@ extern "C" int ocmp_spmv(int nrows, const int* rowptr, const int* colidx, const 
                    (cudaStream_t)stream);
 }
 extern "C" int ocmp_spmv_runs(int nrows, const int* rowptr, const int* colidx, int shift, int nc, int* runlen,
-                              void* stream) {
+                              int* grouped_bad_dev, void* stream) {
     if (nrows <= 0) return 0;
-    if (nc < 2 || nc > 3 || shift <= 0) return ocmp_fail(-1, "ocmp_spmv_runs: nc must be 2 or 3, shift > 0");
-    k_spmv_runs<<<(nrows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nrows, rowptr, colidx, shift, nc, runlen);
+    if (nc < 2 || nc > 3 || shift <= 0 || (long long)nc * shift > nrows)
+        return ocmp_fail(-1, "ocmp_spmv_runs: nc must be 2 or 3, 0 < nc * shift <= nrows");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_spmv_runs<<<(nrows + 255) / 256, 256, 0, st>>>(nrows, rowptr, colidx, shift, nc, runlen);
+    if (grouped_bad_dev) {
+        cudaMemsetAsync(grouped_bad_dev, 0, sizeof(int), st);
+        k_spmv_groups<<<(shift + 255) / 256, 256, 0, st>>>(shift, nc, rowptr, colidx, runlen, grouped_bad_dev);
+    }
     return ocmp_check("ocmp_spmv_runs");
 }
 extern "C" int ocmp_spmv_compressed(int nrows, const int* rowptr, const int* colidx, const double* vals,
-                                    const int* runlen, int shift, int nc, const double* x, double* y, void* stream) {
+                                    const int* runlen, int shift, int nc, int grouped, const double* x, double* y,
+                                    void* stream) {
     return spmv_ep(PROF_SPMV, EP_PLAIN, nrows, rowptr, colidx, vals, nullptr, x, y, nullptr, nullptr, nullptr,
-                   (cudaStream_t)stream, nullptr, SpmvRuns{runlen, shift, nc});
+                   (cudaStream_t)stream, nullptr, SpmvRuns{runlen, shift, nc, grouped ? shift : 0});
 }
 
 extern "C" int ocmp_to_f32(long long n, const double* src, float* dst, void* stream) {
@@ -653,7 +790,11 @@ struct Ctx {
     // the rows an operator application has to compute: a rank's own rows when the halo exchange supplies the others
     static const int* row_list(const ocmp_system* sy) { return (sy->halo_fwd && sy->spmv_rows) ? sy->spmv_rows : nullptr; }
     static int active_rows(const ocmp_system* sy) { return row_list(sy) ? sy->n_spmv_rows : sy->nrows; }
-    static SpmvRuns runs_of(const ocmp_system* sy) { return SpmvRuns{sy->run_len, sy->run_shift, sy->run_nc}; }
+    // grouped product: all rows -> run_grouped nodes; with a row list -> the count of listed rows below run_shift
+    static SpmvRuns runs_of(const ocmp_system* sy) {
+        const int grouped = !sy->run_len ? 0 : row_list(sy) ? sy->n_spmv_groups : sy->run_grouped;
+        return SpmvRuns{sy->run_len, sy->run_shift, sy->run_nc, grouped};
+    }
     static void had(cudaStream_t st, long long n, const double* a, const double* m, const double* r, double* z,
                     double scale, int accumulate) {
         ProfScope ps(PROF_VEC, st);

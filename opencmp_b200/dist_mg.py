@@ -50,6 +50,19 @@ class _Level:
     pass
 
 
+def owned_node_groups(owned: np.ndarray, shift: int, nc: int) -> int:
+    """For the grouped SpMV over a rank's own rows (ocmp_system.n_spmv_groups): the ascending list of owned rows must
+    hold the owned rows below ``shift``, then their nc - 1 copies shifted by ``shift`` (the other components of the same
+    nodes), then the remaining rows. Returns the number of such nodes, or 0 when the components of some node are not
+    owned together."""
+    owned = np.asarray(owned, dtype=bool)
+    first = owned[:shift]
+    for c in range(1, nc):
+        if not np.array_equal(owned[c * shift:(c + 1) * shift], first):
+            return 0
+    return int(first.sum())
+
+
 class DistributedMultigrid:
     """Levels [0 .. L]; level L is the space of the bilinear form ``bf`` (built on the rank's local finest mesh)."""
 
@@ -137,10 +150,11 @@ class DistributedMultigrid:
                 if reuse:
                     continue
                 be.assemble_matrix(lv.program, lv.mat)
-                if lv.replicated:
-                    # redundant work must be bitwise identical on every rank: the scatter-add assembly is not
-                    # (atomic order), and the regularised pressure mode amplifies round-off differences of the
-                    # inverses — so all ranks take rank 0's coarse matrix values
+                from .backend import deterministic_assembly
+                if lv.replicated and not (getattr(be, 'name', '') == 'cuda' and deterministic_assembly()):
+                    # redundant work must be bitwise identical on every rank (the regularised pressure mode amplifies
+                    # round-off differences of the inverses). The two-phase assembly (item-local tiles + ordered
+                    # gather) is; with the atomicAdd scatter (OCMP_DETERMINISTIC=0) all ranks take rank 0's values
                     _broadcast(lv.mat.values)
             else:
                 lv.mat = self.bf.mat
@@ -180,6 +194,11 @@ class DistributedMultigrid:
                 if not hasattr(lv, 'own_rows'):
                     lv.own_rows = be._up(np.nonzero(lv.map.owned)[0].astype(np.int32))
                 s.spmv_rows, s.n_spmv_rows = lv.own_rows.data_ptr(), int(lv.own_rows.numel())
+                if pd.get('runs') is not None and pd['runs'][3]:
+                    s.n_spmv_groups = owned_node_groups(lv.map.owned, pd['runs'][1], pd['runs'][2])
+            if pd.get('runs') is not None:
+                s.run_len, s.run_shift, s.run_nc = pd['runs'][0].data_ptr(), pd['runs'][1], pd['runs'][2]
+                s.run_grouped = pd['runs'][1] if pd['runs'][3] else 0
             if not hasattr(lv, 'work'):
                 lv.work = be.zeros(4 * lv.n)
             arr[l].work = lv.work.data_ptr()

@@ -108,15 +108,17 @@ def test_component_run_spmv_equals_plain_csr_product(name):
         if be.name == 'cuda':
             pd = be.pattern_data(c['fes'])
             assert pd['runs'] is not None
-            runlen, shift, nc = pd['runs']
+            runlen, shift, nc, grouped = pd['runs']
             assert int((runlen > 0).sum()) == c['fes'].ndof          # all rows carry the component runs
-            y = be.zeros(c['fes'].ndof)
-            be._ck(be.lib.ocmp_spmv_compressed(c['fes'].ndof, pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(),
-                                               c['a'].mat.values.data_ptr(), runlen.data_ptr(), shift, nc,
-                                               xv.a.data_ptr(), y.data_ptr(), be._stream()))
-            out.append(be.to_numpy(y))
+            assert grouped                                             # ... and the components of a node share columns
+            for g in (0, 1):                                           # row-wise and node-grouped kernels
+                y = be.zeros(c['fes'].ndof)
+                be._ck(be.lib.ocmp_spmv_compressed(c['fes'].ndof, pd['rowptr'].data_ptr(), pd['colidx'].data_ptr(),
+                                                   c['a'].mat.values.data_ptr(), runlen.data_ptr(), shift, nc, g,
+                                                   xv.a.data_ptr(), y.data_ptr(), be._stream()))
+                out.append(be.to_numpy(y))
         return out
     ref = _with('oracle', run)
     got = _with('cuda', run)
-    assert _rel(got[0], ref[0]) < 1e-12
-    assert _rel(got[1], got[0]) < 1e-13
+    assert _rel(got[0], ref[0]) < 1e-12                 # `mat * x` itself goes through the grouped kernel
+    assert _rel(got[1], ref[0]) < 1e-12 and _rel(got[2], ref[0]) < 1e-12

@@ -76,6 +76,7 @@ class DryCudaBackend(CudaBackend):
         self._mesh_cache, self._space_cache = {}, {}
         self._plan_cache = weakref.WeakKeyDictionary()
         self._dbuf = None
+        self._abuf = None
         self._scal = torch.zeros(64, dtype=torch.float64)
         self.launches = 0
         self.last_iters = 0
@@ -148,7 +149,7 @@ def _invoke(fn, params, monkeypatch, ngs_fixture):
 
 @pytest.mark.parametrize('modname', ['test_gpu_parity', 'test_golden_programs', 'test_golden_fixtures',
                                      'test_zz_gpu_late_additions', 'test_zzz_gpu_unmeasured_kernels',
-                                     'test_zzzz_gpu_matrix_free', 'test_gpu_direct', 'test_gpu_krylov'])
+                                     'test_zzzz_gpu_matrix_free', 'test_gpu_direct', 'test_gpu_krylov', 'test_gpu_deterministic'])
 def test_gpu_test_bodies_execute_on_a_null_device(dry, monkeypatch, modname):
     import importlib
     import opencmp_b200.ngs as ngs

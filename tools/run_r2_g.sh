@@ -4,7 +4,8 @@ mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
 timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 tail -12 $O/pytest_gpu.log
-OCMP_PATCH_STORAGE=fp32 timeout 300 python tools/kern_bench.py 128 2>&1 | tail -5
+OCMP_INVERT_512=0 OCMP_PATCH_STORAGE=fp32 timeout 300 python tools/kern_bench.py 128 2>&1 | grep 'level 5\|pre.Update'
+OCMP_PATCH_STORAGE=fp32 timeout 300 python tools/kern_bench.py 128 2>&1 | tail -9
 timeout 600 python bench.py --no-cpu > $O/bench_default.json 2> $O/bench_default.err; tail -c 300 $O/bench_default.err
 python - <<PY
 import json
