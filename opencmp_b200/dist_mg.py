@@ -150,11 +150,12 @@ class DistributedMultigrid:
                 if reuse:
                     continue
                 be.assemble_matrix(lv.program, lv.mat)
-                from .backend import deterministic_assembly
-                if lv.replicated and not (getattr(be, 'name', '') == 'cuda' and deterministic_assembly()):
+                if lv.replicated:
                     # redundant work must be bitwise identical on every rank (the regularised pressure mode amplifies
-                    # round-off differences of the inverses). The two-phase assembly (item-local tiles + ordered
-                    # gather) is; with the atomicAdd scatter (OCMP_DETERMINISTIC=0) all ranks take rank 0's values
+                    # round-off differences of the inverses). The two-phase assembly is bit-reproducible for identical
+                    # inputs, but the coarse stand-ins of the coefficient fields are clipped to the range of each
+                    # rank's LOCAL fine vector (multigrid.restrict_field), so the inputs differ in the last bits:
+                    # all ranks take rank 0's coarse matrix values (set-up only, a few MB)
                     _broadcast(lv.mat.values)
             else:
                 lv.mat = self.bf.mat
