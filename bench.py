@@ -39,6 +39,10 @@ DEFAULTS = {'ins3d_dim': dict(N=48, order=2), 'ins2d': dict(N=256, order=3)}
 # instead of iterating to a tolerance: the flows relax towards a steady state, so a tolerance-driven loop does 3, 2,
 # then 1 iteration per step and "seconds per step" would depend on which steps the timed region happens to hold.
 PICARD = dict(nonlinear_max_iterations=2, nonlinear_tolerance=(0.0, 0.0))
+# 3-D workload: the diffuse wall's angular velocity oscillates, omega(t) = 1 + 0.5 sin(2 pi t / (10 dt)) — with a steady
+# wall the flow relaxes to rigid rotation within a few steps, the previous solution becomes an almost exact initial
+# guess and GMRES can no longer reduce the residual by 1e-12 relative to the initial one (workloads.INSSphereDIM3D)
+WALL = dict(wall_period=0.1, wall_amp=0.5)
 
 
 def parse(argv=None):
@@ -136,7 +140,7 @@ def _cpu_workload(N, order, workload):
     from opencmp_b200.workloads import INSTaylorGreen, INSSphereDIM3D
     if workload != 'ins3d_dim':
         return INSTaylorGreen(N, order=order, linear_solver='direct', preconditioner=None, **PICARD)
-    w = INSSphereDIM3D(N, order=order, preconditioner=None, nu=1.0, periodic=(False, False, False), **PICARD)
+    w = INSSphereDIM3D(N, order=order, preconditioner=None, nu=1.0, periodic=(False, False, False), **PICARD, **WALL)
 
     def direct():
         inv = w.a.mat.Inverse(w.fes.FreeDofs())
@@ -193,7 +197,8 @@ def workload_config(args, where, N=None, gpus=None):
                    'multigrid-GMRES'.format(N, 2 * gpus - 1))
         return {'workload': 'INS-DIM 3D (BASELINE configs[4]): structured hexes on [-1,1]^3 ({0}^3 on one GPU), Taylor-Hood '
                             'Q{1}/Q{2}, diffuse-interface sphere R=0.5 (erf profile, lambda = 0.25, phi clamped to '
-                            '[1e-10,1]), rotating wall as DIM Dirichlet data, Oseen + implicit Euler, dt=1e-2, nu=1 '
+                            '[1e-10,1]), rotating wall as DIM Dirichlet data with omega(t) = 1 + 0.5 sin(2 pi t / 0.1), Oseen + implicit '
+                            'Euler, dt=1e-2, nu=1 '
                             '(reference models/ins_dim.py forms)'.format(N, args.order, args.order - 1),
                 'N': N, 'order': args.order,
                 'linear_solver': 'GMRES(200) + geometric multigrid V(1,1) on the hex hierarchy, open-star vertex-patch '
@@ -230,7 +235,8 @@ def make_gpu_workload(workload, N, order, world=1, rank=0, layout='sphere'):
     """(workload object, distributed wrapper or None)"""
     if world > 1 and workload == 'ins3d_dim':
         from opencmp_b200.dist_workload import DistributedINSDIM3D
-        d = DistributedINSDIM3D(N, world, rank, order=order, layout='sphere' if layout == 'sphere' else None, **PICARD)
+        d = DistributedINSDIM3D(N, world, rank, order=order, layout='sphere' if layout == 'sphere' else None, **PICARD,
+                                **WALL)
         return d.w, d
     if world > 1:
         from opencmp_b200.dist_workload import DistributedINS
@@ -239,7 +245,7 @@ def make_gpu_workload(workload, N, order, world=1, rank=0, layout='sphere'):
     if workload == 'ins3d_dim':
         from opencmp_b200.workloads import INSSphereDIM3D
         return INSSphereDIM3D(N, order=order, nu=1.0, linear_tolerance=1e-12, periodic=(False, False, False),
-                              **PICARD), None
+                              **PICARD, **WALL), None
     from opencmp_b200.workloads import INSTaylorGreen
     return INSTaylorGreen(N, order=order, **PICARD), None
 

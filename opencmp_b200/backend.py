@@ -359,10 +359,12 @@ class CudaBackend:
     def mdot(self, V, w):
         """Host array of <V_j, w> for the rows of the 2-D device array V (one batched launch + one read-back)."""
         k, n = V.shape
-        self._ck(self.lib.ocmp_mdot(n, V.data_ptr(), V.stride(0), k, w.data_ptr(), self._scal.data_ptr(),
-                                    self._stream()))
+        if V.stride(1) != 1 or not w.is_contiguous():
+            raise ValueError('mdot needs unit-stride rows and a contiguous vector')
+        out = self._scal if k <= self._scal.numel() else self.zeros(k)     # e.g. Anderson mixing with a long history
+        self._ck(self.lib.ocmp_mdot(n, V.data_ptr(), V.stride(0), k, w.data_ptr(), out.data_ptr(), self._stream()))
         self.launches += 1
-        return self._scal[:k].cpu().numpy()
+        return out[:k].cpu().numpy()
 
     def maxpy(self, V, coef, w):
         """w += sum_j coef[j] V_j (coef: host array)."""
@@ -372,6 +374,8 @@ class CudaBackend:
         self.launches += 1
 
     def dot(self, a, b):
+        if not (a.is_contiguous() and b.is_contiguous()):      # BaseVector slices with a step
+            a, b = a.contiguous(), b.contiguous()
         self._ck(self.lib.ocmp_dot(a.numel(), a.data_ptr(), b.data_ptr(), self._scal.data_ptr(), self._stream()))
         self.launches += 1
         return float(self._scal[0].item())

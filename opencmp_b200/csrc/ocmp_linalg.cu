@@ -620,9 +620,12 @@ __global__ void __launch_bounds__(256) k_asm_setup(int npatch, int bs, const int
                     M[pr * bs + j] = t;
                 }
             __syncthreads();
-            double pv = M[k * bs + k];
-            if (fabs(pv) < 1e-300) pv = 1e-300;
-            const double ip = 1.0 / pv;
+            // an exactly vanishing pivot even after the row interchange means the patch matrix is singular (an enclosed
+            // pressure patch with all velocities constrained): that dof is dropped — zero row and column in the stored
+            // inverse, i.e. no correction from this patch — instead of dividing by 0. No relative threshold: the
+            // reference's 1e-10 regularisations make legitimate pivots tiny against the patch's largest entry.
+            const double pv = M[k * bs + k];
+            const double ip = fabs(pv) > 1e-300 ? 1.0 / pv : 0.0;
             for (int i = threadIdx.x; i < bs; i += blockDim.x) fcol[i] = (i == k) ? 0.0 : M[i * bs + k];
             __syncthreads();
             for (int j = threadIdx.x; j < bs; j += blockDim.x) M[k * bs + j] = (j == k) ? ip : M[k * bs + j] * ip;

@@ -79,6 +79,10 @@ __global__ void __launch_bounds__(256, 1) k_patch_invert(int npatch, int bs, con
 #pragma unroll
                     for (int a = 0; a < T; ++a) colk[buf][ty + 16 * a] = M[a][ka];
                     if (ty == kr) {
+                        // no pivoting, and no RELATIVE pivot test either: the reference's regularisation (-1e-10 p q,
+                        // phi clamped at 1e-10) makes legitimate pressure pivots 1e-20 times smaller than the
+                        // velocity ones (a 1e-13 relative threshold was tried in round 2: it sent every patch of the
+                        // INS systems to the pivoted fallback). Only an exactly vanishing / non-finite pivot does.
                         const double d = M[ka][ka];
                         if (!(fabs(d) > 1e-280)) bad = true;
                         pivr[buf] = 1.0 / d;

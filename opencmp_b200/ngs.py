@@ -78,7 +78,17 @@ class Mesh(_Mesh):
         return getattr(self, '_curve_order', 1)
 
     def Curve(self, order):
-        self._curve_order = int(order)       # straight-sided cells: nothing to project onto (see mesh.Mesh.Curve)
+        """NGSolve projects the boundary nodes onto the CAD geometry; the meshes this backend reads (.vol / .msh
+        text files, structured generators) carry no geometry, so cells stay straight-sided. Say so once instead of
+        silently capping the convergence order of curved-boundary configs (curved_elements = True) at the O(h^2)
+        geometry error."""
+        self._curve_order = int(order)
+        if int(order) > 1 and not getattr(Mesh, '_warned_curve', False):
+            import warnings
+            warnings.warn('opencmp_b200: Mesh.Curve({}) has no effect — the mesh carries no boundary geometry, cells stay '
+                          'affine (polygonal boundaries are exact; curved ones keep an O(h^2) geometry error)'
+                          .format(order))
+            Mesh._warned_curve = True
 
     def __call__(self, *pt):
         return MeshPoint(self, pt)
