@@ -474,6 +474,7 @@ def run_b200(args):
                     'ranks': world, 'owned_cells_per_gpu': (dins.gmesh.ne // world) if dins else ne,
                     'picard_per_step': m['clean']['picard'] / args.steps,
                     'gmres_its_per_step': m['clean']['its'] / args.steps,
+                    'ms_per_gmres_iteration': ms / max(1, m['clean']['its']),
                     'gmres_its_per_solve': m['clean']['its_per_solve'],
                     'gmres_its_per_solve_e2e': m['e2e']['its_per_solve'], 'l2_err_u': m['errs'][0],
                     'l2_err_p': m['errs'][1], 'setup_s': t_setup},
