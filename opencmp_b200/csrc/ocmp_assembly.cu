@@ -240,7 +240,7 @@ __device__ __forceinline__ void dof_phys_rows(int kind, int nloc, int nrows, con
 // tile rows / columns, so the loads are mostly broadcasts) for 16 FMAs. Structurally empty block pairs are neither
 // computed nor scattered. The finished tiles are scatter-added through the element -> nnz map (no colouring).
 template <int DIM, int MAXT>
-__global__ void __launch_bounds__(256, (MAXT == 1 ? (DIM == 2 ? 3 : 2) : 1)) k_contract(const __grid_constant__ ocmp_contract_plan P, int item0, int nitems,
+__global__ void __launch_bounds__(256, (MAXT == 1 ? 2 : 1)) k_contract(const __grid_constant__ ocmp_contract_plan P, int item0, int nitems,
                                                   const double* __restrict__ dbuf, double* __restrict__ values) {
     constexpr int GS = GeoT<DIM>::GS;
     extern __shared__ double smem[];
@@ -323,26 +323,31 @@ __global__ void __launch_bounds__(256, (MAXT == 1 ? (DIM == 2 ? 3 : 2) : 1)) k_c
         for (int q0 = 0; q0 < P.nq; q0 += QB) {
             const int nqq = min(QB, P.nq - q0);
             __syncthreads();
-            // D values of these quadrature points
-            for (int k = lane; k < nqq * P.nslots; k += TPE) {
-                const int qq = k / P.nslots, sl = k - qq * P.nslots;
-                dE[k] = (it_own < nitems)
-                    ? __ldg(dbuf + (long long)sl * dstride + (long long)it_own * P.nq + q0 + qq) : 0.0;
+            // D values of these quadrature points (nqq consecutive doubles per slot)
+            for (int sl = lane; sl < P.nslots; sl += TPE) {
+                const double* src = dbuf + (long long)sl * dstride + (long long)it_own * P.nq + q0;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq)
+                    if (qq < nqq) dE[qq * P.nslots + sl] = (it_own < nitems) ? __ldg(src + qq) : 0.0;
             }
-            // physical basis tables of my item: one (point, side, dof) column per thread
-            for (int w = lane; w < nqq * ncol; w += TPE) {
-                const int qq = w / ncol, sd = w - qq * ncol;
+            // physical basis tables of my item: one (side, dof) column per thread, all points of the round
+            for (int sd = lane; sd < ncol; sd += TPE) {
                 const int4 dd = *reinterpret_cast<const int4*>(tDof + 4 * sd);
                 const int s = sd >= P.nloc ? 1 : 0;
                 const int kind = dd.x & 0xff, nr = (dd.x >> 8) & 0xff, nlp = dd.x >> 16, nl = dd.y;
                 const int c = sI[4 * e_own + s];
-                double* out = bE + (qq * nside + s) * P.sbsz + dd.w;
+                double* out0 = bE + s * P.sbsz + dd.w;
                 if (c < 0) {
-                    for (int r = 0; r < nr; ++r) out[r * nlp] = 0.0;
-                } else {
-                    const int lfq = (P.kind == 0 ? 0 : sI[4 * e_own + 2 + s] * P.nq) + q0 + qq;
-                    const double* tq = P.tab + dd.z + (long long)lfq * nr * nl;      // dd.z includes the local dof
-                    const double* g = sG + (e_own * nside + s) * GS;
+                    for (int qq = 0; qq < nqq; ++qq)
+                        for (int r = 0; r < nr; ++r) out0[qq * nside * P.sbsz + r * nlp] = 0.0;
+                    continue;
+                }
+                const int lfq0 = (P.kind == 0 ? 0 : sI[4 * e_own + 2 + s] * P.nq) + q0;
+                const double* tq0 = P.tab + dd.z + (long long)lfq0 * nr * nl;        // dd.z includes the local dof
+                const double* g = sG + (e_own * nside + s) * GS;
+                for (int qq = 0; qq < nqq; ++qq) {
+                    const double* tq = tq0 + (long long)qq * nr * nl;
+                    double* out = out0 + qq * nside * P.sbsz;
                     if (kind == 0) {
                         double R[1 + DIM], PH[MAX_ROWS];
 #pragma unroll
@@ -361,18 +366,23 @@ __global__ void __launch_bounds__(256, (MAXT == 1 ? (DIM == 2 ? 3 : 2) : 1)) k_c
                 }
             }
             __syncthreads();
-            // Z rows of these points
-            for (int w = lane; w < nqq * P.nzd; w += TPE) {
-                const int qq = w / P.nzd, z = w - qq * P.nzd;
-                const int4 zd = *reinterpret_cast<const int4*>(tZ + 4 * z);
-                const double* bq = bE + qq * nside * P.sbsz + zd.z;
-                const double* dq = dE + qq * P.nslots;
-                double sacc = 0.0;
-                for (int k = zd.x; k < zd.y; ++k) {
-                    const int2 en = *reinterpret_cast<const int2*>(tEnt + 2 * k);
-                    sacc = fma(dq[en.x], bq[en.y], sacc);
+            // Z rows of these points: the descriptors of a row are read once for all points of the round
+            {
+                const int bstr = nside * P.sbsz;
+                for (int z = lane; z < P.nzd; z += TPE) {
+                    const int4 zd = *reinterpret_cast<const int4*>(tZ + 4 * z);
+                    const double* bq = bE + zd.z;
+                    double sacc[4] = {0.0, 0.0, 0.0, 0.0};
+                    for (int k = zd.x; k < zd.y; ++k) {
+                        const int2 en = *reinterpret_cast<const int2*>(tEnt + 2 * k);
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq)
+                            if (qq < nqq) sacc[qq] = fma(dE[qq * P.nslots + en.x], bq[qq * bstr + en.y], sacc[qq]);
+                    }
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq)
+                        if (qq < nqq) zE[qq * P.zsz + zd.w] = sacc[qq];
                 }
-                zE[qq * P.zsz + zd.w] = sacc;
             }
             __syncthreads();
             // tile updates: A[i0 + a][j0 + b] += B[row_g][i0 + a] * Z_g[j0 + b] over the segments g of the tile's pair
@@ -563,7 +573,7 @@ extern "C" int ocmp_contract_matrix(const ocmp_contract_plan* plan, int item0, i
     cudaStream_t st = (cudaStream_t)stream;
     const int eb = plan->eb;
     if (eb < 1 || eb > 16 || (eb & (eb - 1))) return ocmp_fail(-1, "eb must be a power of two <= 16");
-    if (plan->qb < 1) return ocmp_fail(-1, "contraction plan: qb must be >= 1");
+    if (plan->qb < 1 || plan->qb > 4) return ocmp_fail(-1, "contraction plan: qb must be 1 .. 4");
     if (plan->ntiles > plan->maxt * (256 / eb) || plan->maxt > 4)
         return ocmp_fail(-1, "contraction plan: more tiles than the threads of an item can hold");
     if (plan->dim == 2) return launch_contract_t<2>(plan, item0, nitems, dbuf, values, st);

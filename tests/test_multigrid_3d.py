@@ -154,6 +154,7 @@ def test_cuda_backend_patch_tables_host_logic(ngs):
     cache = {}
     be.space_data = lambda fes: cache.setdefault(id(fes), {})
     be._up = lambda a, dtype=None: np.asarray(a)
+    be.zeros = lambda n: np.zeros(int(n))
     m = ngs.Mesh(structured_2d([6, 6], scale=(np.pi, np.pi)))
     fes = ngs.FESpace([ngs.HDiv(m, order=3, dirichlet='top|bottom|left|right', dgjumps=True),
                        ngs.L2(m, order=2, dgjumps=True)], dgjumps=True)
@@ -180,6 +181,7 @@ def test_cuda_backend_patch_tables_fp32_stride(ngs, monkeypatch):
     from opencmp_b200.mesh import structured_3d
     be = CudaBackend.__new__(CudaBackend)
     be._up = lambda a, dtype=None: np.asarray(a)
+    be.zeros = lambda n: np.zeros(int(n))
     m3 = ngs.Mesh(structured_3d([4, 4, 4]))
     f3 = ngs.FESpace([ngs.VectorH1(m3, order=2, dirichlet='back|left|front|right|bottom|top'), ngs.H1(m3, order=1)])
     cache = {}

@@ -22,6 +22,9 @@ def _dry_cuda_backend():
     be.device = torch.device('cpu')
     be._mesh_cache, be._space_cache = {}, {}
     be._plan_cache = weakref.WeakKeyDictionary()
+    from test_gpu_paths_dry import _NullLib
+    be.lib = _NullLib()                      # pattern_data marks component runs through the C ABI (a no-op here)
+    be._stream = lambda: None
     return be
 
 
