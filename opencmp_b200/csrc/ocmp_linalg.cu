@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <unordered_map>
 #include <vector>
 #include "../../include/opencmp_b200.h"
 #include "ocmp_common.cuh"
@@ -297,14 +298,33 @@ __global__ void __launch_bounds__(256) k_to_f32(long long n, const double* __res
         dst[i] = (float)src[i];
 }
 
+// Lanes per row from the mean row length (16 for the 100+ non-zeros per row of the high-order / DG systems, 8 or 4
+// for low-order H1 matrices and the multigrid transfer operators: with 16 lanes a 12-entry row of Poisson P2 left
+// half the lanes idle and the product ran at 1.4 TB/s). The row count of a pattern is read back once and remembered.
+static int spmv_lanes(const int* rowptr, int nrows_total) {
+    static std::unordered_map<const int*, int> cache;
+    auto it = cache.find(rowptr);
+    if (it == cache.end()) {
+        int nnz = 0;
+        if (cudaMemcpy(&nnz, rowptr + nrows_total, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) nnz = 0;
+        const double mean = nrows_total > 0 ? (double)nnz / nrows_total : 0.0;
+        const int lanes = mean >= 40.0 ? 16 : mean >= 14.0 ? 8 : 4;
+        if (cache.size() > 4096) cache.clear();
+        it = cache.emplace(rowptr, lanes).first;
+    }
+    return it->second;
+}
+
 // one launch: category `cat`, values from `vals32` when given, else `vals`
 static int spmv_ep(int cat, int ep, int nrows, const int* rowptr, const int* colidx, const double* vals,
                    const float* vals32, const double* x, double* y, const double* b, const double* m,
                    const double* m2, cudaStream_t st, const int* rows = nullptr,
-                   SpmvRuns runs = SpmvRuns{nullptr, 0, 0, 0}) {
+                   SpmvRuns runs = SpmvRuns{nullptr, 0, 0, 0}, int nrows_total = -1) {
     if (nrows <= 0) return 0;
     const int threads = 256;
-    const long long want = ((long long)nrows * 16 + threads - 1) / threads;
+    // a row list (owned rows) does not say where rowptr ends: the callers that pass one also pass the full row count
+    const int lanes = (runs.runlen && runs.grouped > 0) ? 16 : spmv_lanes(rowptr, nrows_total >= 0 ? nrows_total : nrows);
+    const long long want = ((long long)nrows * lanes + threads - 1) / threads;
     const long long cap = (long long)ocmp_sm_count() * 64;
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     ProfScope ps(cat, st);
@@ -328,8 +348,15 @@ static int spmv_ep(int cat, int ep, int nrows, const int* rowptr, const int* col
 #undef SPMV_VEC
         return ocmp_check("ocmp_spmv (grouped)");
     }
-#define SPMV_GO(VT, V, EP) \
-    k_spmv<16, VT, EP><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, V, x, y, b, m, m2, rows, runs)
+#define SPMV_GO(VT, V, EP)                                                                                        \
+    do {                                                                                                          \
+        if (lanes == 16)                                                                                          \
+            k_spmv<16, VT, EP><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, V, x, y, b, m, m2, rows, runs); \
+        else if (lanes == 8)                                                                                      \
+            k_spmv<8, VT, EP><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, V, x, y, b, m, m2, rows, runs);  \
+        else                                                                                                      \
+            k_spmv<4, VT, EP><<<blocks, threads, 0, st>>>(nrows, rowptr, colidx, V, x, y, b, m, m2, rows, runs);  \
+    } while (0)
     if (vals32) {
         if (ep == EP_PLAIN) SPMV_GO(float, vals32, EP_PLAIN);
         else if (ep == EP_RESID) SPMV_GO(float, vals32, EP_RESID);
@@ -811,7 +838,7 @@ struct Ctx {
             if (masked && s->freemask) had(st, n, nullptr, s->freemask, y, y, 1.0, 0);
         } else {
             spmv_ep(PROF_SPMV, masked && s->freemask ? EP_MASK : EP_PLAIN, active_rows(s), s->rowptr, s->colidx,
-                    s->vals, nullptr, x, y, nullptr, s->freemask, nullptr, st, row_list(s), runs_of(s));
+                    s->vals, nullptr, x, y, nullptr, s->freemask, nullptr, st, row_list(s), runs_of(s), s->nrows);
         }
         if (s->halo_fwd) ocmp_halo_run(s->halo_fwd - 1, y, 0, st);
     }
@@ -823,7 +850,7 @@ struct Ctx {
             k_resid<<<grid_for(n), 256, 0, st>>>(n, b, s->freemask, r);
         } else {
             spmv_ep(PROF_SPMV, EP_RESID, active_rows(s), s->rowptr, s->colidx, s->vals, nullptr, x, r, b, s->freemask,
-                    nullptr, st, row_list(s), runs_of(s));
+                    nullptr, st, row_list(s), runs_of(s), s->nrows);
             if (s->halo_fwd) ocmp_halo_run(s->halo_fwd - 1, r, 0, st);
         }
     }
@@ -868,7 +895,7 @@ struct Ctx {
     static void level_residual(const ocmp_system* sy, const double* b, const double* x, double* r, const double* m2,
                                bool refresh, cudaStream_t st) {
         spmv_ep(PROF_SPMV_MG, EP_RESID, active_rows(sy), sy->rowptr, sy->colidx, sy->vals, sy->vals32, x, r, b,
-                sy->freemask, m2, st, row_list(sy), runs_of(sy));
+                sy->freemask, m2, st, row_list(sy), runs_of(sy), sy->nrows);
         if (refresh && sy->halo_fwd) ocmp_halo_run(sy->halo_fwd - 1, r, 0, st);
     }
     // V-cycle on level l: x = MG(b); b is masked on entry, x is masked on exit. Launches per level and cycle with
