@@ -633,11 +633,38 @@ def Integrate(cf, mesh, VOL_or_BND=None, order: int = 5, definedon=None, **kw):
         return get_backend().integrate(lower_form(_scalar_space(mesh), cf, 0, intorder=order))
     cf = CoefficientFunction._lift(cf)
     fes = _scalar_space(mesh)
-    if cf.arr.size == 1:
-        prog = lower_form(fes, cf * dx(definedon=definedon), 0, intorder=order)
-        return get_backend().integrate(prog)
-    return tuple(get_backend().integrate(lower_form(fes, cf[i] * dx(definedon=definedon), 0, intorder=order))
-                 for i in range(cf.arr.size))
+    ids = None if definedon is None else (definedon.kind, tuple(definedon.ids))
+    out = tuple(get_backend().integrate(_integrate_program(fes, cf.arr.reshape(-1)[i], ids, definedon, order))
+                for i in range(cf.arr.size))
+    return out[0] if cf.arr.size == 1 else out
+
+
+_integrate_cache: dict = {}
+
+
+def _integrate_program(fes, entry, ids, definedon, order):
+    """Lowered program of ``Integrate(entry, mesh, order, definedon)``, cached on the STRUCTURE of the integrand: the
+    coefficient DAG is hash-consed (ir.Coef), so the norms a solver loop evaluates every Picard iteration
+    (reference models/ins.py:345-352 rebuilds ``InnerProduct(u - w, u - w)`` each time) map to the same nodes and reuse
+    the program, its launch plans and device tables instead of re-lowering and re-uploading them."""
+    terms = getattr(entry, 't', None)
+    if not isinstance(terms, dict):
+        return lower_form(fes, CoefficientFunction(_arr=_scalar_arr(entry)) * dx(definedon=definedon), 0, intorder=order)
+    key = (id(fes), order, ids, tuple((k, id(v)) for k, v in terms.items()))
+    hit = _integrate_cache.get(key)
+    if hit is not None and hit[1] is fes:
+        return hit[0]
+    prog = lower_form(fes, CoefficientFunction(_arr=_scalar_arr(entry)) * dx(definedon=definedon), 0, intorder=order)
+    if len(_integrate_cache) >= 64:
+        _integrate_cache.pop(next(iter(_integrate_cache)))
+    _integrate_cache[key] = (prog, fes, entry)            # `entry` keeps the hash-consed nodes (and their ids) alive
+    return prog
+
+
+def _scalar_arr(entry):
+    arr = np.empty((), dtype=object)
+    arr[()] = entry
+    return arr
 
 
 def _scalar_space(mesh):

@@ -344,9 +344,13 @@ class INSSphereDIM3D:
     _integrate = INSTaylorGreen._integrate
 
     def apply_dirichlet_bcs(self):
-        """base_model.py:321-341 — homogeneous data on the box faces"""
-        self.gfu.components[0].Set(ngs.CoefficientFunction((0.0, 0.0, 0.0)),
-                                   definedon=self.mesh.Boundaries(self.dirichlet))
+        """base_model.py:321-341 — homogeneous data on the box faces. The coefficient function is the SAME object on
+        every call, like the entries of the reference's BC dictionary: the lowered projection (program, launch plans,
+        contributor lists) is cached on it — a fresh object per call cost 72 ms per projection at 48^3."""
+        if getattr(self, '_g_box', None) is None:
+            self._g_box = ngs.CoefficientFunction((0.0, 0.0, 0.0))
+            self._box_region = self.mesh.Boundaries(self.dirichlet)
+        self.gfu.components[0].Set(self._g_box, definedon=self._box_region)
 
     def linear_solve(self):
         """base_model.py:886-947, linear_solver = GMRes"""
