@@ -176,7 +176,7 @@ def test_cuda_backend_patch_tables_host_logic(ngs):
 
 def test_cuda_backend_patch_tables_fp32_stride(ngs, monkeypatch):
     """OCMP_PATCH_FP32=1 (patch inverses stored in FP32): the patch stride is padded to a multiple of 4 so that every
-    stored column starts 16-byte aligned for the float4 loads of k_patch_apply_f32; the DOF content is unchanged."""
+    stored column starts 16-byte aligned for the bulk copies of k_patch_apply_stream<float>; the DOF content is unchanged."""
     from opencmp_b200.backend import CudaBackend
     from opencmp_b200.mesh import structured_3d
     be = CudaBackend.__new__(CudaBackend)

@@ -1,5 +1,5 @@
 """GPU cases of code paths whose KERNELS have never run on a B200 (written after round 1's GPU budget was spent): the
-reduced-precision storage of the multigrid data (k_patch_invert<T, float / bf16>, k_patch_apply_f32 / _bf16,
+reduced-precision storage of the multigrid data (k_patch_invert<T, float / bf16>, k_patch_apply_stream<float / bf16>,
 k_spmv_f32) and the device-resident mixers (ocmp_mdot / ocmp_maxpy from Python). Collected after everything else, so
 that with ``-x`` a surprise here cannot hide the other results. Their host paths run against the null device in
 tests/test_gpu_paths_dry.py, their index logic is emulated in tests/test_patch_kernel_emulation.py."""
@@ -35,7 +35,7 @@ def _stokes_direct(DG):
 @pytest.mark.parametrize('DG', [False, True])
 def test_fp32_stored_patch_inverses_keep_the_solution(DG, monkeypatch):
     """GMRES + vertex-patch additive Schwarz with the inverses stored in FP32 (k_patch_invert<T, float>,
-    k_patch_apply_f32) vs sparse LU in the oracle: the preconditioner's storage precision must not show in the FP64
+    k_patch_apply_stream<float>) vs sparse LU in the oracle: the preconditioner's storage precision must not show in the FP64
     solution (1e-9 relative, like every solution field)."""
     ref = _with('oracle', _stokes_direct(DG))
     monkeypatch.setenv('OCMP_PATCH_FP32', '1')
@@ -65,7 +65,7 @@ def test_fp32_stored_multigrid_data_keep_iteration_counts(monkeypatch, storage):
 @pytest.mark.parametrize('storage', ['fp32', 'bf16'])
 def test_fp32_stored_multigrid_data_ins_2d(monkeypatch, storage):
     """2-D INS Taylor-Green step (HDiv-DG order 3, closed vertex patches of 132 DOFs: the two-chunk paths of
-    k_patch_apply_f32 / k_patch_apply_bf16): reduced-precision STORAGE of the preconditioner data leaves the iteration
+    k_patch_apply_stream<float / bf16>): reduced-precision STORAGE of the preconditioner data leaves the iteration
     counts (bf16: within 3) and the FP64 solution unchanged."""
     import opencmp_b200.ngs as ngs
     from opencmp_b200.workloads import INSTaylorGreen
