@@ -263,6 +263,27 @@ int ocmp_band_solve(int n, int kl, int ku, int ubw, const double* ab, const int*
 int ocmp_band_gather(int nrows, const int* perm, const double* r, double* b, void* stream);
 int ocmp_band_scatter(int nrows, const int* perm, const double* x, double* out, int accumulate, void* stream);
 
+/* ---- diffuse-interface phase-field generation: the voxel pipeline of the reference's pre-processing,
+ *      reference opencmp/diffuse_interface/interface.py:31-57 (get_binary_2d; ray tracing mesh_helpers.py:268-302) and
+ *      :137-180 (get_phi: erosion -> border -> exact Euclidean distance transform -> erf profile). Arrays are C-ordered
+ *      (n0, n1[, n2]) like the reference's NumPy arrays; n_k = N_k + 1 grid nodes. */
+int ocmp_dim_raytrace_2d(int n0, int n1, double scale0, double scale1, double offset0, double offset1, int N0, int N1,
+                         int npoly, const double* poly_xy, double* binary, void* stream);
+/* fg[v] = 0 on the border voxels of the shape (binary - 3^d erosion), 1 elsewhere: the argument of edt.edt() */
+int ocmp_dim_border(int dim, int n0, int n1, int n2, const double* binary, unsigned char* fg, void* stream);
+/* exact Euclidean distance (in voxels, FP32 like the edt package) of every voxel with fg != 0 to the nearest voxel with
+ * fg == 0; work_a / work_b: n0*n1*n2 int64 each */
+int ocmp_dim_edt(int dim, int n0, int n1, int n2, const unsigned char* fg, long long* work_a, long long* work_b,
+                 float* dist, void* stream);
+/* Rigid-body motion of a node field on the structured grid (reference opencmp/helpers/ngsolve_.py:212-296, evaluated
+ * every time step for moving diffuse interfaces): out[node] = orig(inv_rotation * x_node), multilinear interpolation,
+ * 1 where the pre-image leaves the box. scale / offset / inv_rotation (dim x dim, row-major) are host arrays. */
+int ocmp_dim_rigid_motion(int dim, int n0, int n1, int n2, const double* scale_host, const double* offset_host,
+                          const double* inv_rotation_host, const double* orig, double* out, void* stream);
+/* phi = (erf(dist * h / lmbda) * (2 binary - 1) + 1) / 2 */
+int ocmp_dim_phi(long long n, const float* dist, const double* binary, double h, double lmbda, double* phi,
+                 void* stream);
+
 /* ---- instrumentation: per-category device time from CUDA events recorded around every launch on its own stream.
  * categories: 0 spmv, 1 asm_apply, 2 coefficient eval, 3 matrix contraction, 4 vector contraction, 5 multi-dot,
  * 6 multi-axpy, 7 other vector kernels, 8 preconditioner setup, 9 SpMVs inside the multigrid cycle, 10 halo exchange */

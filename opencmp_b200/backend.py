@@ -116,6 +116,13 @@ def load_library() -> C.CDLL:
     lib.ocmp_band_solve.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, P]
     lib.ocmp_band_gather.argtypes = [C.c_int, P, P, P, P]
     lib.ocmp_band_scatter.argtypes = [C.c_int, P, P, P, C.c_int, P]
+    lib.ocmp_dim_raytrace_2d.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                                         C.c_int, C.c_int, P, P, P]
+    lib.ocmp_dim_border.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, P, P, P]
+    lib.ocmp_dim_edt.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, P, P]
+    lib.ocmp_dim_phi.argtypes = [C.c_longlong, P, P, C.c_double, C.c_double, P, P]
+    lib.ocmp_dim_rigid_motion.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double), C.POINTER(C.c_double), P, P, P]
     lib.ocmp_profile_enable.argtypes = [C.c_int]
     lib.ocmp_profile_enable.restype = None
     lib.ocmp_profile_reset.restype = None
@@ -145,7 +152,8 @@ EXPORTED = ['ocmp_mdot', 'ocmp_maxpy', 'ocmp_krylov_history', 'ocmp_comm_unique_
             'ocmp_asm_setup_f32', 'ocmp_asm_apply_f32', 'ocmp_asm_setup_bf16', 'ocmp_asm_apply_bf16', 'ocmp_to_f32',
             'ocmp_krylov', 'ocmp_krylov_work_len', 'ocmp_last_error', 'ocmp_version',
             'ocmp_band_len', 'ocmp_band_fill', 'ocmp_band_factor', 'ocmp_band_solve', 'ocmp_band_gather',
-            'ocmp_band_scatter', 'ocmp_spmv_runs', 'ocmp_spmv_compressed', 'ocmp_gather_add']
+            'ocmp_band_scatter', 'ocmp_spmv_runs', 'ocmp_spmv_compressed', 'ocmp_gather_add',
+            'ocmp_dim_raytrace_2d', 'ocmp_dim_border', 'ocmp_dim_edt', 'ocmp_dim_phi', 'ocmp_dim_rigid_motion']
 
 
 # storage type of the smoother's patch inverses (ocmp_system.inv_storage): arithmetic is FP64 in every case

@@ -70,3 +70,26 @@ def install_as_ngsolve(force: bool = False, device_mixing: bool = False) -> None
                 sys.modules['pyparsing'] = _pp
             except ImportError:
                 pass
+
+
+def use_device_dim() -> None:
+    """Route the voxel pipeline of the reference's diffuse-interface pre-processing to the device: after
+    ``import opencmp``, ``opencmp.diffuse_interface.interface.get_binary_2d`` and ``.get_phi`` (interface.py:31-57,
+    :137-180) are replaced by the functions of the same name and signature in ``opencmp_b200.dimgen`` (ray tracing,
+    erosion, exact distance transform and erf profile in csrc/ocmp_dim.cu). Needs the CUDA backend to be active when
+    they are called. ``edt.edt`` alone is routed to the device already by ``install_as_ngsolve()`` whenever the CUDA
+    backend is active."""
+    import importlib
+    from . import dimgen
+    interface = importlib.import_module('opencmp.diffuse_interface.interface')
+    interface.get_binary_2d = dimgen.get_binary_2d
+    interface.get_phi = dimgen.get_phi
+    # the per-time-step node loop of moving interfaces (helpers/ngsolve_.py:212-296) -> one launch where it applies
+    helpers = importlib.import_module('opencmp.helpers.ngsolve_')
+    original = helpers.gridfunction_rigid_body_motion
+    if not getattr(original, '__b200__', False):
+        def moved(t, orig_gfu, gfu, inv_R, mesh, N, scale, offset):
+            return dimgen.gridfunction_rigid_body_motion(t, orig_gfu, gfu, inv_R, mesh, N, scale, offset,
+                                                         fallback=original)
+        moved.__b200__ = True
+        helpers.gridfunction_rigid_body_motion = moved

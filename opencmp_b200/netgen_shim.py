@@ -163,7 +163,13 @@ def ReadGmsh(filename: str):
 
 # ---- edt ------------------------------------------------------------------------------------------------------------
 def edt(data, anisotropy=None, black_border=False, **_):
-    """Exact Euclidean distance transform: distance of each non-zero voxel to the nearest zero voxel."""
+    """Exact Euclidean distance transform: distance of each non-zero voxel to the nearest zero voxel. With the CUDA
+    backend active the transform runs on the device (dimgen.edt, csrc/ocmp_dim.cu); CPU runs (oracle backend) use
+    SciPy."""
+    from . import ngs as _ngs
+    if getattr(_ngs._backend, 'name', '') == 'cuda' and anisotropy is None and not black_border:
+        from . import dimgen
+        return dimgen.edt(data)
     import scipy.ndimage as ndi
     a = np.asarray(data) != 0
     if black_border:

@@ -17,7 +17,7 @@ def pytest_configure(config):
 # failure cannot hide the assembly-parity verdict.
 _GPU_ORDER = ['test_gpu_parity.py::test_assembly', 'test_gpu_parity.py::test_integrate', 'test_golden_programs',
               'test_gpu_deterministic', 'test_zz_gpu_late_additions', 'test_zzz_gpu_unmeasured_kernels',
-              'test_zzzz_gpu_matrix_free', 'test_gpu_direct', 'test_gpu_krylov', 'test_gpu_parity.py', 'test_golden_fixtures']
+              'test_zzzz_gpu_matrix_free', 'test_gpu_dimgen', 'test_gpu_direct', 'test_gpu_krylov', 'test_gpu_parity.py', 'test_golden_fixtures']
 
 
 def pytest_collection_modifyitems(config, items):

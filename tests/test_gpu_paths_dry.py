@@ -149,7 +149,7 @@ def _invoke(fn, params, monkeypatch, ngs_fixture):
 
 @pytest.mark.parametrize('modname', ['test_gpu_parity', 'test_golden_programs', 'test_golden_fixtures',
                                      'test_zz_gpu_late_additions', 'test_zzz_gpu_unmeasured_kernels',
-                                     'test_zzzz_gpu_matrix_free', 'test_gpu_direct', 'test_gpu_krylov', 'test_gpu_deterministic'])
+                                     'test_zzzz_gpu_matrix_free', 'test_gpu_direct', 'test_gpu_krylov', 'test_gpu_deterministic', 'test_gpu_dimgen'])
 def test_gpu_test_bodies_execute_on_a_null_device(dry, monkeypatch, modname):
     import importlib
     import opencmp_b200.ngs as ngs

@@ -314,3 +314,36 @@ def test_workload_forms_equal_reference_insdim(ref_tree):
     line = [ln for ln in r.stdout.splitlines() if ln.startswith('RESULT')][0].split()
     assert float(line[3]) < 1e-12 and float(line[4]) < 1e-12, line
     assert float(line[5]) > 1e-3          # the Oseen wind is not trivially zero
+
+
+def test_use_device_dim_patches_the_reference_pre_processing():
+    """compat.use_device_dim(): the reference's own get_binary_2d / get_phi / gridfunction_rigid_body_motion are
+    replaced by the device versions of the same name and signature (subprocess: the patch is process-wide)."""
+    code = textwrap.dedent('''
+        import sys, inspect
+        sys.path.insert(0, {root!r}); sys.path.insert(0, {ref!r})
+        import opencmp_b200.compat as c
+        c.install_as_ngsolve()
+        import opencmp
+        from opencmp.diffuse_interface import interface
+        from opencmp.helpers import ngsolve_ as helpers
+        before = (inspect.signature(interface.get_phi), inspect.signature(interface.get_binary_2d),
+                  inspect.signature(helpers.gridfunction_rigid_body_motion))
+        c.use_device_dim()
+        c.use_device_dim()                                  # idempotent
+        from opencmp_b200 import dimgen
+        assert interface.get_phi is dimgen.get_phi and interface.get_binary_2d is dimgen.get_binary_2d
+        after = (inspect.signature(interface.get_phi), inspect.signature(interface.get_binary_2d),
+                 inspect.signature(helpers.gridfunction_rigid_body_motion))
+        for b, a in zip(before, after):
+            assert list(b.parameters) == list(a.parameters), (b, a)
+        try:
+            interface.get_phi(None, 0.1, [4, 4], [1.0, 1.0], [0.0, 0.0], 2)
+        except RuntimeError as exc:
+            assert 'CUDA backend' in str(exc)               # no CPU fallback behind the device entry points
+        else:
+            raise AssertionError('dimgen must refuse to run without the CUDA backend')
+        print('ok')
+    ''').format(root=ROOT, ref=REF)
+    p = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip().endswith('ok'), p.stderr[-2000:]
