@@ -43,6 +43,8 @@ PICARD = dict(nonlinear_max_iterations=2, nonlinear_tolerance=(0.0, 0.0))
 # wall the flow relaxes to rigid rotation within a few steps, the previous solution becomes an almost exact initial
 # guess and GMRES can no longer reduce the residual by 1e-12 relative to the initial one (workloads.INSSphereDIM3D)
 WALL = dict(wall_period=0.1, wall_amp=0.5)
+# dram (read + write) bytes / algorithmic bytes of k_patch_apply_stream, fine-level launch, ncu --set full on a B200
+PATCH_TRAFFIC_RATIO = {'fp64': 1.016, 'fp32': 1.03, 'bf16': 1.05}
 
 
 def parse(argv=None):
@@ -371,12 +373,26 @@ def rooflines(be, w, prof, ms_prof, picard, peak, peak_src, storage, fp64_peak):
     r_patch = {'kernel': kname + '; additive-Schwarz smoother, all multigrid levels: total bytes / total time)',
                'bound': 'hbm', 'achieved': ap_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': ap_gbs / peak,
                'peak_source': peak_src, 'bytes_per_launch': ap_bytes, 'launches': ap['count'], 'avg_launch_ms': ap_ms,
-               'share_of_step': share['asm_apply'], 'traffic': None,
-               'traffic_note': 'dram bytes per launch of the ncu --set full capture: profiles/r2_ncu_kernels.md'}
+               'share_of_step': share['asm_apply'],
+               # dram__bytes_read + write of the fine-level launch in the ncu --set full captures, relative to the
+               # algorithmic bytes (profiles/r2_ncu_kernels.md): FP64 2.368 / 2.330 GB, FP32 see the same file
+               'traffic': PATCH_TRAFFIC_RATIO.get(storage, 1.0) * ap_bytes if ap['count'] else None,
+               'traffic_note': 'per launch: algorithmic bytes x the dram / algorithmic ratio of the ncu --set full capture '
+                               'of the fine-level launch ({:.3f}; profiles/r2_ncu_kernels.md)'
+                               .format(PATCH_TRAFFIC_RATIO.get(storage, 1.0))}
     r_spmv = {'kernel': 'k_spmv<16, double> fine level (CSR FP64 values + int32 columns; Krylov operator)',
               'bound': 'hbm', 'achieved': spmv_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs / peak,
               'frac_of_8000_nominal': spmv_gbs / 8000.0, 'peak_source': peak_src, 'bytes_per_launch': spmv_bytes,
               'launches': sp['count'], 'avg_launch_ms': spmv_ms, 'share_of_step': share['spmv'], 'traffic': None}
+    mg = prof['spmv_multigrid']
+    mg_gbs = mg['bytes'] / (mg['ms'] * 1e-3) / 1e9 if mg['ms'] > 0 else 0.0
+    r_mg = {'kernel': 'k_spmv / k_spmv_vec inside the multigrid cycle (level residuals with fused epilogue, restriction, '
+                      'prolongation; FP32-stored level matrices when precond_storage != fp64): total bytes / total time',
+            'bound': 'hbm', 'achieved': mg_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': mg_gbs / peak,
+            'peak_source': peak_src, 'bytes_per_launch': mg['bytes'] / max(1, mg['count']), 'launches': mg['count'],
+            'avg_launch_ms': mg['ms'] / max(1, mg['count']), 'share_of_step': share['spmv_multigrid'], 'traffic': None,
+            'bytes_note': 'CSR byte count nnz (value + 4) + 20 rows per product; the node-grouped kernel reads the '
+                          'column indices once per nc x nc values, so its DRAM traffic is lower than this count'}
     asm_ms = prof['coef']['ms'] + prof['contract_matrix']['ms'] + prof['contract_vector']['ms']
     n_asm = max(1, picard)
     asm_mnnz = nnz / (asm_ms / n_asm * 1e-3) / 1e6 if asm_ms > 0 else 0.0
@@ -390,7 +406,7 @@ def rooflines(be, w, prof, ms_prof, picard, peak, peak_src, storage, fp64_peak):
              'flops_per_assembly': flops, 'ms_per_assembly': cm_ms, 'assembly_mnnz_per_s': asm_mnnz,
              'share_of_step': round(share['contract_matrix'] + share['coef'] + share['contract_vector'], 4),
              'note': 'ms_per_assembly also holds the re-discretised coarse multigrid levels when they are rebuilt'}
-    return share, r_patch, r_spmv, r_asm, asm_mnnz, spmv_gbs
+    return share, r_patch, r_spmv, r_asm, asm_mnnz, spmv_gbs, r_mg
 
 
 def measure_workload(args, torch, be, w, dins, steps, warmup, profile_steps, barrier, peaks, fp64_peak, sampler_rank):
@@ -453,10 +469,11 @@ def run_b200(args):
         return
     storage = patch_storage()
     pr = m['prof']
-    share, r_patch, r_spmv, r_asm, asm_mnnz, spmv_gbs = rooflines(be, w, pr['prof'], pr['ms'], pr['picard'], peak,
-                                                                  peak_src, storage, fp64_peak)
+    share, r_patch, r_spmv, r_asm, asm_mnnz, spmv_gbs, r_mg = rooflines(be, w, pr['prof'], pr['ms'], pr['picard'], peak,
+                                                                        peak_src, storage, fp64_peak)
     # the dominant kernel of the step leads the line
-    by_share = sorted(((share['asm_apply'], r_patch), (share['spmv'], r_spmv)), key=lambda x: -x[0])
+    by_share = sorted(((share['asm_apply'], r_patch), (share['spmv'], r_spmv), (share['spmv_multigrid'], r_mg)),
+                      key=lambda x: -x[0])
     sec = ms / 1e3 / args.steps
     line = {
         'metric': 'INS s/timestep', 'value': sec, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
@@ -483,6 +500,7 @@ def run_b200(args):
                                                                                           args.profile_steps),
         'assembly_mnnz_per_s': asm_mnnz, 'spmv_gbs': spmv_gbs,
         'roofline': by_share[0][1], 'roofline_patch_apply': r_patch, 'roofline_spmv': r_spmv,
+        'roofline_spmv_multigrid': r_mg,
         'roofline_assembly': r_asm, 'fp64_peak_tflops': fp64_peak,
         'kernel_time_share': share, 'profiled_ms_per_step': pr['ms'] / max(1, args.profile_steps),
         'e2e': {'value': ms_e2e / 1e3 / args.steps, 'unit': 's', 'h2d_bytes_per_step': m['e2e']['h2d'],
@@ -525,8 +543,8 @@ def run_b200(args):
                 w2, _ = make_gpu_workload('ins2d', a2.N, a2.order)
                 m2 = measure_workload(a2, torch, be, w2, None, 3, 2, 2, barrier, peaks, fp64_peak, None)
                 p2 = m2['prof']
-                sh2, rp2, rs2, ra2, mn2, sg2 = rooflines(be, w2, p2['prof'], p2['ms'], p2['picard'], peak, peak_src,
-                                                         storage, fp64_peak)
+                sh2, rp2, rs2, ra2, mn2, sg2, rm2 = rooflines(be, w2, p2['prof'], p2['ms'], p2['picard'], peak, peak_src,
+                                                              storage, fp64_peak)
                 line['ins2d'] = {'config': workload_config(a2, 'gpu', gpus=1), 'value': m2['clean']['ms'] / 3e3,
                                  'unit': 's', 'steps': 3, 'warmup': 2,
                                  'e2e': {'value': m2['e2e']['ms'] / 3e3, 'unit': 's',
@@ -536,7 +554,8 @@ def run_b200(args):
                                              'picard_per_step': m2['clean']['picard'] / 3,
                                              'l2_err_u': m2['errs'][0], 'l2_err_p': m2['errs'][1]},
                                  'gpu_launches': m2['clean']['launches'], 'assembly_mnnz_per_s': mn2, 'spmv_gbs': sg2,
-                                 'roofline_patch_apply': rp2, 'roofline_spmv': rs2, 'roofline_assembly': ra2,
+                                 'roofline_patch_apply': rp2, 'roofline_spmv': rs2, 'roofline_spmv_multigrid': rm2,
+                                 'roofline_assembly': ra2,
                                  'kernel_time_share': sh2}
             except Exception as exc:                                # pragma: no cover
                 line['ins2d'] = {'error': repr(exc)}

@@ -301,18 +301,20 @@ __global__ void __launch_bounds__(256) k_to_f32(long long n, const double* __res
 // Lanes per row from the mean row length (16 for the 100+ non-zeros per row of the high-order / DG systems, 8 or 4
 // for low-order H1 matrices and the multigrid transfer operators: with 16 lanes a 12-entry row of Poisson P2 left
 // half the lanes idle and the product ran at 1.4 TB/s). The row count of a pattern is read back once and remembered.
-static int spmv_lanes(const int* rowptr, int nrows_total) {
+static int spmv_nnz(const int* rowptr, int nrows_total) {
     static std::unordered_map<const int*, int> cache;
     auto it = cache.find(rowptr);
     if (it == cache.end()) {
         int nnz = 0;
         if (cudaMemcpy(&nnz, rowptr + nrows_total, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) nnz = 0;
-        const double mean = nrows_total > 0 ? (double)nnz / nrows_total : 0.0;
-        const int lanes = mean >= 40.0 ? 16 : mean >= 14.0 ? 8 : 4;
         if (cache.size() > 4096) cache.clear();
-        it = cache.emplace(rowptr, lanes).first;
+        it = cache.emplace(rowptr, nnz).first;
     }
     return it->second;
+}
+static int spmv_lanes(const int* rowptr, int nrows_total) {
+    const double mean = nrows_total > 0 ? (double)spmv_nnz(rowptr, nrows_total) / nrows_total : 0.0;
+    return mean >= 40.0 ? 16 : mean >= 14.0 ? 8 : 4;
 }
 
 // one launch: category `cat`, values from `vals32` when given, else `vals`
@@ -327,6 +329,11 @@ static int spmv_ep(int cat, int ep, int nrows, const int* rowptr, const int* col
     const long long want = ((long long)nrows * lanes + threads - 1) / threads;
     const long long cap = (long long)ocmp_sm_count() * 64;
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
+    {   // algorithmic bytes of this product by the CSR count of SURVEY 8(d): nnz (value + 4) + rows (4 + 8) + cols 8
+        const int ntot = nrows_total >= 0 ? nrows_total : nrows;
+        const double nnz = (double)spmv_nnz(rowptr, ntot) * (ntot > 0 ? (double)nrows / ntot : 0.0);
+        ocmp_prof_bytes(cat, nnz * ((vals32 ? 4.0 : 8.0) + 4.0) + 20.0 * nrows);
+    }
     ProfScope ps(cat, st);
     if (runs.runlen && runs.grouped > 0) {
         // node-grouped product: listed rows (or all rows) = nc * ngroups component rows followed by single rows
