@@ -44,7 +44,8 @@ PICARD = dict(nonlinear_max_iterations=2, nonlinear_tolerance=(0.0, 0.0))
 # guess and GMRES can no longer reduce the residual by 1e-12 relative to the initial one (workloads.INSSphereDIM3D)
 WALL = dict(wall_period=0.1, wall_amp=0.5)
 # dram (read + write) bytes / algorithmic bytes of k_patch_apply_stream, fine-level launch, ncu --set full on a B200
-PATCH_TRAFFIC_RATIO = {'fp64': 1.016, 'fp32': 1.03, 'bf16': 1.05}
+# (profiles/r2_ncu_kernels.md): FP64 2.368 / 2.330 GB, FP32 1.207 / 1.162 GB; bfloat16 was not captured (estimate)
+PATCH_TRAFFIC_RATIO = {'fp64': 1.016, 'fp32': 1.038, 'bf16': 1.05}
 
 
 def parse(argv=None):

@@ -31,11 +31,6 @@ template <typename T> __device__ __forceinline__ double ocmp_load(const T* p) { 
 template <> __device__ __forceinline__ double ocmp_load<__nv_bfloat16>(const __nv_bfloat16* p) {
     return (double)__bfloat162float(__ldg(p));
 }
-// the same from shared memory (no read-only path)
-template <typename T> __device__ __forceinline__ double ocmp_smem_load(const T* p) { return (double)*p; }
-template <> __device__ __forceinline__ double ocmp_smem_load<__nv_bfloat16>(const __nv_bfloat16* p) {
-    return (double)__bfloat162float(*p);
-}
 // optional per-category device timing (CUDA events on the launching stream) and launch counting
 enum { PROF_SPMV = 0, PROF_ASM_APPLY, PROF_COEF, PROF_CONTRACT, PROF_LIN, PROF_MDOT, PROF_MAXPY, PROF_VEC,
        PROF_SETUP, PROF_SPMV_MG, PROF_HALO, PROF_NCAT };

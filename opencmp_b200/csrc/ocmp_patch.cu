@@ -216,11 +216,15 @@ int ocmp_patch_invert_registers_bf16(int npatch, int bs, const int* pd, const in
 // kernel is a pure HBM stream and is built like one: persistent CTAs, each walking its patches as ONE sequence of
 // chunks (a chunk = CC whole columns of the transposed-stored inverse = one contiguous byte range), copied into a
 // ring of NSTAGE shared-memory buffers by the bulk-copy engine (cp.async.bulk + mbarrier transaction counts, issued
-// by one thread), so the bytes in flight per SM are set by the ring, not by registers or occupancy. Thread i owns
-// row i of the current patch and accumulates over the columns of the chunk from shared memory (FP64 FMA; the stored
-// type may be FP64 / FP32 / bfloat16). The right-hand side of the NEXT patch is gathered into a register while the
-// current one streams. Results go to the patch-local output y (coalesced stores, no atomics); k_patch_gather then
-// sums, for every dof, the entries of its patches in a fixed order — the smoother is deterministic.
+// by one thread), so the bytes in flight per SM are set by the ring, not by registers or occupancy. A thread owns
+// VEC = 16 / sizeof(T) consecutive rows (one 128-bit shared-memory load per column: 2 FP64, 4 FP32 or 8 bfloat16
+// entries) and every VEC-th column of the chunk; the VEC column groups are summed through shared memory in a fixed
+// order when the patch ends. One load instruction per 16 bytes instead of one per entry is what keeps the narrow
+// storage types on the HBM roofline instead of the issue rate (FP32 with one row per thread: 0.77 of the peak).
+// Accumulation is FP64 FMA for every storage type. The right-hand side of the NEXT patch is gathered into a register
+// while the current one streams. Results go to the patch-local output y (coalesced stores, no atomics);
+// k_patch_gather then sums, for every dof, the entries of its patches in a fixed order — the smoother is
+// deterministic.
 namespace {
 constexpr int NSTAGE = 4;
 
@@ -251,21 +255,57 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 }
 }  // namespace
 
+// One 128-bit shared-memory load = VEC consecutive rows of one column, widened to FP64. The FP32 -> FP64 widening stays
+// on F2F (XU pipe, 60 % busy at this rate): doing it, or half of it, with integer instructions (re-biased exponent,
+// mantissa spread over two words) was measured slower (0.241 / 0.220 ms against 0.209 ms on the fine level).
+template <typename T> struct RowVec;
+template <> struct RowVec<double> {
+    static constexpr int N = 2;
+    static __device__ __forceinline__ void load(const unsigned char* p, double (&a)[2]) {
+        const double2 v = *reinterpret_cast<const double2*>(p);
+        a[0] = v.x; a[1] = v.y;
+    }
+};
+template <> struct RowVec<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const unsigned char* p, double (&a)[4]) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        a[0] = (double)v.x; a[1] = (double)v.y; a[2] = (double)v.z; a[3] = (double)v.w;
+    }
+};
+template <> struct RowVec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const unsigned char* p, double (&a)[8]) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {           // a bfloat16 is the upper half of the FP32 with the same value
+            a[2 * k] = (double)__uint_as_float(w[k] << 16);
+            a[2 * k + 1] = (double)__uint_as_float(w[k] & 0xffff0000u);
+        }
+    }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_patch_apply_stream(int npatch, int bs, int cc, int nchunk, int stage_bytes,
                                                             const int* __restrict__ pdofs, const T* __restrict__ inv,
                                                             const double* __restrict__ r, double* __restrict__ y) {
+    constexpr int VEC = RowVec<T>::N;
     extern __shared__ __align__(128) unsigned char smraw[];
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smraw);            // NSTAGE barriers
     double* rl = reinterpret_cast<double*>(smraw + 128);                                // bs doubles
     const int rl_bytes = ((bs * 8 + 127) / 128) * 128;
-    unsigned char* stages = smraw + 128 + rl_bytes;
+    double* part = reinterpret_cast<double*>(smraw + 128 + rl_bytes);                   // VEC x bs partial sums
+    unsigned char* stages = smraw + 128 + (1 + VEC) * rl_bytes;
     const int tid = threadIdx.x;
     if ((int)blockIdx.x >= npatch) return;
     const int mine = (npatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const long long total = (long long)mine * nchunk;
     const long long colbytes = (long long)bs * sizeof(T);
     const long long patch_elems = (long long)bs * bs;
+    const int nq = bs / VEC;                 // row groups; bs is a multiple of VEC (16-byte columns)
+    const int q = tid % nq, grp = tid / nq;  // this thread: rows VEC q .. VEC q + VEC - 1, columns grp, grp + VEC, ...
+    const bool worker = grp < VEC;
 
     auto issue = [&](long long g) {          // thread 0: start the copy of chunk g of this CTA's sequence
         const long long k = g / nchunk;
@@ -291,7 +331,10 @@ __global__ void __launch_bounds__(256) k_patch_apply_stream(int npatch, int bs, 
         rl[tid] = d >= 0 ? __ldg(r + d) : 0.0;
     }
     __syncthreads();
-    double acc = 0.0, rnext = 0.0;
+    double acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
+    double rnext = 0.0;
     int c = 0;
     for (long long g = 0; g < total; ++g) {
         const int s = (int)(g % NSTAGE);
@@ -302,28 +345,34 @@ __global__ void __launch_bounds__(256) k_patch_apply_stream(int npatch, int bs, 
         }
         mbar_wait(smem_u32(bars + s), (unsigned)((g / NSTAGE) & 1));
         const int cols = (c == nchunk - 1) ? bs - c * cc : cc;
-        if (tid < bs) {
-            const T* A = reinterpret_cast<const T*>(stages + (size_t)s * stage_bytes) + tid;
+        if (worker) {
+            const unsigned char* A = stages + (size_t)s * stage_bytes + (size_t)q * 16;
             const double* rr = rl + c * cc;
-            int j = 0;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            for (; j + 3 < cols; j += 4) {
-                a0 = fma(ocmp_smem_load(A + (size_t)j * bs), rr[j], a0);
-                a1 = fma(ocmp_smem_load(A + (size_t)(j + 1) * bs), rr[j + 1], a1);
-                a2 = fma(ocmp_smem_load(A + (size_t)(j + 2) * bs), rr[j + 2], a2);
-                a3 = fma(ocmp_smem_load(A + (size_t)(j + 3) * bs), rr[j + 3], a3);
+#pragma unroll 2
+            for (int j = grp; j < cols; j += VEC) {
+                double a[VEC];
+                RowVec<T>::load(A + (size_t)j * colbytes, a);
+                const double rj = rr[j];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] = fma(a[v], rj, acc[v]);
             }
-            for (; j < cols; ++j) a0 = fma(ocmp_smem_load(A + (size_t)j * bs), rr[j], a0);
-            acc += (a0 + a1) + (a2 + a3);
+            if (c == nchunk - 1) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) part[grp * bs + q * VEC + v] = acc[v];
+            }
         }
         __syncthreads();                      // stage s (and, on the last chunk, rl) may be overwritten now
         if (tid == 0 && g + NSTAGE < total) issue(g + NSTAGE);
         if (++c == nchunk) {
             if (tid < bs) {
-                y[p * bs + tid] = acc;
+                double sum = part[tid];
+#pragma unroll
+                for (int v = 1; v < VEC; ++v) sum += part[v * bs + tid];
+                y[p * bs + tid] = sum;
                 rl[tid] = rnext;
             }
-            acc = 0.0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
             c = 0;
             p += gridDim.x;
             __syncthreads();
@@ -354,14 +403,16 @@ static int patch_apply_stream(int npatch, int bs, const int* pd, const T* inv, c
     if (bs > 256) return ocmp_fail(-20, "patch apply: more than 256 dofs per patch");
     if ((bs * sizeof(T)) % 16) return ocmp_fail(-21, "patch apply: the patch stride must keep columns 16-byte aligned");
     const long long colbytes = (long long)bs * sizeof(T);
-    // chunk: whole columns, about 8 KB; at most 64 chunks per patch
+    // chunk: whole columns, about 8 KB. Measured on the fine level of the 128 x 128 Taylor-Hood problem (FP32 storage,
+    // ms per application): 4 KB 0.319, 6 KB 0.218, 8 KB 0.208, 12 KB 0.226, 16 KB 0.281, 24 KB 0.400 — smaller chunks
+    // pay the per-chunk barrier, larger ones leave too few CTAs per SM to cover the FP64 accumulation latency.
     int cc = (int)(8192 / colbytes);
     if (cc < 1) cc = 1;
     if (cc > bs) cc = bs;
     const int nchunk = (bs + cc - 1) / cc;
     const int stage_bytes = (int)(((cc * colbytes) + 127) / 128 * 128);
     const int rl_bytes = ((bs * 8 + 127) / 128) * 128;
-    const size_t smem = 128 + rl_bytes + (size_t)NSTAGE * stage_bytes;
+    const size_t smem = 128 + (size_t)(1 + RowVec<T>::N) * rl_bytes + (size_t)NSTAGE * stage_bytes;
     static size_t configured[3] = {0, 0, 0};
     const int slot = sizeof(T) == 8 ? 0 : sizeof(T) == 4 ? 1 : 2;
     if (smem > 48 * 1024 && smem > configured[slot]) {

@@ -1,6 +1,7 @@
 """Index-level emulation (NumPy) of the smoother application (csrc/ocmp_patch.cu): ``k_patch_apply_stream`` — persistent
-CTAs walking their patches as one sequence of column chunks through a ring of NSTAGE shared-memory stages, thread i
-owning row i — followed by ``k_patch_gather`` over the incidence list built by ``backend.patch_incidence``. Same chunk
+CTAs walking their patches as one sequence of column chunks through a ring of NSTAGE shared-memory stages, a thread
+owning VEC = 16 / sizeof(T) consecutive rows and every VEC-th column, the column groups summed in a fixed order when the
+patch ends — followed by ``k_patch_gather`` over the incidence list built by ``backend.patch_incidence``. Same chunk
 geometry (host-side sizing of ``patch_apply_stream``), same chunk -> (patch, first column, byte offset) arithmetic, same
 stage / parity schedule. The result must equal ``z[dofs] += A_p^-1 r[dofs]`` computed directly from the
 (transposed-stored, rounded) inverses; the arithmetic itself is checked on the GPU."""
@@ -37,6 +38,10 @@ def emulate_stream(npatch, bs, pdofs, inv_flat, r, storage, grid):
     """inv_flat: one flat array of npatch * bs * bs stored entries (A_p[j * bs + i] = (A_p^-1)_{ij})."""
     cc, nchunk, stage_bytes = chunk_geometry(bs, storage)
     es = ELEM[storage]
+    vec = 16 // es
+    assert bs % vec == 0
+    nq = bs // vec
+    nthreads = (bs + 31) // 32 * 32
     y = np.full(npatch * bs, np.nan)
     for block in range(min(grid, npatch)):
         mine = (npatch - block + grid - 1) // grid
@@ -60,7 +65,8 @@ def emulate_stream(npatch, bs, pdofs, inv_flat, r, storage, grid):
             issue(g)
         p = block
         rl = np.array([r[d] if d >= 0 else 0.0 for d in pdofs[p]])
-        acc = np.zeros(bs)
+        acc = np.zeros((nthreads, vec))
+        part = np.full(vec * bs, np.nan)
         c = 0
         for g in range(total):
             s = g % NSTAGE
@@ -72,16 +78,29 @@ def emulate_stream(npatch, bs, pdofs, inv_flat, r, storage, grid):
             waited[s] += 1
             cols = bs - c * cc if c == nchunk - 1 else cc
             A = stages[s]
-            for tid in range(bs):
-                acc[tid] += sum(A[j * bs + tid] * rl[c * cc + j] for j in range(cols))
+            for tid in range(nthreads):
+                q, grp = tid % nq, tid // nq
+                if grp >= vec:                         # threads of the rounded-up last warp do not compute
+                    assert tid >= bs
+                    continue
+                for j in range(grp, cols, vec):
+                    off = j * bs * es + q * 16         # byte offset of this thread's 128-bit load in the stage
+                    assert off % 16 == 0 and off + 16 <= cols * bs * es
+                    for v in range(vec):
+                        acc[tid, v] += A[off // es + v] * rl[c * cc + j]
+                if c == nchunk - 1:
+                    part[grp * bs + q * vec: grp * bs + (q + 1) * vec] = acc[tid]
             if g + NSTAGE < total:
                 issue(g + NSTAGE)
             c += 1
             if c == nchunk:
-                y[p * bs: (p + 1) * bs] = acc
+                assert not np.isnan(part).any()
+                for tid in range(bs):
+                    y[p * bs + tid] = sum(part[v * bs + tid] for v in range(vec))
                 if p + grid < npatch:
                     rl = rnext_vals
-                acc = np.zeros(bs)
+                acc = np.zeros((nthreads, vec))
+                part = np.full(vec * bs, np.nan)
                 c = 0
                 p += grid
     return y
@@ -154,5 +173,6 @@ def test_chunk_geometry_fits_the_shared_memory_budget():
         for bs in range(align, 257, align):
             cc, nchunk, stage_bytes = chunk_geometry(bs, storage)
             assert 1 <= cc <= bs and (nchunk - 1) * cc < bs <= nchunk * cc
-            smem = 128 + (bs * 8 + 127) // 128 * 128 + NSTAGE * stage_bytes
+            vec = 16 // ELEM[storage]
+            smem = 128 + (1 + vec) * ((bs * 8 + 127) // 128 * 128) + NSTAGE * stage_bytes
             assert smem <= 64 * 1024, (storage, bs, smem)

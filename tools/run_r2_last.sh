@@ -1,17 +1,10 @@
 #!/bin/bash
-# Last GPU call of round 2: suite, smoke, fine-level FP32 smoother capture (dram traffic), default bench
+# Last GPU call of round 2: suite, smoke, default bench
 O=gpurun_out/r2_last
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
 timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
-OCMP_PATCH_STORAGE=fp32 timeout 300 ncu --set full --clock-control none -k regex:k_patch_apply_stream -c 2 -o $O/ncu_apply_f32 -f python tools/kern_bench.py 128 > $O/ncu_apply_f32.log 2>&1
-ncu -i $O/ncu_apply_f32.ncu-rep --page raw --csv 2>/dev/null | python -c "
-import csv, sys
-rows = list(csv.reader(sys.stdin)); h = rows[0]
-for r in rows[2:]:
-    print({k: r[h.index(k)] for k in ('Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__grid_size', 'launch__block_size') if k in h})
-"
 timeout 600 python bench.py > $O/bench_1gpu.json 2> $O/bench_1gpu.err; tail -c 300 $O/bench_1gpu.err
 python -c "
 import json
