@@ -23,8 +23,8 @@ from typing import List, Optional
 import numpy as np
 
 from .dist import DofMap, Partition
-from .multigrid import (SmootherLag, clone_space, coarse_state_key, coefficient_fields, mesh_levels, prolongation,
-                        restrict_field, reuse_coarse_enabled)
+from .multigrid import (SmootherLag, clone_space, coarse_mesh_size_scales, coarse_state_key, coefficient_fields,
+                        mesh_levels, prolongation, restrict_field, reuse_coarse_enabled)
 
 
 def _allreduce(vals, like):
@@ -122,6 +122,7 @@ class DistributedMultigrid:
             self.levels.append(lv)
         # coefficient fields (DIM phase field, masks) get a stand-in on every coarse level, finest to coarsest
         cur = {id(gf): gf for gf in cfields}
+        hscale = coarse_mesh_size_scales(L + 1)
         for l in range(L - 1, -1, -1):
             lv, up = self.levels[l], self.levels[l + 1]
             parent_global = up.part.local_cells // (2 ** up.mesh.dim)
@@ -129,7 +130,8 @@ class DistributedMultigrid:
             lv.field_map = {k: restrict_field(g, lv.mesh, parent) for k, g in cur.items()}
             cur = dict(lv.field_map)
             fmap = {id(gf): lv.field_map[id(gf)] for gf in cfields}
-            lv.program = lower_form(lv.fes, bf.integrals, 2, drop_fields=True, field_map=fmap)
+            lv.program = lower_form(lv.fes, bf.integrals, 2, drop_fields=True, field_map=fmap,
+                                    cell_mesh_size_scale=hscale[l])
         self.inv0 = None
         self._native = None
         self._work = None

@@ -184,6 +184,28 @@ class SmootherLag:
         self.last = int(iterations)
 
 
+def inherit_cell_penalty() -> bool:
+    """Coarse-level operators evaluate ``specialcf.mesh_size`` inside cell integrals with the FINE mesh size (default;
+    ``OCMP_MG_COARSE_H=own`` restores the coarse level's own size). The reference's diffuse-interface forms carry the
+    volume penalty alpha = ipc k^2 / h (models/ins_dim.py:60-104 through base_model.py:150): outside the fluid the
+    momentum rows reduce to alpha (1 - phi) u + grad p, i.e. the pressure there obeys a Darcy problem with
+    permeability 1 / alpha ~ h. A coarse operator re-discretised with its own h doubles that permeability per level,
+    so the coarse-grid correction of the smooth pressure modes of the solid region is too small by 2, 4, 8, ... —
+    every additional level adds modes the cycle barely reduces, and the GMRES iteration count grows with the mesh
+    (26 / 46 iterations at 8^3 / 16^3 hexes, 63 at 48^3, 143-325 at 96^3). With the fine level's penalty on every level
+    the count is 21-24 / 26-27 at 8^3 / 16^3 (profiles/r2_mg_penalty_study.md). Interior-penalty terms on facets
+    (DG forms) are left alone: there the level's own h is the right scale."""
+    import os
+    return os.environ.get('OCMP_MG_COARSE_H', 'fine') != 'own'
+
+
+def coarse_mesh_size_scales(nlevels: int) -> list:
+    """Factor on the cell mesh size of the coarse levels 0 .. nlevels - 2 (uniform refinement halves h per level)."""
+    if not inherit_cell_penalty():
+        return [1.0] * (nlevels - 1)
+    return [0.5 ** (nlevels - 1 - l) for l in range(nlevels - 1)]
+
+
 def reuse_coarse_enabled() -> bool:
     import os
     return os.environ.get('OCMP_MG_REUSE_COARSE', '1') != '0'
@@ -215,8 +237,9 @@ class MultigridState:
                 cur = restrict_field(cur, self.spaces[l].mesh)
                 self.field_maps[l][id(gf)] = cur
                 self._coarse_fields.append(cur)
-        self.programs = [lower_form(s, bf.integrals, 2, drop_fields=True, field_map=fm)
-                         for s, fm in zip(self.spaces[:-1], self.field_maps)]
+        self.programs = [lower_form(s, bf.integrals, 2, drop_fields=True, field_map=fm, cell_mesh_size_scale=hs)
+                         for s, fm, hs in zip(self.spaces[:-1], self.field_maps,
+                                              coarse_mesh_size_scales(self.nlevels))]
         self.mats = [ngs.Matrix(s) for s in self.spaces[:-1]]
         self.transfers = []
         for lo, hi in zip(self.spaces[:-1], self.spaces[1:]):

@@ -728,12 +728,25 @@ def form_action(fes, integrals: SumOfIntegrals, gf_root) -> SumOfIntegrals:
 
 
 # ---- lowering ------------------------------------------------------------------------------------------------------
+def scale_cell_mesh_size(c: Coef, scale: float, memo: Optional[dict] = None) -> Coef:
+    """``specialcf.mesh_size`` -> ``scale * specialcf.mesh_size`` throughout one integrand."""
+    factor = Coef.const(float(scale))
+    return _map_leaves(c, lambda leaf: Coef.binary('mul', leaf, factor) if leaf.op == 'h' else leaf,
+                       {} if memo is None else memo)
+
+
 def lower_form(fes, integrals: SumOfIntegrals, arity: int, intorder: Optional[int] = None,
-               drop_fields: bool = False, field_map: Optional[dict] = None) -> FormProgram:
+               drop_fields: bool = False, field_map: Optional[dict] = None,
+               cell_mesh_size_scale: float = 1.0) -> FormProgram:
     """Group the entries of all integrals by (kind, region) and compile one bytecode per group.
 
     ``drop_fields`` (coarse multigrid levels): terms weighted by a DOF vector are dropped, except when every field in
-    them has a coarse-level stand-in in ``field_map`` ({id(fine GridFunction): coarse GridFunction})."""
+    them has a coarse-level stand-in in ``field_map`` ({id(fine GridFunction): coarse GridFunction}).
+
+    ``cell_mesh_size_scale`` (coarse multigrid levels): factor on ``specialcf.mesh_size`` inside CELL integrals, so that
+    a volume penalty alpha = c / h (the diffuse-interface penalisation and Nitsche terms, models/ins_dim.py:60-104)
+    keeps the fine level's value on the coarse levels (multigrid.inherit_cell_penalty). Facet integrals (interior
+    penalty of the DG forms) keep the mesh size of their own level."""
     mesh = fes.mesh
     nrows = fes.nrows
     groups: Dict[tuple, Dict[Tuple[Key, Key], Coef]] = {}
@@ -750,6 +763,9 @@ def lower_form(fes, integrals: SumOfIntegrals, arity: int, intorder: Optional[in
                 elif field_map and all(id(lf.val[0]) in field_map for lf in leaves):
                     kept[k] = substitute_fields(c, field_map, memo)
             s = S(kept)
+        if cell_mesh_size_scale != 1.0 and m.kind == 'vol' and not m.skeleton and not m.element_boundary:
+            hmemo: dict = {}
+            s = S({k: scale_cell_mesh_size(c, cell_mesh_size_scale, hmemo) for k, c in s.t.items()})
         if m.kind == 'vol' and not m.skeleton:
             kind, rkind = 'cell', 'mat'
             nreg = len(mesh.mat_names)
