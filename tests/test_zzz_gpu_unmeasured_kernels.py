@@ -59,7 +59,10 @@ def test_fp32_stored_multigrid_data_keep_iteration_counts(monkeypatch, storage):
     monkeypatch.setenv('OCMP_SPMV_FP32', '1')        # and FP32 copies of the level matrices inside the cycle
     u32, its32 = _with('cuda', run)
     assert max(abs(a - b) for a, b in zip(its32, its64)) <= (1 if storage == 'fp32' else 4)
-    assert _rel(u32, u64) < 1e-7          # both are 1e-12-tolerance solves of a system with condition number > 1e10
+    # both are 1e-12-tolerance solves (preconditioned residual) of a system with condition number > 1e10: each lies
+    # within ~2e-7 of the sparse-LU solution (tests/test_gpu_parity.py::test_ins_dim_3d_multigrid_step compares at
+    # 1e-6), so two differently rounded preconditioners agree to that, not to round-off (bf16: 1.8e-7 measured)
+    assert _rel(u32, u64) < 1e-6
 
 
 @pytest.mark.parametrize('storage', ['fp32', 'bf16'])
