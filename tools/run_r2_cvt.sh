@@ -1,4 +1,7 @@
 #!/bin/bash
+# Record of a measurement: OCMP_PATCH_CHUNK / OCMP_PATCH_CVT were temporary switches of ocmp_patch.cu (chunk size of the
+# bulk copies; FP32 -> FP64 widening on the XU / integer pipe). The measured best (8 KB, F2F) is compiled in, the switches
+# are gone; results: profiles/r2_patch_chunk_sweep.log, profiles/r2_patch_cvt_sweep.log.
 # smoother products: chunk size of the bulk copies (bytes per stage) against the per-chunk synchronisation cost
 O=gpurun_out/r2_cvt
 mkdir -p $O
