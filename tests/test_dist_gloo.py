@@ -288,3 +288,38 @@ def test_halo_plans_of_a_brick_partition_on_four_ranks():
     out = mgr.dict()
     mp.spawn(_block_exchange_worker, args=(world, port, out), nprocs=world, join=True)
     assert len(out) == world and all(v == 3 for v in out.values())       # every brick touches the three others
+
+
+def _dim_counts_worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import opencmp_b200.ngs as ngs
+        from oracle.backend import OracleBackend
+        ngs.set_backend(OracleBackend())
+        from opencmp_b200.dist_workload import DistributedINSDIM3D
+        d = DistributedINSDIM3D(6 if world == 2 else 8, world, rank, layout='sphere', replicate_below=3000,
+                                nonlinear_max_iterations=1, nonlinear_tolerance=(0.0, 0.0), wall_period=0.1)
+        assert d.gmesh.ne == 8 ** 3
+        assert [lv.replicated for lv in d.mg.levels] == [True, True, False]
+        d.step()
+        out[rank] = list(d.w.linear_iterations)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_dim_step_with_thin_interface_keeps_the_single_process_iteration_count():
+    """3-D INS-DIM with the bench's interface width (lambda = 0.25: phi reaches the 1e-10 clamp, the continuity rows of
+    the solid region are scaled down by up to ten orders of magnitude) on 8^3 hexes: two ranks (two bricks, two ghost
+    layers, partitioned finest level, replicated coarse levels with the fine level's volume penalty —
+    multigrid.inherit_cell_penalty) need exactly the GMRES iterations of the single-process run."""
+    counts = {}
+    for world in (1, 2):
+        port = _free_port()
+        mgr = mp.get_context('spawn').Manager()
+        out = mgr.dict()
+        mp.spawn(_dim_counts_worker, args=(world, port, out), nprocs=world, join=True)
+        assert len(out) == world and all(out[r] == out[0] for r in range(world))
+        counts[world] = out[0]
+    assert counts[2] == counts[1] and max(counts[1]) < 30
