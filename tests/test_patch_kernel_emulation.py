@@ -176,3 +176,19 @@ def test_chunk_geometry_fits_the_shared_memory_budget():
             vec = 16 // ELEM[storage]
             smem = 128 + (1 + vec) * ((bs * 8 + 127) // 128 * 128) + NSTAGE * stage_bytes
             assert smem <= 64 * 1024, (storage, bs, smem)
+
+
+def test_packed_bfloat16_pairs_widen_by_bit_moves():
+    """RowVec<__nv_bfloat16>::load: a 32-bit word holds two stored entries; the low one becomes an FP32 by a left shift
+    of 16 bits, the high one by masking the low half away — the same values torch's bfloat16 -> float32 conversion gives
+    (little-endian packing: entry 2k in the low half of word k)."""
+    rng = np.random.default_rng(5)
+    vals = torch.from_numpy(rng.standard_normal(64) * 10.0 ** rng.integers(-12, 12, 64)).to(torch.bfloat16)
+    vals[3], vals[10] = 0.0, -0.0
+    words = vals.view(torch.int16).numpy().view(np.uint16).astype(np.uint32)
+    packed = words[0::2] | (words[1::2] << 16)                       # what one LDS.128 returns, word by word
+    lo = (packed << 16).astype(np.uint32).view(np.float32)
+    hi = (packed & np.uint32(0xffff0000)).view(np.float32)
+    ref = vals.to(torch.float32).numpy()
+    assert np.array_equal(lo.view(np.uint32), ref[0::2].view(np.uint32))
+    assert np.array_equal(hi.view(np.uint32), ref[1::2].view(np.uint32))
