@@ -205,7 +205,8 @@ def workload_config(args, where, N=None, gpus=None):
                             '(reference models/ins_dim.py forms)'.format(N, args.order, args.order - 1),
                 'N': N, 'order': args.order,
                 'linear_solver': 'GMRES(200) + geometric multigrid V(1,1) on the hex hierarchy, open-star vertex-patch '
-                                 'additive Schwarz smoother (damping 0.7), coarse-level phase field, tol 1e-12'
+                                 'additive Schwarz smoother (damping 0.7), coarse-level phase field, coarse operators with the fine '
+                                 'level\'s volume penalty (OCMP_MG_COARSE_H=fine), tol 1e-12'
                 if where == 'gpu' else 'direct (SciPy SuperLU), the reference\'s default linear_solver',
                 'picard_iterations_per_step': 2,
                 'l2': 'inputs larger than L2 (CSR matrix and patch inverses are GBs); no explicit flush',
